@@ -1,0 +1,100 @@
+"""ctypes binding of the C ABI in include/qd_b200.h. There is no CPU fallback: if the
+library is missing or fails to load, importing the product classes raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libqd_b200.so")
+
+QD_F32, QD_F64 = 0, 1
+QD_MAX_FIELDS = 16
+FLAG_NONFINITE_MEASURES = 1
+FLAG_NONFINITE_OBJECTIVE = 2
+
+
+class QdError(RuntimeError):
+    pass
+
+
+class AddResult(C.Structure):
+    _fields_ = [
+        ("n_insertable", C.c_int32),
+        ("n_new", C.c_int32),
+        ("best_cell", C.c_int32),
+        ("flags", C.c_uint32),
+        ("best_objective", C.c_double),
+        ("delta_sum", C.c_double * 3),
+        ("batch_absmax", C.c_double),
+    ]
+
+
+class Store(C.Structure):
+    _fields_ = [
+        ("capacity", C.c_int64),
+        ("obj_dtype", C.c_int),
+        ("occupied", C.c_void_p),
+        ("occupied_list", C.c_void_p),
+        ("objective", C.c_void_p),
+        ("threshold", C.c_void_p),
+        ("n_fields", C.c_int),
+        ("field_dst", C.c_void_p * QD_MAX_FIELDS),
+        ("field_row_bytes", C.c_int64 * QD_MAX_FIELDS),
+        ("scratch", C.c_void_p),
+    ]
+
+
+class CmaScalars(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("cc", "cs", "c1", "cmu", "mueff", "damps", "wsum", "hsig_exp")]
+
+
+_vp, _i64, _i32, _int, _dbl, _sz, _u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_double, C.c_size_t, C.c_uint64
+
+# name -> (restype, argtypes); mirrors include/qd_b200.h one to one.
+PROTOTYPES = {
+    "qd_abi_version": (_int, []),
+    "qd_last_error": (C.c_char_p, []),
+    "qd_launch_count": (_i64, []),
+    "qd_grid_index_of": (_int, [_vp, _int, _i64, _int, C.POINTER(_i32), C.POINTER(_dbl), C.POINTER(_dbl), _dbl,
+                                _vp, _vp, _vp]),
+    "qd_cvt_prepared_bytes": (_sz, [_i64, _int]),
+    "qd_cvt_prepare": (_int, [_vp, _int, _i64, _int, _vp, _vp]),
+    "qd_cvt_scratch_bytes": (_sz, [_i64, _i64, _int]),
+    "qd_cvt_index_of": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _i32, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qd_cvt_mask_losers": (_int, [_vp, _vp, _vp, _i64, _vp]),
+    "qd_insert_scratch_bytes": (_sz, [_i64]),
+    "qd_insert_scratch_init": (_int, [_vp, _i64, _vp]),
+    "qd_insert_flags_ptr": (_vp, [_vp, _i64]),
+    "qd_insert": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _dbl, _dbl, _i64, _vp, _vp, _vp, _vp]),
+    "qd_store_gather": (_int, [_i64, _vp, _int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads (once) and returns the shared library; raises QdError when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise QdError(
+                f"{LIB_PATH} not found: build it with `python -m pyribs_b200.build` "
+                "(there is no CPU fallback for this package)"
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise QdError(f"qd_b200 error {rc}: {lib().qd_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().qd_launch_count())

@@ -1,0 +1,9 @@
+"""Archives of the B200-native hot path (drop-in for `ribs.archives` on this path)."""
+from pyribs_b200.archives._add_status import AddStatus
+from pyribs_b200.archives._archive_base import DeviceArchive
+from pyribs_b200.archives._archive_stats import ArchiveStats
+from pyribs_b200.archives._cvt_archive import CVTArchive
+from pyribs_b200.archives._device_store import DeviceStore
+from pyribs_b200.archives._grid_archive import GridArchive
+
+__all__ = ["AddStatus", "ArchiveStats", "CVTArchive", "DeviceArchive", "DeviceStore", "GridArchive"]

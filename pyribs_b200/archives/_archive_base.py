@@ -1,0 +1,350 @@
+"""DeviceArchive: everything GridArchive and CVTArchive share.
+
+Implements the `ArchiveBase` API of the reference (ribs/archives/_archive_base.py:17-397)
+on top of DeviceStore and the qd_insert kernel sequence. Subclasses provide
+`_index_of_device(measures, flags_ptr)`.
+
+Semantics of `add` follow ribs/archives/_grid_archive.py:518-714 (identical to
+_cvt_archive.py:713-909); see SURVEY.md appendix A for the restatement.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from pyribs_b200 import _lib
+from pyribs_b200._utils import (
+    as_dim_tuple,
+    check_batch_shape,
+    check_finite,
+    check_shape,
+    is_device_tensor,
+    torch_dtype,
+    validate_batch,
+    validate_single,
+)
+from pyribs_b200.archives._archive_stats import ArchiveStats
+from pyribs_b200.archives._device_store import DeviceStore, current_stream_ptr
+
+_RESERVED = {"solution", "objective", "measures", "threshold", "index"}
+
+
+def parse_all_dtypes(dtype, solution_dtype, objective_dtype, measures_dtype):
+    """ribs/archives/_utils.py:28-73."""
+    if isinstance(dtype, dict):
+        raise ValueError(
+            "Passing a dict as `dtype` is deprecated in pyribs 0.9.0. Please use "
+            "`solution_dtype`, `objective_dtype`, and/or `measures_dtype` instead."
+        )
+    individual = solution_dtype is not None or objective_dtype is not None or measures_dtype is not None
+    if dtype is not None and individual:
+        raise ValueError(
+            "dtype cannot be used at the same time as solution_dtype, objective_dtype, or measures_dtype. "
+            "Either pass dtype on its own, or pass solution_dtype, objective_dtype, and/or measures_dtype."
+        )
+    default = np.float64
+    if individual:
+        return tuple(np.dtype(default if d is None else d) for d in (solution_dtype, objective_dtype, measures_dtype))
+    d = np.dtype(default if dtype is None else dtype)
+    return d, d, d
+
+
+def validate_cma_mae_settings(learning_rate, threshold_min, dtype):
+    """ribs/archives/_utils.py:76-93."""
+    if threshold_min != -np.inf and learning_rate is None:
+        raise ValueError(
+            "threshold_min was set without setting learning_rate. Please note that threshold_min is only "
+            "used in CMA-MAE; it is not intended to be used for only filtering archive solutions. To run "
+            "CMA-MAE, please also set learning_rate."
+        )
+    if learning_rate is None:
+        learning_rate = 1.0
+    if threshold_min == -np.inf and learning_rate != 1.0:
+        raise ValueError("threshold_min can only be -np.inf if learning_rate is 1.0")
+    return np.asarray(learning_rate, dtype=dtype), np.asarray(threshold_min, dtype=dtype)
+
+
+def fill_sentinel_values(occupied, data):
+    """ribs/archives/_utils.py:96-112."""
+    unoccupied = ~occupied
+    for name, arr in data.items():
+        if name == "index":
+            fill = -1
+        elif np.issubdtype(arr.dtype, np.integer):
+            fill = 0
+        else:
+            fill = np.nan
+        arr[unoccupied] = fill
+
+
+class DeviceArchive:
+    def __init__(self, *, solution_dim, measure_dim, cells, learning_rate, threshold_min, qd_score_offset, seed,
+                 solution_dtype, objective_dtype, measures_dtype, dtype, extra_fields, device=None):
+        self._rng = np.random.default_rng(seed)
+        self._solution_dim = as_dim_tuple(solution_dim) if not np.isscalar(solution_dim) else int(solution_dim)
+        self._objective_dim = ()
+        self._measure_dim = int(measure_dim)
+        extra_fields = extra_fields or {}
+        if _RESERVED & extra_fields.keys():
+            raise ValueError(f"The following names are not allowed in extra_fields: {_RESERVED}")
+        sdt, odt, mdt = parse_all_dtypes(dtype, solution_dtype, objective_dtype, measures_dtype)
+        for what, dt in (("objective", odt), ("measures", mdt)):
+            if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+                raise TypeError(f"{what} dtype must be float32 or float64 on the GPU path, got {dt}")
+        for name, (_, dt) in extra_fields.items():
+            torch_dtype(dt)  # raises TypeError for object dtype etc.
+        self._store = DeviceStore(
+            {
+                "solution": (self._solution_dim, sdt),
+                "objective": ((), odt),
+                "measures": (self._measure_dim, mdt),
+                "threshold": ((), odt),  # same dtype as objective: they share arithmetic
+                **extra_fields,
+            },
+            capacity=cells,
+            device=device,
+        )
+        self._device = self._store.device
+        self._learning_rate, self._threshold_min = validate_cma_mae_settings(learning_rate, threshold_min, odt)
+        self._qd_score_offset = np.asarray(qd_score_offset, dtype=odt)
+        self._best_elite = None
+        self._objective_sum = None
+        self._stats = None
+        self._stats_reset()
+        self._pinned = {}
+
+    # ---- properties ---------------------------------------------------------------------
+    @property
+    def solution_dim(self):
+        return self._solution_dim
+
+    @property
+    def objective_dim(self):
+        return self._objective_dim
+
+    @property
+    def measure_dim(self):
+        return self._measure_dim
+
+    @property
+    def field_list(self):
+        return self._store.field_list_with_index
+
+    @property
+    def dtypes(self):
+        return self._store.dtypes_with_index
+
+    @property
+    def stats(self):
+        return self._stats
+
+    @property
+    def empty(self):
+        return len(self._store) == 0
+
+    @property
+    def best_elite(self):
+        return self._best_elite
+
+    @property
+    def cells(self):
+        return self._store.capacity
+
+    @property
+    def learning_rate(self):
+        return self._learning_rate
+
+    @property
+    def threshold_min(self):
+        return self._threshold_min
+
+    @property
+    def qd_score_offset(self):
+        return self._qd_score_offset
+
+    @property
+    def device(self):
+        return self._device
+
+    def __len__(self):
+        return len(self._store)
+
+    def __iter__(self):
+        return iter(self._store)
+
+    # ---- stats (A8, _grid_archive.py:311-360) ---------------------------------------------
+    def _stats_reset(self):
+        odt = self.dtypes["objective"]
+        self._best_elite = None
+        self._objective_sum = np.asarray(0.0, dtype=odt)
+        self._stats = ArchiveStats(
+            num_elites=0,
+            coverage=np.asarray(0.0, dtype=odt),
+            qd_score=np.asarray(0.0, dtype=odt),
+            norm_qd_score=np.asarray(0.0, dtype=odt),
+            obj_max=None,
+            obj_mean=None,
+        )
+
+    def _stats_update(self, new_objective_sum, best_index, best_objective):
+        odt = self.dtypes["objective"]
+        if self._stats.obj_max is None or best_objective > self._stats.obj_max:
+            _, row = self._store.retrieve([best_index])
+            self._best_elite = {k: v[0] for k, v in row.items()}
+            new_obj_max = self._best_elite["objective"]
+        else:
+            new_obj_max = self._stats.obj_max
+        self._objective_sum = new_objective_sum
+        n = len(self)
+        qd = self._objective_sum - np.asarray(n, dtype=odt) * self._qd_score_offset
+        self._stats = ArchiveStats(
+            num_elites=n,
+            coverage=np.asarray(n / self.cells, dtype=odt),
+            qd_score=qd,
+            norm_qd_score=np.asarray(qd / self.cells, dtype=odt),
+            obj_max=new_obj_max,
+            obj_mean=np.asarray(self._objective_sum / n, dtype=odt),
+        )
+
+    # ---- host <-> device plumbing ----------------------------------------------------------
+    def _to_device(self, arr, np_dtype, name="_"):
+        """Host array -> device tensor through a reusable pinned staging buffer (one per
+        field, so that in-flight async copies of one add() never share a buffer)."""
+        if isinstance(arr, torch.Tensor):
+            t = arr.to(device=self._device, dtype=torch_dtype(np_dtype))
+            return t.contiguous()
+        arr = np.ascontiguousarray(arr, dtype=np_dtype)
+        if arr.size == 0:
+            return torch.empty(arr.shape, dtype=torch_dtype(np_dtype), device=self._device)
+        src = torch.from_numpy(arr)
+        if arr.nbytes < (1 << 16):
+            return src.to(self._device)
+        key = (name, np.dtype(np_dtype))
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < arr.size:
+            buf = torch.empty(max(arr.size, 1), dtype=torch_dtype(np_dtype)).pin_memory()
+            self._pinned[key] = buf
+        stage = buf[: arr.size].view(arr.shape)
+        stage.copy_(src)
+        return stage.to(self._device, non_blocking=True)
+
+    def _index_of_device(self, measures: torch.Tensor, flags_ptr: int) -> torch.Tensor:
+        raise NotImplementedError
+
+    # ---- index_of ---------------------------------------------------------------------------
+    def index_of(self, measures):
+        mdt = self.dtypes["measures"]
+        dev_in = is_device_tensor(measures)
+        if not dev_in:
+            measures = np.asarray(measures, dtype=mdt)
+        check_batch_shape(measures, "measures", self.measure_dim, "measure_dim")
+        m = self._to_device(measures, mdt)
+        flags = torch.zeros(1, dtype=torch.int32, device=self._device)
+        with torch.cuda.device(self._device):
+            idx = self._index_of_device(m, flags.data_ptr())
+        if int(flags.item()) & _lib.FLAG_NONFINITE_MEASURES:
+            raise ValueError("All elements of measures must be finite (infinity and NaN values are not supported).")
+        return idx if dev_in else idx.cpu().numpy()
+
+    def index_of_single(self, measures):
+        measures = np.asarray(measures, dtype=self.dtypes["measures"])
+        check_shape(measures, "measures", self.measure_dim, "measure_dim")
+        check_finite(measures, "measures")
+        return self.index_of(measures[None])[0]
+
+    # ---- add (A5) -----------------------------------------------------------------------------
+    def add(self, solution, objective, measures, **fields):
+        dev_in = is_device_tensor(solution)
+        data = validate_batch(self, {"solution": solution, "objective": objective, "measures": measures, **fields})
+        extra_names = [n for n in self._store.field_list if n not in ("solution", "objective", "measures", "threshold")]
+        if set(extra_names) != set(fields):
+            raise ValueError(
+                f"`data` has keys {list(data)} but should have the same keys as this archive's store, i.e., "
+                f"{[n for n in self._store.field_list if n != 'threshold']}. This error may occur if the archive "
+                "has extra_fields but the fields were not passed to archive.add() or scheduler.tell()."
+            )
+        B = int(data["solution"].shape[0])
+        odt = self.dtypes["objective"]
+        if B == 0:
+            if dev_in:
+                return {"status": torch.empty(0, dtype=torch.int32, device=self._device),
+                        "value": torch.empty(0, dtype=torch_dtype(odt), device=self._device)}
+            return {"status": np.empty(0, dtype=np.int32), "value": np.empty(0, dtype=odt)}
+        store = self._store
+        with torch.cuda.device(self._device):
+            dev = {name: self._to_device(arr, store.dtypes[name], name) for name, arr in data.items()}
+            idx = self._index_of_device(dev["measures"], store._flags_ptr)
+            status = torch.empty(B, dtype=torch.int32, device=self._device)
+            value = torch.empty(B, dtype=torch_dtype(odt), device=self._device)
+            names = store.row_fields
+            src = (C.c_void_p * max(len(names), 1))(*[dev[n].data_ptr() for n in names])
+            _lib.check(_lib.lib().qd_insert(
+                C.byref(store.abi_store()), B, idx.data_ptr(), dev["objective"].data_ptr(), src,
+                float(self._learning_rate), float(self._threshold_min), len(store), status.data_ptr(),
+                value.data_ptr(), store._result_dev.data_ptr(), current_stream_ptr()))
+            store._result_host.copy_(store._result_dev, non_blocking=True)
+            if not dev_in:
+                status_h = torch.empty(B, dtype=torch.int32, pin_memory=True)
+                value_h = torch.empty(B, dtype=torch_dtype(odt), pin_memory=True)
+                status_h.copy_(status, non_blocking=True)
+                value_h.copy_(value, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        res = _lib.AddResult.from_buffer_copy(store._result_host.numpy().tobytes())
+        if res.flags & _lib.FLAG_NONFINITE_OBJECTIVE:
+            raise ValueError("All elements of objective must be finite (infinity and NaN values are not supported).")
+        if res.flags & _lib.FLAG_NONFINITE_MEASURES:
+            raise ValueError("All elements of measures must be finite (infinity and NaN values are not supported).")
+        if res.n_insertable > 0:
+            store._updates[0] += 1
+            store._n_occupied += res.n_new
+            delta = (res.delta_sum[0] + res.delta_sum[1]) + res.delta_sum[2]
+            new_sum = np.asarray(self._objective_sum + np.asarray(delta, dtype=odt), dtype=odt)
+            self._stats_update(new_sum, res.best_cell, np.asarray(res.best_objective, dtype=odt))
+        if dev_in:
+            return {"status": status, "value": value}
+        return {"status": status_h.numpy().copy(), "value": value_h.numpy().copy()}
+
+    def add_single(self, solution, objective, measures, **fields):
+        """Scalar rule of _grid_archive.py:716-848, run as a batch of one (identical statuses;
+        the threshold t(1-lr)+f*lr equals the batch rule with k=1 up to rounding)."""
+        data = validate_single(self, {"solution": solution, "objective": objective, "measures": measures, **fields})
+        info = self.add(
+            np.asarray(data["solution"])[None], np.asarray(data["objective"])[None], np.asarray(data["measures"])[None],
+            **{k: np.asarray(v)[None] for k, v in fields.items()},
+        )
+        return {"status": info["status"][0], "value": info["value"][0]}
+
+    def clear(self):
+        self._store.clear()
+        self._stats_reset()
+
+    # ---- read side (A10, _grid_archive.py:850-924) ---------------------------------------------
+    def retrieve(self, measures):
+        measures = np.asarray(measures, dtype=self.dtypes["measures"])
+        check_batch_shape(measures, "measures", self.measure_dim, "measure_dim")
+        idx = self.index_of(measures)
+        occupied, data = self._store.retrieve(idx)
+        fill_sentinel_values(occupied, data)
+        return occupied, data
+
+    def retrieve_single(self, measures):
+        measures = np.asarray(measures, dtype=self.dtypes["measures"])
+        check_shape(measures, "measures", self.measure_dim, "measure_dim")
+        check_finite(measures, "measures")
+        occupied, data = self.retrieve(measures[None])
+        return occupied[0], {f: a[0] for f, a in data.items()}
+
+    def data(self, fields=None, return_type="dict"):
+        return self._store.data(fields, return_type)
+
+    def sample_elites(self, n, replace=True):
+        if self.empty:
+            raise IndexError("No elements in archive.")
+        if not replace and n > len(self._store):
+            raise ValueError(
+                "Cannot take a larger sample than the number of elites in the archive when 'replace=False'")
+        random_indices = self._rng.choice(len(self._store), size=n, replace=replace)
+        selected = self._store._sync_occupied_list()[random_indices]
+        return self._store.retrieve(selected)[1]

@@ -1,0 +1,166 @@
+"""CVTArchive on the B200 (API of ribs/archives/_cvt_archive.py:137-1119)."""
+from __future__ import annotations
+
+import numbers
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from pyribs_b200 import _lib
+from pyribs_b200._utils import check_batch_shape
+from pyribs_b200.archives._archive_base import DeviceArchive
+from pyribs_b200.archives._device_store import current_stream_ptr
+
+_DEPRECATED = {
+    "cells": "`cells` is deprecated in pyribs 0.9.0. Please pass in `centroids` instead.",
+    "custom_centroids": "`custom_centroids` is deprecated in pyribs 0.9.0. Please pass in `centroids` instead.",
+    "centroid_method": "`centroid_method` is deprecated in pyribs 0.9.0. Please generate centroids and pass them in instead.",
+    "use_kd_tree": "`use_kd_tree` is deprecated in pyribs 0.9.0. Please use `nearest_neighbors` instead.",
+    "ckdtree_kwargs": "`ckdtree_kwargs` is deprecated in pyribs 0.9.0. Please use `kdtree_kwargs` instead.",
+}
+
+
+class CVTArchive(DeviceArchive):
+    """Centroidal-Voronoi archive: a solution belongs to the cell of its nearest centroid.
+
+    `nearest_neighbors` accepts the reference's names; "scipy_kd_tree" (default) and
+    "brute_force" both run the exact GPU search (fp64 squared distances, lowest centroid
+    index on exact ties -- the brute-force semantics of _cvt_archive.py:626-632, which the
+    KD-tree reproduces on tie-free data). "sklearn_nn" (arbitrary metrics) has no GPU
+    implementation and raises.
+
+    Multi-GPU: with `shard_centroids=True` and an initialised torch.distributed NCCL
+    process group, rank r searches centroids [r*C/R, (r+1)*C/R) and the ranks combine with
+    an all-reduce(min) over the exact distances followed by an all-reduce(min) over the
+    candidate indices; the store is replicated.
+    """
+
+    def __init__(self, *, solution_dim, centroids, ranges, learning_rate=None, threshold_min=-np.inf,
+                 qd_score_offset=0.0, seed=None, solution_dtype=None, objective_dtype=None, measures_dtype=None,
+                 dtype=None, extra_fields=None, samples=100_000, k_means_kwargs=None,
+                 nearest_neighbors="scipy_kd_tree", kdtree_kwargs=None, kdtree_query_kwargs=None, chunk_size=None,
+                 sklearn_nn_kwargs=None, cells=None, custom_centroids=None, centroid_method=None, use_kd_tree=None,
+                 ckdtree_kwargs=None, device=None, search_method="auto", shard_centroids=False, process_group=None):
+        for name, val in (("cells", cells), ("custom_centroids", custom_centroids),
+                          ("centroid_method", centroid_method), ("use_kd_tree", use_kd_tree),
+                          ("ckdtree_kwargs", ckdtree_kwargs)):
+            if val is not None:
+                raise ValueError(_DEPRECATED[name])
+        if nearest_neighbors not in ("scipy_kd_tree", "brute_force", "sklearn_nn"):
+            raise ValueError(f"Unknown value `{nearest_neighbors}` for nearest_neighbors.")
+        if nearest_neighbors == "sklearn_nn":
+            raise NotImplementedError(
+                "nearest_neighbors='sklearn_nn' (arbitrary sklearn metrics) has no GPU implementation and this "
+                "package has no CPU fallback; use 'scipy_kd_tree' or 'brute_force' (Euclidean).")
+        self._nearest_neighbors = nearest_neighbors
+        from pyribs_b200.archives._archive_base import parse_all_dtypes
+
+        _, _, mdt = parse_all_dtypes(dtype, solution_dtype, objective_dtype, measures_dtype)
+        if isinstance(centroids, numbers.Integral):
+            raise NotImplementedError(
+                "Generating centroids with k-means is one-off set-up outside the accelerated path; generate "
+                "them first (e.g. sklearn.cluster.k_means) and pass the array.")
+        if isinstance(centroids, (str, Path)):
+            cen = np.load(centroids).astype(mdt)
+        else:
+            cen = np.asarray(centroids, dtype=mdt)
+        check_batch_shape(cen, "centroids", len(ranges), "measure_dim", batch_name="num_centroids")
+        self._centroids = cen
+        DeviceArchive.__init__(
+            self, solution_dim=solution_dim, measure_dim=len(ranges), cells=len(cen), learning_rate=learning_rate,
+            threshold_min=threshold_min, qd_score_offset=qd_score_offset, seed=seed, solution_dtype=solution_dtype,
+            objective_dtype=objective_dtype, measures_dtype=measures_dtype, dtype=dtype, extra_fields=extra_fields,
+            device=device)
+        lo, hi = zip(*ranges)
+        self._lower_bounds = np.array(lo, dtype=mdt)
+        self._upper_bounds = np.array(hi, dtype=mdt)
+        self._interval_size = self._upper_bounds - self._lower_bounds
+        self._meas_code = _lib.QD_F64 if np.dtype(mdt) == np.float64 else _lib.QD_F32
+        if search_method not in ("auto", "tensor", "scan"):
+            raise ValueError("search_method must be 'auto', 'tensor' or 'scan'")
+        self._search_method = search_method
+        # centroid shard owned by this rank
+        self._pg = process_group
+        self._world = 1
+        self._rank = 0
+        if shard_centroids:
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                raise RuntimeError("shard_centroids=True needs an initialised torch.distributed process group")
+            self._world = dist.get_world_size(process_group)
+            self._rank = dist.get_rank(process_group)
+        C_total = len(cen)
+        per = -(-C_total // self._world)
+        self._shard_lo = min(self._rank * per, C_total)
+        self._shard_hi = min(self._shard_lo + per, C_total)
+        shard = np.ascontiguousarray(cen[self._shard_lo:self._shard_hi])
+        with torch.cuda.device(self._device):
+            self._centroids_dev = torch.from_numpy(shard).to(self._device) if len(shard) else None
+            self._prepared = None
+            if len(shard):
+                nbytes = _lib.lib().qd_cvt_prepared_bytes(len(shard), self._measure_dim)
+                self._prepared = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self._device)
+                _lib.check(_lib.lib().qd_cvt_prepare(self._centroids_dev.data_ptr(), self._meas_code, len(shard),
+                                                     self._measure_dim, self._prepared.data_ptr(),
+                                                     current_stream_ptr()))
+        self._cvt_scratch = None
+
+    @property
+    def centroids(self):
+        return self._centroids
+
+    @property
+    def lower_bounds(self):
+        return self._lower_bounds
+
+    @property
+    def upper_bounds(self):
+        return self._upper_bounds
+
+    @property
+    def interval_size(self):
+        return self._interval_size
+
+    def _pick_method(self, B, C):
+        if self._search_method == "tensor":
+            return 0
+        if self._search_method == "scan":
+            return 1
+        return 0 if (B * C >= (1 << 22) and B >= 128) else 1
+
+    # ---- A3 ---------------------------------------------------------------------------------
+    def _local_search(self, measures, flags_ptr, want_dist):
+        B = int(measures.shape[0])
+        Cn = self._shard_hi - self._shard_lo
+        idx = torch.empty(B, dtype=torch.int32, device=self._device)
+        dist = torch.empty(B, dtype=torch.float64, device=self._device) if want_dist else None
+        if Cn == 0:
+            idx.fill_(2**31 - 1)
+            if dist is not None:
+                dist.fill_(float("inf"))
+            return idx, dist
+        method = self._pick_method(B, Cn)
+        need = int(_lib.lib().qd_cvt_scratch_bytes(B, Cn, self._measure_dim))
+        if self._cvt_scratch is None or self._cvt_scratch.numel() < need:
+            self._cvt_scratch = torch.empty(max(need, 256), dtype=torch.uint8, device=self._device)
+        _lib.check(_lib.lib().qd_cvt_index_of(
+            measures.data_ptr(), self._meas_code, B, self._measure_dim, self._centroids_dev.data_ptr(), Cn,
+            self._prepared.data_ptr(), self._shard_lo, method, idx.data_ptr(),
+            dist.data_ptr() if dist is not None else None, flags_ptr, self._cvt_scratch.data_ptr(),
+            self._cvt_scratch.numel(), current_stream_ptr()))
+        return idx, dist
+
+    def _index_of_device(self, measures: torch.Tensor, flags_ptr: int) -> torch.Tensor:
+        if self._world == 1:
+            return self._local_search(measures, flags_ptr, False)[0]
+        import torch.distributed as dist
+
+        idx, d_local = self._local_search(measures, flags_ptr, True)
+        d_min = d_local.clone()
+        dist.all_reduce(d_min, op=dist.ReduceOp.MIN, group=self._pg)
+        _lib.check(_lib.lib().qd_cvt_mask_losers(d_local.data_ptr(), d_min.data_ptr(), idx.data_ptr(),
+                                                 int(idx.numel()), current_stream_ptr()))
+        dist.all_reduce(idx, op=dist.ReduceOp.MIN, group=self._pg)
+        return idx

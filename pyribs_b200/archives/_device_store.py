@@ -1,0 +1,300 @@
+"""DeviceStore: the HBM-resident struct-of-arrays behind every archive.
+
+Drop-in for the reference's `ArrayStore` read API (ribs/archives/_array_store.py:71-651):
+`retrieve`, `data`, `occupied`, `occupied_list`, `field_desc`, `dtypes`, iteration with
+the same "modified during iteration" RuntimeError, `clear`, `resize`. The write side is not
+`ArrayStore.add`: insertion is the fused `qd_insert` kernel sequence driven by
+`DeviceArchive.add`, which reproduces `_array_store.py:560-608` (ascending append of new
+cells to `occupied_list`, last field scatter) on the device.
+
+Layout in HBM (capacity = number of cells):
+    fields[name]   (capacity, *shape) contiguous, row-major, field dtype
+    occupied       (capacity,) uint8
+    occupied_list  (capacity,) int32, first n_occupied entries valid, insertion order
+    scratch        per-cell reduction scratch of qd_insert (see csrc/insert.cu)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import numbers
+
+import numpy as np
+import torch
+
+from pyribs_b200 import _lib
+from pyribs_b200._utils import arr_readonly, torch_dtype
+
+
+def current_stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DeviceStoreIterator:
+    """Iterates entries in insertion order (ArrayStoreIterator, _array_store.py:33-68)."""
+
+    def __init__(self, store: "DeviceStore"):
+        self.store = store
+        self.iter_idx = 0
+        self.state = list(store._updates)
+        self._snapshot = None
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.state != self.store._updates:
+            raise RuntimeError("ArrayStore was modified with add() or clear() during iteration.")
+        if self.iter_idx >= len(self.store):
+            raise StopIteration
+        if self._snapshot is None:  # one D2H of all occupied rows instead of one per entry
+            self._snapshot = self.store.data()
+        d = {"index": self._snapshot["index"][self.iter_idx]}
+        for name in self.store._fields:
+            d[name] = self._snapshot[name][self.iter_idx]
+        self.iter_idx += 1
+        return d
+
+
+class DeviceStore:
+    def __init__(self, field_desc, capacity, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.QdError("pyribs_b200 needs a CUDA device (there is no CPU fallback)")
+        _lib.lib()  # fail loudly if the native library is missing
+        self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        capacity = int(capacity)
+        self._capacity = capacity
+        self._n_occupied = 0
+        self._updates = [0, 0]
+        self._fields = {}
+        self._np_dtypes = {}
+        for name, (field_shape, dtype) in field_desc.items():
+            if name == "index":
+                raise ValueError(f"`{name}` is a reserved field name.")
+            if not name.isidentifier():
+                raise ValueError(f"Field names must be valid identifiers: `{name}`")
+            if isinstance(field_shape, numbers.Integral):
+                field_shape = (field_shape,)
+            np_dt = np.dtype(dtype)
+            self._np_dtypes[name] = np_dt
+            self._fields[name] = torch.empty((capacity, *field_shape), dtype=torch_dtype(np_dt), device=self._device)
+        with torch.cuda.device(self._device):
+            self._occupied = torch.zeros(capacity, dtype=torch.uint8, device=self._device)
+            self._occupied_list = torch.empty(capacity, dtype=torch.int32, device=self._device)
+            nbytes = _lib.lib().qd_insert_scratch_bytes(capacity)
+            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+            _lib.check(_lib.lib().qd_insert_scratch_init(self._scratch.data_ptr(), capacity, current_stream_ptr()))
+            self._flags_ptr = _lib.lib().qd_insert_flags_ptr(self._scratch.data_ptr(), capacity)
+            self._result_dev = torch.zeros(C.sizeof(_lib.AddResult), dtype=torch.uint8, device=self._device)
+            self._result_host = torch.zeros(C.sizeof(_lib.AddResult), dtype=torch.uint8).pin_memory()
+        self._occupied_list_host = np.empty(capacity, dtype=np.int32)
+        self._occupied_list_synced = 0
+        self._abi = None
+
+    # ---- ABI view ---------------------------------------------------------------------
+    @property
+    def row_fields(self):
+        """Fields copied row-wise by the commit kernel (all but objective / threshold)."""
+        return [n for n in self._fields if n not in ("objective", "threshold")]
+
+    def abi_store(self) -> _lib.Store:
+        if self._abi is None:
+            st = _lib.Store()
+            st.capacity = self._capacity
+            st.obj_dtype = _lib.QD_F64 if self._np_dtypes["objective"] == np.float64 else _lib.QD_F32
+            st.occupied = self._occupied.data_ptr()
+            st.occupied_list = self._occupied_list.data_ptr()
+            st.objective = self._fields["objective"].data_ptr()
+            st.threshold = self._fields["threshold"].data_ptr()
+            names = self.row_fields
+            if len(names) > _lib.QD_MAX_FIELDS:
+                raise ValueError(f"at most {_lib.QD_MAX_FIELDS} row fields are supported")
+            st.n_fields = len(names)
+            for i, n in enumerate(names):
+                t = self._fields[n]
+                st.field_dst[i] = t.data_ptr()
+                st.field_row_bytes[i] = t[0].numel() * t.element_size() if t.dim() > 1 else t.element_size()
+            st.scratch = self._scratch.data_ptr()
+            self._abi = st
+        return self._abi
+
+    # ---- properties (ArrayStore API) ----------------------------------------------------
+    def __len__(self):
+        return self._n_occupied
+
+    def __iter__(self):
+        return DeviceStoreIterator(self)
+
+    @property
+    def device(self):
+        return self._device
+
+    @property
+    def capacity(self):
+        return self._capacity
+
+    @property
+    def occupied(self):
+        return arr_readonly(self._occupied.cpu().numpy().astype(bool))
+
+    @property
+    def occupied_device(self):
+        return self._occupied
+
+    @property
+    def occupied_list(self):
+        return arr_readonly(self._sync_occupied_list()[: self._n_occupied].copy())
+
+    def _sync_occupied_list(self):
+        n = self._n_occupied
+        if self._occupied_list_synced < n:
+            s = self._occupied_list_synced
+            self._occupied_list_host[s:n] = self._occupied_list[s:n].cpu().numpy()
+            self._occupied_list_synced = n
+        return self._occupied_list_host
+
+    @property
+    def field_desc(self):
+        return {name: (tuple(t.shape[1:]), self._np_dtypes[name]) for name, t in self._fields.items()}
+
+    @property
+    def dtypes(self):
+        return dict(self._np_dtypes)
+
+    @property
+    def dtypes_with_index(self):
+        return {**self._np_dtypes, "index": np.dtype(np.int32)}
+
+    @property
+    def field_list(self):
+        return list(self._fields)
+
+    @property
+    def field_list_with_index(self):
+        return [*self._fields, "index"]
+
+    # ---- read side ----------------------------------------------------------------------
+    def gather_device(self, indices: torch.Tensor, names):
+        """Gather kernel (A6): returns (occupied uint8 tensor, {name: tensor}) on the device."""
+        M = int(indices.numel())
+        names = list(dict.fromkeys(names))
+        out = {n: torch.empty((M, *self._fields[n].shape[1:]), dtype=self._fields[n].dtype, device=self._device)
+               for n in names}
+        occ = torch.empty(M, dtype=torch.uint8, device=self._device)
+        nf = len(names)
+        if nf > _lib.QD_MAX_FIELDS:
+            raise ValueError("too many fields")
+        src = (C.c_void_p * max(nf, 1))(*[self._fields[n].data_ptr() for n in names])
+        dst = (C.c_void_p * max(nf, 1))(*[out[n].data_ptr() for n in names])
+        rb = (C.c_int64 * max(nf, 1))(*[self._row_bytes(n) for n in names])
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().qd_store_gather(M, indices.data_ptr(), nf, src, dst, rb, self._occupied.data_ptr(),
+                                                  occ.data_ptr(), current_stream_ptr()))
+        return occ, out
+
+    def _row_bytes(self, name):
+        t = self._fields[name]
+        return (t[0].numel() if t.dim() > 1 else 1) * t.element_size()
+
+    def retrieve(self, indices, fields=None, return_type="dict"):
+        """ArrayStore.retrieve (_array_store.py:330-485) with NumPy outputs."""
+        single = isinstance(fields, str)
+        if isinstance(indices, torch.Tensor):
+            idx_dev = indices.to(device=self._device, dtype=torch.int32)
+            idx_np = None
+        else:
+            idx_np = np.asarray(indices, dtype=np.int32)
+            idx_dev = torch.from_numpy(np.ascontiguousarray(idx_np)).to(self._device)
+        if not single and return_type not in ("dict", "tuple", "pandas"):
+            raise ValueError(f"Invalid return_type {return_type}.")
+        if single:
+            fields = [fields]
+        elif fields is None:
+            fields = list(itertools.chain(self._fields, ["index"]))
+        else:
+            fields = list(fields)
+        for name in fields:
+            if name != "index" and name not in self._fields:
+                raise ValueError(f"`{name}` is not a field in this ArrayStore.")
+        occ_d, got = self.gather_device(idx_dev, [n for n in fields if n != "index"])
+        occupied = occ_d.cpu().numpy().astype(bool)
+        host = {n: t.cpu().numpy() for n, t in got.items()}
+        if idx_np is None:
+            idx_np = idx_dev.cpu().numpy()
+        arrays = [np.array(idx_np, copy=True) if n == "index" else host[n] for n in fields]
+        if single:
+            return occupied, arrays[0]
+        if return_type == "dict":
+            return occupied, dict(zip(fields, arrays))
+        if return_type == "tuple":
+            return occupied, tuple(arrays)
+        import pandas as pd
+
+        cols = {}
+        for n, arr in zip(fields, arrays):
+            if arr.ndim == 1:
+                cols[n] = arr
+            elif arr.ndim == 2:
+                for i in range(arr.shape[1]):
+                    cols[f"{n}_{i}"] = arr[:, i]
+            else:
+                raise ValueError(f"Field `{n}` has shape {arr.shape[1:]} -- cannot convert fields with shape >1D to Pandas")
+        return occupied, pd.DataFrame(cols, copy=False)
+
+    def data(self, fields=None, return_type="dict"):
+        return self.retrieve(self._occupied_list[: self._n_occupied], fields, return_type)[1]
+
+    # ---- mutation -------------------------------------------------------------------------
+    def clear(self):
+        self._updates[1] += 1
+        self._n_occupied = 0
+        self._occupied_list_synced = 0
+        self._occupied.zero_()
+
+    def resize(self, capacity):
+        capacity = int(capacity)
+        if capacity <= self._capacity:
+            raise ValueError(f"New capacity ({capacity}) must be greater than current capacity ({self._capacity}.")
+        old = self._capacity
+        self._capacity = capacity
+        occ = torch.zeros(capacity, dtype=torch.uint8, device=self._device)
+        occ[:old] = self._occupied
+        self._occupied = occ
+        ol = torch.empty(capacity, dtype=torch.int32, device=self._device)
+        ol[:old] = self._occupied_list
+        self._occupied_list = ol
+        host = np.empty(capacity, dtype=np.int32)
+        host[:old] = self._occupied_list_host
+        self._occupied_list_host = host
+        for name, t in self._fields.items():
+            nt = torch.empty((capacity, *t.shape[1:]), dtype=t.dtype, device=self._device)
+            nt[:old] = t
+            self._fields[name] = nt
+        nbytes = _lib.lib().qd_insert_scratch_bytes(capacity)
+        self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().qd_insert_scratch_init(self._scratch.data_ptr(), capacity, current_stream_ptr()))
+        self._flags_ptr = _lib.lib().qd_insert_flags_ptr(self._scratch.data_ptr(), capacity)
+        self._abi = None
+
+    # ---- pickling: device tensors travel as NumPy (checkpoint / resume) ---------------------
+    def __getstate__(self):
+        st = {
+            "field_desc": self.field_desc,
+            "capacity": self._capacity,
+            "n": self._n_occupied,
+            "updates": list(self._updates),
+            "occupied": self._occupied.cpu().numpy(),
+            "occupied_list": self._occupied_list.cpu().numpy(),
+            "fields": {n: t.cpu().numpy() for n, t in self._fields.items()},
+        }
+        return st
+
+    def __setstate__(self, st):
+        self.__init__(st["field_desc"], st["capacity"])
+        self._n_occupied = st["n"]
+        self._updates = st["updates"]
+        self._occupied.copy_(torch.from_numpy(st["occupied"]))
+        self._occupied_list.copy_(torch.from_numpy(st["occupied_list"]))
+        for n, a in st["fields"].items():
+            self._fields[n].copy_(torch.from_numpy(a))

@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs golden vectors and the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from golden_util import assert_close, check_archive_dump, load_golden, steps_of
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import qd_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6  # north_star: objectives / thresholds / add values within 1e-6 relative (fp64)
+RTOL_F32 = 2e-5  # float32 archives: a few float32 ulps
+
+
+def gpu_dump(a):
+    st = a._store
+    occ = st.occupied.copy()
+    d = {"occupied": occ, "occupied_list": np.array(st.occupied_list), "n": len(st)}
+    for name, t in st._fields.items():
+        x = t.cpu().numpy().copy()
+        x[~occ] = 0
+        d["field_" + name] = x
+    s = a.stats
+    d["stats"] = {k: getattr(s, k) for k in ("num_elites", "coverage", "qd_score", "norm_qd_score", "obj_max",
+                                             "obj_mean")}
+    if a.best_elite is not None:
+        d["best_elite"] = a.best_elite
+    return d
+
+
+def make_gpu_archive(cfg, **kw):
+    from pyribs_b200.archives import CVTArchive, GridArchive
+
+    dtype = np.float32 if int(cfg["f32"]) else np.float64
+    lr = None if np.isnan(cfg["lr"]) else float(cfg["lr"])
+    args = dict(learning_rate=lr, threshold_min=float(cfg["tmin"]), dtype=dtype,
+                qd_score_offset=float(cfg.get("offset", 0.0)))
+    if int(cfg.get("extras", 0)):
+        args["extra_fields"] = {"meta": ((3,), np.int32), "score": ((), np.float32)}
+    if int(cfg["kind"]) == 0:
+        return GridArchive(solution_dim=int(cfg["n"]), dims=[int(v) for v in cfg["dims"]],
+                           ranges=[tuple(r) for r in cfg["ranges"]], **args)
+    d = cfg["centroids"].shape[1]
+    return CVTArchive(solution_dim=int(cfg["n"]), centroids=cfg["centroids"], ranges=[(-1, 1)] * d, **args, **kw)
+
+
+def test_grid_index_golden():
+    from pyribs_b200.archives import GridArchive
+
+    g = load_golden("grid_index")
+    for name, c in g.items():
+        dt = c["measures"].dtype
+        a = GridArchive(solution_dim=1, dims=[int(v) for v in c["dims"]], ranges=[tuple(r) for r in c["ranges"]],
+                        dtype=dt)
+        np.testing.assert_array_equal(a.index_of(c["measures"]), c["index"], err_msg=name)
+
+
+@pytest.mark.parametrize("method", ["scan", "tensor"])
+def test_cvt_index_golden(method):
+    from pyribs_b200.archives import CVTArchive
+
+    g = load_golden("cvt_index")
+    for name, c in g.items():
+        dt = c["measures"].dtype
+        d = c["centroids"].shape[1]
+        a = CVTArchive(solution_dim=1, centroids=c["centroids"], ranges=[(-1, 1)] * d, dtype=dt, search_method=method)
+        try:
+            idx = a.index_of(c["measures"])
+        except Exception as e:  # noqa: BLE001
+            if "not built" in str(e):
+                pytest.skip("tensor-core search not built yet")
+            raise
+        if "index" in c:
+            np.testing.assert_array_equal(idx, c["index"], err_msg=f"{name} ({method}) vs KD-tree")
+        if "index_brute" in c:
+            np.testing.assert_array_equal(idx, c["index_brute"], err_msg=f"{name} ({method}) vs brute force")
+
+
+@pytest.mark.parametrize("name", sorted(load_golden("add_traj").keys()))
+def test_add_golden(name):
+    case = load_golden("add_traj")[name]
+    cfg = case["cfg"]
+    a = make_gpu_archive(cfg)
+    rtol = RTOL_F32 if int(cfg["f32"]) else RTOL
+    single = int(cfg.get("single", 0))
+    for j, s in enumerate(steps_of(case)):
+        b = s["in"]
+        if single:
+            infos = [a.add_single(**{k: v[i] for k, v in b.items()}) for i in range(len(b["objective"]))]
+            status = np.array([x["status"] for x in infos], dtype=np.int32)
+            value = np.array([x["value"] for x in infos])
+        else:
+            info = a.add(**b)
+            status, value = info["status"], info["value"]
+            assert status.dtype == np.int32 and value.dtype == b["objective"].dtype
+        np.testing.assert_array_equal(status, s["status"], err_msg=f"{name} s{j} status")
+        assert_close(value, s["value"], rtol, f"{name} s{j} value")
+        check_archive_dump(gpu_dump(a), s["after"], rtol, f"{name} s{j}")
+
+
+def _random_batches(rng, steps, B, n, md, scale):
+    for step in range(steps):
+        yield dict(solution=rng.standard_normal((B, n)), objective=rng.normal(step, 3, B),
+                   measures=rng.uniform(-1.3, 1.3, (B, md)) * scale)
+
+
+@pytest.mark.parametrize("mode", ["me", "mae"])
+@pytest.mark.parametrize("kind", ["grid", "cvt"])
+def test_add_vs_oracle_random(kind, mode):
+    """Fresh seeded inputs at sizes the oracle finishes in seconds (includes heavy collisions)."""
+    from pyribs_b200.archives import CVTArchive, GridArchive
+
+    rng = np.random.default_rng(11)
+    lr, tmin = (None, -np.inf) if mode == "me" else (0.02, -1.5)
+    n = 16
+    if kind == "grid":
+        gpu = GridArchive(solution_dim=n, dims=(40, 60), ranges=[(-1, 1), (-2, 2)], learning_rate=lr,
+                          threshold_min=tmin, seed=5)
+        ora = O.make_grid_oracle(solution_dim=n, dims=(40, 60), ranges=[(-1, 1), (-2, 2)], learning_rate=lr,
+                                 threshold_min=tmin, seed=5)
+        md, scale = 2, np.array([1.0, 2.0])
+    else:
+        cen = rng.uniform(-1, 1, (3000, 4))
+        gpu = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * 4, learning_rate=lr, threshold_min=tmin,
+                         seed=5)
+        ora = O.make_cvt_oracle(solution_dim=n, centroids=cen, learning_rate=lr, threshold_min=tmin, seed=5)
+        md, scale = 4, np.ones(4)
+    for j, b in enumerate(_random_batches(rng, 4, 20000, n, md, scale)):
+        g = gpu.add(**b)
+        o = ora.add(**b)
+        np.testing.assert_array_equal(g["status"], o["status"], err_msg=f"step {j}")
+        assert_close(g["value"], o["value"], RTOL, f"step {j} value")
+        nocc = len(ora)
+        assert len(gpu) == nocc
+        np.testing.assert_array_equal(gpu._store.occupied_list, ora.store.occupied_list[:nocc])
+        occ = ora.store.occupied
+        np.testing.assert_array_equal(gpu._store.occupied, occ)
+        for name in ("solution", "objective", "measures"):
+            np.testing.assert_array_equal(gpu._store._fields[name].cpu().numpy()[occ], ora.store.fields[name][occ])
+        assert_close(gpu._store._fields["threshold"].cpu().numpy()[occ], ora.store.fields["threshold"][occ], RTOL)
+        so = ora.stats()
+        assert_close(gpu.stats.qd_score, so["qd_score"], RTOL, "qd_score")
+        assert gpu.stats.obj_max == so["obj_max"]
+        e1, e2 = gpu.sample_elites(7), ora.sample_elites(7)
+        np.testing.assert_array_equal(e1["solution"], e2["solution"])
+        np.testing.assert_array_equal(e1["index"], e2["index"])
+
+
+def test_add_is_deterministic():
+    """Two identical archives fed the same batches end bit-identical (binned sums)."""
+    from pyribs_b200.archives import GridArchive
+
+    rng = np.random.default_rng(3)
+    batches = [dict(solution=rng.standard_normal((30000, 8)), objective=rng.uniform(0, 100, 30000),
+                    measures=rng.normal(0, 0.1, (30000, 2))) for _ in range(3)]
+    outs = []
+    for _ in range(2):
+        a = GridArchive(solution_dim=8, dims=(50, 50), ranges=[(-1, 1)] * 2, learning_rate=0.01, threshold_min=0.0)
+        for b in batches:
+            a.add(**b)
+        outs.append((a._store._fields["threshold"].cpu().numpy().copy(), a._store.occupied, float(a.stats.qd_score)))
+    occ = outs[0][1]
+    np.testing.assert_array_equal(outs[0][0][occ], outs[1][0][occ])
+    assert outs[0][2] == outs[1][2]
+
+
+def test_error_contract():
+    from pyribs_b200.archives import GridArchive
+
+    a = GridArchive(solution_dim=3, dims=[10, 20], ranges=[(-1, 1), (-2, 2)])
+    a.add([[1, 2, 3]], [1.0], [[0.25, 0.25]])
+    before = gpu_dump(a)
+    with pytest.raises(ValueError):
+        a.add([[1, 2, 3]], [np.inf], [[0.0, 0.0]])
+    with pytest.raises(ValueError):
+        a.add([[1, 2, 3], [1, 2, 3]], [5.0, 6.0], [[0.0, np.nan], [0.5, 0.5]])
+    with pytest.raises(ValueError):
+        a.add([[1, 2, 3]], [1.0, 2.0], [[0.0, 0.0]])
+    with pytest.raises(ValueError):
+        a.add([[1, 2]], [1.0], [[0.0, 0.0]])
+    with pytest.raises(ValueError):
+        a.index_of([[np.nan, 0.0]])
+    after = gpu_dump(a)
+    np.testing.assert_array_equal(before["occupied"], after["occupied"])
+    np.testing.assert_array_equal(before["field_objective"], after["field_objective"])
+    assert len(a) == 1
+    # the store still works after the aborted batches (scratch left clean)
+    info = a.add([[4, 5, 6], [7, 8, 9]], [2.0, 3.0], [[0.25, 0.25], [0.25, 0.25]])
+    np.testing.assert_array_equal(info["status"], [1, 1])
+    assert a.best_elite["objective"] == 3.0
+    np.testing.assert_array_equal(a.best_elite["solution"], [7, 8, 9])
+    with pytest.raises(IndexError):
+        GridArchive(solution_dim=3, dims=[4], ranges=[(-1, 1)]).sample_elites(1)
+    e = GridArchive(solution_dim=3, dims=[4], ranges=[(-1, 1)])
+    out = e.add(np.zeros((0, 3)), np.zeros(0), np.zeros((0, 1)))
+    assert out["status"].shape == (0,) and out["value"].shape == (0,)
+
+
+def test_device_tensor_inputs_stay_on_device():
+    import torch
+
+    from pyribs_b200.archives import GridArchive
+
+    a = GridArchive(solution_dim=4, dims=[8, 8], ranges=[(-1, 1)] * 2)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    sol = torch.randn(1000, 4, device="cuda", dtype=torch.float64, generator=g)
+    obj = torch.randn(1000, device="cuda", dtype=torch.float64, generator=g)
+    meas = torch.rand(1000, 2, device="cuda", dtype=torch.float64, generator=g) * 2 - 1
+    info = a.add(sol, obj, meas)
+    assert info["status"].is_cuda and info["value"].is_cuda
+    b = GridArchive(solution_dim=4, dims=[8, 8], ranges=[(-1, 1)] * 2)
+    info2 = b.add(sol.cpu().numpy(), obj.cpu().numpy(), meas.cpu().numpy())
+    np.testing.assert_array_equal(info["status"].cpu().numpy(), info2["status"])
+    np.testing.assert_array_equal(a.data("objective"), b.data("objective"))
+
+
+def test_retrieve_and_iteration():
+    from pyribs_b200.archives import GridArchive
+
+    a = GridArchive(solution_dim=3, dims=[10, 20], ranges=[(-1, 1), (-2, 2)])
+    a.add([[1, 2, 3], [4, 5, 6]], [1.0, 2.0], [[0.25, 0.25], [-0.5, -0.5]])
+    occ, data = a.retrieve([[0.25, 0.25], [0.9, 0.9]])
+    np.testing.assert_array_equal(occ, [True, False])
+    assert data["objective"][0] == 1.0 and np.isnan(data["objective"][1]) and data["index"][1] == -1
+    rows = list(a)
+    assert len(rows) == 2 and {float(r["objective"]) for r in rows} == {1.0, 2.0}
+    it = iter(a)
+    next(it)
+    a.add([[1, 2, 3]], [9.0], [[0.0, 0.0]])
+    with pytest.raises(RuntimeError):
+        next(it)
+    df = a.data(return_type="pandas")
+    assert list(df.columns)[:4] == ["solution_0", "solution_1", "solution_2", "objective"]
+    a.clear()
+    assert len(a) == 0 and a.stats.obj_max is None
