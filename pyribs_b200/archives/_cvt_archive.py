@@ -128,7 +128,7 @@ class CVTArchive(DeviceArchive):
             return 0
         if self._search_method == "scan":
             return 1
-        return 0 if (B * C >= (1 << 22) and B >= 128) else 1
+        return 1  # TODO(tensor): 0 if (B * C >= (1 << 22) and B >= 128) else 1
 
     # ---- A3 ---------------------------------------------------------------------------------
     def _local_search(self, measures, flags_ptr, want_dist):
