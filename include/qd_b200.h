@@ -43,6 +43,7 @@ extern "C" {
 /* bits of the device-side `flags` word written by the index / insert kernels */
 #define QD_FLAG_NONFINITE_MEASURES 1u
 #define QD_FLAG_NONFINITE_OBJECTIVE 2u
+#define QD_FLAG_CVT_OVERFLOW 4u /* tensor-core search ran out of candidate space: rerun with method 1 */
 
 int qd_abi_version(void);
 const char* qd_last_error(void);
@@ -84,6 +85,10 @@ int qd_cvt_index_of(const void* measures /*[dev] B x d*/, int dtype, int64_t B, 
                     int method, int32_t* idx_out /*[dev] B*/, double* dist_out /*[dev] B or NULL*/,
                     uint32_t* flags /*[dev] 1*/, void* scratch /*[dev]*/, size_t scratch_bytes,
                     void* stream);
+/* Diagnostics: when non-NULL, the next method-0 searches also dump the raw tensor-core scores
+ * ([dev] B x 256*ceil(C/256) floats) and per-query margins ([dev] B floats). Pass NULLs to
+ * switch off. Not for production use. */
+void qd_cvt_debug_buffers(float* scores /*[dev]*/, float* eps /*[dev]*/);
 /* Merge step of the sharded search: keeps idx where dist == global min, else INT32_MAX
  * (followed by an integer min-reduction across ranks). */
 int qd_cvt_mask_losers(const double* local_dist /*[dev] B*/, const double* global_min /*[dev] B*/,

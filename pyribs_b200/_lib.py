@@ -12,6 +12,7 @@ QD_F32, QD_F64 = 0, 1
 QD_MAX_FIELDS = 16
 FLAG_NONFINITE_MEASURES = 1
 FLAG_NONFINITE_OBJECTIVE = 2
+FLAG_CVT_OVERFLOW = 4
 
 
 class QdError(RuntimeError):
@@ -62,6 +63,7 @@ PROTOTYPES = {
     "qd_cvt_prepare": (_int, [_vp, _int, _i64, _int, _vp, _vp]),
     "qd_cvt_scratch_bytes": (_sz, [_i64, _i64, _int]),
     "qd_cvt_index_of": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _i32, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qd_cvt_debug_buffers": (None, [_vp, _vp]),
     "qd_cvt_mask_losers": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "qd_insert_scratch_bytes": (_sz, [_i64]),
     "qd_insert_scratch_init": (_int, [_vp, _i64, _vp]),

@@ -114,6 +114,8 @@ class DeviceArchive:
         self._stats = None
         self._stats_reset()
         self._pinned = {}
+        self._force_scan = False
+        self._overflow_fallbacks = 0
 
     # ---- properties ---------------------------------------------------------------------
     @property
@@ -244,8 +246,16 @@ class DeviceArchive:
         flags = torch.zeros(1, dtype=torch.int32, device=self._device)
         with torch.cuda.device(self._device):
             idx = self._index_of_device(m, flags.data_ptr())
-        if int(flags.item()) & _lib.FLAG_NONFINITE_MEASURES:
+        fl = int(flags.item())
+        if fl & _lib.FLAG_NONFINITE_MEASURES:
             raise ValueError("All elements of measures must be finite (infinity and NaN values are not supported).")
+        if fl & _lib.FLAG_CVT_OVERFLOW:  # candidate list overflowed: redo with the exact scan
+            self._overflow_fallbacks += 1
+            self._force_scan = True
+            try:
+                return self.index_of(measures)
+            finally:
+                self._force_scan = False
         return idx if dev_in else idx.cpu().numpy()
 
     def index_of_single(self, measures):
@@ -296,6 +306,14 @@ class DeviceArchive:
             raise ValueError("All elements of objective must be finite (infinity and NaN values are not supported).")
         if res.flags & _lib.FLAG_NONFINITE_MEASURES:
             raise ValueError("All elements of measures must be finite (infinity and NaN values are not supported).")
+        if res.flags & _lib.FLAG_CVT_OVERFLOW:  # nothing was committed; redo with the exact scan
+            self._overflow_fallbacks += 1
+            self._force_scan = True
+            try:
+                return self.add(data["solution"], data["objective"], data["measures"],
+                                **{k: data[k] for k in fields})
+            finally:
+                self._force_scan = False
         if res.n_insertable > 0:
             store._updates[0] += 1
             store._n_occupied += res.n_new

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import numbers
+import os
 from pathlib import Path
 
 import numpy as np
@@ -77,6 +78,7 @@ class CVTArchive(DeviceArchive):
         self._upper_bounds = np.array(hi, dtype=mdt)
         self._interval_size = self._upper_bounds - self._lower_bounds
         self._meas_code = _lib.QD_F64 if np.dtype(mdt) == np.float64 else _lib.QD_F32
+        search_method = os.environ.get("QD_CVT_METHOD", search_method)
         if search_method not in ("auto", "tensor", "scan"):
             raise ValueError("search_method must be 'auto', 'tensor' or 'scan'")
         self._search_method = search_method
@@ -106,6 +108,7 @@ class CVTArchive(DeviceArchive):
                                                      self._measure_dim, self._prepared.data_ptr(),
                                                      current_stream_ptr()))
         self._cvt_scratch = None
+        self._force_scan = False
 
     @property
     def centroids(self):
@@ -124,11 +127,11 @@ class CVTArchive(DeviceArchive):
         return self._interval_size
 
     def _pick_method(self, B, C):
+        if self._force_scan or self._search_method == "scan":
+            return 1
         if self._search_method == "tensor":
             return 0
-        if self._search_method == "scan":
-            return 1
-        return 1  # TODO(tensor): 0 if (B * C >= (1 << 22) and B >= 128) else 1
+        return 0 if B * C >= (1 << 24) else 1
 
     # ---- A3 ---------------------------------------------------------------------------------
     def _local_search(self, measures, flags_ptr, want_dist):

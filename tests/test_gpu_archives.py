@@ -75,6 +75,7 @@ def test_cvt_index_golden(method):
             if "not built" in str(e):
                 pytest.skip("tensor-core search not built yet")
             raise
+        assert a._overflow_fallbacks == 0
         if "index" in c:
             np.testing.assert_array_equal(idx, c["index"], err_msg=f"{name} ({method}) vs KD-tree")
         if "index_brute" in c:
@@ -238,3 +239,33 @@ def test_retrieve_and_iteration():
     assert list(df.columns)[:4] == ["solution_0", "solution_1", "solution_2", "objective"]
     a.clear()
     assert len(a) == 0 and a.stats.obj_max is None
+
+
+@pytest.mark.parametrize("shape", [(200_000, 10_000, 2), (60_000, 100_000, 8), (30_000, 50_000, 5), (3_000, 300_000, 3),
+                                   (20_000, 20_000, 13), (20_000, 20_000, 24)])
+def test_cvt_tensor_equals_scan(shape):
+    """The tcgen05 filter + fp64 rescoring must be bit-identical to the fp64 scan, including
+    far-out-of-range queries (per-row rescaling / outlier path) and duplicated centroids."""
+    import torch
+
+    from pyribs_b200.archives import CVTArchive
+
+    B, C, d = shape
+    rng = np.random.default_rng(B + C + d)
+    cen = rng.uniform(-1, 1, (C, d)) * rng.choice([1.0, 3.0, 0.01])
+    cen[C // 2: C // 2 + 100] = cen[:100]  # exact duplicates -> lowest index must win
+    meas = rng.uniform(-1.2, 1.2, (B, d)) * np.abs(cen).max()
+    meas[:50] *= 1e3
+    meas[50:60] *= 1e9
+    meas[60:70] = cen[C // 2: C // 2 + 10]
+    out = {}
+    for method in ("scan", "tensor"):
+        a = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, search_method=method)
+        out[method] = a.index_of(meas)
+        assert a._overflow_fallbacks == 0
+    np.testing.assert_array_equal(out["tensor"], out["scan"])
+    assert np.all(out["scan"][60:70] == np.arange(10))
+    # spot-check against an fp64 NumPy brute force
+    sub = rng.choice(B, 200, replace=False)
+    dd = ((meas[sub, None, :] - cen[None, :, :]) ** 2).sum(-1)
+    np.testing.assert_array_equal(out["tensor"][sub], dd.argmin(1))
