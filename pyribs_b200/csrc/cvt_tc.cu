@@ -18,10 +18,10 @@
 // in NumPy's summation order and the lowest index among exact minima wins, which makes the
 // result bit-identical to the fp64 scan (method 1).
 //
-// CTA = 128 queries x a contiguous range of 256-centroid tiles; 10 warps:
+// CTA = 128 queries x a contiguous range of 256-centroid tiles; 18 warps:
 //   warp 0      bulk-copy (TMA, cp.async.bulk) producer of B tiles, 4-stage mbarrier ring
 //   warp 1      TMEM allocation + single-thread tcgen05.mma issue, 2 accumulator buffers
-//   warps 2-9   epilogue: warp w reads TMEM lanes 32*(w%4).., columns 128*((w-2)/4)..
+//   warps 2-17  epilogue: warp w reads TMEM lanes 32*(w%4).., columns 64*((w-2)/4)..
 #include <cuda_fp16.h>
 
 #include "cvt_common.cuh"
@@ -32,9 +32,10 @@ constexpr int kTileM = 128;         // queries per CTA (TMEM lanes)
 constexpr int kTileN = 256;         // centroids per MMA / accumulator buffer (TMEM columns)
 constexpr int kStages = 4;          // B-tile ring depth
 constexpr int kMaxKSteps = 4;       // K = 16 * ksteps
-constexpr int kThreads = 320;       // 10 warps
+constexpr int kEpiWarps = 16;       // 4 per SM sub-partition
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kEpiWarp0 = 2;
-constexpr int kWarpBuf = 256;       // candidates staged per epilogue warp before one global reservation
+constexpr int kWarpBuf = 192;       // candidates staged per epilogue warp before one global reservation
 constexpr int kRegions = 1024;      // candidate list is split into independently filled regions
 
 struct PreparedHeader {  // lives at the start of the prepared image (device memory)
@@ -52,11 +53,23 @@ struct SearchScratch {
   uint32_t* n_outliers;
   unsigned long long* bestd;  // B
   int32_t* outliers;          // B
-  int2* cand;                 // kRegions * region_cap
+  int2* cand;                 // kRegions * region_cap: (query, first column of an 8-group)
+  float* cand_score;          // kRegions * region_cap: tensor-core score of the group's minimum
+  uint32_t* best_approx;      // B: ordered-uint image of the smallest tensor-core score per query
+  float* eps;                 // B: per-query margin
   uint32_t region_cap;
   float* dbg_scores;  // diagnostics only: B x (ntiles*256) raw accumulator values, or NULL
   float* dbg_eps;     // diagnostics only: B margins, or NULL
 };
+
+// monotone float -> uint map (so that atomicMin on the image orders like the floats)
+__device__ __forceinline__ uint32_t ford(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unford(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
 
 __host__ __device__ inline void pick_split(int d, int& P, int& ksteps) {
   P = (3 * d + 3 <= 32) ? 3 : 1;
@@ -226,6 +239,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float min3(float a, float b, float c) {
   float d;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -254,7 +280,10 @@ struct SmemLayout {
   uint64_t full[kStages], empty[kStages], tfull[2], tempty[2];
   uint32_t tmem_base;
   float eps[kTileM];
-  int2 wbuf[8][kWarpBuf];  // per-epilogue-warp candidate staging (flushed in bulk)
+  int2 wbuf[kEpiWarps][kWarpBuf];  // per-epilogue-warp candidate staging (flushed in bulk)
+  float wscore[kEpiWarps][kWarpBuf];
+  uint32_t rowbest[kTileM];  // ordered-uint running minimum shared by the 4 warps of a row
+  uint32_t wcnt[kEpiWarps];
 };
 
 // ------------------------------------------------------------------------------------------
@@ -283,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sm.tfull[a], 1);
-      mbar_init(&sm.tempty[a], 8);  // one arrive per epilogue warp
+      mbar_init(&sm.tempty[a], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -361,6 +390,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       ws.outliers[slot] = (int32_t)q;
     }
     sm.eps[r] = eps;
+    sm.rowbest[r] = 0xFFFFFFFFu;
+    if (q < B && blockIdx.y == 0) ws.eps[q] = eps;
     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
   }
   tc_fence_before();
@@ -400,105 +431,124 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // ===== epilogue ==========================================================================
+    constexpr int kColsPerWarp = kTileN / (kEpiWarps / 4);  // 64
     const int quarter = warp & 3;
-    const int half = (warp - kEpiWarp0) >> 2;
+    const int cq = (warp - kEpiWarp0) >> 2;
+    const int ew = warp - kEpiWarp0;
     const int r = quarter * 32 + lane;
     const int64_t q = q0 + r;
     const float eps = sm.eps[r];
     const bool live = (q < B) && eps > 0.f;
-    float best = INFINITY, thr = INFINITY;
+    // A candidate is a GROUP of 8 consecutive centroids (q, first column): the rescoring kernel
+    // evaluates all 8 exactly, so the hot loop never has to locate individual columns.
+    float best = 3.0e38f;
+    float thr = live ? 3.0e38f : -INFINITY;  // dead rows never trigger; masked columns are +inf
     const int32_t C_total = (int32_t)hdr->C;
     const uint32_t region = (blockIdx.x * gridDim.y + blockIdx.y) % kRegions;
     int2* rcand = ws.cand + (size_t)region * ws.region_cap;
-    int2* wb = sm.wbuf[warp - kEpiWarp0];
-    int wcount = 0;  // warp-uniform
-    auto flush = [&]() {
-      if (wcount > 0) {
+    float* rscore = ws.cand_score + (size_t)region * ws.region_cap;
+    int2* wb = sm.wbuf[ew];
+    float* wbs = sm.wscore[ew];
+    uint32_t* wcnt = &sm.wcnt[ew];
+    if (lane == 0) *wcnt = 0u;
+    __syncwarp();
+    auto flush = [&]() {  // warp-uniform
+      __syncwarp();
+      const uint32_t n = min(*wcnt, (uint32_t)kWarpBuf);
+      if (n > 0) {
         uint32_t gbase = 0;
-        if (lane == 0) gbase = atomicAdd(&ws.region_count[region], (uint32_t)wcount);
+        if (lane == 0) gbase = atomicAdd(&ws.region_count[region], n);
         gbase = __shfl_sync(0xffffffffu, gbase, 0);
-        for (int e = lane; e < wcount; e += 32) {
-          if (gbase + e < ws.region_cap)
+        for (uint32_t e = lane; e < n; e += 32) {
+          if (gbase + e < ws.region_cap) {
             rcand[gbase + e] = wb[e];
-          else
+            rscore[gbase + e] = wbs[e];
+          } else {
             atomicOr(flags, QD_FLAG_CVT_OVERFLOW);
+          }
         }
-        wcount = 0;
       }
       __syncwarp();
+      if (lane == 0) *wcnt = 0u;
+      __syncwarp();
+    };
+    static_assert(kColsPerWarp == 64, "the epilogue below loads two 32-column chunks per tile");
+    auto process = [&](uint32_t (&raw)[32], const int32_t c0) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (ws.dbg_scores && q < B) {
+        const int64_t ld = (int64_t)ntiles * kTileN;
+        for (int j = 0; j < 32; ++j) ws.dbg_scores[q * ld + c0 + j] = v[j];
+        ws.dbg_eps[q] = eps;
+      }
+      if (c0 + 32 > C_total) {  // last tile: mask the padding columns (warp-uniform)
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j >= C_total) v[j] = INFINITY;
+      }
+      float gm[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float a = min3(v[8 * g], v[8 * g + 1], v[8 * g + 2]);
+        const float b = min3(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]);
+        gm[g] = min3(a, b, fminf(v[8 * g + 6], v[8 * g + 7]));
+      }
+      const float m = fminf(min3(gm[0], gm[1], gm[2]), gm[3]);
+      if (m <= thr) {
+        best = fminf(best, m);
+        thr = best + eps;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (gm[g] <= thr) {
+            const uint32_t pos = atomicAdd(wcnt, 1u);  // shared-memory atomic
+            if (pos < (uint32_t)kWarpBuf) {
+              wb[pos] = make_int2((int)q, c0 + 8 * g);
+              wbs[pos] = gm[g];
+            } else {
+              const uint32_t slot = atomicAdd(&ws.region_count[region], 1u);
+              if (slot < ws.region_cap) {
+                rcand[slot] = make_int2((int)q, c0 + 8 * g);
+                rscore[slot] = gm[g];
+              } else {
+                atomicOr(flags, QD_FLAG_CVT_OVERFLOW);
+              }
+            }
+          }
+        }
+      }
     };
     for (int i = 0; i < my_tiles; ++i) {
       const int acc = i & 1;
       const uint32_t aph = (i >> 1) & 1;
       mbar_wait(&sm.tfull[acc], aph);
       tc_fence_after();
-      const int32_t cbase = (tile_begin + i) * kTileN + half * 128;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kTileN + half * 128 + ch * 32), v);
-        if (ws.dbg_scores && q < B) {
-          const int64_t ld = (int64_t)ntiles * kTileN;
-          for (int j = 0; j < 32; ++j) ws.dbg_scores[q * ld + cbase + ch * 32 + j] = v[j];
-          ws.dbg_eps[q] = eps;
-        }
-        if (cbase + ch * 32 + 32 > C_total) {  // last tile: mask the padding columns (warp-uniform)
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cbase + ch * 32 + j >= C_total) v[j] = INFINITY;
-        }
-        float m = min3(v[0], v[1], v[2]);
-#pragma unroll
-        for (int j = 3; j + 1 < 32; j += 2) m = min3(m, v[j], v[j + 1]);
-        m = fminf(m, v[31]);
-        const bool trig = live && m <= thr && m < 3.0e38f;
-        if (__any_sync(0xffffffffu, trig)) {  // rare once the running minimum has settled
-          uint32_t hit = 0u;
-          if (trig) {
-            best = fminf(best, m);
-            thr = best + eps;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) hit |= (v[j] <= thr) ? (1u << j) : 0u;
-          }
-          const int cnt = __popc(hit);
-          int incl = cnt;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int t2 = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t2;
-          }
-          const int total = __shfl_sync(0xffffffffu, incl, 31);
-          if (wcount + total > kWarpBuf) flush();
-          if (total <= kWarpBuf) {
-            int pos = wcount + incl - cnt;
-            while (hit) {
-              const int bit = __ffs(hit) - 1;
-              hit &= hit - 1;
-              wb[pos++] = make_int2((int)q, cbase + ch * 32 + bit);
-            }
-            wcount += total;
-            __syncwarp();
-          } else {  // pathological chunk (mass ties): straight to global memory
-            uint32_t gbase = 0;
-            if (lane == 0) gbase = atomicAdd(&ws.region_count[region], (uint32_t)total);
-            gbase = __shfl_sync(0xffffffffu, gbase, 0) + (uint32_t)(incl - cnt);
-            while (hit) {
-              const int bit = __ffs(hit) - 1;
-              hit &= hit - 1;
-              if (gbase < ws.region_cap)
-                rcand[gbase] = make_int2((int)q, cbase + ch * 32 + bit);
-              else
-                atomicOr(flags, QD_FLAG_CVT_OVERFLOW);
-              ++gbase;
-            }
-          }
+      const int32_t cbase = (tile_begin + i) * kTileN + cq * kColsPerWarp;
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kTileN + cq * kColsPerWarp);
+      uint32_t ra[32], rb[32];
+      tmem_ld32_nowait(taddr, ra);
+      tmem_ld32_nowait(taddr + 32, rb);
+      // pick up the row's running minimum from the other three warps while the loads fly
+      if (live) {
+        const float shared_best = unford(sm.rowbest[r]);
+        if (shared_best < best) {
+          best = shared_best;
+          thr = best + eps;
         }
       }
+      const float best_in = best;
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.tempty[acc]);
+      if (lane == 0) mbar_arrive(&sm.tempty[acc]);  // values are in registers: release the buffer early
+      process(ra, cbase);
+      process(rb, cbase + 32);
+      if (best < best_in) atomicMin(&sm.rowbest[r], ford(best));
+      __syncwarp();
+      if (*wcnt > (uint32_t)(kWarpBuf / 2)) flush();
     }
     flush();
+    if (live && best < 3.0e38f) atomicMin(&ws.best_approx[q], ford(best));
   }
   tc_fence_before();
   __syncthreads();
@@ -512,6 +562,7 @@ __global__ void search_init_kernel(int64_t B, SearchScratch ws, int32_t* __restr
   const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   for (int64_t i = i0; i < B; i += (int64_t)gridDim.x * blockDim.x) {
     ws.bestd[i] = 0x7FF0000000000000ull;  // +inf
+    ws.best_approx[i] = 0xFFFFFFFFu;
     idx[i] = INT32_MAX;
   }
   if (i0 < kRegions) ws.region_count[i0] = 0u;
@@ -525,20 +576,32 @@ __global__ void __launch_bounds__(256) rescore_kernel(const T* __restrict__ meas
   for (uint32_t region = blockIdx.x; region < kRegions; region += gridDim.x) {
     const uint32_t n = min(ws.region_count[region], ws.region_cap);
     const int2* rc = ws.cand + (size_t)region * ws.region_cap;
-    for (uint32_t slot = threadIdx.x; slot < n; slot += blockDim.x) {
-      const int2 qc = rc[slot];
-      if (qc.y >= C) continue;  // padding column
+    const float* rs = ws.cand_score + (size_t)region * ws.region_cap;
+    // one thread per candidate group. Groups whose tensor-core minimum is above the query's
+    // final (smallest score + margin) are stale running-minimum records and are skipped.
+    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+      const int2 qc = rc[e];
+      if (!(rs[e] <= unford(ws.best_approx[qc.x]) + ws.eps[qc.x])) continue;
       double x[QD_MAX_MEASURE_DIM], c[QD_MAX_MEASURE_DIM];
-      for (int k = 0; k < d; ++k) {
-        x[k] = (double)meas[(int64_t)qc.x * d + k];
-        c[k] = (double)cent[(int64_t)qc.y * d + k];
+      for (int k = 0; k < d; ++k) x[k] = (double)meas[(int64_t)qc.x * d + k];
+      unsigned long long mbits = 0xFFFFFFFFFFFFFFFFull;
+      int32_t mcol = INT32_MAX;
+      const unsigned long long target = PASS == 1 ? ws.bestd[qc.x] : 0ull;
+      for (int j = 0; j < 8; ++j) {
+        const int32_t col = qc.y + j;
+        if (col >= C) break;  // padding columns
+        for (int k = 0; k < d; ++k) c[k] = (double)cent[(int64_t)col * d + k];
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(sqdist_np<0>(x, c, d));
+        if (PASS == 0) {
+          mbits = bits < mbits ? bits : mbits;
+        } else if (bits == target && mcol == INT32_MAX) {
+          mcol = col;
+        }
       }
-      const double dd = sqdist_np<0>(x, c, d);
-      const unsigned long long bits = (unsigned long long)__double_as_longlong(dd);
       if (PASS == 0) {
-        atomicMin(&ws.bestd[qc.x], bits);
-      } else if (bits == ws.bestd[qc.x]) {
-        atomicMin(&idx[qc.x], qc.y + base);  // lowest index among exact ties (np.argmin)
+        if (mbits != 0xFFFFFFFFFFFFFFFFull) atomicMin(&ws.bestd[qc.x], mbits);
+      } else if (mcol != INT32_MAX) {
+        atomicMin(&idx[qc.x], mcol + base);  // lowest index among exact ties (np.argmin)
       }
     }
   }
@@ -605,8 +668,9 @@ static uint32_t region_cap_for(int64_t B) {
 }
 
 static size_t search_scratch_bytes(int64_t B) {
-  return a256(kRegions * 4) + 256 + a256((size_t)B * 8) + a256((size_t)B * 4) +
-         a256((size_t)kRegions * region_cap_for(B) * sizeof(int2));
+  return a256(kRegions * 4) + 256 + a256((size_t)B * 8) + 3 * a256((size_t)B * 4) +
+         a256((size_t)kRegions * region_cap_for(B) * sizeof(int2)) +
+         a256((size_t)kRegions * region_cap_for(B) * sizeof(float));
 }
 
 static SearchScratch carve_search(void* base, int64_t B) {
@@ -620,8 +684,14 @@ static SearchScratch carve_search(void* base, int64_t B) {
   p += a256((size_t)B * 8);
   ws.outliers = (int32_t*)p;
   p += a256((size_t)B * 4);
-  ws.cand = (int2*)p;
+  ws.best_approx = (uint32_t*)p;
+  p += a256((size_t)B * 4);
+  ws.eps = (float*)p;
+  p += a256((size_t)B * 4);
   ws.region_cap = region_cap_for(B);
+  ws.cand = (int2*)p;
+  p += a256((size_t)kRegions * ws.region_cap * sizeof(int2));
+  ws.cand_score = (float*)p;
   ws.dbg_scores = nullptr;
   ws.dbg_eps = nullptr;
   return ws;
