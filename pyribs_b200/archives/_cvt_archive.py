@@ -131,7 +131,7 @@ class CVTArchive(DeviceArchive):
             return 1
         if self._search_method == "tensor":
             return 0
-        return 0 if B * C >= (1 << 24) else 1
+        return 0 if B * C >= (1 << 26) else 1
 
     # ---- A3 ---------------------------------------------------------------------------------
     def _local_search(self, measures, flags_ptr, want_dist):

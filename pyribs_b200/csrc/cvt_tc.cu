@@ -289,7 +289,7 @@ struct SmemLayout {
 // ------------------------------------------------------------------------------------------
 // main search kernel
 // ------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1)
     cvt_tc_kernel(const T* __restrict__ meas, int64_t B, int d, const unsigned char* __restrict__ prepared,
                   int tiles_per_cta, SearchScratch ws, uint32_t* flags) {
@@ -473,51 +473,33 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
     };
     static_assert(kColsPerWarp == 64, "the epilogue below loads two 32-column chunks per tile");
-    auto process = [&](uint32_t (&raw)[32], const int32_t c0) {
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-      if (ws.dbg_scores && q < B) {
-        const int64_t ld = (int64_t)ntiles * kTileN;
-        for (int j = 0; j < 32; ++j) ws.dbg_scores[q * ld + c0 + j] = v[j];
-        ws.dbg_eps[q] = eps;
-      }
-      if (c0 + 32 > C_total) {  // last tile: mask the padding columns (warp-uniform)
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j >= C_total) v[j] = INFINITY;
-      }
-      float gm[4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float a = min3(v[8 * g], v[8 * g + 1], v[8 * g + 2]);
-        const float b = min3(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]);
-        gm[g] = min3(a, b, fminf(v[8 * g + 6], v[8 * g + 7]));
-      }
-      const float m = fminf(min3(gm[0], gm[1], gm[2]), gm[3]);
-      if (m <= thr) {
-        best = fminf(best, m);
-        thr = best + eps;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (gm[g] <= thr) {
-            const uint32_t pos = atomicAdd(wcnt, 1u);  // shared-memory atomic
-            if (pos < (uint32_t)kWarpBuf) {
-              wb[pos] = make_int2((int)q, c0 + 8 * g);
-              wbs[pos] = gm[g];
-            } else {
-              const uint32_t slot = atomicAdd(&ws.region_count[region], 1u);
-              if (slot < ws.region_cap) {
-                rcand[slot] = make_int2((int)q, c0 + 8 * g);
-                rscore[slot] = gm[g];
-              } else {
-                atomicOr(flags, QD_FLAG_CVT_OVERFLOW);
-              }
-            }
-          }
+    const int32_t qi = (int32_t)q;
+    auto push = [&](int32_t col, float score) {
+      const uint32_t pos = atomicAdd(wcnt, 1u);  // shared-memory atomic
+      if (pos < (uint32_t)kWarpBuf) {
+        wb[pos] = make_int2(qi, col);
+        wbs[pos] = score;
+      } else {
+        const uint32_t slot = atomicAdd(&ws.region_count[region], 1u);
+        if (slot < ws.region_cap) {
+          rcand[slot] = make_int2(qi, col);
+          rscore[slot] = score;
+        } else {
+          atomicOr(flags, QD_FLAG_CVT_OVERFLOW);
         }
       }
     };
+    // group minima of one 32-column chunk: 4 groups of 8, 3-input min tree
+    auto group_min = [&](const uint32_t (&raw)[32], float (&gm)[4]) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float a = min3(__uint_as_float(raw[8 * g]), __uint_as_float(raw[8 * g + 1]), __uint_as_float(raw[8 * g + 2]));
+        const float b =
+            min3(__uint_as_float(raw[8 * g + 3]), __uint_as_float(raw[8 * g + 4]), __uint_as_float(raw[8 * g + 5]));
+        gm[g] = min3(a, b, fminf(__uint_as_float(raw[8 * g + 6]), __uint_as_float(raw[8 * g + 7])));
+      }
+    };
+    const int last_full = (C_total / kTileN);  // tiles with index < last_full have no padding columns
     for (int i = 0; i < my_tiles; ++i) {
       const int acc = i & 1;
       const uint32_t aph = (i >> 1) & 1;
@@ -529,23 +511,52 @@ __global__ void __launch_bounds__(kThreads, 1)
       tmem_ld32_nowait(taddr, ra);
       tmem_ld32_nowait(taddr + 32, rb);
       // pick up the row's running minimum from the other three warps while the loads fly
-      if (live) {
-        const float shared_best = unford(sm.rowbest[r]);
-        if (shared_best < best) {
-          best = shared_best;
-          thr = best + eps;
-        }
+      const float shared_best = unford(sm.rowbest[r]);
+      if (shared_best < best) {
+        best = shared_best;
+        thr = live ? best + eps : thr;
       }
-      const float best_in = best;
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.tempty[acc]);  // values are in registers: release the buffer early
-      process(ra, cbase);
-      process(rb, cbase + 32);
-      if (best < best_in) atomicMin(&sm.rowbest[r], ford(best));
-      __syncwarp();
-      if (*wcnt > (uint32_t)(kWarpBuf / 2)) flush();
+      if (DBG) {
+        if (ws.dbg_scores && q < B) {
+          const int64_t ld = (int64_t)ntiles * kTileN;
+          for (int j = 0; j < 32; ++j) {
+            ws.dbg_scores[q * ld + cbase + j] = __uint_as_float(ra[j]);
+            ws.dbg_scores[q * ld + cbase + 32 + j] = __uint_as_float(rb[j]);
+          }
+          ws.dbg_eps[q] = eps;
+        }
+      }
+      if (tile_begin + i >= last_full) {  // tail tile: mask the padding columns (warp-uniform, once per CTA)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (cbase + j >= C_total) ra[j] = 0x7f800000u;
+          if (cbase + 32 + j >= C_total) rb[j] = 0x7f800000u;
+        }
+      }
+      float ga[4], gb[4];
+      group_min(ra, ga);
+      group_min(rb, gb);
+      const float m = min3(min3(ga[0], ga[1], ga[2]), min3(ga[3], gb[0], gb[1]), fminf(gb[2], gb[3]));
+      const bool trig = m <= thr;
+      if (__any_sync(0xffffffffu, trig)) {  // rare once the running minimum has settled
+        if (trig) {
+          best = fminf(best, m);
+          thr = best + eps;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (ga[g] <= thr) push(cbase + 8 * g, ga[g]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (gb[g] <= thr) push(cbase + 32 + 8 * g, gb[g]);
+          atomicMin(&sm.rowbest[r], ford(best));
+        }
+        __syncwarp();
+        if (*wcnt > (uint32_t)(kWarpBuf / 2)) flush();
+      }
     }
     flush();
     if (live && best < 3.0e38f) atomicMin(&ws.best_approx[q], ford(best));
@@ -722,14 +733,18 @@ int tc_impl(const T* meas, int64_t B, int d, const T* cent, int64_t C, const uns
   static bool attr_set[2] = {false, false};
   const size_t smem = sizeof(SmemLayout) + 1024;
   if (!attr_set[sizeof(T) == 8]) {
-    QD_CHECK_CUDA(cudaFuncSetAttribute(cvt_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QD_CHECK_CUDA(cudaFuncSetAttribute(cvt_tc_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QD_CHECK_CUDA(cudaFuncSetAttribute(cvt_tc_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[sizeof(T) == 8] = true;
   }
   int rc;
   search_init_kernel<<<grid_for(B > kRegions ? B : kRegions, 256), 256, 0, s>>>(B, ws, idx);
   if ((rc = check_launch("search_init_kernel"))) return rc;
   dim3 grid(qtiles, csplit);
-  cvt_tc_kernel<T><<<grid, kThreads, smem, s>>>(meas, B, d, prepared, tiles_per_cta, ws, flags);
+  if (ws.dbg_scores)
+    cvt_tc_kernel<T, true><<<grid, kThreads, smem, s>>>(meas, B, d, prepared, tiles_per_cta, ws, flags);
+  else
+    cvt_tc_kernel<T, false><<<grid, kThreads, smem, s>>>(meas, B, d, prepared, tiles_per_cta, ws, flags);
   if ((rc = check_launch("cvt_tc_kernel"))) return rc;
   const int rgrid = kRegions;
   rescore_kernel<T, 0><<<rgrid, 256, 0, s>>>(meas, cent, C, d, base, ws, idx);
