@@ -152,6 +152,61 @@ int qd_store_gather(int64_t M, const int32_t* idx /*[dev] M*/, int n_fields,
                     const uint8_t* occupied /*[dev] or NULL*/, uint8_t* occupied_out /*[dev] or NULL*/,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * A12-A14  evolution strategies   ribs/emitters/opt/_cma_es.py, _sep_cma_es.py,
+ *                                 _lm_ma_es.py
+ * All strategy state is fp64 in device memory. `status` is a device block of 8 doubles:
+ *   [0] sigma  [1] ||ps||^2 of the last tell  [2] max / [3] min of the (diagonal) covariance
+ * so that ask -> tell -> ask never synchronises with the host. `z` holds unit normals
+ * (rows x n), filled by qd_fill_normal (Philox4x32-10 + Box-Muller) or injected by the
+ * caller for parity runs. `row_ids` (optional, [dev] rows int32) redirects sample k to
+ * X[row_ids[k]] -- the bounds-resampling loop of the reference (_cma_es.py:208-225)
+ * re-asks only the rows that fell outside the bounds.
+ * ---------------------------------------------------------------------------------- */
+int qd_fill_normal(double* out /*[dev] count*/, int64_t count, uint64_t seed, uint64_t offset, void* stream);
+/* oob[k] = any coordinate of X[row_ids[k]] outside [lower, upper]   (_cma_es.py:190-194) */
+int qd_es_out_of_bounds(const double* X, int64_t rows, int64_t n, const int32_t* row_ids,
+                        const double* lower /*[dev] n*/, const double* upper /*[dev] n*/,
+                        int32_t* oob /*[dev] rows*/, void* stream);
+/* Weighted parent reduction shared by the three tells:
+ *   out_mean[j] = sum_k w[k] X[rank[k]][j]                       (_cma_es.py:297)
+ *   out_sq[j]   = sum_k w[k] (X[rank[k]][j] - old_mean[j])^2     (_sep_cma_es.py:303)
+ * out_mean / out_sq / old_mean may be NULL. */
+size_t qd_wsum_partial_bytes(int64_t mu, int64_t n);
+int qd_weighted_rows(const double* X /*[dev] lam x n*/, int64_t n, const int64_t* rank /*[dev] mu*/,
+                     const double* w /*[dev] mu*/, int64_t mu, const double* old_mean,
+                     double* out_mean, double* out_sq, void* partial /*[dev]*/, void* stream);
+/* scalar strategy parameters, computed on the host exactly as _calc_strat_params does */
+typedef struct qd_cma_scalars {
+  double cc, cs, c1, cmu, mueff, damps, wsum;
+  double hsig_exp; /* 2 * current_eval / batch_size, after the increment (_cma_es.py:305) */
+} qd_cma_scalars;
+size_t qd_es_workspace_doubles(int64_t n);
+/* sep-CMA-ES   (_sep_cma_es.py:140-191 ask, :257-311 tell) */
+int qd_sep_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
+               const double* C /*[dev] n diagonal*/, const double* status, double* X, void* stream);
+int qd_sep_tell(int64_t n, const double* new_mean, const double* rank_mu /*[dev] n*/, double* mean, double* pc,
+                double* ps, double* C, double* status, const qd_cma_scalars* sc /*[host]*/,
+                double* workspace /*[dev] qd_es_workspace_doubles(n)*/, void* stream);
+/* CMA-ES       (_cma_es.py:51-82 eigen refresh, :181-237 ask, :274-328 tell) */
+int qd_sym_max(int64_t n, double* A /*[dev] n x n*/, void* stream);          /* A = max(A, A^T) */
+int qd_cma_transform(int64_t n, const double* Bmat, const double* eigvals, double* T, void* stream); /* T = B*sqrt(eig) */
+int qd_cma_invsqrt(int64_t n, const double* Bmat, const double* eigvals, double* invsqrt, void* stream);
+int qd_cma_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
+               const double* T /*[dev] n x n*/, const double* status, double* X, void* stream);
+/* Cnext receives the updated covariance (C is read-only); mean/pc/ps/status update in place. */
+int qd_cma_tell(int64_t n, const double* X, const int64_t* rank, const double* w, int64_t mu,
+                const double* new_mean, const double* invsqrt, double* mean, double* pc, double* ps,
+                const double* Cmat, double* Cnext, double* status, const qd_cma_scalars* sc /*[host]*/,
+                double* workspace, void* stream);
+/* LM-MA-ES     (_lm_ma_es.py:126-194 ask, :209-239 tell) */
+int qd_lmma_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
+                const double* status, const double* M /*[dev] n_vectors x n*/, const double* cd /*[dev]*/,
+                int64_t itrs, double* X, void* stream);
+int qd_lmma_tell(int64_t n, int64_t n_vectors, const double* new_mean, const double* z_mean, double* mean,
+                 double* ps, double* M, const double* cc /*[dev] n_vectors*/, double csigma, double mueff,
+                 double* status, double* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,4 +5,4 @@ strategy does, and raises if the CUDA library under `_C/` is missing (no CPU fal
 """
 __version__ = "0.1.0"
 
-from pyribs_b200 import archives  # noqa: F401,E402
+from pyribs_b200 import archives, emitters, schedulers  # noqa: F401,E402

@@ -70,6 +70,21 @@ PROTOTYPES = {
     "qd_insert_flags_ptr": (_vp, [_vp, _i64]),
     "qd_insert": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _dbl, _dbl, _i64, _vp, _vp, _vp, _vp]),
     "qd_store_gather": (_int, [_i64, _vp, _int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _vp, _vp, _vp]),
+    "qd_fill_normal": (_int, [_vp, _i64, _u64, _u64, _vp]),
+    "qd_es_out_of_bounds": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "qd_wsum_partial_bytes": (_sz, [_i64, _i64]),
+    "qd_weighted_rows": (_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "qd_es_workspace_doubles": (_sz, [_i64]),
+    "qd_sep_ask": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qd_sep_tell": (_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(CmaScalars), _vp, _vp]),
+    "qd_sym_max": (_int, [_i64, _vp, _vp]),
+    "qd_cma_transform": (_int, [_i64, _vp, _vp, _vp, _vp]),
+    "qd_cma_invsqrt": (_int, [_i64, _vp, _vp, _vp, _vp]),
+    "qd_cma_ask": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qd_cma_tell": (_int, [_i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                           C.POINTER(CmaScalars), _vp, _vp]),
+    "qd_lmma_ask": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "qd_lmma_tell": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -15,7 +15,7 @@ OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-diag-suppress", "128", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "--extended-lambda", "-diag-suppress", "128", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
 
 def sources():

@@ -1,0 +1,170 @@
+"""Shared plumbing of the device-resident evolution strategies.
+
+API contract: ribs/emitters/opt/_evolution_strategy_base.py:25-118 -- constructor kwargs
+`(sigma0, solution_dim, batch_size, seed, dtype, lower_bounds, upper_bounds, **es_kwargs)`,
+attributes `batch_size, sigma0, solution_dim, dtype`, methods `reset / ask / tell /
+check_stop`.
+
+Randomness: the reference draws from NumPy's PCG64, which a GPU cannot replay. Two modes:
+  * default -- unit normals come from the library's Philox4x32-10 kernel (counter-based, so
+    a run is reproducible for a given seed);
+  * parity  -- `ask(z=...)` accepts the (batch, n) unit normals explicitly (tests inject the
+    same z into the CPU oracle).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+import torch
+
+from pyribs_b200 import _lib
+from pyribs_b200._utils import arr_readonly
+
+BOUNDS_SAMPLING_THRESHOLD = 100
+BOUNDS_WARNING = (
+    "During bounds handling, this ES resampled at least "
+    f"{BOUNDS_SAMPLING_THRESHOLD} times. This may indicate that your solution space bounds are too tight."
+)
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def es_weights(mu):
+    """ribs/emitters/opt/_cma_es.py:241-246."""
+    w = np.log(mu + 0.5) - np.log(np.arange(1, mu + 1))
+    w = w / np.sum(w)
+    mueff = np.sum(w) ** 2 / np.sum(w**2)
+    return w, mueff
+
+
+class DeviceES:
+    """Base: device buffers, RNG, bounds resampling loop, weighted parent reduction."""
+
+    def __init__(self, sigma0, solution_dim, batch_size=None, seed=None, dtype=np.float64, lower_bounds=-np.inf,
+                 upper_bounds=np.inf, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.QdError("pyribs_b200 needs a CUDA device (there is no CPU fallback)")
+        self._L = _lib.lib()
+        self.batch_size = 4 + int(3 * np.log(solution_dim)) if batch_size is None else int(batch_size)
+        self.sigma0 = sigma0
+        self.solution_dim = int(solution_dim)
+        self.dtype = dtype
+        self.lower_bounds = np.asarray(lower_bounds, dtype=dtype)
+        self.upper_bounds = np.asarray(upper_bounds, dtype=dtype)
+        self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        ss = seed if isinstance(seed, np.random.SeedSequence) else np.random.SeedSequence(seed)
+        self._seed = int(ss.generate_state(1, dtype=np.uint64)[0])
+        self._rng_offset = 0
+        n = self.solution_dim
+        self._bounded = bool(np.any(np.isfinite(self.lower_bounds)) or np.any(np.isfinite(self.upper_bounds)))
+        if self._bounded:
+            lo = np.broadcast_to(self.lower_bounds.astype(np.float64), (n,)).copy()
+            hi = np.broadcast_to(self.upper_bounds.astype(np.float64), (n,)).copy()
+            self._lo_d = torch.from_numpy(lo).to(self._device)
+            self._hi_d = torch.from_numpy(hi).to(self._device)
+        f64 = dict(dtype=torch.float64, device=self._device)
+        self._status = torch.zeros(8, **f64)
+        self._ws = torch.zeros(int(self._L.qd_es_workspace_doubles(n)), **f64)
+        self._new_mean = torch.empty(n, **f64)
+        self._partial = None
+        self._solutions = None
+        self._z = None
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def _normals(self, rows):
+        z = torch.empty((rows, self.solution_dim), dtype=torch.float64, device=self._device)
+        cnt = z.numel()
+        _lib.check(self._L.qd_fill_normal(z.data_ptr(), cnt, self._seed, self._rng_offset, stream_ptr()))
+        self._rng_offset += (cnt + 1) // 2
+        return z
+
+    def _as_z(self, z, rows):
+        if z is None:
+            return self._normals(rows)
+        if not isinstance(z, torch.Tensor):
+            z = torch.from_numpy(np.ascontiguousarray(z, dtype=np.float64))
+        z = z.to(device=self._device, dtype=torch.float64).contiguous()
+        assert tuple(z.shape) == (rows, self.solution_dim), "z must be (rows, solution_dim)"
+        return z
+
+    def _sample_rows(self, z, rows, row_ids):
+        """Writes rows of self._solutions from unit normals `z`; implemented by subclasses."""
+        raise NotImplementedError
+
+    def ask(self, batch_size=None, z=None, return_device=False):
+        """Samples `batch_size` solutions (reference ask loops, e.g. _cma_es.py:199-237).
+
+        Returns a read-only NumPy array by default (drop-in); `return_device=True` returns the
+        CUDA tensor that `tell` will re-read, without a device->host copy.
+        """
+        lam = self.batch_size if batch_size is None else int(batch_size)
+        n = self.solution_dim
+        with torch.cuda.device(self._device):
+            self._solutions = torch.empty((lam, n), dtype=torch.float64, device=self._device)
+            self._prepare_ask(lam)
+            zz = self._as_z(z, lam)
+            self._z = zz
+            self._sample_rows(zz, lam, None)
+            if self._bounded:
+                remaining = torch.arange(lam, dtype=torch.int32, device=self._device)
+                itrs = 0
+                while True:
+                    oob = torch.empty(remaining.numel(), dtype=torch.int32, device=self._device)
+                    _lib.check(self._L.qd_es_out_of_bounds(
+                        self._solutions.data_ptr(), remaining.numel(), n, remaining.data_ptr(), self._lo_d.data_ptr(),
+                        self._hi_d.data_ptr(), oob.data_ptr(), stream_ptr()))
+                    remaining = remaining[oob.bool()].contiguous()
+                    itrs += 1
+                    if remaining.numel() == 0:
+                        break
+                    if itrs > BOUNDS_SAMPLING_THRESHOLD:
+                        warnings.warn(BOUNDS_WARNING, stacklevel=2)
+                    znew = self._normals(remaining.numel())
+                    self._z[remaining.long()] = znew
+                    self._sample_rows(znew, remaining.numel(), remaining)
+        if return_device:
+            return self._solutions
+        out = self._solutions.cpu().numpy()
+        if np.dtype(self.dtype) != np.float64:
+            out = out.astype(self.dtype)
+        return arr_readonly(out)
+
+    def _prepare_ask(self, lam):
+        pass
+
+    def _weighted(self, X, rank_d, w_d, mu, old_mean, out_mean, out_sq):
+        n = self.solution_dim
+        need = int(self._L.qd_wsum_partial_bytes(mu, n)) // 8
+        if self._partial is None or self._partial.numel() < need:
+            self._partial = torch.empty(need, dtype=torch.float64, device=self._device)
+        _lib.check(self._L.qd_weighted_rows(
+            X.data_ptr(), n, rank_d.data_ptr(), w_d.data_ptr(), mu, None if old_mean is None else old_mean.data_ptr(),
+            None if out_mean is None else out_mean.data_ptr(), None if out_sq is None else out_sq.data_ptr(),
+            self._partial.data_ptr(), stream_ptr()))
+
+    def _rank_to_device(self, ranking_indices, num_parents):
+        if isinstance(ranking_indices, torch.Tensor):
+            r = ranking_indices[:num_parents].to(device=self._device, dtype=torch.int64).contiguous()
+        else:
+            r = torch.from_numpy(np.ascontiguousarray(np.asarray(ranking_indices)[:num_parents], dtype=np.int64)).to(
+                self._device)
+        return r
+
+    @property
+    def sigma(self):
+        return float(self._status[0].item())
+
+    @staticmethod
+    def _flat(ranking_values):
+        rv = np.asarray(ranking_values)
+        return len(rv) >= 2 and np.linalg.norm(rv[0] - rv[-1]) < 1e-12
+
+    def _scalars(self, **kw):
+        sc = _lib.CmaScalars()
+        for k, v in kw.items():
+            setattr(sc, k, float(v))
+        return sc

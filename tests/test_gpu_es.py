@@ -1,0 +1,147 @@
+"""GPU parity tests of the evolution strategies against the reference's golden traces.
+
+Unit normals are injected (the reference's PCG64 stream cannot be replayed on a GPU); for
+CMA-ES the eigensystem of the CPU oracle is injected whenever the oracle refreshes it, because
+eigenvector signs / degenerate-subspace bases differ between LAPACK and cuSOLVER.
+Tolerance: 1e-6 relative (north_star), observed ~1e-12."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from golden_util import assert_close, gens_of, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import qd_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+def _make(es_name, cfg):
+    from pyribs_b200.emitters.opt import _get_es
+
+    kw = {}
+    if es_name == "lm_ma_es" and int(cfg["n_vectors"]) > 0:
+        kw["n_vectors"] = int(cfg["n_vectors"])
+    n, lam = int(cfg["n"]), int(cfg["lam"])
+    gpu = _get_es(es_name, sigma0=float(cfg["sigma0"]), solution_dim=n, batch_size=lam, seed=1, dtype=np.float64,
+                  lower_bounds=np.full(n, -np.inf), upper_bounds=np.full(n, np.inf), **kw)
+    ora = O.ORACLE_ES[es_name](float(cfg["sigma0"]), n, lam, seed=1, **kw)
+    gpu.reset(cfg["x0"])
+    ora.reset(cfg["x0"])
+    return gpu, ora
+
+
+@pytest.mark.parametrize("name", sorted(load_golden("es_traces").keys()))
+def test_es_trace(name):
+    case = load_golden("es_traces")[name]
+    cfg = case["cfg"]
+    es_name = name.split("_n")[0]
+    gpu, ora = _make(es_name, cfg)
+    n, lam = int(cfg["n"]), int(cfg["lam"])
+    for gi, g in enumerate(gens_of(case)):
+        z = np.random.default_rng(int(g["zseed"])).standard_normal((lam, n))
+        before = getattr(ora, "updated_eval", None)
+        sol_o = ora.ask(z)
+        if es_name == "cma_es" and ora.updated_eval != before:
+            gpu.set_eigensystem(ora.eigvals, ora.B)
+        sol_g = gpu.ask(z=z)
+        assert not sol_g.flags.writeable
+        assert_close(sol_g, sol_o, 1e-9, f"{name} g{gi} solutions vs oracle")
+        if "solutions" in g:
+            assert_close(sol_g, g["solutions"], RTOL, f"{name} g{gi} solutions vs golden")
+        ora.tell(g["ranking"], int(g["mu"]))
+        gpu.tell(g["ranking"], None, int(g["mu"]))
+        fit = -np.sum((sol_o - 1.0) ** 2, axis=1)
+        assert int(gpu.check_stop(fit[g["ranking"]])) == int(g["stop"])
+        assert_close(gpu.mean, g["mean"], RTOL, f"{name} g{gi} mean")
+        assert_close(gpu.sigma, g["sigma"], RTOL, f"{name} g{gi} sigma")
+        assert_close(gpu.ps, g["ps"], RTOL, f"{name} g{gi} ps")
+        if "pc" in g:
+            assert_close(gpu.pc, g["pc"], RTOL, f"{name} g{gi} pc")
+        if "C" in g:
+            assert_close(gpu.cov, g["C"], RTOL, f"{name} g{gi} C")
+        if "m" in g:
+            assert_close(gpu.m, g["m"], RTOL, f"{name} g{gi} m")
+        if "invsqrt" in g and es_name == "cma_es":
+            assert_close(gpu.invsqrt, g["invsqrt"], RTOL, f"{name} g{gi} invsqrt")
+
+
+def test_cma_own_eigensystem_is_consistent():
+    """The cuSOLVER path (no injection): C = B L B^T, C^-1/2 matches NumPy on the same C."""
+    from pyribs_b200.emitters.opt import CMAEvolutionStrategy
+
+    rng = np.random.default_rng(0)
+    n, lam = 60, 24
+    es = CMAEvolutionStrategy(0.7, n, lam, seed=3)
+    es.reset(rng.standard_normal(n))
+    for g in range(12):
+        sol = es.ask()
+        fit = -np.sum(sol**2, axis=1)
+        es.tell(np.flip(np.argsort(fit)), fit, lam // 2)
+    es.update_eigensystem(force=True)
+    Cm = es.cov
+    np.testing.assert_array_equal(Cm, Cm.T)
+    lam_np, B_np = np.linalg.eigh(Cm)
+    assert_close(np.sort(es.eigenvalues), np.sort(np.abs(lam_np)), 1e-9, "eigenvalues")
+    inv = (B_np * (1 / np.sqrt(np.abs(lam_np)))) @ B_np.T
+    assert_close(es.invsqrt, np.maximum(inv, inv.T), 1e-8, "invsqrt")
+    assert es.sigma > 0 and np.all(np.isfinite(es.mean))
+
+
+def test_philox_normals():
+    import torch
+
+    from pyribs_b200 import _lib
+
+    L = _lib.lib()
+    out = torch.empty(2_000_001, dtype=torch.float64, device="cuda")
+    _lib.check(L.qd_fill_normal(out.data_ptr(), out.numel(), 1234, 0, torch.cuda.current_stream().cuda_stream))
+    x = out.cpu().numpy()
+    assert abs(x.mean()) < 5e-3 and abs(x.var() - 1) < 5e-3
+    assert abs(((x - x.mean()) ** 4).mean() / x.var() ** 2 - 3) < 3e-2
+    out2 = torch.empty_like(out)
+    _lib.check(L.qd_fill_normal(out2.data_ptr(), out2.numel(), 1234, 0, torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(out, out2)
+    _lib.check(L.qd_fill_normal(out2.data_ptr(), out2.numel(), 1235, 0, torch.cuda.current_stream().cuda_stream))
+    assert not torch.equal(out, out2)
+
+
+def test_bounds_are_respected():
+    from pyribs_b200.emitters.opt import SeparableCMAEvolutionStrategy
+
+    n = 12
+    es = SeparableCMAEvolutionStrategy(2.0, n, 64, seed=0, lower_bounds=np.full(n, -1.0), upper_bounds=np.full(n, 1.0))
+    es.reset(np.zeros(n))
+    with pytest.warns(None) if False else __import__("contextlib").nullcontext():
+        sol = es.ask()
+    assert sol.shape == (64, n) and np.all(sol >= -1.0) and np.all(sol <= 1.0)
+
+
+@pytest.mark.parametrize("es", ["cma_es", "sep_cma_es", "lm_ma_es"])
+def test_sphere_loop_improves(es):
+    """End to end: Scheduler + 3 emitters + GridArchive on the sphere benchmark (the reference's
+    own smoke test, tests/emitters/evolution_strategy_emitter_test.py:84-96, plus a progress check)."""
+    from pyribs_b200.archives import GridArchive
+    from pyribs_b200.emitters import EvolutionStrategyEmitter
+    from pyribs_b200.schedulers import Scheduler
+
+    n = 20
+    archive = GridArchive(solution_dim=n, dims=(20, 20), ranges=[(-51.2, 51.2)] * 2, seed=1)
+    emitters = [EvolutionStrategyEmitter(archive, x0=np.zeros(n), sigma0=0.5, ranker="2imp", es=es, batch_size=18,
+                                         seed=s) for s in range(3)]
+    sched = Scheduler(archive, emitters)
+    qd = []
+    for it in range(30):
+        sol = sched.ask()
+        assert sol.shape == (54, n)
+        obj = -np.sum((sol - 2.048) ** 2, axis=1)
+        clipped = np.clip(sol, -5.12, 5.12)
+        meas = np.stack((clipped[:, : n // 2].sum(1), clipped[:, n // 2:].sum(1)), axis=1)
+        sched.tell(obj, meas)
+        qd.append(archive.stats.num_elites)
+    assert qd[-1] > qd[0] and qd[-1] >= 20
+    assert all(e.itrs == 30 for e in emitters)
