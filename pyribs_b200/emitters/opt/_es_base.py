@@ -150,7 +150,7 @@ class DeviceES:
         if isinstance(ranking_indices, torch.Tensor):
             r = ranking_indices[:num_parents].to(device=self._device, dtype=torch.int64).contiguous()
         else:
-            r = torch.from_numpy(np.ascontiguousarray(np.asarray(ranking_indices)[:num_parents], dtype=np.int64)).to(
+            r = torch.from_numpy(np.array(np.asarray(ranking_indices)[:num_parents], dtype=np.int64, copy=True)).to(
                 self._device)
         return r
 
