@@ -81,8 +81,21 @@ def fill_sentinel_values(occupied, data):
 
 class DeviceArchive:
     def __init__(self, *, solution_dim, measure_dim, cells, learning_rate, threshold_min, qd_score_offset, seed,
-                 solution_dtype, objective_dtype, measures_dtype, dtype, extra_fields, device=None):
+                 solution_dtype, objective_dtype, measures_dtype, dtype, extra_fields, device=None,
+                 data_parallel=False, process_group=None):
         self._rng = np.random.default_rng(seed)
+        # data-parallel insertion: every rank passes its own slice of the global batch to add();
+        # indices are computed locally, then (index, objective, row fields) are all-gathered over
+        # NCCL and every rank commits the same global batch to its replica (bit-identical replicas:
+        # the insert kernels are deterministic).
+        self._dp_world, self._dp_rank, self._dp_group = 1, 0, process_group
+        if data_parallel:
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                raise RuntimeError("data_parallel=True needs an initialised torch.distributed process group")
+            self._dp_world = dist.get_world_size(process_group)
+            self._dp_rank = dist.get_rank(process_group)
         self._solution_dim = as_dim_tuple(solution_dim) if not np.isscalar(solution_dim) else int(solution_dim)
         self._objective_dim = ()
         self._measure_dim = int(measure_dim)
@@ -114,6 +127,9 @@ class DeviceArchive:
         self._stats = None
         self._stats_reset()
         self._pinned = {}
+        self._outbuf = {}
+        self._copy_stream = None
+        self._copy_event = None
         self._force_scan = False
         self._overflow_fallbacks = 0
 
@@ -223,6 +239,8 @@ class DeviceArchive:
         src = torch.from_numpy(arr)
         if arr.nbytes < (1 << 16):
             return src.to(self._device)
+        if src.is_pinned():  # caller already staged the batch in page-locked memory
+            return src.to(self._device, non_blocking=True)
         key = (name, np.dtype(np_dtype))
         buf = self._pinned.get(key)
         if buf is None or buf.numel() < arr.size:
@@ -234,6 +252,46 @@ class DeviceArchive:
 
     def _index_of_device(self, measures: torch.Tensor, flags_ptr: int) -> torch.Tensor:
         raise NotImplementedError
+
+    def _gather_global_batch(self, idx, dev, B_local):
+        """All-gathers the per-rank slices (equal sizes on every rank) into the global batch and
+        ORs the validation flags across ranks."""
+        import torch.distributed as dist
+
+        W = self._dp_world
+
+        def gather(t):
+            out = torch.empty((W * t.shape[0], *t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(out, t.contiguous(), group=self._dp_group)
+            return out
+
+        store = self._store
+        off = store._flags_ptr - store._scratch.data_ptr()
+        flags = store._scratch[off:off + 4].view(torch.int32)
+        bits = torch.stack([(flags >> b) & 1 for b in range(3)]).reshape(3)  # NCCL has no bitwise OR: MAX per bit
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=self._dp_group)
+        flags.copy_((bits[0] | (bits[1] << 1) | (bits[2] << 2)).reshape(1))
+        g_idx = gather(idx)
+        g_dev = {name: gather(t) for name, t in dev.items()}
+        return g_idx, g_dev, W * B_local
+
+    def _out_buffers(self, B, dev_in):
+        """status / value outputs. Host-mode calls reuse one device + one pinned pair per batch
+        size (page-locked allocations cost more than the whole insertion); device-mode calls
+        get fresh tensors because the caller keeps them."""
+        odt = torch_dtype(self.dtypes["objective"])
+        if dev_in:
+            return (torch.empty(B, dtype=torch.int32, device=self._device),
+                    torch.empty(B, dtype=odt, device=self._device), None, None)
+        buf = self._outbuf.get(B)
+        if buf is None:
+            if len(self._outbuf) > 8:
+                self._outbuf.clear()
+            buf = (torch.empty(B, dtype=torch.int32, device=self._device),
+                   torch.empty(B, dtype=odt, device=self._device),
+                   torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=odt).pin_memory())
+            self._outbuf[B] = buf
+        return buf
 
     # ---- index_of ---------------------------------------------------------------------------
     def index_of(self, measures):
@@ -284,10 +342,27 @@ class DeviceArchive:
             return {"status": np.empty(0, dtype=np.int32), "value": np.empty(0, dtype=odt)}
         store = self._store
         with torch.cuda.device(self._device):
-            dev = {name: self._to_device(arr, store.dtypes[name], name) for name, arr in data.items()}
+            # measures + objective first: the index kernels only need those, so the (much larger)
+            # solution / extra-field rows travel host->device on a side stream while the search runs
+            dev = {name: self._to_device(data[name], store.dtypes[name], name) for name in ("measures", "objective")}
             idx = self._index_of_device(dev["measures"], store._flags_ptr)
-            status = torch.empty(B, dtype=torch.int32, device=self._device)
-            value = torch.empty(B, dtype=torch_dtype(odt), device=self._device)
+            rest = [n for n in data if n not in dev]
+            if dev_in or all(isinstance(data[n], torch.Tensor) for n in rest):
+                for n in rest:
+                    dev[n] = self._to_device(data[n], store.dtypes[n], n)
+            else:
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self._device)
+                    self._copy_event = torch.cuda.Event()
+                with torch.cuda.stream(self._copy_stream):
+                    for n in rest:
+                        dev[n] = self._to_device(data[n], store.dtypes[n], n)
+                    self._copy_event.record(self._copy_stream)
+                torch.cuda.current_stream().wait_event(self._copy_event)
+            B_local = B
+            if self._dp_world > 1:
+                idx, dev, B = self._gather_global_batch(idx, dev, B_local)
+            status, value, status_h, value_h = self._out_buffers(B, dev_in)
             names = store.row_fields
             src = (C.c_void_p * max(len(names), 1))(*[dev[n].data_ptr() for n in names])
             _lib.check(_lib.lib().qd_insert(
@@ -296,8 +371,6 @@ class DeviceArchive:
                 value.data_ptr(), store._result_dev.data_ptr(), current_stream_ptr()))
             store._result_host.copy_(store._result_dev, non_blocking=True)
             if not dev_in:
-                status_h = torch.empty(B, dtype=torch.int32, pin_memory=True)
-                value_h = torch.empty(B, dtype=torch_dtype(odt), pin_memory=True)
                 status_h.copy_(status, non_blocking=True)
                 value_h.copy_(value, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -320,9 +393,11 @@ class DeviceArchive:
             delta = (res.delta_sum[0] + res.delta_sum[1]) + res.delta_sum[2]
             new_sum = np.asarray(self._objective_sum + np.asarray(delta, dtype=odt), dtype=odt)
             self._stats_update(new_sum, res.best_cell, np.asarray(res.best_objective, dtype=odt))
+        lo, hi = self._dp_rank * B_local, (self._dp_rank + 1) * B_local  # this rank's slice of the global batch
         if dev_in:
-            return {"status": status, "value": value}
-        return {"status": status_h.numpy().copy(), "value": value_h.numpy().copy()}
+            return {"status": status[lo:hi], "value": value[lo:hi]} if self._dp_world > 1 else \
+                {"status": status, "value": value}
+        return {"status": status_h.numpy()[lo:hi].copy(), "value": value_h.numpy()[lo:hi].copy()}
 
     def add_single(self, solution, objective, measures, **fields):
         """Scalar rule of _grid_archive.py:716-848, run as a batch of one (identical statuses;

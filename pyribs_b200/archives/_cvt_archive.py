@@ -22,6 +22,30 @@ _DEPRECATED = {
 }
 
 
+def merge_sharded_argmin(idx, d_local, group, mask_losers):
+    """Combines per-rank (exact distance, global index) results of a centroid-sharded search.
+
+    all_reduce(MIN) over the distances, every rank masks its index unless it holds the global
+    minimum (`mask_losers(d_local, d_min, idx)` sets losers to INT32_MAX), all_reduce(MIN) over
+    the indices: the lowest index among exact ties wins, as np.argmin over the unsharded
+    centroid array would. Works on any backend (NCCL on the GPU path,
+    gloo in the CPU tests)."""
+    import torch.distributed as dist
+
+    d_min = d_local.clone()
+    dist.all_reduce(d_min, op=dist.ReduceOp.MIN, group=group)
+    mask_losers(d_local, d_min, idx)
+    dist.all_reduce(idx, op=dist.ReduceOp.MIN, group=group)
+    return idx, d_min
+
+
+def shard_bounds(n_centroids, world, rank):
+    """Contiguous centroid range [lo, hi) owned by `rank`."""
+    per = -(-n_centroids // world)
+    lo = min(rank * per, n_centroids)
+    return lo, min(lo + per, n_centroids)
+
+
 class CVTArchive(DeviceArchive):
     """Centroidal-Voronoi archive: a solution belongs to the cell of its nearest centroid.
 
@@ -42,7 +66,8 @@ class CVTArchive(DeviceArchive):
                  dtype=None, extra_fields=None, samples=100_000, k_means_kwargs=None,
                  nearest_neighbors="scipy_kd_tree", kdtree_kwargs=None, kdtree_query_kwargs=None, chunk_size=None,
                  sklearn_nn_kwargs=None, cells=None, custom_centroids=None, centroid_method=None, use_kd_tree=None,
-                 ckdtree_kwargs=None, device=None, search_method="auto", shard_centroids=False, process_group=None):
+                 ckdtree_kwargs=None, device=None, search_method="auto", shard_centroids=False, data_parallel=False,
+                 process_group=None):
         for name, val in (("cells", cells), ("custom_centroids", custom_centroids),
                           ("centroid_method", centroid_method), ("use_kd_tree", use_kd_tree),
                           ("ckdtree_kwargs", ckdtree_kwargs)):
@@ -72,7 +97,7 @@ class CVTArchive(DeviceArchive):
             self, solution_dim=solution_dim, measure_dim=len(ranges), cells=len(cen), learning_rate=learning_rate,
             threshold_min=threshold_min, qd_score_offset=qd_score_offset, seed=seed, solution_dtype=solution_dtype,
             objective_dtype=objective_dtype, measures_dtype=measures_dtype, dtype=dtype, extra_fields=extra_fields,
-            device=device)
+            device=device, data_parallel=data_parallel, process_group=process_group)
         lo, hi = zip(*ranges)
         self._lower_bounds = np.array(lo, dtype=mdt)
         self._upper_bounds = np.array(hi, dtype=mdt)
@@ -93,10 +118,7 @@ class CVTArchive(DeviceArchive):
                 raise RuntimeError("shard_centroids=True needs an initialised torch.distributed process group")
             self._world = dist.get_world_size(process_group)
             self._rank = dist.get_rank(process_group)
-        C_total = len(cen)
-        per = -(-C_total // self._world)
-        self._shard_lo = min(self._rank * per, C_total)
-        self._shard_hi = min(self._shard_lo + per, C_total)
+        self._shard_lo, self._shard_hi = shard_bounds(len(cen), self._world, self._rank)
         shard = np.ascontiguousarray(cen[self._shard_lo:self._shard_hi])
         with torch.cuda.device(self._device):
             self._centroids_dev = torch.from_numpy(shard).to(self._device) if len(shard) else None
@@ -158,12 +180,11 @@ class CVTArchive(DeviceArchive):
     def _index_of_device(self, measures: torch.Tensor, flags_ptr: int) -> torch.Tensor:
         if self._world == 1:
             return self._local_search(measures, flags_ptr, False)[0]
-        import torch.distributed as dist
-
         idx, d_local = self._local_search(measures, flags_ptr, True)
-        d_min = d_local.clone()
-        dist.all_reduce(d_min, op=dist.ReduceOp.MIN, group=self._pg)
-        _lib.check(_lib.lib().qd_cvt_mask_losers(d_local.data_ptr(), d_min.data_ptr(), idx.data_ptr(),
-                                                 int(idx.numel()), current_stream_ptr()))
-        dist.all_reduce(idx, op=dist.ReduceOp.MIN, group=self._pg)
+
+        def mask(d_loc, d_min, ix):
+            _lib.check(_lib.lib().qd_cvt_mask_losers(d_loc.data_ptr(), d_min.data_ptr(), ix.data_ptr(),
+                                                     int(ix.numel()), current_stream_ptr()))
+
+        idx, _ = merge_sharded_argmin(idx, d_local, self._pg, mask)
         return idx

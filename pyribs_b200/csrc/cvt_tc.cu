@@ -581,7 +581,7 @@ __global__ void search_init_kernel(int64_t B, SearchScratch ws, int32_t* __restr
 }
 
 template <typename T, int PASS>
-__global__ void __launch_bounds__(256) rescore_kernel(const T* __restrict__ meas, const T* __restrict__ cent, int64_t C,
+__global__ void __launch_bounds__(1024) rescore_kernel(const T* __restrict__ meas, const T* __restrict__ cent, int64_t C,
                                                       int d, int32_t base, SearchScratch ws,
                                                       int32_t* __restrict__ idx) {
   for (uint32_t region = blockIdx.x; region < kRegions; region += gridDim.x) {
@@ -747,9 +747,9 @@ int tc_impl(const T* meas, int64_t B, int d, const T* cent, int64_t C, const uns
     cvt_tc_kernel<T, false><<<grid, kThreads, smem, s>>>(meas, B, d, prepared, tiles_per_cta, ws, flags);
   if ((rc = check_launch("cvt_tc_kernel"))) return rc;
   const int rgrid = kRegions;
-  rescore_kernel<T, 0><<<rgrid, 256, 0, s>>>(meas, cent, C, d, base, ws, idx);
+  rescore_kernel<T, 0><<<rgrid, 1024, 0, s>>>(meas, cent, C, d, base, ws, idx);
   if ((rc = check_launch("rescore_kernel<0>"))) return rc;
-  rescore_kernel<T, 1><<<rgrid, 256, 0, s>>>(meas, cent, C, d, base, ws, idx);
+  rescore_kernel<T, 1><<<rgrid, 1024, 0, s>>>(meas, cent, C, d, base, ws, idx);
   if ((rc = check_launch("rescore_kernel<1>"))) return rc;
   outlier_scan_kernel<T><<<kNumSMs, 256, 0, s>>>(meas, cent, C, d, base, ws, idx);
   if ((rc = check_launch("outlier_scan_kernel"))) return rc;

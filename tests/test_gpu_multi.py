@@ -1,0 +1,89 @@
+"""Two-GPU tests (NCCL): data-parallel insertion and centroid-sharded CVT search must reproduce
+the single-archive oracle on the global batch. Skipped on boxes with fewer than 2 GPUs."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import qd_oracle as O
+
+    from pyribs_b200.archives import CVTArchive, GridArchive
+
+    rng = np.random.default_rng(7)
+    n, Bl = 6, 5000
+    ok = True
+    # (1) data-parallel GridArchive (CMA-MAE) vs oracle on the concatenated batch
+    gpu = GridArchive(solution_dim=n, dims=(30, 30), ranges=[(-1, 1)] * 2, learning_rate=0.05, threshold_min=0.0,
+                      data_parallel=True)
+    ora = O.make_grid_oracle(solution_dim=n, dims=(30, 30), ranges=[(-1, 1)] * 2, learning_rate=0.05,
+                             threshold_min=0.0)
+    cen = rng.uniform(-1, 1, (4000, 3))
+    cvt = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * 3, shard_centroids=True, search_method="tensor")
+    cvt_dp = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * 3, data_parallel=True)
+    ora_cvt = O.make_cvt_oracle(solution_dim=n, centroids=cen)
+    for step in range(3):
+        g = dict(solution=rng.standard_normal((world * Bl, n)), objective=rng.uniform(0, 10, world * Bl) + step,
+                 measures=rng.normal(0, 0.3, (world * Bl, 2)).clip(-1, 1))
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        out = gpu.add(g["solution"][sl], g["objective"][sl], g["measures"][sl])
+        ref = ora.add(**g)
+        ok &= bool(np.array_equal(out["status"], ref["status"][sl]))
+        ok &= bool(np.allclose(out["value"], ref["value"][sl], rtol=1e-9, atol=0))
+        ok &= len(gpu) == len(ora)
+        ok &= bool(np.array_equal(gpu._store.occupied_list, ora.store.occupied_list[: len(ora)]))
+        occ = ora.store.occupied
+        ok &= bool(np.allclose(gpu._store._fields["threshold"].cpu().numpy()[occ], ora.store.fields["threshold"][occ],
+                               rtol=1e-9))
+        # (2) centroid-sharded CVT: every rank passes the FULL batch, each searches its shard
+        m3 = rng.uniform(-1.1, 1.1, (world * Bl, 3))
+        g3 = dict(solution=g["solution"], objective=g["objective"], measures=m3)
+        out3 = cvt.add(**g3)
+        ref3 = ora_cvt.add(**g3)
+        ok &= bool(np.array_equal(out3["status"], ref3["status"]))
+        ok &= bool(np.array_equal(cvt.index_of(m3), ora_cvt.index_fn(m3)))
+        # (3) data-parallel CVT: each rank passes its slice
+        out4 = cvt_dp.add(g3["solution"][sl], g3["objective"][sl], m3[sl])
+        ok &= bool(np.array_equal(out4["status"], ref3["status"][sl]))
+        ok &= len(cvt_dp) == len(ora_cvt)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_insertion():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
