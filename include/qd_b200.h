@@ -49,6 +49,8 @@ int qd_abi_version(void);
 const char* qd_last_error(void);
 /* Number of kernels this library has launched in the calling process (all threads). */
 int64_t qd_launch_count(void);
+/* cudaStreamSynchronize(stream): the one blocking call of add() (the host needs qd_add_result). */
+int qd_stream_synchronize(void* stream);
 
 /* ------------------------------------------------------------------------------------
  * A2  GridArchive.index_of      ribs/archives/_grid_archive.py:362-410, 432-450
@@ -102,7 +104,8 @@ int qd_cvt_mask_losers(const double* local_dist /*[dev] B*/, const double* globa
 typedef struct qd_add_result {
   int32_t n_insertable; /* rows with status != 0 */
   int32_t n_new;        /* newly occupied cells */
-  int32_t best_cell;    /* cell of the highest-objective winner (lowest cell on ties) */
+  int32_t best_cell;    /* cell of the highest-objective winner (lowest cell on ties); -1 when the
+                           batch did not beat prev_obj_max */
   uint32_t flags;       /* QD_FLAG_* */
   double best_objective;
   double delta_sum[3]; /* exact 3-bin split of sum(new objective - old objective) */
@@ -140,8 +143,18 @@ uint32_t* qd_insert_flags_ptr(void* scratch /*[dev]*/, int64_t capacity);
 int qd_insert(const qd_store* store, int64_t B, const int32_t* idx /*[dev] B*/,
               const void* objective /*[dev] B*/, const void* const* field_src /*[host] n_fields dev ptrs*/,
               double learning_rate, double threshold_min, int64_t n_occupied_before,
+              double prev_obj_max /* archive's obj_max before the call, NaN if none: best_cell is
+                                     only resolved when the batch beats it (_grid_archive.py:331-341) */,
               int32_t* status_out /*[dev] B*/, void* value_out /*[dev] B*/,
               qd_add_result* result /*[dev]*/, void* stream);
+/* GridArchive.add with A2 fused into the first pass (measures are read once, idx_out is
+ * written for the later passes and for the caller). Arguments as qd_grid_index_of + qd_insert. */
+int qd_grid_insert(const qd_store* store, int64_t B, const void* measures /*[dev] B x d*/, int meas_dtype,
+                   int d, const int32_t* dims /*[host]*/, const double* lower /*[host]*/,
+                   const double* interval /*[host]*/, double epsilon, const void* objective,
+                   const void* const* field_src, double learning_rate, double threshold_min,
+                   int64_t n_occupied_before, double prev_obj_max, int32_t* idx_out /*[dev] B*/,
+                   int32_t* status_out, void* value_out, qd_add_result* result, void* stream);
 
 /* A6  ArrayStore.retrieve      ribs/archives/_array_store.py:330-485
  * Gathers rows `idx` of every listed field plus the occupied flag. */

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "qd_abi_version": (_int, []),
     "qd_last_error": (C.c_char_p, []),
     "qd_launch_count": (_i64, []),
+    "qd_stream_synchronize": (_int, [_vp]),
     "qd_grid_index_of": (_int, [_vp, _int, _i64, _int, C.POINTER(_i32), C.POINTER(_dbl), C.POINTER(_dbl), _dbl,
                                 _vp, _vp, _vp]),
     "qd_cvt_prepared_bytes": (_sz, [_i64, _int]),
@@ -68,7 +69,11 @@ PROTOTYPES = {
     "qd_insert_scratch_bytes": (_sz, [_i64]),
     "qd_insert_scratch_init": (_int, [_vp, _i64, _vp]),
     "qd_insert_flags_ptr": (_vp, [_vp, _i64]),
-    "qd_insert": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _dbl, _dbl, _i64, _vp, _vp, _vp, _vp]),
+    "qd_insert": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _dbl, _dbl, _i64, _dbl, _vp, _vp, _vp,
+                         _vp]),
+    "qd_grid_insert": (_int, [C.POINTER(Store), _i64, _vp, _int, _int, C.POINTER(_i32), C.POINTER(_dbl),
+                              C.POINTER(_dbl), _dbl, _vp, C.POINTER(_vp), _dbl, _dbl, _i64, _dbl, _vp, _vp, _vp, _vp,
+                              _vp]),
     "qd_store_gather": (_int, [_i64, _vp, _int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _vp, _vp, _vp]),
     "qd_fill_normal": (_int, [_vp, _i64, _u64, _u64, _vp]),
     "qd_es_out_of_bounds": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -122,6 +122,8 @@ class DeviceArchive:
         self._device = self._store.device
         self._learning_rate, self._threshold_min = validate_cma_mae_settings(learning_rate, threshold_min, odt)
         self._qd_score_offset = np.asarray(qd_score_offset, dtype=odt)
+        self._lr_f = float(self._learning_rate)
+        self._tmin_f = float(self._threshold_min)
         self._best_elite = None
         self._objective_sum = None
         self._stats = None
@@ -130,6 +132,7 @@ class DeviceArchive:
         self._outbuf = {}
         self._copy_stream = None
         self._copy_event = None
+        self._fused_index_insert = False  # GridArchive: index_of fused into the first insert pass
         self._force_scan = False
         self._overflow_fallbacks = 0
 
@@ -345,7 +348,8 @@ class DeviceArchive:
             # measures + objective first: the index kernels only need those, so the (much larger)
             # solution / extra-field rows travel host->device on a side stream while the search runs
             dev = {name: self._to_device(data[name], store.dtypes[name], name) for name in ("measures", "objective")}
-            idx = self._index_of_device(dev["measures"], store._flags_ptr)
+            fused = self._dp_world == 1 and self._fused_index_insert
+            idx = None if fused else self._index_of_device(dev["measures"], store._flags_ptr)
             rest = [n for n in data if n not in dev]
             if dev_in or all(isinstance(data[n], torch.Tensor) for n in rest):
                 for n in rest:
@@ -365,15 +369,19 @@ class DeviceArchive:
             status, value, status_h, value_h = self._out_buffers(B, dev_in)
             names = store.row_fields
             src = (C.c_void_p * max(len(names), 1))(*[dev[n].data_ptr() for n in names])
-            _lib.check(_lib.lib().qd_insert(
-                C.byref(store.abi_store()), B, idx.data_ptr(), dev["objective"].data_ptr(), src,
-                float(self._learning_rate), float(self._threshold_min), len(store), status.data_ptr(),
-                value.data_ptr(), store._result_dev.data_ptr(), current_stream_ptr()))
+            prev_max = float("nan") if self._stats.obj_max is None else float(self._stats.obj_max)
+            if fused:
+                self._grid_insert(dev, B, src, prev_max, status, value)
+            else:
+                _lib.check(_lib.lib().qd_insert(
+                    C.byref(store.abi_store()), B, idx.data_ptr(), dev["objective"].data_ptr(), src,
+                    self._lr_f, self._tmin_f, len(store), prev_max, status.data_ptr(),
+                    value.data_ptr(), store._result_dev.data_ptr(), current_stream_ptr()))
             store._result_host.copy_(store._result_dev, non_blocking=True)
             if not dev_in:
                 status_h.copy_(status, non_blocking=True)
                 value_h.copy_(value, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            _lib.check(_lib.lib().qd_stream_synchronize(current_stream_ptr()))
         res = _lib.AddResult.from_buffer_copy(store._result_host.numpy().tobytes())
         if res.flags & _lib.FLAG_NONFINITE_OBJECTIVE:
             raise ValueError("All elements of objective must be finite (infinity and NaN values are not supported).")

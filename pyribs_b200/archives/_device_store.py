@@ -27,7 +27,9 @@ from pyribs_b200._utils import arr_readonly, torch_dtype
 
 
 def current_stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream (the C accessor is ~10x cheaper than
+    torch.cuda.current_stream())."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 class DeviceStoreIterator:
@@ -163,7 +165,10 @@ class DeviceStore:
 
     @property
     def dtypes_with_index(self):
-        return {**self._np_dtypes, "index": np.dtype(np.int32)}
+        d = self.__dict__.get("_dtypes_wi")
+        if d is None:
+            d = self.__dict__["_dtypes_wi"] = {**self._np_dtypes, "index": np.dtype(np.int32)}
+        return d
 
     @property
     def field_list(self):

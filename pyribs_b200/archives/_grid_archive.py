@@ -45,6 +45,8 @@ class GridArchive(DeviceArchive):
         self._boundaries = self._compute_boundaries(self._dims, self._lower_bounds, self._upper_bounds)
         self._epsilon = np.asarray(epsilon, dtype=mdt)
         self._refresh_abi_consts()
+        self._fused_index_insert = True
+        self._idx_buf = None
 
     def _refresh_abi_consts(self):
         d = len(self._dims)
@@ -52,6 +54,7 @@ class GridArchive(DeviceArchive):
         self._c_lower = (C.c_double * d)(*[float(v) for v in self._lower_bounds])
         self._c_interval = (C.c_double * d)(*[float(v) for v in self._interval_size])
         self._meas_code = _lib.QD_F64 if self.dtypes["measures"] == np.float64 else _lib.QD_F32
+        self._eps_f = float(self._epsilon)
 
     @staticmethod
     def _compute_boundaries(dims, lower_bounds, upper_bounds):
@@ -91,6 +94,17 @@ class GridArchive(DeviceArchive):
             float(self._epsilon), idx.data_ptr(), flags_ptr, current_stream_ptr()))
         return idx
 
+    def _grid_insert(self, dev, B, src, prev_max, status, value):
+        """A2 + A4-A8 in one ABI call (qd_grid_insert): measures are read once."""
+        store = self._store
+        if self._idx_buf is None or self._idx_buf.numel() < B:
+            self._idx_buf = torch.empty(B, dtype=torch.int32, device=self._device)
+        _lib.check(_lib.lib().qd_grid_insert(
+            C.byref(store.abi_store()), B, dev["measures"].data_ptr(), self._meas_code, len(self._dims), self._c_dims,
+            self._c_lower, self._c_interval, self._eps_f, dev["objective"].data_ptr(), src,
+            self._lr_f, self._tmin_f, len(store), prev_max, self._idx_buf.data_ptr(),
+            status.data_ptr(), value.data_ptr(), store._result_dev.data_ptr(), current_stream_ptr()))
+
     def grid_to_int_index(self, grid_indices):
         grid_indices = np.asarray(grid_indices)
         check_batch_shape(grid_indices, "grid_indices", self.measure_dim, "measure_dim")
@@ -116,5 +130,6 @@ class GridArchive(DeviceArchive):
         self._boundaries = self._compute_boundaries(self._dims, self._lower_bounds, self._upper_bounds)
         self._store = DeviceStore(self._store.field_desc, capacity=int(np.prod(self._dims)), device=self._device)
         self._refresh_abi_consts()
+        self._idx_buf = None
         self._stats_reset()
         self.add(**cur)

@@ -19,3 +19,8 @@ void set_error(const char* fmt, ...) {
 extern "C" int qd_abi_version(void) { return QD_ABI_VERSION; }
 extern "C" const char* qd_last_error(void) { return qd::g_err; }
 extern "C" int64_t qd_launch_count(void) { return qd::g_launches.load(); }
+
+extern "C" int qd_stream_synchronize(void* stream) {
+  QD_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return QD_OK;
+}

@@ -30,7 +30,7 @@ BOUNDS_WARNING = (
 
 
 def stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def es_weights(mu):
