@@ -53,8 +53,8 @@ struct SearchScratch {
   uint32_t* n_outliers;
   unsigned long long* bestd;  // B
   int32_t* outliers;          // B
-  int2* cand;                 // kRegions * region_cap: (query, first column of an 8-group)
-  float* cand_score;          // kRegions * region_cap: tensor-core score of the group's minimum
+  int2* cand;                 // kRegions * region_cap: (query, first column of a 64-column slice)
+  float* cand_score;          // kRegions * region_cap: tensor-core minimum of that slice
   uint32_t* best_approx;      // B: ordered-uint image of the smallest tensor-core score per query
   float* eps;                 // B: per-query margin
   uint32_t region_cap;
@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
     };
     static_assert(kColsPerWarp == 64, "the epilogue below loads two 32-column chunks per tile");
+    static_assert(kColsPerWarp == 64, "rescore_kernel assumes 64-column candidates (kCandCols)");
     const int32_t qi = (int32_t)q;
     auto push = [&](int32_t col, float score) {
       const uint32_t pos = atomicAdd(wcnt, 1u);  // shared-memory atomic
@@ -489,15 +490,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     };
-    // group minima of one 32-column chunk: 4 groups of 8, 3-input min tree
-    auto group_min = [&](const uint32_t (&raw)[32], float (&gm)[4]) {
+    // minimum of one 32-column chunk with the 3-input min tree (16 FMNMX3-class ops)
+    auto chunk_min = [&](const uint32_t (&raw)[32]) {
+      float t[10];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float a = min3(__uint_as_float(raw[8 * g]), __uint_as_float(raw[8 * g + 1]), __uint_as_float(raw[8 * g + 2]));
-        const float b =
-            min3(__uint_as_float(raw[8 * g + 3]), __uint_as_float(raw[8 * g + 4]), __uint_as_float(raw[8 * g + 5]));
-        gm[g] = min3(a, b, fminf(__uint_as_float(raw[8 * g + 6]), __uint_as_float(raw[8 * g + 7])));
-      }
+      for (int g = 0; g < 10; ++g)
+        t[g] = min3(__uint_as_float(raw[3 * g]), __uint_as_float(raw[3 * g + 1]), __uint_as_float(raw[3 * g + 2]));
+      const float a = min3(t[0], t[1], t[2]), b = min3(t[3], t[4], t[5]), c = min3(t[6], t[7], t[8]);
+      return min3(min3(a, b, c), t[9], fminf(__uint_as_float(raw[30]), __uint_as_float(raw[31])));
     };
     const int last_full = (C_total / kTileN);  // tiles with index < last_full have no padding columns
     for (int i = 0; i < my_tiles; ++i) {
@@ -537,21 +537,16 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (cbase + 32 + j >= C_total) rb[j] = 0x7f800000u;
         }
       }
-      float ga[4], gb[4];
-      group_min(ra, ga);
-      group_min(rb, gb);
-      const float m = min3(min3(ga[0], ga[1], ga[2]), min3(ga[3], gb[0], gb[1]), fminf(gb[2], gb[3]));
+      // A candidate is this warp's whole 64-column slice of the tile (q, first column, its minimum):
+      // the rescoring kernel filters stale records and evaluates the 64 centroids exactly, so the
+      // hot loop never has to locate individual columns.
+      const float m = fminf(chunk_min(ra), chunk_min(rb));
       const bool trig = m <= thr;
       if (__any_sync(0xffffffffu, trig)) {  // rare once the running minimum has settled
         if (trig) {
           best = fminf(best, m);
           thr = best + eps;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            if (ga[g] <= thr) push(cbase + 8 * g, ga[g]);
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            if (gb[g] <= thr) push(cbase + 32 + 8 * g, gb[g]);
+          push(cbase, m);
           atomicMin(&sm.rowbest[r], ford(best));
         }
         __syncwarp();
@@ -580,42 +575,95 @@ __global__ void search_init_kernel(int64_t B, SearchScratch ws, int32_t* __restr
   if (i0 == 0) *ws.n_outliers = 0u;
 }
 
-template <typename T, int PASS>
-__global__ void __launch_bounds__(1024) rescore_kernel(const T* __restrict__ meas, const T* __restrict__ cent, int64_t C,
-                                                      int d, int32_t base, SearchScratch ws,
-                                                      int32_t* __restrict__ idx) {
+constexpr int kCandCols = 64;  // columns per candidate (= kTileN / (kEpiWarps / 4))
+
+// PASS 0: bestd[q] = min exact distance; PASS 1: idx[q] = lowest index attaining it.
+// Each lane filters one candidate (stale running-minimum records: slice minimum above the query's
+// final minimum + margin); the warp then evaluates every surviving slice together, 2 columns per lane,
+// in fp64 with NumPy's summation order.
+template <typename T, int D, int PASS>
+__global__ void __launch_bounds__(256) rescore_kernel(const T* __restrict__ meas, const T* __restrict__ cent, int64_t C,
+                                                     int d_rt, int32_t base, SearchScratch ws,
+                                                     int32_t* __restrict__ idx) {
+  const int d = D > 0 ? D : d_rt;
+  constexpr int XN = D > 0 ? D : QD_MAX_MEASURE_DIM;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (uint32_t region = blockIdx.x; region < kRegions; region += gridDim.x) {
     const uint32_t n = min(ws.region_count[region], ws.region_cap);
     const int2* rc = ws.cand + (size_t)region * ws.region_cap;
     const float* rs = ws.cand_score + (size_t)region * ws.region_cap;
-    // one thread per candidate group. Groups whose tensor-core minimum is above the query's
-    // final (smallest score + margin) are stale running-minimum records and are skipped.
-    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
-      const int2 qc = rc[e];
-      if (!(rs[e] <= unford(ws.best_approx[qc.x]) + ws.eps[qc.x])) continue;
-      double x[QD_MAX_MEASURE_DIM], c[QD_MAX_MEASURE_DIM];
-      for (int k = 0; k < d; ++k) x[k] = (double)meas[(int64_t)qc.x * d + k];
-      unsigned long long mbits = 0xFFFFFFFFFFFFFFFFull;
-      int32_t mcol = INT32_MAX;
-      const unsigned long long target = PASS == 1 ? ws.bestd[qc.x] : 0ull;
-      for (int j = 0; j < 8; ++j) {
-        const int32_t col = qc.y + j;
-        if (col >= C) break;  // padding columns
-        for (int k = 0; k < d; ++k) c[k] = (double)cent[(int64_t)col * d + k];
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(sqdist_np<0>(x, c, d));
-        if (PASS == 0) {
-          mbits = bits < mbits ? bits : mbits;
-        } else if (bits == target && mcol == INT32_MAX) {
-          mcol = col;
-        }
+    for (uint32_t e0 = (blockIdx.y * nwarp + warp) * 32; e0 < n; e0 += gridDim.y * nwarp * 32) {
+      const uint32_t e = e0 + lane;
+      int2 qc = make_int2(0, 0);
+      bool keep = false;
+      if (e < n) {
+        qc = rc[e];
+        keep = rs[e] <= unford(ws.best_approx[qc.x]) + ws.eps[qc.x];
       }
-      if (PASS == 0) {
-        if (mbits != 0xFFFFFFFFFFFFFFFFull) atomicMin(&ws.bestd[qc.x], mbits);
-      } else if (mcol != INT32_MAX) {
-        atomicMin(&idx[qc.x], mcol + base);  // lowest index among exact ties (np.argmin)
+      unsigned m = __ballot_sync(0xffffffffu, keep);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int q = __shfl_sync(0xffffffffu, qc.x, src);
+        const int c0 = __shfl_sync(0xffffffffu, qc.y, src);
+        double x[XN];
+#pragma unroll
+        for (int k = 0; k < XN; ++k)
+          if (k < d) x[k] = (double)meas[(int64_t)q * d + k];
+        unsigned long long mbits = 0xFFFFFFFFFFFFFFFFull;
+        int32_t mcol = INT32_MAX;
+        const unsigned long long target = PASS == 1 ? ws.bestd[q] : 0ull;
+#pragma unroll
+        for (int h = 0; h < kCandCols / 32; ++h) {
+          const int32_t col = c0 + h * 32 + lane;
+          if (col < C) {
+            double c[XN];
+#pragma unroll
+            for (int k = 0; k < XN; ++k)
+              if (k < d) c[k] = (double)cent[(int64_t)col * d + k];
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(sqdist_np<D>(x, c, d));
+            if (PASS == 0)
+              mbits = bits < mbits ? bits : mbits;
+            else if (bits == target)
+              mcol = min(mcol, col);
+          }
+        }
+        if (PASS == 0) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, mbits, o);
+            mbits = t2 < mbits ? t2 : mbits;
+          }
+          if (lane == 0 && mbits != 0xFFFFFFFFFFFFFFFFull) atomicMin(&ws.bestd[q], mbits);
+        } else {
+          mcol = __reduce_min_sync(0xffffffffu, mcol);
+          if (lane == 0 && mcol != INT32_MAX) atomicMin(&idx[q], mcol + base);  // lowest index on exact ties
+        }
       }
     }
   }
+}
+
+template <typename T, int PASS>
+static int launch_rescore(const T* meas, const T* cent, int64_t C, int d, int32_t base, SearchScratch ws, int32_t* idx,
+                          cudaStream_t s) {
+  // blockIdx.x = region, blockIdx.y splits a region's candidates so that a warp sees at most a few
+  // of them (the per-candidate work is a chain of dependent gathers)
+  const dim3 grid(kRegions, 8);
+#define QD_RS(DD) rescore_kernel<T, DD, PASS><<<grid, 256, 0, s>>>(meas, cent, C, d, base, ws, idx)
+  switch (d) {
+    case 1: QD_RS(1); break;
+    case 2: QD_RS(2); break;
+    case 3: QD_RS(3); break;
+    case 4: QD_RS(4); break;
+    case 5: QD_RS(5); break;
+    case 6: QD_RS(6); break;
+    case 8: QD_RS(8); break;
+    default: QD_RS(0);
+  }
+#undef QD_RS
+  return check_launch("rescore_kernel");
 }
 
 // queries that could not be represented in the fp16 image: one CTA scans all centroids
@@ -746,11 +794,8 @@ int tc_impl(const T* meas, int64_t B, int d, const T* cent, int64_t C, const uns
   else
     cvt_tc_kernel<T, false><<<grid, kThreads, smem, s>>>(meas, B, d, prepared, tiles_per_cta, ws, flags);
   if ((rc = check_launch("cvt_tc_kernel"))) return rc;
-  const int rgrid = kRegions;
-  rescore_kernel<T, 0><<<rgrid, 1024, 0, s>>>(meas, cent, C, d, base, ws, idx);
-  if ((rc = check_launch("rescore_kernel<0>"))) return rc;
-  rescore_kernel<T, 1><<<rgrid, 1024, 0, s>>>(meas, cent, C, d, base, ws, idx);
-  if ((rc = check_launch("rescore_kernel<1>"))) return rc;
+  if ((rc = launch_rescore<T, 0>(meas, cent, C, d, base, ws, idx, s))) return rc;
+  if ((rc = launch_rescore<T, 1>(meas, cent, C, d, base, ws, idx, s))) return rc;
   outlier_scan_kernel<T><<<kNumSMs, 256, 0, s>>>(meas, cent, C, d, base, ws, idx);
   if ((rc = check_launch("outlier_scan_kernel"))) return rc;
   search_finish_kernel<<<grid_for(B, 256), 256, 0, s>>>(B, ws, idx, base, dist);
