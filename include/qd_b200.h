@@ -133,6 +133,8 @@ int qd_insert_scratch_init(void* scratch /*[dev]*/, int64_t capacity, void* stre
  * device (the store stays untouched, the host raises ValueError after reading
  * qd_add_result.flags). qd_insert clears the word at the end of every call. */
 uint32_t* qd_insert_flags_ptr(void* scratch /*[dev]*/, int64_t capacity);
+/* *out = OR of in[0..n): merges the validation flags gathered from all ranks of a data-parallel add. */
+int qd_flags_or(const uint32_t* in /*[dev] n*/, int n, uint32_t* out /*[dev] 1*/, void* stream);
 
 /* One batched insertion. `idx` comes from qd_grid_index_of / qd_cvt_index_of.
  * n_occupied_before is the store's element count before the call; new cells are appended

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "qd_insert_scratch_bytes": (_sz, [_i64]),
     "qd_insert_scratch_init": (_int, [_vp, _i64, _vp]),
     "qd_insert_flags_ptr": (_vp, [_vp, _i64]),
+    "qd_flags_or": (_int, [_vp, _int, _vp, _vp]),
     "qd_insert": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _dbl, _dbl, _i64, _dbl, _vp, _vp, _vp,
                          _vp]),
     "qd_grid_insert": (_int, [C.POINTER(Store), _i64, _vp, _int, _int, C.POINTER(_i32), C.POINTER(_dbl),

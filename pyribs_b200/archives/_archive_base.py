@@ -256,27 +256,38 @@ class DeviceArchive:
     def _index_of_device(self, measures: torch.Tensor, flags_ptr: int) -> torch.Tensor:
         raise NotImplementedError
 
-    def _gather_global_batch(self, idx, dev, B_local):
-        """All-gathers the per-rank slices (equal sizes on every rank) into the global batch and
-        ORs the validation flags across ranks."""
+    def _all_gather_many(self, tensors):
+        """All-gathers several equally-sharded tensors over NCCL."""
         import torch.distributed as dist
 
         W = self._dp_world
+        outs = [torch.empty((W * t.shape[0], *t.shape[1:]), dtype=t.dtype, device=t.device) for t in tensors]
+        ins = [t.contiguous() for t in tensors]
+        for o, t in zip(outs, ins):  # (torch's coalescing manager measured slower than separate launches)
+            dist.all_gather_into_tensor(o, t, group=self._dp_group)
+        return outs
 
-        def gather(t):
-            out = torch.empty((W * t.shape[0], *t.shape[1:]), dtype=t.dtype, device=t.device)
-            dist.all_gather_into_tensor(out, t.contiguous(), group=self._dp_group)
-            return out
-
+    def _gather_global_batch(self, idx, dev, B_local, skip=()):
+        """All-gathers the per-rank slices (equal sizes on every rank) into the global batch and
+        ORs the validation flags across ranks. `idx` may be None (already global)."""
         store = self._store
         off = store._flags_ptr - store._scratch.data_ptr()
         flags = store._scratch[off:off + 4].view(torch.int32)
-        bits = torch.stack([(flags >> b) & 1 for b in range(3)]).reshape(3)  # NCCL has no bitwise OR: MAX per bit
-        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=self._dp_group)
-        flags.copy_((bits[0] | (bits[1] << 1) | (bits[2] << 2)).reshape(1))
-        g_idx = gather(idx)
-        g_dev = {name: gather(t) for name, t in dev.items()}
-        return g_idx, g_dev, W * B_local
+        names = [n for n in dev if n not in skip]
+        tensors = [flags] + ([idx] if idx is not None else []) + [dev[n] for n in names]
+        outs = self._all_gather_many(tensors)
+        _lib.check(_lib.lib().qd_flags_or(outs[0].data_ptr(), int(outs[0].numel()), flags.data_ptr(),
+                                          current_stream_ptr()))
+        k = 1
+        g_idx = idx
+        if idx is not None:
+            g_idx = outs[k]
+            k += 1
+        g_dev = dict(dev)
+        for n in names:
+            g_dev[n] = outs[k]
+            k += 1
+        return g_idx, g_dev, self._dp_world * B_local
 
     def _out_buffers(self, B, dev_in):
         """status / value outputs. Host-mode calls reuse one device + one pinned pair per batch
@@ -349,6 +360,10 @@ class DeviceArchive:
             # solution / extra-field rows travel host->device on a side stream while the search runs
             dev = {name: self._to_device(data[name], store.dtypes[name], name) for name in ("measures", "objective")}
             fused = self._dp_world == 1 and self._fused_index_insert
+            global_search = self._dp_world > 1 and getattr(self, "_world", 1) > 1  # centroid-sharded CVT
+            if global_search:
+                # every rank searches ALL queries against its centroid shard: gather the measures first
+                dev["measures"] = self._all_gather_many([dev["measures"]])[0]
             idx = None if fused else self._index_of_device(dev["measures"], store._flags_ptr)
             rest = [n for n in data if n not in dev]
             if dev_in or all(isinstance(data[n], torch.Tensor) for n in rest):
@@ -365,7 +380,10 @@ class DeviceArchive:
                 torch.cuda.current_stream().wait_event(self._copy_event)
             B_local = B
             if self._dp_world > 1:
-                idx, dev, B = self._gather_global_batch(idx, dev, B_local)
+                if global_search:  # idx and measures are already global
+                    _, dev, B = self._gather_global_batch(None, dev, B_local, skip=("measures",))
+                else:
+                    idx, dev, B = self._gather_global_batch(idx, dev, B_local)
             status, value, status_h, value_h = self._out_buffers(B, dev_in)
             names = store.row_fields
             src = (C.c_void_p * max(len(names), 1))(*[dev[n].data_ptr() for n in names])

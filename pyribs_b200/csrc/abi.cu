@@ -24,3 +24,18 @@ extern "C" int qd_stream_synchronize(void* stream) {
   QD_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return QD_OK;
 }
+
+namespace qd {
+__global__ void flags_or_kernel(const uint32_t* __restrict__ in, int n, uint32_t* out) {
+  uint32_t v = 0;
+  for (int i = threadIdx.x; i < n; i += 32) v |= in[i];
+  v = __reduce_or_sync(0xffffffffu, v);
+  if (threadIdx.x == 0) *out = v;
+}
+}  // namespace qd
+
+extern "C" int qd_flags_or(const uint32_t* in, int n, uint32_t* out, void* stream) {
+  QD_REQUIRE(in && out && n >= 1, "bad arguments");
+  qd::flags_or_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(in, n, out);
+  return qd::check_launch("flags_or_kernel");
+}

@@ -42,6 +42,8 @@ def _worker(rank, world, port, q):
     cen = rng.uniform(-1, 1, (4000, 3))
     cvt = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * 3, shard_centroids=True, search_method="tensor")
     cvt_dp = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * 3, data_parallel=True)
+    cvt_both = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * 3, data_parallel=True, shard_centroids=True,
+                          search_method="tensor")
     ora_cvt = O.make_cvt_oracle(solution_dim=n, centroids=cen)
     for step in range(3):
         g = dict(solution=rng.standard_normal((world * Bl, n)), objective=rng.uniform(0, 10, world * Bl) + step,
@@ -67,6 +69,11 @@ def _worker(rank, world, port, q):
         out4 = cvt_dp.add(g3["solution"][sl], g3["objective"][sl], m3[sl])
         ok &= bool(np.array_equal(out4["status"], ref3["status"][sl]))
         ok &= len(cvt_dp) == len(ora_cvt)
+        # (4) both: rows sharded over the ranks AND centroids sharded over the ranks
+        out5 = cvt_both.add(g3["solution"][sl], g3["objective"][sl], m3[sl])
+        ok &= bool(np.array_equal(out5["status"], ref3["status"][sl]))
+        ok &= len(cvt_both) == len(ora_cvt)
+        ok &= bool(np.array_equal(cvt_both._store.occupied_list, ora_cvt.store.occupied_list[: len(ora_cvt)]))
     q.put((rank, ok))
     dist.destroy_process_group()
 
