@@ -236,9 +236,18 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
     flops = 2.0 * B * WORKLOAD["centroids"] * WORKLOAD["measure_dim"]
     ach = flops / (ms_k / args.steps * 1e-3) / 1e12
+    # dram bytes of one cvt_tc_kernel launch from the committed `ncu --set full` capture
+    # (profiles/r01_top_kernels_ncu_full.txt: 2.375 MB read + 768 B written)
+    ncu_traffic = 2_375_424 + 768
+    pairs = float(B) * WORKLOAD["centroids"]
     roofline = {
-        "kernel": "cvt nearest-centroid search", "bound": "tensor", "achieved": ach, "peak": peak_tf,
-        "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+        "kernel": "cvt nearest-centroid search (cvt_tc_kernel + rescoring)", "bound": "tensor", "achieved": ach,
+        "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": ncu_traffic,
+        "note": "d=2: 4 GFLOP of useful contraction per launch; the kernel is bound by the TMEM->register epilogue "
+                "that must inspect every one of the B*C accumulators (measured tcgen05.ld ceiling 96 fp32/clk/SM, "
+                "tools/tmem_bw.cu), not by the tensor pipe",
+        "pairs_per_s": pairs / (ms_k / args.steps * 1e-3),
+        "tmem_read_ceiling_pairs_per_s": 96 * 148 * 1.965e9,
         "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1590",
         "flops_per_launch": flops, "ms_per_search": ms_k / args.steps, "launches_per_search": k_launches / args.steps,
     }

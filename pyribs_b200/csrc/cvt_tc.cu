@@ -55,6 +55,7 @@ struct SearchScratch {
   int32_t* outliers;          // B
   int2* cand;                 // kRegions * region_cap: (query, first column of a 64-column slice)
   float* cand_score;          // kRegions * region_cap: tensor-core minimum of that slice
+  unsigned long long* cand_bits;  // kRegions * region_cap: exact minimum distance of the slice (pass 0 -> 1)
   uint32_t* best_approx;      // B: ordered-uint image of the smallest tensor-core score per query
   float* eps;                 // B: per-query margin
   uint32_t region_cap;
@@ -577,22 +578,24 @@ __global__ void search_init_kernel(int64_t B, SearchScratch ws, int32_t* __restr
 
 constexpr int kCandCols = 64;  // columns per candidate (= kTileN / (kEpiWarps / 4))
 
-// PASS 0: bestd[q] = min exact distance; PASS 1: idx[q] = lowest index attaining it.
-// Each lane filters one candidate (stale running-minimum records: slice minimum above the query's
-// final minimum + margin); the warp then evaluates every surviving slice together, 2 columns per lane,
-// in fp64 with NumPy's summation order.
-template <typename T, int D, int PASS>
+// Exact rescoring, pass 0. Each lane filters one candidate (stale running-minimum records: slice
+// minimum above the query's final minimum + margin). Surviving slices are evaluated four at a time,
+// one per 8-lane group, 8 columns per lane, in fp64 with NumPy's summation order; the group's
+// (minimum distance, lowest column attaining it) goes back into the candidate record and the distance
+// into bestd[q] with atomicMin. Pass 1 is then a per-candidate compare: no distance is computed twice.
+template <typename T, int D>
 __global__ void __launch_bounds__(256) rescore_kernel(const T* __restrict__ meas, const T* __restrict__ cent, int64_t C,
-                                                     int d_rt, int32_t base, SearchScratch ws,
-                                                     int32_t* __restrict__ idx) {
+                                                     int d_rt, SearchScratch ws) {
   const int d = D > 0 ? D : d_rt;
   constexpr int XN = D > 0 ? D : QD_MAX_MEASURE_DIM;
   const int lane = threadIdx.x & 31;
+  const int grp = lane >> 3, gl = lane & 7;
   const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (uint32_t region = blockIdx.x; region < kRegions; region += gridDim.x) {
     const uint32_t n = min(ws.region_count[region], ws.region_cap);
-    const int2* rc = ws.cand + (size_t)region * ws.region_cap;
+    int2* rc = ws.cand + (size_t)region * ws.region_cap;
     const float* rs = ws.cand_score + (size_t)region * ws.region_cap;
+    unsigned long long* rb = ws.cand_bits + (size_t)region * ws.region_cap;
     for (uint32_t e0 = (blockIdx.y * nwarp + warp) * 32; e0 < n; e0 += gridDim.y * nwarp * 32) {
       const uint32_t e = e0 + lane;
       int2 qc = make_int2(0, 0);
@@ -600,58 +603,80 @@ __global__ void __launch_bounds__(256) rescore_kernel(const T* __restrict__ meas
       if (e < n) {
         qc = rc[e];
         keep = rs[e] <= unford(ws.best_approx[qc.x]) + ws.eps[qc.x];
+        if (!keep) rc[e].y = INT32_MAX;  // stale: pass 1 skips it
       }
       unsigned m = __ballot_sync(0xffffffffu, keep);
       while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const int q = __shfl_sync(0xffffffffu, qc.x, src);
-        const int c0 = __shfl_sync(0xffffffffu, qc.y, src);
-        double x[XN];
-#pragma unroll
-        for (int k = 0; k < XN; ++k)
-          if (k < d) x[k] = (double)meas[(int64_t)q * d + k];
+        // this group's survivor: the grp-th set bit of m (if any)
+        unsigned mm = m;
+        for (int k = 0; k < grp; ++k) mm &= mm - 1;
+        const int src = mm ? __ffs(mm) - 1 : -1;
+        // drop the (up to) four survivors taken in this round
+        for (int k = 0; k < 4 && m; ++k) m &= m - 1;
+        const int q = __shfl_sync(0xffffffffu, qc.x, src < 0 ? 0 : src);
+        const int c0 = __shfl_sync(0xffffffffu, qc.y, src < 0 ? 0 : src);
         unsigned long long mbits = 0xFFFFFFFFFFFFFFFFull;
         int32_t mcol = INT32_MAX;
-        const unsigned long long target = PASS == 1 ? ws.bestd[q] : 0ull;
+        if (src >= 0) {
+          double x[XN];
 #pragma unroll
-        for (int h = 0; h < kCandCols / 32; ++h) {
-          const int32_t col = c0 + h * 32 + lane;
-          if (col < C) {
-            double c[XN];
+          for (int k = 0; k < XN; ++k)
+            if (k < d) x[k] = (double)meas[(int64_t)q * d + k];
+#pragma unroll 2
+          for (int h = 0; h < kCandCols / 8; ++h) {
+            const int32_t col = c0 + h * 8 + gl;
+            if (col < C) {
+              double c[XN];
 #pragma unroll
-            for (int k = 0; k < XN; ++k)
-              if (k < d) c[k] = (double)cent[(int64_t)col * d + k];
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(sqdist_np<D>(x, c, d));
-            if (PASS == 0)
-              mbits = bits < mbits ? bits : mbits;
-            else if (bits == target)
-              mcol = min(mcol, col);
+              for (int k = 0; k < XN; ++k)
+                if (k < d) c[k] = (double)cent[(int64_t)col * d + k];
+              const unsigned long long bits = (unsigned long long)__double_as_longlong(sqdist_np<D>(x, c, d));
+              if (bits < mbits) {  // ascending columns per lane: strict < keeps the lowest column
+                mbits = bits;
+                mcol = col;
+              }
+            }
           }
         }
-        if (PASS == 0) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, mbits, o);
-            mbits = t2 < mbits ? t2 : mbits;
+        for (int o = 1; o < 8; o <<= 1) {  // (distance, column) lexicographic minimum over the 8-lane group
+          const unsigned long long tb = __shfl_xor_sync(0xffffffffu, mbits, o);
+          const int32_t tc = __shfl_xor_sync(0xffffffffu, mcol, o);
+          if (tb < mbits || (tb == mbits && tc < mcol)) {
+            mbits = tb;
+            mcol = tc;
           }
-          if (lane == 0 && mbits != 0xFFFFFFFFFFFFFFFFull) atomicMin(&ws.bestd[q], mbits);
-        } else {
-          mcol = __reduce_min_sync(0xffffffffu, mcol);
-          if (lane == 0 && mcol != INT32_MAX) atomicMin(&idx[q], mcol + base);  // lowest index on exact ties
+        }
+        if (src >= 0 && gl == 0) {
+          rc[e0 + src].y = mcol;
+          rb[e0 + src] = mbits;
+          if (mcol != INT32_MAX) atomicMin(&ws.bestd[q], mbits);
         }
       }
     }
   }
 }
 
-template <typename T, int PASS>
+// pass 1: idx[q] = lowest column among the candidates that attain bestd[q] (np.argmin's first minimum)
+__global__ void __launch_bounds__(256) rescore_pick_kernel(SearchScratch ws, int32_t base, int32_t* __restrict__ idx) {
+  for (uint32_t region = blockIdx.x; region < kRegions; region += gridDim.x) {
+    const uint32_t n = min(ws.region_count[region], ws.region_cap);
+    const int2* rc = ws.cand + (size_t)region * ws.region_cap;
+    const unsigned long long* rb = ws.cand_bits + (size_t)region * ws.region_cap;
+    for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < n; e += gridDim.y * blockDim.x) {
+      const int2 qc = rc[e];
+      if (qc.y != INT32_MAX && rb[e] == ws.bestd[qc.x]) atomicMin(&idx[qc.x], qc.y + base);
+    }
+  }
+}
+
+template <typename T>
 static int launch_rescore(const T* meas, const T* cent, int64_t C, int d, int32_t base, SearchScratch ws, int32_t* idx,
                           cudaStream_t s) {
   // blockIdx.x = region, blockIdx.y splits a region's candidates so that a warp sees at most a few
   // of them (the per-candidate work is a chain of dependent gathers)
   const dim3 grid(kRegions, 8);
-#define QD_RS(DD) rescore_kernel<T, DD, PASS><<<grid, 256, 0, s>>>(meas, cent, C, d, base, ws, idx)
+#define QD_RS(DD) rescore_kernel<T, DD><<<grid, 256, 0, s>>>(meas, cent, C, d, ws)
   switch (d) {
     case 1: QD_RS(1); break;
     case 2: QD_RS(2); break;
@@ -663,7 +688,10 @@ static int launch_rescore(const T* meas, const T* cent, int64_t C, int d, int32_
     default: QD_RS(0);
   }
 #undef QD_RS
-  return check_launch("rescore_kernel");
+  int rc = check_launch("rescore_kernel");
+  if (rc) return rc;
+  rescore_pick_kernel<<<dim3(kRegions, 2), 256, 0, s>>>(ws, base, idx);
+  return check_launch("rescore_pick_kernel");
 }
 
 // queries that could not be represented in the fp16 image: one CTA scans all centroids
@@ -729,7 +757,8 @@ static uint32_t region_cap_for(int64_t B) {
 static size_t search_scratch_bytes(int64_t B) {
   return a256(kRegions * 4) + 256 + a256((size_t)B * 8) + 3 * a256((size_t)B * 4) +
          a256((size_t)kRegions * region_cap_for(B) * sizeof(int2)) +
-         a256((size_t)kRegions * region_cap_for(B) * sizeof(float));
+         a256((size_t)kRegions * region_cap_for(B) * sizeof(float)) +
+         a256((size_t)kRegions * region_cap_for(B) * sizeof(unsigned long long));
 }
 
 static SearchScratch carve_search(void* base, int64_t B) {
@@ -751,6 +780,8 @@ static SearchScratch carve_search(void* base, int64_t B) {
   ws.cand = (int2*)p;
   p += a256((size_t)kRegions * ws.region_cap * sizeof(int2));
   ws.cand_score = (float*)p;
+  p += a256((size_t)kRegions * ws.region_cap * sizeof(float));
+  ws.cand_bits = (unsigned long long*)p;
   ws.dbg_scores = nullptr;
   ws.dbg_eps = nullptr;
   return ws;
@@ -794,8 +825,7 @@ int tc_impl(const T* meas, int64_t B, int d, const T* cent, int64_t C, const uns
   else
     cvt_tc_kernel<T, false><<<grid, kThreads, smem, s>>>(meas, B, d, prepared, tiles_per_cta, ws, flags);
   if ((rc = check_launch("cvt_tc_kernel"))) return rc;
-  if ((rc = launch_rescore<T, 0>(meas, cent, C, d, base, ws, idx, s))) return rc;
-  if ((rc = launch_rescore<T, 1>(meas, cent, C, d, base, ws, idx, s))) return rc;
+  if ((rc = launch_rescore<T>(meas, cent, C, d, base, ws, idx, s))) return rc;
   outlier_scan_kernel<T><<<kNumSMs, 256, 0, s>>>(meas, cent, C, d, base, ws, idx);
   if ((rc = check_launch("outlier_scan_kernel"))) return rc;
   search_finish_kernel<<<grid_for(B, 256), 256, 0, s>>>(B, ws, idx, base, dist);
