@@ -205,6 +205,12 @@ int qd_sep_tell(int64_t n, const double* new_mean, const double* rank_mu /*[dev]
                 double* workspace /*[dev] qd_es_workspace_doubles(n)*/, void* stream);
 /* CMA-ES       (_cma_es.py:51-82 eigen refresh, :181-237 ask, :274-328 tell) */
 int qd_sym_max(int64_t n, double* A /*[dev] n x n*/, void* stream);          /* A = max(A, A^T) */
+/* Batched symmetric eigendecomposition, n <= 150 (parallel cyclic Jacobi, one CTA per matrix):
+ * eig ascending, eigenvectors in the COLUMNS of V (the LAPACK convention np.linalg.eigh follows,
+ * _cma_es.py:70). sweeps (optional, [dev] batch) receives the number of sweeps used. */
+int qd_sym_eigh_batched(int64_t n, int64_t batch, const double* A /*[dev] batch x n x n*/,
+                        double* eig /*[dev] batch x n*/, double* V /*[dev] batch x n x n*/,
+                        int* sweeps /*[dev] batch or NULL*/, void* stream);
 int qd_cma_transform(int64_t n, const double* Bmat, const double* eigvals, double* T, void* stream); /* T = B*sqrt(eig) */
 int qd_cma_invsqrt(int64_t n, const double* Bmat, const double* eigvals, double* invsqrt, void* stream);
 int qd_cma_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,

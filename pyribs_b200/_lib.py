@@ -84,6 +84,7 @@ PROTOTYPES = {
     "qd_sep_ask": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qd_sep_tell": (_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(CmaScalars), _vp, _vp]),
     "qd_sym_max": (_int, [_i64, _vp, _vp]),
+    "qd_sym_eigh_batched": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "qd_cma_transform": (_int, [_i64, _vp, _vp, _vp, _vp]),
     "qd_cma_invsqrt": (_int, [_i64, _vp, _vp, _vp, _vp]),
     "qd_cma_ask": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

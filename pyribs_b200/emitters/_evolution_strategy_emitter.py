@@ -138,3 +138,5 @@ class EvolutionStrategyEmitter:
             self._opt.reset(new_x0)
             self._ranker.reset(self, self._archive)
             self._restarts += 1
+        if hasattr(self._opt, "prefetch_ask"):
+            self._opt.prefetch_ask()  # sampling for the next round overlaps with the other emitters' tells

@@ -48,6 +48,11 @@ class CMAEvolutionStrategy(DeviceES):
         return w, mueff, cc, cs, c1, cmu
 
     def reset(self, x0):
+        self._cancel_prefetch()
+        with torch.cuda.stream(self._es_stream()):
+            self._reset(x0)
+
+    def _reset(self, x0):
         n = self.solution_dim
         self.current_eval = 0
         self._mean.copy_(torch.from_numpy(np.array(x0, dtype=np.float64)))
@@ -64,39 +69,43 @@ class CMAEvolutionStrategy(DeviceES):
         self._eig_max = 1.0
         self._status.zero_()
         self._status[0] = float(self.sigma0)
+        self._status[2] = 1.0
+        self._status[3] = 1.0
 
     @property
     def mean(self):
-        return self._mean.cpu().numpy()
+        return self._to_host(self._mean)
 
     @property
     def pc(self):
-        return self._pc.cpu().numpy()
+        return self._to_host(self._pc)
 
     @property
     def ps(self):
-        return self._ps.cpu().numpy()
+        return self._to_host(self._ps)
 
     @property
     def cov(self):
-        return self._C.cpu().numpy()
+        return self._to_host(self._C)
 
     @property
     def invsqrt(self):
-        return self._invsqrt.cpu().numpy()
+        return self._to_host(self._invsqrt)
 
     @property
     def eigenvalues(self):
-        return self._eig.cpu().numpy()
+        return self._to_host(self._eig)
 
     def set_eigensystem(self, eigenvalues, eigenbasis):
         """Parity hook: installs (Lambda, B) computed elsewhere (eigenvector signs / the basis of
         degenerate subspaces differ between LAPACK and cuSOLVER, and the sample m + B sqrt(L) z
         depends on them)."""
-        self._L.qd_sym_max(self.solution_dim, self._C.data_ptr(), stream_ptr())  # C = max(C, C^T), :67
-        self._eig.copy_(torch.from_numpy(np.asarray(eigenvalues, dtype=np.float64)))
-        self._B.copy_(torch.from_numpy(np.ascontiguousarray(eigenbasis, dtype=np.float64)))
-        self._finish_eigensystem()
+        self._cancel_prefetch()
+        with torch.cuda.stream(self._es_stream()):
+            self._L.qd_sym_max(self.solution_dim, self._C.data_ptr(), stream_ptr())  # C = max(C, C^T), :67
+            self._eig.copy_(torch.from_numpy(np.asarray(eigenvalues, dtype=np.float64)))
+            self._B.copy_(torch.from_numpy(np.ascontiguousarray(eigenbasis, dtype=np.float64)))
+            self._finish_eigensystem()
         self.updated_eval = self.current_eval
 
     def _finish_eigensystem(self):
@@ -105,19 +114,31 @@ class CMAEvolutionStrategy(DeviceES):
                                             stream_ptr()))
         _lib.check(self._L.qd_cma_invsqrt(n, self._B.data_ptr(), self._eig.data_ptr(), self._invsqrt.data_ptr(),
                                           stream_ptr()))
-        mm = torch.stack((self._eig.max(), self._eig.min())).cpu().numpy()
-        self._eig_max = float(mm[0])
-        self.condition_number = float(mm[0] / mm[1])
+        # eigenvalue extrema stay on the device (status[2], status[3]); check_stop reads them later
+        self._status[2] = self._eig.max()
+        self._status[3] = self._eig.min()
 
     def update_eigensystem(self, force=False):
         """DecompMatrix.update_eigensystem, _cma_es.py:51-82."""
         if not force and self.current_eval <= self.updated_eval + self.lazy_gap_evals:
             return False
+        if force:
+            self._cancel_prefetch()
+            with torch.cuda.stream(self._es_stream()):
+                return self._refresh_now()
+        return self._refresh_now()
+
+    def _refresh_now(self):
         n = self.solution_dim
         _lib.check(self._L.qd_sym_max(n, self._C.data_ptr(), stream_ptr()))
-        lam, B = torch.linalg.eigh(self._C)
-        self._eig.copy_(lam.abs())
-        self._B.copy_(B)
+        if n <= 150:  # own Jacobi solver: no host synchronisation, so refreshes of different emitters overlap
+            _lib.check(self._L.qd_sym_eigh_batched(n, 1, self._C.data_ptr(), self._eig.data_ptr(), self._B.data_ptr(),
+                                                   None, stream_ptr()))
+            self._eig.abs_()
+        else:
+            lam, B = torch.linalg.eigh(self._C)
+            self._eig.copy_(lam.abs())
+            self._B.copy_(B)
         self._finish_eigensystem()
         self.updated_eval = self.current_eval
         return True
@@ -140,7 +161,7 @@ class CMAEvolutionStrategy(DeviceES):
             return
         w, mueff, cc, cs, c1, cmu = self._calc_strat_params(num_parents)
         damps = 1 + 2 * max(0, np.sqrt((mueff - 1) / (n + 1)) - 1) + cs
-        with torch.cuda.device(self._device):
+        with torch.cuda.device(self._device), torch.cuda.stream(self._es_stream()):
             rank_d = self._rank_to_device(ranking_indices, num_parents)
             w_d = torch.from_numpy(w).to(self._device)
             self._weighted(self._solutions, rank_d, w_d, num_parents, None, self._new_mean, None)
@@ -155,8 +176,10 @@ class CMAEvolutionStrategy(DeviceES):
 
     def check_stop(self, ranking_values):
         """_cma_es.py:161-179."""
+        st = self._read_status()
+        self.condition_number = st[2] / st[3]
         if self.condition_number > 1e14:
             return True
-        if self.sigma * np.sqrt(self._eig_max) < 1e-11:
+        if st[0] * np.sqrt(st[2]) < 1e-11:
             return True
         return bool(self._flat(ranking_values))

@@ -73,6 +73,12 @@ class DeviceES:
         self._partial = None
         self._solutions = None
         self._z = None
+        self._stream = None
+        self._ask_event = None
+        self._host_buf = None
+        self._pending = None
+        self._host_ready = False
+        self._rng_mark = 0
 
     # ---- helpers ------------------------------------------------------------------------------
     def _normals(self, rows):
@@ -95,21 +101,35 @@ class DeviceES:
         """Writes rows of self._solutions from unit normals `z`; implemented by subclasses."""
         raise NotImplementedError
 
-    def ask(self, batch_size=None, z=None, return_device=False):
-        """Samples `batch_size` solutions (reference ask loops, e.g. _cma_es.py:199-237).
+    # ---- ask: enqueue (own stream) + wait -------------------------------------------------------
+    def _es_stream(self):
+        """Every ES owns a CUDA stream: the kernels of different emitters (in particular the
+        single-CTA eigensolver of a covariance refresh) overlap on the GPU."""
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=self._device)
+            self._ask_event = torch.cuda.Event()
+        return self._stream
 
-        Returns a read-only NumPy array by default (drop-in); `return_device=True` returns the
-        CUDA tensor that `tell` will re-read, without a device->host copy.
-        """
-        lam = self.batch_size if batch_size is None else int(batch_size)
+    def _enqueue_host_copy(self):
+        lam, n = self._solutions.shape
+        with torch.cuda.device(self._device), torch.cuda.stream(self._es_stream()):
+            if self._host_buf is None or tuple(self._host_buf.shape) != (lam, n):
+                self._host_buf = torch.empty((lam, n), dtype=torch.float64).pin_memory()
+            self._host_buf.copy_(self._solutions, non_blocking=True)
+            self._ask_event.record(self._stream)
+        self._host_ready = True
+
+    def _enqueue_ask(self, lam, z, want_host=True):
+        """Enqueues sampling of `lam` solutions (+ optionally the device->host copy) on the ES stream."""
         n = self.solution_dim
-        with torch.cuda.device(self._device):
+        stream = self._es_stream()
+        with torch.cuda.device(self._device), torch.cuda.stream(stream):
             self._solutions = torch.empty((lam, n), dtype=torch.float64, device=self._device)
             self._prepare_ask(lam)
             zz = self._as_z(z, lam)
             self._z = zz
             self._sample_rows(zz, lam, None)
-            if self._bounded:
+            if self._bounded:  # resampling loop of the reference (needs the host to see the violations)
                 remaining = torch.arange(lam, dtype=torch.int32, device=self._device)
                 itrs = 0
                 while True:
@@ -122,13 +142,51 @@ class DeviceES:
                     if remaining.numel() == 0:
                         break
                     if itrs > BOUNDS_SAMPLING_THRESHOLD:
-                        warnings.warn(BOUNDS_WARNING, stacklevel=2)
+                        warnings.warn(BOUNDS_WARNING, stacklevel=3)
                     znew = self._normals(remaining.numel())
                     self._z[remaining.long()] = znew
                     self._sample_rows(znew, remaining.numel(), remaining)
+            self._ask_event.record(stream)
+        self._host_ready = False
+        if want_host:
+            self._enqueue_host_copy()
+        self._pending = lam
+
+    def prefetch_ask(self):
+        """Starts the next default `ask()` right away (called by the emitter at the end of `tell`), so
+        that by the time the scheduler asks, the samples of all emitters have been produced
+        concurrently. Identical results: `ask` is a pure function of the ES state and the RNG
+        counter, and nothing changes either between this call and the next `ask`."""
+        if self._pending is None and not self._bounded:
+            self._rng_mark = self._rng_offset
+            # small batches also start their device->host copy now; big ones wait to see what ask() wants
+            self._enqueue_ask(self.batch_size, None, want_host=self.batch_size * self.solution_dim * 8 <= (8 << 20))
+
+    def _cancel_prefetch(self):
+        if self._pending is not None:
+            self._ask_event.synchronize()
+            self._rng_offset = self._rng_mark
+            self._pending = None
+
+    def ask(self, batch_size=None, z=None, return_device=False):
+        """Samples `batch_size` solutions (reference ask loops, e.g. _cma_es.py:199-237).
+
+        Returns a read-only NumPy array by default (drop-in); `return_device=True` returns the
+        CUDA tensor that `tell` will re-read, without a device->host copy.
+        """
+        lam = self.batch_size if batch_size is None else int(batch_size)
+        if self._pending is not None and (z is not None or lam != self._pending):
+            self._cancel_prefetch()
+        if self._pending is None:
+            self._enqueue_ask(lam, z, want_host=not return_device)
+        self._pending = None
         if return_device:
+            torch.cuda.current_stream().wait_event(self._ask_event)
             return self._solutions
-        out = self._solutions.cpu().numpy()
+        if not self._host_ready:
+            self._enqueue_host_copy()
+        self._ask_event.synchronize()
+        out = self._host_buf.numpy().copy()
         if np.dtype(self.dtype) != np.float64:
             out = out.astype(self.dtype)
         return arr_readonly(out)
@@ -154,9 +212,18 @@ class DeviceES:
                 self._device)
         return r
 
+    def _to_host(self, t):
+        with torch.cuda.stream(self._es_stream()):
+            return t.cpu().numpy()
+
+    def _read_status(self):
+        """Device status block -> NumPy (ordered after everything enqueued on the ES stream)."""
+        with torch.cuda.stream(self._es_stream()):
+            return self._status.cpu().numpy()
+
     @property
     def sigma(self):
-        return float(self._status[0].item())
+        return float(self._read_status()[0])
 
     @staticmethod
     def _flat(ranking_values):

@@ -32,6 +32,11 @@ class LMMAEvolutionStrategy(DeviceES):
         self.current_gens = None
 
     def reset(self, x0):
+        self._cancel_prefetch()
+        with torch.cuda.stream(self._es_stream()):
+            self._reset(x0)
+
+    def _reset(self, x0):
         self.current_gens = 0
         self._mean.copy_(torch.from_numpy(np.array(x0, dtype=np.float64)))
         self._ps.zero_()
@@ -41,15 +46,15 @@ class LMMAEvolutionStrategy(DeviceES):
 
     @property
     def mean(self):
-        return self._mean.cpu().numpy()
+        return self._to_host(self._mean)
 
     @property
     def ps(self):
-        return self._ps.cpu().numpy()
+        return self._to_host(self._ps)
 
     @property
     def m(self):
-        return self._m.cpu().numpy()
+        return self._to_host(self._m)
 
     def _sample_rows(self, z, rows, row_ids):
         itrs = min(self.current_gens, self.n_vectors)
@@ -66,7 +71,7 @@ class LMMAEvolutionStrategy(DeviceES):
         if num_parents == 0:
             return
         w, mueff = es_weights(num_parents)
-        with torch.cuda.device(self._device):
+        with torch.cuda.device(self._device), torch.cuda.stream(self._es_stream()):
             rank_d = self._rank_to_device(ranking_indices, num_parents)
             w_d = torch.from_numpy(w).to(self._device)
             self._weighted(self._z, rank_d, w_d, num_parents, None, self._z_mean, None)

@@ -37,6 +37,11 @@ class SeparableCMAEvolutionStrategy(DeviceES):
         return w, mueff, cc, cs, c1_sep, cmu_sep
 
     def reset(self, x0):
+        self._cancel_prefetch()
+        with torch.cuda.stream(self._es_stream()):
+            self._reset(x0)
+
+    def _reset(self, x0):
         self.current_eval = 0
         self._mean.copy_(torch.from_numpy(np.array(x0, dtype=np.float64)))
         self._pc.zero_()
@@ -50,19 +55,19 @@ class SeparableCMAEvolutionStrategy(DeviceES):
     # state views (NumPy copies) used by tests and check_stop
     @property
     def mean(self):
-        return self._mean.cpu().numpy()
+        return self._to_host(self._mean)
 
     @property
     def pc(self):
-        return self._pc.cpu().numpy()
+        return self._to_host(self._pc)
 
     @property
     def ps(self):
-        return self._ps.cpu().numpy()
+        return self._to_host(self._ps)
 
     @property
     def cov(self):
-        return self._C.cpu().numpy()
+        return self._to_host(self._C)
 
     def _sample_rows(self, z, rows, row_ids):
         _lib.check(self._L.qd_sep_ask(
@@ -79,7 +84,7 @@ class SeparableCMAEvolutionStrategy(DeviceES):
             return
         w, mueff, cc, cs, c1, cmu = self._calc_strat_params(num_parents)
         damps = 1 + 2 * max(0, np.sqrt((mueff - 1) / (n + 1)) - 1) + cs
-        with torch.cuda.device(self._device):
+        with torch.cuda.device(self._device), torch.cuda.stream(self._es_stream()):
             rank_d = self._rank_to_device(ranking_indices, num_parents)
             w_d = torch.from_numpy(w).to(self._device)
             self._weighted(self._solutions, rank_d, w_d, num_parents, self._mean, self._new_mean, self._rank_mu)
@@ -92,7 +97,7 @@ class SeparableCMAEvolutionStrategy(DeviceES):
 
     def check_stop(self, ranking_values):
         """_sep_cma_es.py:121-138 (condition number, sigma * sqrt(max C), flat fitness)."""
-        st = self._status.cpu().numpy()
+        st = self._read_status()
         sigma, cmax, cmin = st[0], st[2], st[3]
         if cmax / cmin > 1e14:
             return True

@@ -144,3 +144,37 @@ def test_sphere_loop_improves(es):
         qd.append(archive.stats.num_elites)
     assert qd[-1] > qd[0]
     assert all(e.itrs == 30 for e in emitters)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 36, 100, 101, 150])
+def test_batched_jacobi_eigh(n):
+    """Own eigensolver vs NumPy/LAPACK: eigenvalues, orthogonality and reconstruction."""
+    import torch
+
+    from pyribs_b200 import _lib
+
+    rng = np.random.default_rng(n)
+    batch = 5
+    mats = []
+    for b in range(batch):
+        G = rng.standard_normal((n, n))
+        A = G @ G.T / n + np.diag(rng.uniform(0, 10.0 ** rng.integers(-3, 4), n))
+        if b == 0:
+            A = np.eye(n)  # fully degenerate (the ES start state)
+        mats.append((A + A.T) / 2)
+    A = np.stack(mats)
+    Ad = torch.from_numpy(A).cuda()
+    eig = torch.empty(batch, n, dtype=torch.float64, device="cuda")
+    V = torch.empty(batch, n, n, dtype=torch.float64, device="cuda")
+    sweeps = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().qd_sym_eigh_batched(n, batch, Ad.data_ptr(), eig.data_ptr(), V.data_ptr(), sweeps.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+    eig, V = eig.cpu().numpy(), V.cpu().numpy()
+    assert int(sweeps.max()) < 40
+    for b in range(batch):
+        ref = np.linalg.eigvalsh(A[b])
+        scale = np.abs(ref).max()
+        assert np.all(np.diff(eig[b]) >= 0)
+        assert np.max(np.abs(eig[b] - ref)) <= 1e-12 * scale
+        assert np.max(np.abs(V[b].T @ V[b] - np.eye(n))) <= 1e-12
+        assert np.max(np.abs((V[b] * eig[b]) @ V[b].T - A[b])) <= 1e-12 * scale

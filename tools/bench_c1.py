@@ -1,0 +1,62 @@
+"""BASELINE.json configs[0]: sphere CMA-ME -- GridArchive 100x100, solution_dim=100, 15
+EvolutionStrategyEmitters x batch 36 (examples/sphere.py `cma_me_imp`). Times ask + evaluate + tell
+per iteration for this repo (GPU) and for the CPU oracle port of the same loop."""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+def sphere(sol):
+    n = sol.shape[1]; best = n * 5.12 ** 2; worst = 0  # examples/sphere.py:960-1017 (shifted sphere, linear projection)
+    shift = 5.12 * 0.4
+    obj = (best - np.sum((sol - shift) ** 2, axis=1)) / best * 100  # normalised to ~[.., 100]
+    c = np.clip(sol, -5.12, 5.12)
+    meas = np.stack((c[:, : n // 2].sum(1), c[:, n // 2:].sum(1)), axis=1)
+    return obj, meas
+
+def run_gpu(iters, n=100, E=15, lam=36):
+    from pyribs_b200.archives import GridArchive
+    from pyribs_b200.emitters import EvolutionStrategyEmitter
+    from pyribs_b200.schedulers import Scheduler
+    mb = n / 2 * 5.12
+    a = GridArchive(solution_dim=n, dims=(100, 100), ranges=[(-mb, mb)] * 2, seed=1)
+    seeds = np.random.SeedSequence(1).spawn(E)
+    ems = [EvolutionStrategyEmitter(a, x0=np.zeros(n), sigma0=0.5, ranker="2imp", selection_rule="filter",
+                                    restart_rule="no_improvement", batch_size=lam, seed=s) for s in seeds]
+    s = Scheduler(a, ems)
+    for _ in range(10):
+        sol = s.ask(); s.tell(*sphere(sol))
+    t0 = time.perf_counter(); t_ask = t_tell = 0.0
+    for _ in range(iters):
+        t1 = time.perf_counter(); sol = s.ask(); t2 = time.perf_counter()
+        o, m = sphere(sol); t3 = time.perf_counter(); s.tell(o, m); t4 = time.perf_counter()
+        t_ask += t2 - t1; t_tell += t4 - t3
+    dt = time.perf_counter() - t0
+    return dict(it_per_s=iters / dt, solutions_per_s=iters * E * lam / dt, ask_ms=t_ask / iters * 1e3,
+                tell_ms=t_tell / iters * 1e3, elites=len(a), qd=float(a.stats.qd_score), restarts=sum(e.restarts for e in ems))
+
+def run_cpu(iters, n=100, E=15, lam=36):
+    import qd_oracle as O
+    mb = n / 2 * 5.12
+    a = O.make_grid_oracle(solution_dim=n, dims=(100, 100), ranges=[(-mb, mb)] * 2, seed=1)
+    es = [O.OracleCMAES(0.5, n, lam, seed=i) for i in range(E)]
+    for e in es: e.reset(np.zeros(n))
+    def step():
+        sols = [e.ask() for e in es]; sol = np.concatenate(sols); o, m = sphere(sol)
+        info = a.add(sol, o, m)
+        for i, e in enumerate(es):
+            sl = slice(i * lam, (i + 1) * lam)
+            idx, rv = O.rank_two_stage(info["status"][sl], info["value"][sl])
+            new = int(info["status"][sl].astype(bool).sum())
+            e.tell(idx, new)
+            if e.check_stop(rv[idx]) or new == 0:
+                e.reset(a.sample_elites(1)["solution"][0])
+    for _ in range(10): step()
+    t0 = time.perf_counter()
+    for _ in range(iters): step()
+    dt = time.perf_counter() - t0
+    return dict(it_per_s=iters / dt, solutions_per_s=iters * E * lam / dt, elites=len(a))
+
+if __name__ == "__main__":
+    iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    print(json.dumps({"case": "C1 sphere CMA-ME 15x36 n=100", "gpu": run_gpu(iters), "cpu_oracle_port": run_cpu(iters), "cores": os.cpu_count()}))
