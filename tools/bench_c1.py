@@ -1,5 +1,5 @@
-"""BASELINE.json configs[0]: sphere CMA-ME -- GridArchive 100x100, solution_dim=100, 15
-EvolutionStrategyEmitters x batch 36 (examples/sphere.py `cma_me_imp`). Times ask + evaluate + tell
+"""BASELINE.json configs[0] / configs[2]: sphere CMA-ME (GridArchive 100x100, 15 emitters x 36) or, with
+`c3`, CMA-MAE lr=0.01 (GridArchive 500x500, 100 emitters x 512, ranker imp, selection mu, restart basic). Times ask + evaluate + tell
 per iteration for this repo (GPU) and for the CPU oracle port of the same loop."""
 import json, os, sys, time
 import numpy as np
@@ -14,15 +14,19 @@ def sphere(sol):
     meas = np.stack((c[:, : n // 2].sum(1), c[:, n // 2:].sum(1)), axis=1)
     return obj, meas
 
-def run_gpu(iters, n=100, E=15, lam=36):
+def run_gpu(iters, n=100, E=15, lam=36, c3=False):
     from pyribs_b200.archives import GridArchive
     from pyribs_b200.emitters import EvolutionStrategyEmitter
     from pyribs_b200.schedulers import Scheduler
     mb = n / 2 * 5.12
-    a = GridArchive(solution_dim=n, dims=(100, 100), ranges=[(-mb, mb)] * 2, seed=1)
+    if c3:
+        a = GridArchive(solution_dim=n, dims=(500, 500), ranges=[(-mb, mb)] * 2, learning_rate=0.01, threshold_min=0.0, seed=1)
+    else:
+        a = GridArchive(solution_dim=n, dims=(100, 100), ranges=[(-mb, mb)] * 2, seed=1)
     seeds = np.random.SeedSequence(1).spawn(E)
-    ems = [EvolutionStrategyEmitter(a, x0=np.zeros(n), sigma0=0.5, ranker="2imp", selection_rule="filter",
-                                    restart_rule="no_improvement", batch_size=lam, seed=s) for s in seeds]
+    kw = dict(ranker="imp", selection_rule="mu", restart_rule="basic") if c3 else dict(
+        ranker="2imp", selection_rule="filter", restart_rule="no_improvement")
+    ems = [EvolutionStrategyEmitter(a, x0=np.zeros(n), sigma0=0.5, batch_size=lam, seed=s, **kw) for s in seeds]
     s = Scheduler(a, ems)
     for _ in range(10):
         sol = s.ask(); s.tell(*sphere(sol))
@@ -35,10 +39,11 @@ def run_gpu(iters, n=100, E=15, lam=36):
     return dict(it_per_s=iters / dt, solutions_per_s=iters * E * lam / dt, ask_ms=t_ask / iters * 1e3,
                 tell_ms=t_tell / iters * 1e3, elites=len(a), qd=float(a.stats.qd_score), restarts=sum(e.restarts for e in ems))
 
-def run_cpu(iters, n=100, E=15, lam=36):
+def run_cpu(iters, n=100, E=15, lam=36, c3=False):
     import qd_oracle as O
     mb = n / 2 * 5.12
-    a = O.make_grid_oracle(solution_dim=n, dims=(100, 100), ranges=[(-mb, mb)] * 2, seed=1)
+    a = (O.make_grid_oracle(solution_dim=n, dims=(500, 500), ranges=[(-mb, mb)] * 2, learning_rate=0.01, threshold_min=0.0, seed=1)
+         if c3 else O.make_grid_oracle(solution_dim=n, dims=(100, 100), ranges=[(-mb, mb)] * 2, seed=1))
     es = [O.OracleCMAES(0.5, n, lam, seed=i) for i in range(E)]
     for e in es: e.reset(np.zeros(n))
     def step():
@@ -46,6 +51,12 @@ def run_cpu(iters, n=100, E=15, lam=36):
         info = a.add(sol, o, m)
         for i, e in enumerate(es):
             sl = slice(i * lam, (i + 1) * lam)
+            if c3:
+                idx, rv = O.rank_one_key(info["value"][sl]); new = lam // 2
+                e.tell(idx, new)
+                if e.check_stop(rv[idx]):
+                    e.reset(a.sample_elites(1)["solution"][0])
+                continue
             idx, rv = O.rank_two_stage(info["status"][sl], info["value"][sl])
             new = int(info["status"][sl].astype(bool).sum())
             e.tell(idx, new)
@@ -59,4 +70,8 @@ def run_cpu(iters, n=100, E=15, lam=36):
 
 if __name__ == "__main__":
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-    print(json.dumps({"case": "C1 sphere CMA-ME 15x36 n=100", "gpu": run_gpu(iters), "cpu_oracle_port": run_cpu(iters), "cores": os.cpu_count()}))
+    if len(sys.argv) > 2 and sys.argv[2] == "c3":
+        print(json.dumps({"case": "C3 sphere CMA-MAE 100x512 n=100, grid 500x500", "gpu": run_gpu(iters, E=100, lam=512, c3=True),
+                          "cpu_oracle_port": run_cpu(max(3, iters // 5), E=100, lam=512, c3=True), "cores": os.cpu_count()}))
+    else:
+        print(json.dumps({"case": "C1 sphere CMA-ME 15x36 n=100", "gpu": run_gpu(iters), "cpu_oracle_port": run_cpu(iters), "cores": os.cpu_count()}))
