@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--search", default="auto", choices=["auto", "tensor", "scan"])
+    ap.add_argument("--search", default="auto", choices=["auto", "tensor", "scan", "bucket"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -75,11 +75,19 @@ int qd_grid_index_of(const void* measures /*[dev] B x d*/, int dtype, int64_t B,
  *   qd_cvt_index_of searches one shard: cell ids are `index_base + local row`;
  *   `dist_out` (optional) receives the exact fp64 squared distance of the winner so
  *   shards on different GPUs can be merged with a min-reduction.
- *   method: 0 = tensor-core filter (tcgen05) + fp64 rescoring, 1 = plain fp64 scan.
+ *   method: 0 = tensor-core filter (tcgen05) + fp64 rescoring, 1 = plain fp64 scan,
+ *           2 = bucket grid (measure_dim <= 3; the GPU analogue of the reference's default
+ *               KD-tree, _cvt_archive.py:605-609): `prepared` is then the structure built by
+ *               qd_cvt_bucket_prepare. All three return identical indices.
  * ---------------------------------------------------------------------------------- */
 size_t qd_cvt_prepared_bytes(int64_t C, int d);
 int qd_cvt_prepare(const void* centroids /*[dev] C x d*/, int dtype, int64_t C, int d,
                    void* prepared /*[dev]*/, void* stream);
+/* Bucket grid over a centroid shard (built where the reference builds its KD-tree,
+ * _cvt_archive.py:410-429); 0 bytes = unsupported measure_dim. */
+size_t qd_cvt_bucket_bytes(int64_t C, int d);
+int qd_cvt_bucket_prepare(const void* centroids /*[dev] C x d*/, int dtype, int64_t C, int d,
+                          void* buckets /*[dev] qd_cvt_bucket_bytes*/, void* stream);
 size_t qd_cvt_scratch_bytes(int64_t B, int64_t C, int d);
 int qd_cvt_index_of(const void* measures /*[dev] B x d*/, int dtype, int64_t B, int d,
                     const void* centroids /*[dev] C x d*/, int64_t C,

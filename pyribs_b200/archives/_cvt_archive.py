@@ -104,8 +104,10 @@ class CVTArchive(DeviceArchive):
         self._interval_size = self._upper_bounds - self._lower_bounds
         self._meas_code = _lib.QD_F64 if np.dtype(mdt) == np.float64 else _lib.QD_F32
         search_method = os.environ.get("QD_CVT_METHOD", search_method)
-        if search_method not in ("auto", "tensor", "scan"):
-            raise ValueError("search_method must be 'auto', 'tensor' or 'scan'")
+        if search_method not in ("auto", "tensor", "scan", "bucket"):
+            raise ValueError("search_method must be 'auto', 'tensor', 'scan' or 'bucket'")
+        if search_method == "bucket" and self._measure_dim > 3:
+            raise ValueError("search_method='bucket' supports measure_dim <= 3")
         self._search_method = search_method
         # centroid shard owned by this rank
         self._pg = process_group
@@ -123,7 +125,15 @@ class CVTArchive(DeviceArchive):
         with torch.cuda.device(self._device):
             self._centroids_dev = torch.from_numpy(shard).to(self._device) if len(shard) else None
             self._prepared = None
-            if len(shard):
+            self._buckets = None
+            if len(shard) and self._measure_dim <= 3 and search_method in ("auto", "bucket"):
+                # low measure_dim: bucket grid, the analogue of the KD-tree the reference builds here
+                nbytes = int(_lib.lib().qd_cvt_bucket_bytes(len(shard), self._measure_dim))
+                self._buckets = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+                _lib.check(_lib.lib().qd_cvt_bucket_prepare(self._centroids_dev.data_ptr(), self._meas_code,
+                                                            len(shard), self._measure_dim,
+                                                            self._buckets.data_ptr(), current_stream_ptr()))
+            elif len(shard):
                 nbytes = _lib.lib().qd_cvt_prepared_bytes(len(shard), self._measure_dim)
                 self._prepared = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self._device)
                 _lib.check(_lib.lib().qd_cvt_prepare(self._centroids_dev.data_ptr(), self._meas_code, len(shard),
@@ -151,6 +161,8 @@ class CVTArchive(DeviceArchive):
     def _pick_method(self, B, C):
         if self._force_scan or self._search_method == "scan":
             return 1
+        if self._buckets is not None:
+            return 2
         if self._search_method == "tensor":
             return 0
         return 0 if B * C >= (1 << 26) else 1
@@ -167,12 +179,13 @@ class CVTArchive(DeviceArchive):
                 dist.fill_(float("inf"))
             return idx, dist
         method = self._pick_method(B, Cn)
-        need = int(_lib.lib().qd_cvt_scratch_bytes(B, Cn, self._measure_dim))
+        need = int(_lib.lib().qd_cvt_scratch_bytes(B, Cn, self._measure_dim)) if method == 0 else 256
         if self._cvt_scratch is None or self._cvt_scratch.numel() < need:
             self._cvt_scratch = torch.empty(max(need, 256), dtype=torch.uint8, device=self._device)
+        prepared = self._buckets if method == 2 else self._prepared
         _lib.check(_lib.lib().qd_cvt_index_of(
             measures.data_ptr(), self._meas_code, B, self._measure_dim, self._centroids_dev.data_ptr(), Cn,
-            self._prepared.data_ptr(), self._shard_lo, method, idx.data_ptr(),
+            prepared.data_ptr() if prepared is not None else None, self._shard_lo, method, idx.data_ptr(),
             dist.data_ptr() if dist is not None else None, flags_ptr, self._cvt_scratch.data_ptr(),
             self._cvt_scratch.numel(), current_stream_ptr()))
         return idx, dist

@@ -1,0 +1,375 @@
+// A3, low measure_dim: exact nearest centroid through a uniform bucket grid (method 2).
+//
+// Reference: ribs/archives/_cvt_archive.py:579-609. The reference's default is a KD-tree
+// (scipy.spatial.KDTree.query, k=1): a spatial index, not a B x C contraction. For
+// measure_dim <= 3 this file is its GPU analogue. The centroids of a shard are binned once
+// (qd_cvt_bucket_prepare, the moment the reference builds its tree, :410-429) into G^d
+// equal buckets over their bounding box, stored bucket-major (CSR: start[], points, ids).
+// A query walks Chebyshev rings of buckets around its own bucket, evaluating the exact
+// fp64 squared distance (cvt_common.cuh, NumPy's summation order) of every centroid it
+// meets, and stops when the best distance found is below a conservative lower bound on
+// anything outside the rings already visited. The (distance, index) minimum is taken
+// lexicographically, so the result is bit-identical to the fp64 scan / np.argmin
+// (_cvt_archive.py:632) -- lowest centroid index on exact ties.
+//
+// Cost per query: ~9 (2-D) / ~27 (3-D) buckets of ~2 centroids, against C evaluations
+// for the scan and C accumulator reads for the tensor-core filter; the whole structure of
+// the 10k-centroid 2-D case (220 KB) lives in L1/L2.
+#include "cvt_common.cuh"
+
+namespace qd {
+
+constexpr int kBucketMaxDim = 3;
+constexpr int kBucketHeaderBytes = 256;
+
+struct BucketHeader {
+  double lo[kBucketMaxDim];
+  double w[kBucketMaxDim];
+  double inv_w[kBucketMaxDim];
+  double margin;  // absolute slack on the ring lower bound (covers face / binning rounding)
+  int32_t G[kBucketMaxDim];
+  int32_t nb;
+  int32_t C;
+  int32_t d;
+};
+static_assert(sizeof(BucketHeader) <= kBucketHeaderBytes, "header too large");
+
+struct BucketView {
+  BucketHeader* h;
+  double* mm;       // 2*d running min / max of the centroid coordinates
+  int32_t* start;   // nb + 1
+  int32_t* cursor;  // nb (build only)
+  int32_t* ids;     // C
+  double* pts;      // C * d, bucket-major
+};
+
+static int64_t bucket_count(int64_t C, int d) {
+  // ~2 centroids per bucket
+  double g = ceil(pow((double)C / 2.0, 1.0 / d));
+  int64_t G = g < 1 ? 1 : (int64_t)g;
+  int64_t nb = 1;
+  for (int k = 0; k < d; ++k) nb *= G;
+  return nb;
+}
+static int grid_side(int64_t C, int d) {
+  double g = ceil(pow((double)C / 2.0, 1.0 / d));
+  return g < 1 ? 1 : (int)g;
+}
+
+static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
+
+static BucketView carve_bucket(void* base, int64_t C, int d) {
+  const int64_t nb = bucket_count(C, d);
+  BucketView v;
+  char* p = (char*)base;
+  v.h = (BucketHeader*)p;
+  p += kBucketHeaderBytes;
+  v.mm = (double*)p;
+  p += 256;
+  v.start = (int32_t*)p;
+  p += a256((size_t)(nb + 1) * 4);
+  v.cursor = (int32_t*)p;
+  p += a256((size_t)nb * 4);
+  v.ids = (int32_t*)p;
+  p += a256((size_t)C * 4);
+  v.pts = (double*)p;
+  return v;
+}
+
+static size_t bucket_bytes(int64_t C, int d) {
+  const int64_t nb = bucket_count(C, d);
+  return kBucketHeaderBytes + 256 + a256((size_t)(nb + 1) * 4) + a256((size_t)nb * 4) + a256((size_t)C * 4) +
+         a256((size_t)C * d * 8);
+}
+
+// ---- build -------------------------------------------------------------------------------
+__global__ void bucket_init_kernel(BucketView v, int d, int64_t nb) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < d) {
+    v.mm[i] = INFINITY;
+    v.mm[d + i] = -INFINITY;
+  }
+  for (int64_t b = i; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+    v.start[b] = 0;
+    v.cursor[b] = 0;
+  }
+  if (i == 0) v.start[nb] = 0;
+}
+
+__device__ __forceinline__ void atomic_min_double(double* a, double x) {
+  // order-preserving key on the bit pattern; coordinates are finite here
+  unsigned long long* p = (unsigned long long*)a;
+  unsigned long long old = *p;
+  while (__longlong_as_double((long long)old) > x) {
+    unsigned long long prev = atomicCAS(p, old, (unsigned long long)__double_as_longlong(x));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+__device__ __forceinline__ void atomic_max_double(double* a, double x) {
+  unsigned long long* p = (unsigned long long*)a;
+  unsigned long long old = *p;
+  while (__longlong_as_double((long long)old) < x) {
+    unsigned long long prev = atomicCAS(p, old, (unsigned long long)__double_as_longlong(x));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
+template <typename T>
+__global__ void bucket_minmax_kernel(const T* __restrict__ cent, int64_t C, int d, BucketView v) {
+  double lo[kBucketMaxDim], hi[kBucketMaxDim];
+  for (int k = 0; k < d; ++k) {
+    lo[k] = INFINITY;
+    hi[k] = -INFINITY;
+  }
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < C; c += (int64_t)gridDim.x * blockDim.x)
+    for (int k = 0; k < d; ++k) {
+      const double x = (double)cent[c * d + k];
+      if (finite_d(x)) {
+        lo[k] = fmin(lo[k], x);
+        hi[k] = fmax(hi[k], x);
+      }
+    }
+  for (int k = 0; k < d; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fmin(lo[k], __shfl_down_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmax(hi[k], __shfl_down_sync(0xffffffffu, hi[k], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (lo[k] != INFINITY) atomic_min_double(&v.mm[k], lo[k]);
+      if (hi[k] != -INFINITY) atomic_max_double(&v.mm[d + k], hi[k]);
+    }
+  }
+}
+
+__global__ void bucket_header_kernel(BucketView v, int64_t C, int d, int G) {
+  if (threadIdx.x || blockIdx.x) return;
+  BucketHeader h;
+  double scale = 0.0;
+  for (int k = 0; k < kBucketMaxDim; ++k) {
+    h.lo[k] = 0.0;
+    h.w[k] = 1.0;
+    h.inv_w[k] = 0.0;
+    h.G[k] = 1;
+  }
+  int64_t nb = 1;
+  for (int k = 0; k < d; ++k) {
+    double lo = v.mm[k], hi = v.mm[d + k];
+    if (!(lo <= hi)) lo = hi = 0.0;  // no finite coordinate at all
+    const double ext = hi - lo;
+    h.lo[k] = lo;
+    if (ext > 0.0 && finite_d(ext)) {
+      h.G[k] = G;
+      h.w[k] = ext / (double)G;
+      h.inv_w[k] = (double)G / ext;
+    } else {  // degenerate axis: a single slice (inv_w = 0 sends everything to slice 0)
+      h.G[k] = 1;
+      h.w[k] = 1.0;
+      h.inv_w[k] = 0.0;
+    }
+    scale = fmax(scale, fmax(fabs(lo), fabs(hi)));
+    nb *= h.G[k];
+  }
+  h.margin = scale * 1e-11 + 1e-300;
+  h.nb = (int32_t)nb;
+  h.C = (int32_t)C;
+  h.d = d;
+  *v.h = h;
+}
+
+template <int D>
+__device__ __forceinline__ int bucket_coord(double x, int k, const BucketHeader& h) {
+  double t = (x - h.lo[k]) * h.inv_w[k];
+  int g = (t >= 0.0) ? ((t < 2147483000.0) ? (int)t : 2147483000) : 0;  // NaN -> 0
+  return min(g, h.G[k] - 1);
+}
+
+template <typename T>
+__global__ void bucket_count_kernel(const T* __restrict__ cent, int64_t C, int d, BucketView v, bool fill) {
+  const BucketHeader h = *v.h;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < C; c += (int64_t)gridDim.x * blockDim.x) {
+    int b = 0;
+    for (int k = 0; k < d; ++k) b = b * h.G[k] + bucket_coord<0>((double)cent[c * d + k], k, h);
+    if (!fill) {
+      atomicAdd(&v.start[b + 1], 1);
+    } else {
+      const int pos = v.start[b] + atomicAdd(&v.cursor[b], 1);
+      v.ids[pos] = (int32_t)c;
+      for (int k = 0; k < d; ++k) v.pts[(int64_t)pos * d + k] = (double)cent[c * d + k];
+    }
+  }
+}
+
+// single-block inclusive scan over start[1..nb] (set-up path, once per archive)
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(BucketView v, int64_t nb) {
+  __shared__ int32_t sh[1024];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 1; base <= nb; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    int32_t x = i <= nb ? v.start[i] : 0;
+    sh[threadIdx.x] = x;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i <= nb) v.start[i] = sh[threadIdx.x] + carry;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+}
+
+// ---- search ------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void scan_range(const double* __restrict__ x, const BucketView& v, int p0, int p1,
+                                           double& best, int32_t& bi) {
+  for (int p = p0; p < p1; ++p) {
+    double c[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) c[k] = __ldg(v.pts + (int64_t)p * D + k);
+    const double dd = sqdist_np<D>(x, c, D);
+    const int32_t id = __ldg(v.ids + p);
+    if (dd < best || (dd == best && id < bi)) {
+      best = dd;
+      bi = id;
+    }
+  }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) cvt_bucket_kernel(const T* __restrict__ meas, int64_t B, BucketView v,
+                                                       int32_t base, int32_t* __restrict__ idx,
+                                                       double* __restrict__ dist_out, uint32_t* flags) {
+  __shared__ BucketHeader h;
+  if (threadIdx.x == 0) h = *v.h;
+  __syncthreads();
+  bool bad = false;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < B; q += (int64_t)gridDim.x * blockDim.x) {
+    double x[D];
+    int bx[D];
+    bool qbad = false;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      x[k] = (double)meas[q * D + k];
+      qbad |= !finite_d(x[k]);
+      bx[k] = bucket_coord<D>(x[k], k, h);
+    }
+    bad |= qbad;
+    double best = INFINITY;
+    int32_t bi = INT32_MAX;
+    int maxG = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) maxG = max(maxG, h.G[k]);
+    for (int r = 0; r < maxG && !qbad; ++r) {
+      // rows over the leading D-1 axes; the last axis is contiguous in the CSR layout
+      const int lo1 = D >= 2 ? max(bx[0] - r, 0) : 0, hi1 = D >= 2 ? min(bx[0] + r, h.G[0] - 1) : 0;
+      for (int a = lo1; a <= hi1; ++a) {
+        const int lo2 = D >= 3 ? max(bx[1] - r, 0) : 0, hi2 = D >= 3 ? min(bx[1] + r, h.G[1] - 1) : 0;
+        for (int b2 = lo2; b2 <= hi2; ++b2) {
+          int row = 0;
+          bool shell = false;  // some leading axis already sits at Chebyshev distance r
+          if (D >= 2) {
+            row = a;
+            shell |= (abs(a - bx[0]) == r);
+          }
+          if (D >= 3) {
+            row = row * h.G[1] + b2;
+            shell |= (abs(b2 - bx[1]) == r);
+          }
+          const int GL = h.G[D - 1];
+          const int c0 = bx[D - 1] - r, c1 = bx[D - 1] + r;
+          const int rowbase = row * GL;
+          if (shell || r == 0) {
+            const int s0 = max(c0, 0), s1 = min(c1, GL - 1);
+            scan_range<D>(x, v, __ldg(v.start + rowbase + s0), __ldg(v.start + rowbase + s1 + 1), best, bi);
+          } else {
+            if (c0 >= 0) scan_range<D>(x, v, __ldg(v.start + rowbase + c0), __ldg(v.start + rowbase + c0 + 1), best, bi);
+            if (c1 < GL) scan_range<D>(x, v, __ldg(v.start + rowbase + c1), __ldg(v.start + rowbase + c1 + 1), best, bi);
+          }
+        }
+      }
+      // everything not visited yet lies beyond one of the faces of the (2r+1)-box
+      double lb = INFINITY;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        if (bx[k] - r > 0) lb = fmin(lb, x[k] - (h.lo[k] + (double)(bx[k] - r) * h.w[k]));
+        if (bx[k] + r < h.G[k] - 1) lb = fmin(lb, (h.lo[k] + (double)(bx[k] + r + 1) * h.w[k]) - x[k]);
+      }
+      if (lb == INFINITY) break;  // the box covers the whole grid
+      lb = lb * (1.0 - 1e-11) - h.margin;  // far larger than any rounding of the faces / the binning
+      if (lb > 0.0 && best < lb * lb) break;
+    }
+    idx[q] = qbad ? base : ((bi == INT32_MAX ? 0 : bi) + base);
+    if (dist_out) dist_out[q] = qbad ? INFINITY : best;
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, QD_FLAG_NONFINITE_MEASURES);
+}
+
+template <typename T>
+static int launch_bucket(const T* meas, int64_t B, int d, BucketView v, int32_t base, int32_t* idx, double* dist,
+                         uint32_t* flags, cudaStream_t s) {
+  const int grid = grid_for(B, 256, 8);
+  switch (d) {
+    case 1: cvt_bucket_kernel<T, 1><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags); break;
+    case 2: cvt_bucket_kernel<T, 2><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags); break;
+    case 3: cvt_bucket_kernel<T, 3><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags); break;
+    default: set_error("bucket search supports measure_dim <= 3"); return QD_ERR_UNSUPPORTED;
+  }
+  return check_launch("cvt_bucket_kernel");
+}
+
+int cvt_bucket_index_of(const void* measures, int dtype, int64_t B, int d, int64_t C, const void* buckets,
+                        int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags, cudaStream_t s) {
+  BucketView v = carve_bucket(const_cast<void*>(buckets), C, d);
+  if (dtype == QD_F64)
+    return launch_bucket<double>((const double*)measures, B, d, v, index_base, idx_out, dist_out, flags, s);
+  return launch_bucket<float>((const float*)measures, B, d, v, index_base, idx_out, dist_out, flags, s);
+}
+
+}  // namespace qd
+
+extern "C" size_t qd_cvt_bucket_bytes(int64_t C, int d) {
+  if (C < 1 || d < 1 || d > qd::kBucketMaxDim) return 0;
+  return qd::bucket_bytes(C, d);
+}
+
+extern "C" int qd_cvt_bucket_prepare(const void* centroids, int dtype, int64_t C, int d, void* buckets, void* stream) {
+  using namespace qd;
+  QD_REQUIRE(d >= 1 && d <= kBucketMaxDim, "bucket search supports measure_dim in [1, 3]");
+  QD_REQUIRE(dtype == QD_F32 || dtype == QD_F64, "dtype must be QD_F32 or QD_F64");
+  QD_REQUIRE(C >= 1 && C < ((int64_t)1 << 31), "centroid count must be in [1, 2^31)");
+  QD_REQUIRE(centroids && buckets, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  BucketView v = carve_bucket(buckets, C, d);
+  const int64_t nb = bucket_count(C, d);
+  const int G = grid_side(C, d);
+  bucket_init_kernel<<<grid_for(nb > 64 ? nb : 64, 256), 256, 0, s>>>(v, d, nb);
+  int rc = check_launch("bucket_init_kernel");
+  if (rc) return rc;
+  const int grid = grid_for(C, 256, 4);
+  if (dtype == QD_F64)
+    bucket_minmax_kernel<double><<<grid, 256, 0, s>>>((const double*)centroids, C, d, v);
+  else
+    bucket_minmax_kernel<float><<<grid, 256, 0, s>>>((const float*)centroids, C, d, v);
+  if ((rc = check_launch("bucket_minmax_kernel"))) return rc;
+  bucket_header_kernel<<<1, 32, 0, s>>>(v, C, d, G);
+  if ((rc = check_launch("bucket_header_kernel"))) return rc;
+  for (int pass = 0; pass < 2; ++pass) {
+    if (dtype == QD_F64)
+      bucket_count_kernel<double><<<grid, 256, 0, s>>>((const double*)centroids, C, d, v, pass == 1);
+    else
+      bucket_count_kernel<float><<<grid, 256, 0, s>>>((const float*)centroids, C, d, v, pass == 1);
+    if ((rc = check_launch("bucket_count_kernel"))) return rc;
+    if (pass == 0) {
+      bucket_scan_kernel<<<1, 1024, 0, s>>>(v, nb);
+      if ((rc = check_launch("bucket_scan_kernel"))) return rc;
+    }
+  }
+  return QD_OK;
+}

@@ -90,6 +90,9 @@ __global__ void mask_losers_kernel(const double* __restrict__ local, const doubl
 int cvt_tc_index_of(const void* measures, int dtype, int64_t B, int d, const void* centroids, int64_t C,
                     const void* prepared, int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags,
                     void* scratch, size_t scratch_bytes, cudaStream_t s);  // cvt_tc.cu
+int cvt_bucket_index_of(const void* measures, int dtype, int64_t B, int d, int64_t C, const void* buckets,
+                        int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags,
+                        cudaStream_t s);  // cvt_bucket.cu
 
 }  // namespace qd
 
@@ -110,7 +113,11 @@ extern "C" int qd_cvt_index_of(const void* measures, int dtype, int64_t B, int d
     return launch_scan<float>((const float*)measures, B, d, (const float*)centroids, C, index_base, idx_out, dist_out,
                               flags, s);
   }
-  QD_REQUIRE(method == 0, "method must be 0 (tensor-core) or 1 (fp64 scan)");
+  if (method == 2) {
+    QD_REQUIRE(prepared != nullptr, "method 2 needs the bucket grid built by qd_cvt_bucket_prepare");
+    return cvt_bucket_index_of(measures, dtype, B, d, C, prepared, index_base, idx_out, dist_out, flags, s);
+  }
+  QD_REQUIRE(method == 0, "method must be 0 (tensor-core), 1 (fp64 scan) or 2 (bucket grid)");
   QD_REQUIRE(prepared != nullptr, "method 0 needs the image built by qd_cvt_prepare");
   return cvt_tc_index_of(measures, dtype, B, d, centroids, C, prepared, index_base, idx_out, dist_out, flags, scratch,
                          scratch_bytes, s);

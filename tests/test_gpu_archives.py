@@ -60,7 +60,7 @@ def test_grid_index_golden():
         np.testing.assert_array_equal(a.index_of(c["measures"]), c["index"], err_msg=name)
 
 
-@pytest.mark.parametrize("method", ["scan", "tensor"])
+@pytest.mark.parametrize("method", ["scan", "tensor", "bucket"])
 def test_cvt_index_golden(method):
     from pyribs_b200.archives import CVTArchive
 
@@ -68,6 +68,8 @@ def test_cvt_index_golden(method):
     for name, c in g.items():
         dt = c["measures"].dtype
         d = c["centroids"].shape[1]
+        if method == "bucket" and d > 3:
+            continue
         a = CVTArchive(solution_dim=1, centroids=c["centroids"], ranges=[(-1, 1)] * d, dtype=dt, search_method=method)
         try:
             idx = a.index_of(c["measures"])
@@ -102,6 +104,47 @@ def test_add_golden(name):
         np.testing.assert_array_equal(status, s["status"], err_msg=f"{name} s{j} status")
         assert_close(value, s["value"], rtol, f"{name} s{j} value")
         check_archive_dump(gpu_dump(a), s["after"], rtol, f"{name} s{j}")
+
+
+@pytest.mark.parametrize("case", ["uniform", "clustered", "degenerate_axis", "one_centroid", "lattice_ties", "f32"])
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_cvt_bucket_equals_scan(case, d):
+    """The bucket-grid search (measure_dim <= 3) must return exactly what the fp64 scan returns:
+    empty buckets, clustered centroids, a zero-extent axis, queries outside the bounding box,
+    exact ties on a lattice (lowest index wins) and float32 archives."""
+    from pyribs_b200.archives import CVTArchive
+
+    rng = np.random.default_rng(d * 100 + len(case))
+    C, B = 5000, 20000
+    dt = np.float32 if case == "f32" else np.float64
+    if case == "clustered":
+        cen = np.concatenate([rng.normal(m, 0.01, (C // 5, d)) for m in rng.uniform(-1, 1, (5, d))])
+    elif case == "one_centroid":
+        cen = rng.uniform(-1, 1, (1, d))
+    elif case == "lattice_ties":
+        side = int(round(C ** (1.0 / d)))
+        cen = np.stack(np.meshgrid(*[np.arange(side) / 4.0] * d, indexing="ij"), -1).reshape(-1, d)
+        cen = np.concatenate([cen, cen[::7]])  # duplicates: the first copy must win
+    else:
+        cen = rng.uniform(-1, 1, (C, d))
+    if case == "degenerate_axis":
+        cen[:, -1] = 0.25
+    span = np.abs(cen).max() + 0.1
+    meas = rng.uniform(-1.2, 1.2, (B, d)) * span
+    if case == "lattice_ties":
+        meas[: B // 2] = np.round(meas[: B // 2] * 8) / 8  # many exactly equidistant queries
+    meas[:20] *= 50.0
+    meas[20:25] *= 1e6
+    cen, meas = cen.astype(dt), meas.astype(dt)
+    out = {}
+    for method in ("scan", "bucket"):
+        a = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, search_method=method, dtype=dt)
+        out[method] = a.index_of(meas)
+    np.testing.assert_array_equal(out["bucket"], out["scan"])
+    if dt == np.float64:
+        sub = rng.choice(B, 300, replace=False)
+        dd = ((meas[sub, None, :] - cen[None, :, :]) ** 2).sum(-1)
+        np.testing.assert_array_equal(out["bucket"][sub], dd.argmin(1))
 
 
 def _random_batches(rng, steps, B, n, md, scale):
@@ -259,11 +302,13 @@ def test_cvt_tensor_equals_scan(shape):
     meas[50:60] *= 1e9
     meas[60:70] = cen[C // 2: C // 2 + 10]
     out = {}
-    for method in ("scan", "tensor"):
+    for method in ("scan", "tensor") + (("bucket",) if d <= 3 else ()):
         a = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, search_method=method)
         out[method] = a.index_of(meas)
         assert a._overflow_fallbacks == 0
     np.testing.assert_array_equal(out["tensor"], out["scan"])
+    if "bucket" in out:
+        np.testing.assert_array_equal(out["bucket"], out["scan"])
     assert np.all(out["scan"][60:70] == np.arange(10))
     # spot-check against an fp64 NumPy brute force
     sub = rng.choice(B, 200, replace=False)
