@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 1
+#define QD_ABI_VERSION 2
 
 #define QD_OK 0
 #define QD_ERR_INVALID_ARG (-1)
@@ -113,11 +113,22 @@ typedef struct qd_add_result {
   int32_t n_insertable; /* rows with status != 0 */
   int32_t n_new;        /* newly occupied cells */
   int32_t best_cell;    /* cell of the highest-objective winner (lowest cell on ties); -1 when the
-                           batch did not beat prev_obj_max */
-  uint32_t flags;       /* QD_FLAG_* */
+                           batch did not beat the archive's best objective */
+  uint32_t flags;       /* QD_FLAG_* of THIS call */
   double best_objective;
   double delta_sum[3]; /* exact 3-bin split of sum(new objective - old objective) */
   double batch_absmax; /* max |objective| of the batch */
+  /* store state after the call (kept on the device between calls, so add() needs no host
+   * round trip): what _stats_update (_grid_archive.py:325-360) consumes */
+  int64_t n_occupied;     /* len(store) */
+  double objective_sum;   /* running sum of the elites' objectives, rounded in the objective dtype */
+  double obj_max;         /* valid when has_obj_max */
+  int32_t has_obj_max;
+  uint32_t last_failed_flags; /* `flags` of the most recent call that failed validation */
+  uint64_t n_commits;     /* calls that inserted at least one row (ArrayStore.updates[ADD]) */
+  uint64_t best_serial;   /* bumps whenever the best-elite snapshot was replaced */
+  uint64_t n_failed;      /* calls dropped because of a non-finite objective / measure: a host that
+                             did not wait for every call raises ValueError when this advances */
 } qd_add_result;
 
 typedef struct qd_store {
@@ -126,12 +137,17 @@ typedef struct qd_store {
   uint8_t* occupied;          /* [dev] capacity */
   int32_t* occupied_list;     /* [dev] capacity, insertion order */
   void* objective;            /* [dev] capacity */
-  void* threshold;            /* [dev] capacity */
+  void* threshold;            /* [dev] capacity; NaN marks an unoccupied cell (qd_store_clear) */
   int n_fields;               /* row fields copied verbatim: solution, measures, extras */
   void* field_dst[QD_MAX_FIELDS];        /* [dev] capacity x row_bytes */
   int64_t field_row_bytes[QD_MAX_FIELDS];
   void* scratch;              /* [dev] qd_insert_scratch_bytes(capacity), zeroed once by
                                  qd_insert_scratch_init; every call leaves it clean */
+  void* best_snapshot;        /* [dev] qd_best_snapshot_bytes(store) or NULL: copy of the best
+                                 elite's row taken the moment it became the best
+                                 (_grid_archive.py:331-341). Layout: double objective, double
+                                 threshold, int32 cell, pad to 32 bytes, then every row field at
+                                 16-byte aligned offsets in field order */
 } qd_store;
 
 size_t qd_insert_scratch_bytes(int64_t capacity);
@@ -144,27 +160,44 @@ uint32_t* qd_insert_flags_ptr(void* scratch /*[dev]*/, int64_t capacity);
 /* *out = OR of in[0..n): merges the validation flags gathered from all ranks of a data-parallel add. */
 int qd_flags_or(const uint32_t* in /*[dev] n*/, int n, uint32_t* out /*[dev] 1*/, void* stream);
 
-/* One batched insertion. `idx` comes from qd_grid_index_of / qd_cvt_index_of.
- * n_occupied_before is the store's element count before the call; new cells are appended
- * to occupied_list[n_occupied_before ...] in ascending cell order.
+size_t qd_best_snapshot_bytes(const qd_store* store);
+/* ArrayStore.clear (_array_store.py:610-616) + _stats_reset: occupancy 0, thresholds NaN, element
+ * count / objective sum / best objective reset. Also the initialiser of a fresh store. */
+int qd_store_clear(const qd_store* store, void* stream);
+/* Restores the device-side store state after the fields were loaded from a checkpoint
+ * (re-marks the thresholds of unoccupied cells). */
+int qd_store_set_state(const qd_store* store, int64_t n_occupied, double objective_sum, int has_obj_max,
+                       double obj_max, double objective_absmax, void* stream);
+/* Writes the store-state half of qd_add_result (per-call fields zero) to out [dev]. */
+int qd_store_read_state(const qd_store* store, qd_add_result* out /*[dev]*/, void* stream);
+
+/* One batched insertion = ONE persistent cooperative kernel. `idx` comes from qd_grid_index_of /
+ * qd_cvt_index_of. New cells are appended to occupied_list in ascending cell order after the
+ * store's current element count (device state).
  * learning_rate / threshold_min as validated by ribs/archives/_utils.py:76-93
  * (threshold_min == -inf selects the CMA-ME / MAP-Elites rule).
- * result [dev]: one qd_add_result, read by the host after the stream is synchronised. */
+ * part: QD_INSERT_WHOLE runs everything in one launch. A caller whose row fields (field_src:
+ * solutions, measures, extras) are still in flight on another stream issues QD_INSERT_CLASSIFY
+ * (needs idx / objective only; status_out / value_out and the thresholds are final afterwards),
+ * makes `stream` wait for the rows, then issues QD_INSERT_COMMIT (row copy, occupied_list,
+ * stats, result) with the same arguments.
+ * result [dev]: one qd_add_result, valid once the stream has run the call. */
+#define QD_INSERT_WHOLE 0
+#define QD_INSERT_CLASSIFY 1
+#define QD_INSERT_COMMIT 2
 int qd_insert(const qd_store* store, int64_t B, const int32_t* idx /*[dev] B*/,
               const void* objective /*[dev] B*/, const void* const* field_src /*[host] n_fields dev ptrs*/,
-              double learning_rate, double threshold_min, int64_t n_occupied_before,
-              double prev_obj_max /* archive's obj_max before the call, NaN if none: best_cell is
-                                     only resolved when the batch beats it (_grid_archive.py:331-341) */,
+              double learning_rate, double threshold_min,
               int32_t* status_out /*[dev] B*/, void* value_out /*[dev] B*/,
-              qd_add_result* result /*[dev]*/, void* stream);
+              qd_add_result* result /*[dev]*/, int part, void* stream);
 /* GridArchive.add with A2 fused into the first pass (measures are read once, idx_out is
  * written for the later passes and for the caller). Arguments as qd_grid_index_of + qd_insert. */
 int qd_grid_insert(const qd_store* store, int64_t B, const void* measures /*[dev] B x d*/, int meas_dtype,
                    int d, const int32_t* dims /*[host]*/, const double* lower /*[host]*/,
                    const double* interval /*[host]*/, double epsilon, const void* objective,
                    const void* const* field_src, double learning_rate, double threshold_min,
-                   int64_t n_occupied_before, double prev_obj_max, int32_t* idx_out /*[dev] B*/,
-                   int32_t* status_out, void* value_out, qd_add_result* result, void* stream);
+                   int32_t* idx_out /*[dev] B*/, int32_t* status_out, void* value_out,
+                   qd_add_result* result, int part, void* stream);
 
 /* A6  ArrayStore.retrieve      ribs/archives/_array_store.py:330-485
  * Gathers rows `idx` of every listed field plus the occupied flag. */

@@ -13,6 +13,7 @@ QD_MAX_FIELDS = 16
 FLAG_NONFINITE_MEASURES = 1
 FLAG_NONFINITE_OBJECTIVE = 2
 FLAG_CVT_OVERFLOW = 4
+INSERT_WHOLE, INSERT_CLASSIFY, INSERT_COMMIT = 0, 1, 2
 
 
 class QdError(RuntimeError):
@@ -28,6 +29,14 @@ class AddResult(C.Structure):
         ("best_objective", C.c_double),
         ("delta_sum", C.c_double * 3),
         ("batch_absmax", C.c_double),
+        ("n_occupied", C.c_int64),
+        ("objective_sum", C.c_double),
+        ("obj_max", C.c_double),
+        ("has_obj_max", C.c_int32),
+        ("last_failed_flags", C.c_uint32),
+        ("n_commits", C.c_uint64),
+        ("best_serial", C.c_uint64),
+        ("n_failed", C.c_uint64),
     ]
 
 
@@ -43,6 +52,7 @@ class Store(C.Structure):
         ("field_dst", C.c_void_p * QD_MAX_FIELDS),
         ("field_row_bytes", C.c_int64 * QD_MAX_FIELDS),
         ("scratch", C.c_void_p),
+        ("best_snapshot", C.c_void_p),
     ]
 
 
@@ -72,10 +82,13 @@ PROTOTYPES = {
     "qd_insert_scratch_init": (_int, [_vp, _i64, _vp]),
     "qd_insert_flags_ptr": (_vp, [_vp, _i64]),
     "qd_flags_or": (_int, [_vp, _int, _vp, _vp]),
-    "qd_insert": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _dbl, _dbl, _i64, _dbl, _vp, _vp, _vp,
-                         _vp]),
+    "qd_best_snapshot_bytes": (_sz, [C.POINTER(Store)]),
+    "qd_store_clear": (_int, [C.POINTER(Store), _vp]),
+    "qd_store_set_state": (_int, [C.POINTER(Store), _i64, _dbl, _int, _dbl, _dbl, _vp]),
+    "qd_store_read_state": (_int, [C.POINTER(Store), _vp, _vp]),
+    "qd_insert": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _dbl, _dbl, _vp, _vp, _vp, _int, _vp]),
     "qd_grid_insert": (_int, [C.POINTER(Store), _i64, _vp, _int, _int, C.POINTER(_i32), C.POINTER(_dbl),
-                              C.POINTER(_dbl), _dbl, _vp, C.POINTER(_vp), _dbl, _dbl, _i64, _dbl, _vp, _vp, _vp, _vp,
+                              C.POINTER(_dbl), _dbl, _vp, C.POINTER(_vp), _dbl, _dbl, _vp, _vp, _vp, _vp, _int,
                               _vp]),
     "qd_store_gather": (_int, [_i64, _vp, _int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _vp, _vp, _vp]),
     "qd_fill_normal": (_int, [_vp, _i64, _u64, _u64, _vp]),

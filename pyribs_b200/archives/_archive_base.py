@@ -125,6 +125,7 @@ class DeviceArchive:
         self._lr_f = float(self._learning_rate)
         self._tmin_f = float(self._threshold_min)
         self._best_elite = None
+        self._best_serial = 0
         self._objective_sum = None
         self._stats = None
         self._stats_reset()
@@ -133,6 +134,9 @@ class DeviceArchive:
         self._copy_stream = None
         self._copy_event = None
         self._fused_index_insert = False  # GridArchive: index_of fused into the first insert pass
+        self._sync_device_adds = False    # True: add() of CUDA tensors also waits and validates like NumPy input
+        self._inflight = None
+        self._needs_flag_check = False
         self._force_scan = False
         self._overflow_fallbacks = 0
 
@@ -159,14 +163,16 @@ class DeviceArchive:
 
     @property
     def stats(self):
+        self._sync()
         return self._stats
 
     @property
     def empty(self):
-        return len(self._store) == 0
+        return len(self) == 0
 
     @property
     def best_elite(self):
+        self._sync()
         return self._best_elite
 
     @property
@@ -190,10 +196,54 @@ class DeviceArchive:
         return self._device
 
     def __len__(self):
+        self._sync()
         return len(self._store)
 
     def __iter__(self):
+        self._sync()
         return iter(self._store)
+
+    # ---- device-resident state -> host mirror ------------------------------------------------
+    _ERR_OBJ = "All elements of objective must be finite (infinity and NaN values are not supported)."
+    _ERR_MEAS = "All elements of measures must be finite (infinity and NaN values are not supported)."
+
+    def _raise_for_flags(self, flags):
+        if flags & _lib.FLAG_NONFINITE_OBJECTIVE:
+            raise ValueError(self._ERR_OBJ)
+        if flags & _lib.FLAG_NONFINITE_MEASURES:
+            raise ValueError(self._ERR_MEAS)
+
+    def _sync(self):
+        """Insertions given CUDA tensors are only enqueued (the element count, objective sum, best
+        objective and best-elite snapshot live on the device, csrc/insert.cu); anything that needs
+        them on the host lands here. A batch dropped by the device-side finite check surfaces as
+        the reference's ValueError at this point."""
+        store = self._store
+        if not store._pending:
+            return
+        flags = store.sync()
+        self._apply_state(store._last)
+        self._raise_for_flags(flags)
+
+    def _apply_state(self, res):
+        """_stats_update (_grid_archive.py:325-360) from the device-side running state."""
+        odt = self.dtypes["objective"]
+        if res.best_serial != self._best_serial:
+            self._best_serial = int(res.best_serial)
+            self._best_elite = self._store.read_snapshot()
+        n = int(res.n_occupied)
+        if n == 0 or not res.has_obj_max:
+            return
+        self._objective_sum = np.asarray(res.objective_sum, dtype=odt)
+        qd = self._objective_sum - np.asarray(n, dtype=odt) * self._qd_score_offset
+        self._stats = ArchiveStats(
+            num_elites=n,
+            coverage=np.asarray(n / self.cells, dtype=odt),
+            qd_score=qd,
+            norm_qd_score=np.asarray(qd / self.cells, dtype=odt),
+            obj_max=self._best_elite["objective"] if self._best_elite is not None else np.asarray(res.obj_max, odt),
+            obj_mean=np.asarray(self._objective_sum / n, dtype=odt),
+        )
 
     # ---- stats (A8, _grid_archive.py:311-360) ---------------------------------------------
     def _stats_reset(self):
@@ -207,26 +257,6 @@ class DeviceArchive:
             norm_qd_score=np.asarray(0.0, dtype=odt),
             obj_max=None,
             obj_mean=None,
-        )
-
-    def _stats_update(self, new_objective_sum, best_index, best_objective):
-        odt = self.dtypes["objective"]
-        if self._stats.obj_max is None or best_objective > self._stats.obj_max:
-            _, row = self._store.retrieve([best_index])
-            self._best_elite = {k: v[0] for k, v in row.items()}
-            new_obj_max = self._best_elite["objective"]
-        else:
-            new_obj_max = self._stats.obj_max
-        self._objective_sum = new_objective_sum
-        n = len(self)
-        qd = self._objective_sum - np.asarray(n, dtype=odt) * self._qd_score_offset
-        self._stats = ArchiveStats(
-            num_elites=n,
-            coverage=np.asarray(n / self.cells, dtype=odt),
-            qd_score=qd,
-            norm_qd_score=np.asarray(qd / self.cells, dtype=odt),
-            obj_max=new_obj_max,
-            obj_mean=np.asarray(self._objective_sum / n, dtype=odt),
         )
 
     # ---- host <-> device plumbing ----------------------------------------------------------
@@ -366,6 +396,7 @@ class DeviceArchive:
                 dev["measures"] = self._all_gather_many([dev["measures"]])[0]
             idx = None if fused else self._index_of_device(dev["measures"], store._flags_ptr)
             rest = [n for n in data if n not in dev]
+            rows_event = None
             if dev_in or all(isinstance(data[n], torch.Tensor) for n in rest):
                 for n in rest:
                     dev[n] = self._to_device(data[n], store.dtypes[n], n)
@@ -377,7 +408,10 @@ class DeviceArchive:
                     for n in rest:
                         dev[n] = self._to_device(data[n], store.dtypes[n], n)
                     self._copy_event.record(self._copy_stream)
-                torch.cuda.current_stream().wait_event(self._copy_event)
+                if self._dp_world > 1:
+                    torch.cuda.current_stream().wait_event(self._copy_event)
+                else:  # only the row-copy phase of the insertion waits for the solutions (qd_insert)
+                    rows_event = self._copy_event
             B_local = B
             if self._dp_world > 1:
                 if global_search:  # idx and measures are already global
@@ -387,25 +421,42 @@ class DeviceArchive:
             status, value, status_h, value_h = self._out_buffers(B, dev_in)
             names = store.row_fields
             src = (C.c_void_p * max(len(names), 1))(*[dev[n].data_ptr() for n in names])
-            prev_max = float("nan") if self._stats.obj_max is None else float(self._stats.obj_max)
-            if fused:
-                self._grid_insert(dev, B, src, prev_max, status, value)
+            def insert(part):
+                if fused:
+                    self._grid_insert(dev, B, src, status, value, part)
+                else:
+                    _lib.check(_lib.lib().qd_insert(
+                        C.byref(store.abi_store()), B, idx.data_ptr(), dev["objective"].data_ptr(), src,
+                        self._lr_f, self._tmin_f, status.data_ptr(), value.data_ptr(),
+                        store._result_dev.data_ptr(), part, current_stream_ptr()))
+
+            if rows_event is None:
+                insert(_lib.INSERT_WHOLE)
             else:
-                _lib.check(_lib.lib().qd_insert(
-                    C.byref(store.abi_store()), B, idx.data_ptr(), dev["objective"].data_ptr(), src,
-                    self._lr_f, self._tmin_f, len(store), prev_max, status.data_ptr(),
-                    value.data_ptr(), store._result_dev.data_ptr(), current_stream_ptr()))
+                # status / value are final after the first part: they travel back while the solutions
+                # are still travelling in (full-duplex PCIe); only the row copy waits for them
+                insert(_lib.INSERT_CLASSIFY)
+                status_h.copy_(status, non_blocking=True)
+                value_h.copy_(value, non_blocking=True)
+                torch.cuda.current_stream().wait_event(rows_event)
+                insert(_lib.INSERT_COMMIT)
+            store._pending = True
+            lo, hi = self._dp_rank * B_local, (self._dp_rank + 1) * B_local  # this rank's slice of the batch
+            if dev_in and not self._sync_device_adds and not self._needs_flag_check:
+                # CUDA tensors in, CUDA tensors out: nothing to wait for. Stats / len / the finite
+                # check are read back lazily (_sync).
+                self._inflight = dev  # keeps the batch alive until the stream has consumed it
+                return {"status": status[lo:hi], "value": value[lo:hi]} if self._dp_world > 1 else \
+                    {"status": status, "value": value}
             store._result_host.copy_(store._result_dev, non_blocking=True)
-            if not dev_in:
+            if not dev_in and rows_event is None:
                 status_h.copy_(status, non_blocking=True)
                 value_h.copy_(value, non_blocking=True)
             _lib.check(_lib.lib().qd_stream_synchronize(current_stream_ptr()))
         res = _lib.AddResult.from_buffer_copy(store._result_host.numpy().tobytes())
-        if res.flags & _lib.FLAG_NONFINITE_OBJECTIVE:
-            raise ValueError("All elements of objective must be finite (infinity and NaN values are not supported).")
-        if res.flags & _lib.FLAG_NONFINITE_MEASURES:
-            raise ValueError("All elements of measures must be finite (infinity and NaN values are not supported).")
-        if res.flags & _lib.FLAG_CVT_OVERFLOW:  # nothing was committed; redo with the exact scan
+        flags = store.consume(res) | res.flags
+        if flags & _lib.FLAG_CVT_OVERFLOW and not flags & (_lib.FLAG_NONFINITE_OBJECTIVE | _lib.FLAG_NONFINITE_MEASURES):
+            # candidate list of the tensor-core search overflowed; nothing was committed: redo with the exact scan
             self._overflow_fallbacks += 1
             self._force_scan = True
             try:
@@ -413,13 +464,8 @@ class DeviceArchive:
                                 **{k: data[k] for k in fields})
             finally:
                 self._force_scan = False
-        if res.n_insertable > 0:
-            store._updates[0] += 1
-            store._n_occupied += res.n_new
-            delta = (res.delta_sum[0] + res.delta_sum[1]) + res.delta_sum[2]
-            new_sum = np.asarray(self._objective_sum + np.asarray(delta, dtype=odt), dtype=odt)
-            self._stats_update(new_sum, res.best_cell, np.asarray(res.best_objective, dtype=odt))
-        lo, hi = self._dp_rank * B_local, (self._dp_rank + 1) * B_local  # this rank's slice of the global batch
+        self._raise_for_flags(flags)
+        self._apply_state(res)
         if dev_in:
             return {"status": status[lo:hi], "value": value[lo:hi]} if self._dp_world > 1 else \
                 {"status": status, "value": value}
@@ -436,6 +482,7 @@ class DeviceArchive:
         return {"status": info["status"][0], "value": info["value"][0]}
 
     def clear(self):
+        self._sync()
         self._store.clear()
         self._stats_reset()
 
@@ -461,6 +508,7 @@ class DeviceArchive:
     def sample_elites(self, n, replace=True):
         if self.empty:
             raise IndexError("No elements in archive.")
+        self._sync()
         if not replace and n > len(self._store):
             raise ValueError(
                 "Cannot take a larger sample than the number of elites in the archive when 'replace=False'")

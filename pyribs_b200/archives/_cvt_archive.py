@@ -179,6 +179,9 @@ class CVTArchive(DeviceArchive):
                 dist.fill_(float("inf"))
             return idx, dist
         method = self._pick_method(B, Cn)
+        # the tensor-core filter can (rarely) overflow its candidate list, which is only visible in the
+        # flags of the finished call: such insertions are waited for even when given CUDA tensors
+        self._needs_flag_check = method == 0
         need = int(_lib.lib().qd_cvt_scratch_bytes(B, Cn, self._measure_dim)) if method == 0 else 256
         if self._cvt_scratch is None or self._cvt_scratch.numel() < need:
             self._cvt_scratch = torch.empty(max(need, 256), dtype=torch.uint8, device=self._device)

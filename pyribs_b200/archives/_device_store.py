@@ -38,6 +38,7 @@ class DeviceStoreIterator:
     def __init__(self, store: "DeviceStore"):
         self.store = store
         self.iter_idx = 0
+        store.sync()
         self.state = list(store._updates)
         self._snapshot = None
 
@@ -45,6 +46,7 @@ class DeviceStoreIterator:
         return self
 
     def __next__(self):
+        self.store.sync()
         if self.state != self.store._updates:
             raise RuntimeError("ArrayStore was modified with add() or clear() during iteration.")
         if self.iter_idx >= len(self.store):
@@ -89,9 +91,21 @@ class DeviceStore:
             self._flags_ptr = _lib.lib().qd_insert_flags_ptr(self._scratch.data_ptr(), capacity)
             self._result_dev = torch.zeros(C.sizeof(_lib.AddResult), dtype=torch.uint8, device=self._device)
             self._result_host = torch.zeros(C.sizeof(_lib.AddResult), dtype=torch.uint8).pin_memory()
+            self._abi = None
+            self._snapshot = None
+            nsnap = int(_lib.lib().qd_best_snapshot_bytes(C.byref(self.abi_store())))
+            self._snapshot = torch.zeros(nsnap, dtype=torch.uint8, device=self._device)
+            self._abi = None
+            # occupancy 0, thresholds NaN (= unoccupied), device-side element count / stats reset
+            _lib.check(_lib.lib().qd_store_clear(C.byref(self.abi_store()), current_stream_ptr()))
         self._occupied_list_host = np.empty(capacity, dtype=np.int32)
         self._occupied_list_synced = 0
-        self._abi = None
+        # Device-resident store state (csrc/insert.cu InsertState) mirrored lazily on the host:
+        # `_pending` is set by every enqueued insertion whose qd_add_result was not read back yet.
+        self._pending = False
+        self._commits_base = 0
+        self._failed_seen = 0
+        self._last = None  # last consumed qd_add_result
 
     # ---- ABI view ---------------------------------------------------------------------
     @property
@@ -117,11 +131,54 @@ class DeviceStore:
                 st.field_dst[i] = t.data_ptr()
                 st.field_row_bytes[i] = t[0].numel() * t.element_size() if t.dim() > 1 else t.element_size()
             st.scratch = self._scratch.data_ptr()
+            st.best_snapshot = self._snapshot.data_ptr() if self._snapshot is not None else None
             self._abi = st
         return self._abi
 
+    # ---- host mirror of the device-side state -------------------------------------------------
+    def consume(self, res):
+        """Adopts a qd_add_result read back from the device. Returns the flags of a call that was
+        dropped by validation and not reported yet (0 otherwise)."""
+        self._pending = False
+        self._last = res
+        self._n_occupied = int(res.n_occupied)
+        self._updates[0] = self._commits_base + int(res.n_commits)
+        if res.n_failed > self._failed_seen:
+            self._failed_seen = int(res.n_failed)
+            return int(res.last_failed_flags) or int(res.flags)
+        return 0
+
+    def sync(self):
+        """Reads the device-side store state back if insertions are still in flight. Returns the
+        unreported validation flags (see consume)."""
+        if not self._pending:
+            return 0
+        with torch.cuda.device(self._device):
+            self._result_host.copy_(self._result_dev, non_blocking=True)
+            _lib.check(_lib.lib().qd_stream_synchronize(current_stream_ptr()))
+        return self.consume(_lib.AddResult.from_buffer_copy(self._result_host.numpy().tobytes()))
+
+    def read_snapshot(self):
+        """Best-elite snapshot taken on the device (layout: include/qd_b200.h qd_store.best_snapshot)."""
+        raw = self._snapshot.cpu().numpy()
+        head = raw[:24].view(np.float64)
+        out = {"objective": np.asarray(head[0], dtype=self._np_dtypes["objective"])[()],
+               "threshold": np.asarray(head[1], dtype=self._np_dtypes["threshold"])[()],
+               "index": np.int32(raw[16:20].view(np.int32)[0])}
+        off = 32
+        for n in self.row_fields:
+            t = self._fields[n]
+            rb = self._row_bytes(n)
+            out[n] = raw[off:off + rb].view(self._np_dtypes[n]).reshape(tuple(t.shape[1:])).copy()
+            if out[n].ndim == 0:
+                out[n] = out[n][()]
+            off += (rb + 15) // 16 * 16
+        return {k: out[k] for k in [*self._fields, "index"]}
+
     # ---- properties (ArrayStore API) ----------------------------------------------------
     def __len__(self):
+        if self._pending:
+            self.sync()
         return self._n_occupied
 
     def __iter__(self):
@@ -140,6 +197,11 @@ class DeviceStore:
         return arr_readonly(self._occupied.cpu().numpy().astype(bool))
 
     @property
+    def updates(self):
+        self.sync()
+        return list(self._updates)
+
+    @property
     def occupied_device(self):
         return self._occupied
 
@@ -148,7 +210,7 @@ class DeviceStore:
         return arr_readonly(self._sync_occupied_list()[: self._n_occupied].copy())
 
     def _sync_occupied_list(self):
-        n = self._n_occupied
+        n = len(self)
         if self._occupied_list_synced < n:
             s = self._occupied_list_synced
             self._occupied_list_host[s:n] = self._occupied_list[s:n].cpu().numpy()
@@ -247,19 +309,36 @@ class DeviceStore:
         return occupied, pd.DataFrame(cols, copy=False)
 
     def data(self, fields=None, return_type="dict"):
-        return self.retrieve(self._occupied_list[: self._n_occupied], fields, return_type)[1]
+        return self.retrieve(self._occupied_list[: len(self)], fields, return_type)[1]
 
     # ---- mutation -------------------------------------------------------------------------
     def clear(self):
+        self.sync()
         self._updates[1] += 1
         self._n_occupied = 0
         self._occupied_list_synced = 0
-        self._occupied.zero_()
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().qd_store_clear(C.byref(self.abi_store()), current_stream_ptr()))
+
+    def _push_state(self, objective_sum, obj_max, absmax):
+        """Re-seeds the device-side state (after resize / unpickling)."""
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().qd_store_set_state(
+                C.byref(self.abi_store()), self._n_occupied, float(objective_sum), int(obj_max is not None),
+                float(obj_max) if obj_max is not None else 0.0, float(absmax), current_stream_ptr()))
+            _lib.check(_lib.lib().qd_store_read_state(C.byref(self.abi_store()), self._result_dev.data_ptr(),
+                                                      current_stream_ptr()))
+        self._pending = True
+        self._commits_base = self._updates[0]
+        self._failed_seen = 0
+        self.sync()
 
     def resize(self, capacity):
         capacity = int(capacity)
         if capacity <= self._capacity:
             raise ValueError(f"New capacity ({capacity}) must be greater than current capacity ({self._capacity}.")
+        self.sync()
+        last = self._last
         old = self._capacity
         self._capacity = capacity
         occ = torch.zeros(capacity, dtype=torch.uint8, device=self._device)
@@ -281,9 +360,14 @@ class DeviceStore:
             _lib.check(_lib.lib().qd_insert_scratch_init(self._scratch.data_ptr(), capacity, current_stream_ptr()))
         self._flags_ptr = _lib.lib().qd_insert_flags_ptr(self._scratch.data_ptr(), capacity)
         self._abi = None
+        osum = last.objective_sum if last is not None else 0.0
+        omax = last.obj_max if last is not None and last.has_obj_max else None
+        absmax = float(self._fields["objective"][self._occupied.bool()].abs().max().item()) if self._n_occupied else 0.0
+        self._push_state(osum, omax, absmax)
 
     # ---- pickling: device tensors travel as NumPy (checkpoint / resume) ---------------------
     def __getstate__(self):
+        self.sync()
         st = {
             "field_desc": self.field_desc,
             "capacity": self._capacity,
@@ -303,3 +387,9 @@ class DeviceStore:
         self._occupied_list.copy_(torch.from_numpy(st["occupied_list"]))
         for n, a in st["fields"].items():
             self._fields[n].copy_(torch.from_numpy(a))
+        # objective sum / best objective are re-seeded by the owning archive (DeviceArchive.__setstate__);
+        # a bare store restores the element count and re-marks unoccupied thresholds
+        occ = st["occupied"].astype(bool)
+        obj = st["fields"]["objective"][occ] if "objective" in st["fields"] else np.zeros(0)
+        self._push_state(float(obj.sum()) if obj.size else 0.0, float(obj.max()) if obj.size else None,
+                         float(np.abs(obj).max()) if obj.size else 0.0)

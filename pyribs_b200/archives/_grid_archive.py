@@ -94,7 +94,7 @@ class GridArchive(DeviceArchive):
             float(self._epsilon), idx.data_ptr(), flags_ptr, current_stream_ptr()))
         return idx
 
-    def _grid_insert(self, dev, B, src, prev_max, status, value):
+    def _grid_insert(self, dev, B, src, status, value, part):
         """A2 + A4-A8 in one ABI call (qd_grid_insert): measures are read once."""
         store = self._store
         if self._idx_buf is None or self._idx_buf.numel() < B:
@@ -102,8 +102,8 @@ class GridArchive(DeviceArchive):
         _lib.check(_lib.lib().qd_grid_insert(
             C.byref(store.abi_store()), B, dev["measures"].data_ptr(), self._meas_code, len(self._dims), self._c_dims,
             self._c_lower, self._c_interval, self._eps_f, dev["objective"].data_ptr(), src,
-            self._lr_f, self._tmin_f, len(store), prev_max, self._idx_buf.data_ptr(),
-            status.data_ptr(), value.data_ptr(), store._result_dev.data_ptr(), current_stream_ptr()))
+            self._lr_f, self._tmin_f, self._idx_buf.data_ptr(),
+            status.data_ptr(), value.data_ptr(), store._result_dev.data_ptr(), part, current_stream_ptr()))
 
     def grid_to_int_index(self, grid_indices):
         grid_indices = np.asarray(grid_indices)

@@ -1,30 +1,58 @@
 // A4-A8: the body of GridArchive.add / CVTArchive.add after index_of
 // (reference ribs/archives/_grid_archive.py:623-712 == _cvt_archive.py:818-907, formerly
-// batch_entries_with_threshold; store side ribs/archives/_array_store.py:535-608).
+// batch_entries_with_threshold; store side ribs/archives/_array_store.py:535-608; stats
+// _grid_archive.py:325-360).
 //
-// Sort-free, deterministic design. Per-cell scratch in HBM (clean between calls):
-//   best[c]  u64  order key of the highest insertable objective          (atomicMax)
-//   win[c]   i32  lowest batch row holding that objective                (atomicMin)
-//   cnt[c]   u32  number of insertable rows (CMA-MAE)                    (atomicAdd)
-//   bins[c]  3xf64 exactly-summable split of the insertable objectives   (atomicAdd, exact)
-// Passes over the batch (HBM-bound, B rows):
-//   classify  (grid: fused with index_of) status / value vs the PRE-batch store; best, cnt, batch
-//             |objective| max; an equal-objective collision in a cell raises the tie flag
-//   resolve   only when needed: first-wins tie break (tie flag) and CMA-MAE objective sums
-//   select    decides the winner of every touched cell and appends (row, cell) to a compact list
-//   update    one thread per winner: threshold, occupancy, objective-sum delta, batch best
-//   copy      flat HBM stream moving the winners' row fields into the store
-//   bestcell  over the CELLS, only when the batch beat the archive's previous best objective:
-//             lowest cell holding the new global best
-//   append    new cells appended to occupied_list in ascending cell order (bitmap scan)
-// A non-finite objective or measure (flag set by this or the index kernel) turns commit into
-// a scratch clean-up, so the store is untouched when the host raises ValueError
-// (ribs/_utils.py:18-31).
+// ONE persistent cooperative kernel per add(): every CTA is resident (grid <= SMs x occupancy),
+// the phases below are separated by grid-wide barriers instead of kernel boundaries, and all
+// cross-call state (element count, objective sum, best objective, best-elite snapshot) lives in
+// device memory, so add() needs no host round trip between calls.
+//
+// Sort-free and deterministic. Per-cell scratch: one 32-byte record (one L2 sector), clean
+// between calls:
+//   best  u64  order key of the highest insertable objective            (atomicMax)
+//   w0,w1 i64  two-level fixed-point sum of the insertable objectives   (atomicAdd, CMA-MAE);
+//              the low bits of w1 carry the row count
+//   win   i32  lowest batch row holding `best`                          (atomicMin, ties only)
+// The threshold array doubles as the occupancy test of the row passes: unoccupied cells hold NaN
+// (the reference never reads the threshold of an unoccupied cell, _grid_archive.py:628-630), so
+// a row costs ONE scattered load + its atomics. Scattered accesses (~1.3 clk/lane/SM), not HBM
+// bytes, bound the row passes; everything else streams.
+//
+// Phases (B rows, W winners, N cells):
+//   0 absmax    CMA-MAE only: max |objective| fixes the fixed-point scale of the sums
+//   1 classify  (grid: fused with index_of) status / value vs the PRE-batch store; best; sums;
+//               an equal-objective collision in a cell raises the tie flag
+//   2 resolve   only after a tie: first-in-batch wins (_grid_archive.py:693-696)
+//   3 select    winner of every touched cell -> compact (row, cell) list
+//   4 update    one thread per winner: threshold, objective, occupancy, objective-sum delta
+//   5 copy      flat HBM stream of the winners' row fields into the store
+//   6 best/cnt  lowest winning cell holding the new best objective; new-cell bitmap counts
+//   7 publish   occupied_list append in ascending cell order (_array_store.py:586-600), stats,
+//               best-elite snapshot, qd_add_result; re-arms the per-call globals
+// A non-finite objective or measure turns phases 3.. into a scratch clean-up, so the store is
+// untouched when the host raises ValueError (ribs/_utils.py:18-31).
+#include <cooperative_groups.h>
+
 #include "grid_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace qd {
 
-struct InsertGlobals {
+constexpr int kThreads = 512;
+constexpr int kMaxCtas = kNumSMs * 4;  // upper bound on the persistent grid
+
+struct __align__(32) Cell {
+  unsigned long long best;
+  long long w0;
+  long long w1;
+  int32_t win;
+  uint32_t cnt;  // only when the count does not fit the low bits of w1 (B >= 2^24)
+};
+
+struct InsertState {
+  // ---- per call (re-armed by the publish phase) ----
   unsigned long long gbest_key;
   unsigned long long absmax_bits;
   int32_t best_cell;
@@ -34,172 +62,124 @@ struct InsertGlobals {
   uint32_t tie_flag;  // two insertable rows of one cell share the cell's best objective
   uint32_t n_winners;
   double dsum[3];
-  double store_absmax;  // persistent: max |objective| ever offered to the store
+  // ---- persistent ----
+  double store_absmax;            // max |objective| ever offered to the store
+  long long n_occupied;           // len(store)
+  unsigned long long obj_max_key; // order key of stats.obj_max, 0 = no elite yet
+  double objective_sum;           // running sum of elite objectives, rounded as the objective dtype
+  unsigned long long n_commits;   // calls that inserted something (ArrayStore.updates[ADD])
+  unsigned long long best_serial; // bumps whenever the best-elite snapshot is replaced
+  unsigned long long n_failed;    // calls dropped by validation
+  uint32_t last_failed_flags;     // flags of the most recent such call
+  uint32_t pad;
 };
 
 struct Scratch {
-  unsigned long long* best;
-  double* bins;  // 3 * capacity
-  int32_t* win;
-  uint32_t* cnt;
+  Cell* cell;
   uint32_t* newmask;
-  uint32_t* blockcnt;
-  int2* wlist;  // (batch row, cell) of this call's winners, at most one per cell
-  InsertGlobals* g;
+  uint32_t* ctacnt;  // kMaxCtas
+  int2* wlist;       // (batch row, cell) of this call's winners, at most one per cell
+  InsertState* g;
 };
-
-constexpr int kAppendThreads = 1024;
-constexpr int kWordsPerThread = 4;
-constexpr int kWordsPerBlock = kAppendThreads * kWordsPerThread;
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static Scratch carve(void* base, int64_t N) {
   Scratch s;
   char* p = (char*)base;
-  s.best = (unsigned long long*)p;
-  p += align_up((size_t)N * 8, 256);
-  s.bins = (double*)p;
-  p += align_up((size_t)N * 24, 256);
-  s.win = (int32_t*)p;
-  p += align_up((size_t)N * 4, 256);
-  s.cnt = (uint32_t*)p;
-  p += align_up((size_t)N * 4, 256);
-  int64_t words = (N + 31) / 32;
+  s.cell = (Cell*)p;
+  p += align_up((size_t)N * sizeof(Cell), 256);
+  const int64_t words = (N + 31) / 32;
   s.newmask = (uint32_t*)p;
   p += align_up((size_t)words * 4, 256);
-  int64_t nblk = (words + kWordsPerBlock - 1) / kWordsPerBlock;
-  s.blockcnt = (uint32_t*)p;
-  p += align_up((size_t)nblk * 4, 256);
+  s.ctacnt = (uint32_t*)p;
+  p += align_up((size_t)kMaxCtas * 4, 256);
   s.wlist = (int2*)p;
   p += align_up((size_t)N * 8, 256);
-  s.g = (InsertGlobals*)p;
+  s.g = (InsertState*)p;
   return s;
 }
 
 static size_t scratch_bytes(int64_t N) {
-  int64_t words = (N + 31) / 32;
-  int64_t nblk = (words + kWordsPerBlock - 1) / kWordsPerBlock;
-  return align_up((size_t)N * 8, 256) + align_up((size_t)N * 24, 256) + 2 * align_up((size_t)N * 4, 256) +
-         align_up((size_t)words * 4, 256) + align_up((size_t)nblk * 4, 256) + align_up((size_t)N * 8, 256) +
-         align_up(sizeof(InsertGlobals), 256);
+  const int64_t words = (N + 31) / 32;
+  return align_up((size_t)N * sizeof(Cell), 256) + align_up((size_t)words * 4, 256) +
+         align_up((size_t)kMaxCtas * 4, 256) + align_up((size_t)N * 8, 256) + align_up(sizeof(InsertState), 256);
 }
 
 __global__ void scratch_init_kernel(Scratch s, int64_t N) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t c = i; c < N; c += stride) {
-    s.best[c] = 0ull;
-    s.bins[3 * c] = s.bins[3 * c + 1] = s.bins[3 * c + 2] = 0.0;
-    s.win[c] = INT32_MAX;
-    s.cnt[c] = 0u;
+    Cell z;
+    z.best = 0ull;
+    z.w0 = z.w1 = 0ll;
+    z.win = INT32_MAX;
+    z.cnt = 0u;
+    s.cell[c] = z;
   }
   for (int64_t w = i; w < (N + 31) / 32; w += stride) s.newmask[w] = 0u;
   if (i == 0) {
-    InsertGlobals g;
-    g.gbest_key = 0ull;
-    g.absmax_bits = 0ull;
+    InsertState g;
+    memset(&g, 0, sizeof(g));
     g.best_cell = INT32_MAX;
-    g.n_insertable = g.n_new = g.flags = g.tie_flag = g.n_winners = 0u;
-    g.dsum[0] = g.dsum[1] = g.dsum[2] = 0.0;
-    g.store_absmax = 0.0;
     *s.g = g;
   }
 }
 
-// ---------------------------------------------------------------------------------------
-template <typename T, typename MT, int D, bool FUSED>
-__global__ void __launch_bounds__(256) classify_kernel(int64_t B, int32_t* __restrict__ idx,
-                                                       const MT* __restrict__ meas,
-                                                       const __grid_constant__ GridParams gp,
-                                                       const T* __restrict__ obj,
-                                                       const uint8_t* __restrict__ occupied,
-                                                       const T* __restrict__ thr, T tmin, bool cma_me, bool mae,
-                                                       int32_t* __restrict__ status, T* __restrict__ value,
-                                                       Scratch s) {
-  uint32_t ncan = 0;
-  double amax = 0.0;
-  bool bad = false, bad_meas = false, tie = false;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
-    int32_t c;
-    if constexpr (FUSED) {
-      c = grid_cell_of<MT, D>(meas, i, gp, bad_meas);  // A2 fused into the first pass
-      idx[i] = c;
-    } else {
-      c = idx[i];
-    }
-    const T o = obj[i];
-    const bool fin = sizeof(T) == 8 ? finite_d((double)o) : finite_f((float)o);
-    bad |= !fin;
-    const bool occ = occupied[c] != 0;
-    const T t = occ ? thr[c] : tmin;  // _grid_archive.py:628-630
-    const bool can = fin && (o > t);  // :636
-    status[i] = can ? (occ ? 1 : 2) : 0;
-    const T tval = (can && !occ) ? (cma_me ? (T)0 : tmin) : t;  // :646-648
-    value[i] = o - tval;                                        // :649
-    if (can) {
-      const unsigned long long key = ord_key((double)o);
-      const unsigned long long old = atomicMax(&s.best[c], key);
-      tie |= (old == key);
-      if (mae) atomicAdd(&s.cnt[c], 1u);
-      ++ncan;
-    }
-    if (fin) amax = fmax(amax, fabs((double)o));
-  }
-  if (tie) s.g->tie_flag = 1u;
-  if (bad_meas) atomicOr(&s.g->flags, QD_FLAG_NONFINITE_MEASURES);
-  // block reduction
-  __shared__ uint32_t sh_n[8];
-  __shared__ double sh_a[8];
-  __shared__ int sh_bad;
-  if (threadIdx.x == 0) sh_bad = 0;
-  for (int o2 = 16; o2 > 0; o2 >>= 1) {
-    ncan += __shfl_down_sync(0xffffffffu, ncan, o2);
-    amax = fmax(amax, __shfl_down_sync(0xffffffffu, amax, o2));
-  }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) {
-    sh_n[threadIdx.x >> 5] = ncan;
-    sh_a[threadIdx.x >> 5] = amax;
-  }
-  if (bad) sh_bad = 1;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t n = 0;
-    double a = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-      n += sh_n[w];
-      a = fmax(a, sh_a[w]);
-    }
-    if (n) atomicAdd(&s.g->n_insertable, n);
-    if (a > 0.0) atomicMax(&s.g->absmax_bits, (unsigned long long)__double_as_longlong(a));
-    if (sh_bad) atomicOr(&s.g->flags, QD_FLAG_NONFINITE_OBJECTIVE);
+// ---- fixed-point accumulation of the insertable objectives of a cell (CMA-MAE) -----------
+// x * 2^s0 is rounded to an integer q0 (|q0| <= 2^(62-b), 2^b > B rows: the int64 sum cannot
+// overflow); the exact remainder, scaled again, gives q1. Integer adds are associative, so the
+// cell sums do not depend on the order the atomics land in. The mean of a cell is exact to
+// 2^-(lvl0+lvl1+1) of the batch maximum (2^-54 at 16M rows, better below) -- tighter than the
+// reference's sequential fp64 sum.
+struct FxConst {
+  double scale0, scale1;  // x -> level-0 integer; level-0 remainder -> level-1 integer
+  double inv0, inv1;      // back to doubles
+  int b;                  // count bits at the bottom of w1 (0: separate counter)
+};
+
+__host__ __device__ inline FxConst make_fx(double absmax, int64_t B) {
+  int e;
+  if (!(absmax > 0.0)) absmax = 1e-280;
+  frexp(absmax, &e);  // absmax < 2^e
+  if (e < -900) e = -900;
+  int b = 1;
+  while (((int64_t)1 << b) <= B) ++b;
+  FxConst k;
+  const int lvl0 = 62 - b;
+  const bool packed = b <= 24;
+  const int lvl1 = packed ? 63 - 2 * b : 62 - b;
+  k.b = packed ? b : 0;
+  k.scale0 = ldexp(1.0, lvl0 - e);
+  k.scale1 = ldexp(1.0, lvl1);
+  k.inv0 = ldexp(1.0, e - lvl0);
+  k.inv1 = ldexp(1.0, e - lvl0 - lvl1);
+  return k;
+}
+
+__device__ __forceinline__ void fx_add(Cell* c, double x, const FxConst& k) {
+  const double xs = __dmul_rn(x, k.scale0);
+  const long long q0 = __double2ll_rn(xs);
+  const double r = __dsub_rn(xs, (double)q0);  // exact
+  const long long q1 = __double2ll_rn(__dmul_rn(r, k.scale1));
+  if (q0) atomicAdd((unsigned long long*)&c->w0, (unsigned long long)q0);
+  if (k.b) {
+    atomicAdd((unsigned long long*)&c->w1, ((unsigned long long)q1 << k.b) + 1ull);
+  } else {
+    if (q1) atomicAdd((unsigned long long*)&c->w1, (unsigned long long)q1);
+    atomicAdd(&c->cnt, 1u);
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) resolve_kernel(int64_t B, const int32_t* __restrict__ idx,
-                                                      const T* __restrict__ obj,
-                                                      const int32_t* __restrict__ status, bool mae, Scratch s) {
-  if (s.g->flags) return;
-  if (s.g->n_insertable == 0) return;
-  if (!mae && !s.g->tie_flag) return;  // unique cell maxima: commit identifies winners by their key
-  BinConst bc;
-  if (mae) bc = make_bins(__longlong_as_double((long long)s.g->absmax_bits), B);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
-    if (status[i] == 0) continue;
-    const int32_t c = idx[i];
-    const double o = (double)obj[i];
-    if (ord_key(o) == s.best[c]) atomicMin(&s.win[c], (int32_t)i);  // first in batch wins ties (:693-696)
-    if (mae) {
-      double h0, h1, h2;
-      bin_split(o, bc, h0, h1, h2);
-      double* b = &s.bins[3 * (int64_t)c];
-      if (h0 != 0.0) atomicAdd(b, h0);
-      if (h1 != 0.0) atomicAdd(b + 1, h1);
-      if (h2 != 0.0) atomicAdd(b + 2, h2);
-    }
+__device__ __forceinline__ void fx_read(const Cell& c, const FxConst& k, double& sum, uint32_t& count) {
+  long long s1 = c.w1;
+  if (k.b) {
+    count = (uint32_t)((unsigned long long)s1 & ((1ull << k.b) - 1ull));
+    s1 = (s1 - (long long)count) >> k.b;
+  } else {
+    count = c.cnt;
   }
+  sum = __dadd_rn(__dmul_rn((double)c.w0, k.inv0), __dmul_rn((double)s1, k.inv1));
 }
 
 struct FieldCopy {
@@ -207,72 +187,28 @@ struct FieldCopy {
   const char* src[QD_MAX_FIELDS];
   char* dst[QD_MAX_FIELDS];
   int64_t row_bytes[QD_MAX_FIELDS];
-  int vec[QD_MAX_FIELDS];  // 16, 8, 4 or 1
+  int64_t snap_off[QD_MAX_FIELDS];  // offset of the field inside the best-elite snapshot
+  int vec[QD_MAX_FIELDS];           // 16, 8, 4 or 1
 };
 
-__device__ __forceinline__ void warp_copy_row(const char* __restrict__ src, char* __restrict__ dst, int64_t bytes,
-                                              int vec, int lane) {
-  if (vec == 16) {
-    for (int64_t o = lane * 16; o < bytes; o += 32 * 16)
-      *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(src + o);
-  } else if (vec == 8) {
-    for (int64_t o = lane * 8; o < bytes; o += 32 * 8)
-      *reinterpret_cast<uint2*>(dst + o) = *reinterpret_cast<const uint2*>(src + o);
-  } else if (vec == 4) {
-    for (int64_t o = lane * 4; o < bytes; o += 32 * 4)
-      *reinterpret_cast<uint32_t*>(dst + o) = *reinterpret_cast<const uint32_t*>(src + o);
-  } else {
-    for (int64_t o = lane; o < bytes; o += 32) dst[o] = src[o];
-  }
-}
-
-// select: one pass over the rows that only decides who won and appends (row, cell) to the winner list
 template <typename T>
-__global__ void __launch_bounds__(256) select_kernel(int64_t B, const int32_t* __restrict__ idx,
-                                                     const T* __restrict__ obj, const int32_t* __restrict__ status,
-                                                     bool mae, Scratch s) {
-  const int lane = threadIdx.x & 31;
-  if (s.g->n_insertable == 0) return;
-  if (s.g->flags) {  // validation failed: leave the store alone, clean the scratch
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
-      if (status[i] == 0) continue;
-      const int64_t c = idx[i];
-      s.best[c] = 0ull;
-      s.cnt[c] = 0u;
-    }
-    return;
-  }
-  const bool use_win = mae || s.g->tie_flag;  // resolve_kernel ran: win[] holds the first row of each cell maximum
-  // block-wide append: one global atomic per 256 rows (a same-address atomic per warp would serialise)
-  __shared__ uint32_t s_cnt[8];
-  __shared__ uint32_t s_base;
-  const int wi = threadIdx.x >> 5;
-  for (int64_t b0 = (int64_t)blockIdx.x * 256; b0 < B; b0 += (int64_t)gridDim.x * 256) {
-    const int64_t i = b0 + threadIdx.x;
-    int32_t c = 0;
-    bool iswin = false;
-    if (i < B && status[i] != 0) {
-      c = idx[i];
-      iswin = use_win ? (s.win[c] == (int32_t)i) : (ord_key((double)obj[i]) == s.best[c]);
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, iswin);
-    if (lane == 0) s_cnt[wi] = __popc(m);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t tot = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t n = s_cnt[k];
-        s_cnt[k] = tot;
-        tot += n;
-      }
-      s_base = tot ? atomicAdd(&s.g->n_winners, tot) : 0u;
-    }
-    __syncthreads();
-    if (iswin) s.wlist[s_base + s_cnt[wi] + __popc(m & ((1u << lane) - 1u))] = make_int2((int32_t)i, c);
-    __syncthreads();
-  }
-}
+struct InsertArgs {
+  int64_t B, N;
+  int32_t* idx;
+  const void* measures;  // fused grid index only
+  const T* obj;
+  uint8_t* occupied;
+  int32_t* occupied_list;
+  T* store_obj;
+  T* store_thr;
+  T tmin, lr;
+  int mae;
+  int32_t* status;
+  T* value;
+  char* snapshot;  // best-elite snapshot buffer or NULL
+  qd_add_result* result;
+  Scratch s;
+};
 
 // (1 - lr)^k for integral k >= 1 by binary powering (deterministic; k = 1 returns the base exactly)
 __device__ __forceinline__ double powi(double b, uint32_t k) {
@@ -286,43 +222,172 @@ __device__ __forceinline__ double powi(double b, uint32_t k) {
   return r;
 }
 
-// update: one thread per winner -- threshold, objective, occupancy, objective-sum delta, batch best
 template <typename T>
-__global__ void __launch_bounds__(256) update_kernel(int64_t B, const T* __restrict__ obj,
-                                                     uint8_t* __restrict__ occupied, T* __restrict__ store_obj,
-                                                     T* __restrict__ store_thr, T tmin, T lr, bool mae, Scratch s) {
-  if (s.g->flags) return;
-  const int64_t W = s.g->n_winners;
-  if (W == 0) return;
+__device__ __forceinline__ bool is_finite_t(T o) {
+  return sizeof(T) == 8 ? finite_d((double)o) : finite_f((float)o);
+}
+
+// ---- phase 0 ----------------------------------------------------------------------------------
+template <typename T>
+__device__ void phase_absmax(const InsertArgs<T>& a) {
+  double amax = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x) {
+    const T o = a.obj[i];
+    if (is_finite_t(o)) amax = fmax(amax, fabs((double)o));
+  }
+  for (int o2 = 16; o2 > 0; o2 >>= 1) amax = fmax(amax, __shfl_down_sync(0xffffffffu, amax, o2));
+  if ((threadIdx.x & 31) == 0 && amax > 0.0)
+    atomicMax(&a.s.g->absmax_bits, (unsigned long long)__double_as_longlong(amax));
+}
+
+// ---- phase 1 ----------------------------------------------------------------------------------
+template <typename T, typename MT, int D, bool FUSED>
+__device__ void phase_classify(const InsertArgs<T>& a, const GridParams& gp) {
+  const bool mae = a.mae;
+  const bool cma_me = !mae;
+  FxConst fx;
+  if (mae) fx = make_fx(__longlong_as_double((long long)a.s.g->absmax_bits), a.B);
+  uint32_t ncan = 0;
+  double amax = 0.0;
+  bool bad = false, bad_meas = false, tie = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x) {
+    int32_t c;
+    if constexpr (FUSED) {
+      c = grid_cell_of<MT, D>((const MT*)a.measures, i, gp, bad_meas);  // A2 fused into the first pass
+      a.idx[i] = c;
+    } else {
+      c = a.idx[i];
+    }
+    const T o = a.obj[i];
+    const bool fin = is_finite_t(o);
+    bad |= !fin;
+    const T tc = a.store_thr[c];
+    const bool occ = (tc == tc);      // unoccupied cells hold NaN
+    const T t = occ ? tc : a.tmin;    // _grid_archive.py:628-630
+    const bool can = fin && (o > t);  // :636
+    a.status[i] = can ? (occ ? 1 : 2) : 0;
+    const T tval = (can && !occ) ? (cma_me ? (T)0 : a.tmin) : t;  // :646-648
+    a.value[i] = o - tval;                                        // :649
+    if (can) {
+      Cell* cell = &a.s.cell[c];
+      const unsigned long long key = ord_key((double)o);
+      const unsigned long long old = atomicMax(&cell->best, key);
+      tie |= (old == key);
+      if (mae) fx_add(cell, (double)o, fx);
+      ++ncan;
+    }
+    if (!mae && fin) amax = fmax(amax, fabs((double)o));
+  }
+  if (tie) a.s.g->tie_flag = 1u;
+  if (bad_meas) atomicOr(&a.s.g->flags, QD_FLAG_NONFINITE_MEASURES);
+  if (bad) atomicOr(&a.s.g->flags, QD_FLAG_NONFINITE_OBJECTIVE);
+  for (int o2 = 16; o2 > 0; o2 >>= 1) {
+    ncan += __shfl_down_sync(0xffffffffu, ncan, o2);
+    amax = fmax(amax, __shfl_down_sync(0xffffffffu, amax, o2));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (ncan) atomicAdd(&a.s.g->n_insertable, ncan);
+    if (amax > 0.0) atomicMax(&a.s.g->absmax_bits, (unsigned long long)__double_as_longlong(amax));
+  }
+}
+
+// ---- phase 2 (only after a tie) ------------------------------------------------------------------
+template <typename T>
+__device__ void phase_resolve(const InsertArgs<T>& a) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x) {
+    if (a.status[i] == 0) continue;
+    Cell* cell = &a.s.cell[a.idx[i]];
+    if (ord_key((double)a.obj[i]) == cell->best) atomicMin(&cell->win, (int32_t)i);  // first in batch wins
+  }
+}
+
+// ---- phase 3 ----------------------------------------------------------------------------------
+template <typename T>
+__device__ void phase_cleanup(const InsertArgs<T>& a) {  // validation failed: leave the store alone
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x) {
+    if (a.status[i] == 0) continue;
+    Cell* cell = &a.s.cell[a.idx[i]];
+    cell->best = 0ull;
+    cell->w0 = cell->w1 = 0ll;
+    cell->cnt = 0u;
+    cell->win = INT32_MAX;
+  }
+}
+
+template <typename T>
+__device__ void phase_select(const InsertArgs<T>& a, bool use_win, uint32_t* s_cnt, uint32_t* s_base) {
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  constexpr int NW = kThreads / 32;
+  // block-wide append: one global atomic per kThreads rows
+  for (int64_t b0 = (int64_t)blockIdx.x * kThreads; b0 < a.B; b0 += (int64_t)gridDim.x * kThreads) {
+    const int64_t i = b0 + threadIdx.x;
+    int32_t c = 0;
+    bool iswin = false;
+    if (i < a.B && a.status[i] != 0) {
+      c = a.idx[i];
+      const Cell* cell = &a.s.cell[c];
+      iswin = use_win ? (cell->win == (int32_t)i) : (ord_key((double)a.obj[i]) == cell->best);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, iswin);
+    if (lane == 0) s_cnt[wi] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const uint32_t n = s_cnt[k];
+        s_cnt[k] = tot;
+        tot += n;
+      }
+      *s_base = tot ? atomicAdd(&a.s.g->n_winners, tot) : 0u;
+    }
+    __syncthreads();
+    if (iswin) a.s.wlist[*s_base + s_cnt[wi] + __popc(m & ((1u << lane) - 1u))] = make_int2((int32_t)i, c);
+    __syncthreads();
+  }
+}
+
+// ---- phase 4: one thread per winner --------------------------------------------------------------
+template <typename T>
+__device__ void phase_update(const InsertArgs<T>& a, bool use_win, double (*sh_d)[kThreads / 32], uint32_t* sh_n,
+                             unsigned long long* sh_k) {
+  const InsertState* g = a.s.g;
+  const int64_t W = g->n_winners;
+  const bool mae = a.mae;
   const int lane = threadIdx.x & 31;
-  const bool use_win = mae || s.g->tie_flag;
-  BinConst bc = make_bins(__longlong_as_double((long long)s.g->absmax_bits) + s.g->store_absmax, B);
+  const double batch_absmax = __longlong_as_double((long long)g->absmax_bits);
+  const BinConst bc = make_bins(batch_absmax + g->store_absmax, a.B);
+  FxConst fx;
+  if (mae) fx = make_fx(batch_absmax, a.B);
   double d0 = 0.0, d1 = 0.0, d2 = 0.0;
   uint32_t nnew = 0;
   unsigned long long kbest = 0ull;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < W; t += (int64_t)gridDim.x * blockDim.x) {
-    const int2 rc = s.wlist[t];
+    const int2 rc = a.s.wlist[t];
     const int32_t c = rc.y;
-    const T o = obj[rc.x];
-    const bool occ = occupied[c] != 0;
-    const T old_obj = occ ? store_obj[c] : (T)0;
+    const T o = a.obj[rc.x];
+    const T tc = a.store_thr[c];
+    const bool occ = (tc == tc);
+    const T old_obj = occ ? a.store_obj[c] : (T)0;
     T newthr;
     if (!mae) {
       newthr = o;  // :663-665
     } else {       // _compute_thresholds, :473-516 (fp64 arithmetic after NumPy promotion)
-      const uint32_t kc = s.cnt[c];
+      const Cell cell = a.s.cell[c];
+      double S;
+      uint32_t kc;
+      fx_read(cell, fx, S, kc);
+      S = (double)(T)S;
       const double k = (double)kc;
-      const double* b = &s.bins[3 * (int64_t)c];
-      const double S = (double)(T)__dadd_rn(__dadd_rn(b[0], b[1]), b[2]);
-      const double tcell = (double)(occ ? store_thr[c] : tmin);
-      const double ratio = powi((double)((T)1 - lr), kc);
+      const double tcell = (double)(occ ? tc : a.tmin);
+      const double ratio = powi((double)((T)1 - a.lr), kc);
       newthr = (T)__dadd_rn(__dmul_rn(ratio, tcell), __dmul_rn(__ddiv_rn(S, k), __dsub_rn(1.0, ratio)));
     }
-    store_thr[c] = newthr;
-    store_obj[c] = o;
+    a.store_thr[c] = newthr;
+    a.store_obj[c] = o;
     if (!occ) {
-      occupied[c] = 1;
-      atomicOr(&s.newmask[c >> 5], 1u << (c & 31));
+      a.occupied[c] = 1;
+      atomicOr(&a.s.newmask[c >> 5], 1u << (c & 31));
       ++nnew;
     }
     double h0, h1, h2;
@@ -333,12 +398,12 @@ __global__ void __launch_bounds__(256) update_kernel(int64_t B, const T* __restr
     const unsigned long long k2 = ord_key((double)o);
     kbest = k2 > kbest ? k2 : kbest;
     // scratch back to its clean state
-    s.best[c] = 0ull;
-    if (use_win) s.win[c] = INT32_MAX;
-    if (mae) {
-      s.cnt[c] = 0u;
-      s.bins[3 * (int64_t)c] = s.bins[3 * (int64_t)c + 1] = s.bins[3 * (int64_t)c + 2] = 0.0;
-    }
+    Cell z;
+    z.best = 0ull;
+    z.w0 = z.w1 = 0ll;
+    z.win = INT32_MAX;
+    z.cnt = 0u;
+    a.s.cell[c] = z;
   }
   // warp -> block -> global accumulation (bins add exactly, so the grouping does not matter)
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
@@ -349,9 +414,6 @@ __global__ void __launch_bounds__(256) update_kernel(int64_t B, const T* __restr
     unsigned long long ok = __shfl_down_sync(0xffffffffu, kbest, o2);
     kbest = ok > kbest ? ok : kbest;
   }
-  __shared__ double sh_d[3][8];
-  __shared__ uint32_t sh_n[8];
-  __shared__ unsigned long long sh_k[8];
   const int wi = threadIdx.x >> 5;
   if (lane == 0) {
     sh_d[0][wi] = d0;
@@ -362,28 +424,27 @@ __global__ void __launch_bounds__(256) update_kernel(int64_t B, const T* __restr
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int k = 1; k < 8; ++k) {
+    for (int k = 1; k < kThreads / 32; ++k) {
       d0 += sh_d[0][k];
       d1 += sh_d[1][k];
       d2 += sh_d[2][k];
       nnew += sh_n[k];
       kbest = sh_k[k] > kbest ? sh_k[k] : kbest;
     }
-    if (d0 != 0.0) atomicAdd(&s.g->dsum[0], d0);
-    if (d1 != 0.0) atomicAdd(&s.g->dsum[1], d1);
-    if (d2 != 0.0) atomicAdd(&s.g->dsum[2], d2);
-    if (nnew) atomicAdd(&s.g->n_new, nnew);
-    if (kbest) atomicMax(&s.g->gbest_key, kbest);
+    if (d0 != 0.0) atomicAdd(&a.s.g->dsum[0], d0);
+    if (d1 != 0.0) atomicAdd(&a.s.g->dsum[1], d1);
+    if (d2 != 0.0) atomicAdd(&a.s.g->dsum[2], d2);
+    if (nnew) atomicAdd(&a.s.g->n_new, nnew);
+    if (kbest) atomicMax(&a.s.g->gbest_key, kbest);
   }
+  __syncthreads();
 }
 
-// Row scatter of the winners (_array_store.py:605-608): every (winner, 16-byte chunk) pair is one
-// work item of a flat grid-stride loop, four loads in flight per thread, so the kernel is a plain
-// HBM stream: 2 * row_bytes per winner.
-__global__ void __launch_bounds__(256) copy_rows_kernel(const __grid_constant__ FieldCopy fc, Scratch s) {
-  if (s.g->flags) return;
+// ---- phase 5: row scatter of the winners (_array_store.py:605-608) --------------------------------
+// Every (winner, 16-byte chunk) pair is one work item of a flat grid-stride loop, four loads in
+// flight per thread: a plain HBM stream of 2 * row_bytes per winner.
+__device__ void phase_copy(const FieldCopy& fc, const Scratch& s) {
   const int64_t W = s.g->n_winners;
-  if (W == 0) return;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   for (int f = 0; f < fc.n; ++f) {
@@ -404,7 +465,7 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const __grid_constant__ 
           if (item < total) {
             const int64_t wn = item / nch, ch = item - wn * nch;
             const int2 rc = s.wlist[wn];
-            v[u] = *reinterpret_cast<const uint4*>(src + (int64_t)rc.x * rb + ch * 16);
+            v[u] = __ldcs(reinterpret_cast<const uint4*>(src + (int64_t)rc.x * rb + ch * 16));
             doff[u] = (int64_t)rc.y * rb + ch * 16;
           }
         }
@@ -429,120 +490,219 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const __grid_constant__ 
   }
 }
 
+// ---- phase 6 ----------------------------------------------------------------------------------
+// Words of the new-cell bitmap owned by one CTA: a contiguous chunk, so that the concatenation of
+// the CTAs' outputs in CTA order is the ascending cell order np.nonzero produces.
+__device__ __forceinline__ void word_chunk(int64_t words, int64_t& w0, int64_t& w1) {
+  const int64_t per = (words + gridDim.x - 1) / gridDim.x;
+  w0 = min((int64_t)blockIdx.x * per, words);
+  w1 = min(w0 + per, words);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256) bestcell_kernel(int64_t N, const uint8_t* __restrict__ occupied,
-                                                       const T* __restrict__ store_obj, double prev_obj_max,
-                                                       Scratch s) {
-  if (s.g->flags || s.g->n_insertable == 0) return;
-  const unsigned long long gk = s.g->gbest_key;
-  if (gk == 0ull) return;
-  const double gbest = ord_unkey(gk);
-  if (prev_obj_max == prev_obj_max && !(gbest > prev_obj_max)) return;  // not NaN and no new record
-  int32_t m = INT32_MAX;
-  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < N; c += (int64_t)gridDim.x * blockDim.x)
-    if (occupied[c] && (double)store_obj[c] == gbest) m = min(m, (int32_t)c);
-  m = __reduce_min_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31) == 0 && m != INT32_MAX) atomicMin(&s.g->best_cell, m);
-}
-
-// ---- occupied_list append: ascending cell order (_array_store.py:586-600) --------------
-__global__ void __launch_bounds__(kAppendThreads) append_count_kernel(int64_t words, Scratch s) {
-  const int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock + (int64_t)threadIdx.x * kWordsPerThread;
-  uint32_t n = 0;
-#pragma unroll
-  for (int k = 0; k < kWordsPerThread; ++k)
-    if (w0 + k < words) n += __popc(s.newmask[w0 + k]);
-  n = __reduce_add_sync(0xffffffffu, n);
-  __shared__ uint32_t sh[32];
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = n;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    uint32_t v = sh[threadIdx.x];
-    v = __reduce_add_sync(0xffffffffu, v);
-    if (threadIdx.x == 0) s.blockcnt[blockIdx.x] = v;
-  }
-}
-
-__global__ void __launch_bounds__(kAppendThreads) append_emit_kernel(int64_t words, int32_t* __restrict__ occupied_list,
-                                                                     int64_t n_before, int64_t B, Scratch s,
-                                                                     qd_add_result* result) {
-  __shared__ uint32_t sh[32];
-  __shared__ uint32_t sh_base;
-  // exclusive offset of this block = sum of earlier block counts
-  uint32_t part = 0;
-  for (int b = threadIdx.x; b < (int)blockIdx.x; b += kAppendThreads) part += s.blockcnt[b];
-  part = __reduce_add_sync(0xffffffffu, part);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    uint32_t v = __reduce_add_sync(0xffffffffu, sh[threadIdx.x]);
-    if (threadIdx.x == 0) sh_base = v;
-  }
-  __syncthreads();
-  const uint32_t block_base = sh_base;
-  __syncthreads();
-  // in-block exclusive scan of per-thread popcounts
-  const int64_t w0 = (int64_t)blockIdx.x * kWordsPerBlock + (int64_t)threadIdx.x * kWordsPerThread;
-  uint32_t wv[kWordsPerThread];
-  uint32_t n = 0;
-#pragma unroll
-  for (int k = 0; k < kWordsPerThread; ++k) {
-    wv[k] = (w0 + k < words) ? s.newmask[w0 + k] : 0u;
-    n += __popc(wv[k]);
-  }
-  uint32_t incl = n;
-  const int lane = threadIdx.x & 31;
-  for (int o2 = 1; o2 < 32; o2 <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o2);
-    if (lane >= o2) incl += t;
-  }
-  if (lane == 31) sh[threadIdx.x >> 5] = incl;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    uint32_t v = sh[threadIdx.x];
-    uint32_t iv = v;
-    for (int o2 = 1; o2 < 32; o2 <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, iv, o2);
-      if (lane >= o2) iv += t;
+__device__ void phase_best_and_count(const InsertArgs<T>& a, bool new_record, bool any_new, uint32_t* sh) {
+  const InsertState* g = a.s.g;
+  if (new_record) {  // lowest winning cell holding the batch maximum (_stats_update's argmax, :331-341)
+    const int64_t W = g->n_winners;
+    const unsigned long long gk = g->gbest_key;
+    int32_t m = INT32_MAX;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < W; t += (int64_t)gridDim.x * blockDim.x) {
+      const int2 rc = a.s.wlist[t];
+      if (ord_key((double)a.obj[rc.x]) == gk) m = min(m, rc.y);
     }
-    sh[threadIdx.x] = iv - v;  // exclusive warp offsets
+    m = __reduce_min_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m != INT32_MAX) atomicMin(&a.s.g->best_cell, m);
   }
-  __syncthreads();
-  int64_t pos = n_before + block_base + sh[threadIdx.x >> 5] + (incl - n);
-#pragma unroll
-  for (int k = 0; k < kWordsPerThread; ++k) {
-    uint32_t m = wv[k];
-    if (m) {
-      s.newmask[w0 + k] = 0u;
-      while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        occupied_list[pos++] = (int32_t)((w0 + k) * 32 + bit);
+  if (any_new) {
+    int64_t w0, w1;
+    word_chunk((a.N + 31) / 32, w0, w1);
+    uint32_t n = 0;
+    for (int64_t w = w0 + threadIdx.x; w < w1; w += blockDim.x) n += __popc(a.s.newmask[w]);
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0u;
+      v = __reduce_add_sync(0xffffffffu, v);
+      if (threadIdx.x == 0) a.s.ctacnt[blockIdx.x] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- phase 7 ----------------------------------------------------------------------------------
+template <typename T>
+__device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool committed, bool new_record,
+                              bool any_new, int64_t n_before, uint32_t* sh, uint32_t* sh_base) {
+  InsertState* gp = a.s.g;
+  const int lane = threadIdx.x & 31;
+  if (any_new) {
+    // exclusive offset of this CTA = sum of the counts of the CTAs before it
+    uint32_t part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += blockDim.x) part += a.s.ctacnt[b];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) sh[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0u;
+      v = __reduce_add_sync(0xffffffffu, v);
+      if (threadIdx.x == 0) *sh_base = v;
+    }
+    __syncthreads();
+    int64_t pos0 = n_before + *sh_base;
+    __syncthreads();
+    int64_t w0, w1;
+    word_chunk((a.N + 31) / 32, w0, w1);
+    for (int64_t wb = w0; wb < w1; wb += blockDim.x) {  // ordered tiles of one word per thread
+      const int64_t w = wb + threadIdx.x;
+      uint32_t m = w < w1 ? a.s.newmask[w] : 0u;
+      const uint32_t n = __popc(m);
+      uint32_t incl = n;
+      for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o2);
+        if (lane >= o2) incl += t;
+      }
+      if (lane == 31) sh[threadIdx.x >> 5] = incl;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const uint32_t v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0u;
+        uint32_t iv = v;
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, iv, o2);
+          if (lane >= o2) iv += t;
+        }
+        sh[threadIdx.x] = iv - v;  // exclusive warp offsets
+        if (threadIdx.x == 31) *sh_base = iv;
+      }
+      __syncthreads();
+      int64_t pos = pos0 + sh[threadIdx.x >> 5] + (incl - n);
+      if (m) {
+        a.s.newmask[w] = 0u;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          a.occupied_list[pos++] = (int32_t)(w * 32 + bit);
+        }
+      }
+      pos0 += *sh_base;
+      __syncthreads();
+    }
+  }
+  if (blockIdx.x != 0) return;
+  // CTA 0: best-elite snapshot, then stats + result + re-arm
+  const int32_t best_cell = gp->best_cell;
+  const bool snap = committed && new_record && best_cell != INT32_MAX && a.snapshot != nullptr;
+  if (snap) {
+    for (int f = 0; f < fc.n; ++f) {
+      const char* sp = fc.dst[f] + (int64_t)best_cell * fc.row_bytes[f];
+      char* dp = a.snapshot + fc.snap_off[f];
+      for (int64_t o = threadIdx.x; o < fc.row_bytes[f]; o += blockDim.x) dp[o] = sp[o];
+    }
+  }
+  if (threadIdx.x == 0) {
+    InsertState g = *gp;
+    const double delta = (double)(T)__dadd_rn(__dadd_rn(g.dsum[0], g.dsum[1]), g.dsum[2]);
+    if (committed) {
+      g.n_occupied += g.n_new;
+      g.objective_sum = (double)(T)(g.objective_sum + delta);  // _grid_archive.py:707-712
+      g.n_commits += 1;
+      g.store_absmax = fmax(g.store_absmax, __longlong_as_double((long long)g.absmax_bits));
+      if (new_record) {
+        g.obj_max_key = g.gbest_key;
+        g.best_serial += 1;
+        if (a.snapshot) {  // header: objective, threshold (as doubles), cell
+          double* hd = (double*)a.snapshot;
+          hd[0] = (double)a.store_obj[best_cell];
+          hd[1] = (double)a.store_thr[best_cell];
+          *(int32_t*)(hd + 2) = best_cell;
+        }
       }
     }
-  }
-  // block 0 publishes the result and re-arms the globals for the next call
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    InsertGlobals g = *s.g;
+    if (g.flags) {
+      g.n_failed += 1;
+      g.last_failed_flags = g.flags;
+    }
     qd_add_result r;
     r.n_insertable = (int32_t)g.n_insertable;
-    r.n_new = (int32_t)g.n_new;
-    r.best_cell = g.best_cell == INT32_MAX ? -1 : g.best_cell;
+    r.n_new = committed ? (int32_t)g.n_new : 0;
+    r.best_cell = (committed && new_record && best_cell != INT32_MAX) ? best_cell : -1;
     r.flags = g.flags;
     r.best_objective = g.gbest_key ? ord_unkey(g.gbest_key) : 0.0;
     r.delta_sum[0] = g.dsum[0];
     r.delta_sum[1] = g.dsum[1];
     r.delta_sum[2] = g.dsum[2];
     r.batch_absmax = __longlong_as_double((long long)g.absmax_bits);
-    *result = r;
-    if (!g.flags) g.store_absmax = fmax(g.store_absmax, r.batch_absmax);
+    r.n_occupied = g.n_occupied;
+    r.objective_sum = g.objective_sum;
+    r.obj_max = g.obj_max_key ? ord_unkey(g.obj_max_key) : 0.0;
+    r.has_obj_max = g.obj_max_key ? 1 : 0;
+    r.last_failed_flags = g.last_failed_flags;
+    r.n_commits = g.n_commits;
+    r.best_serial = g.best_serial;
+    r.n_failed = g.n_failed;
+    *a.result = r;
     g.gbest_key = 0ull;
     g.absmax_bits = 0ull;
     g.best_cell = INT32_MAX;
     g.n_insertable = g.n_new = g.flags = g.tie_flag = g.n_winners = 0u;
     g.dsum[0] = g.dsum[1] = g.dsum[2] = 0.0;
-    *s.g = g;
+    *gp = g;
   }
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------
+// Phases [phase_lo, phase_hi] run inside one launch; a launch boundary stands in for the barrier
+// when add() is split in two (host batches: the row copy waits for the H2D of the solutions).
+template <typename T, typename MT, int D, bool FUSED>
+__global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_constant__ InsertArgs<T> a,
+                                                           const __grid_constant__ GridParams gp,
+                                                           const __grid_constant__ FieldCopy fc, int phase_lo,
+                                                           int phase_hi) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t sh_u[kThreads / 32 + 32];
+  __shared__ uint32_t sh_base;
+  __shared__ double sh_d[3][kThreads / 32];
+  __shared__ unsigned long long sh_k[kThreads / 32];
+  const InsertState* g = a.s.g;
+  const bool mae = a.mae;
+  const int64_t n_before = g->n_occupied;  // CTA 0 advances it in the publish phase
+
+  if (phase_lo <= 0 && mae) {
+    phase_absmax<T>(a);
+    grid.sync();
+  }
+  if (phase_lo <= 1 && phase_hi >= 1) {
+    phase_classify<T, MT, D, FUSED>(a, gp);
+    grid.sync();
+  }
+  // the globals below were last written before a barrier / launch boundary: uniform over the grid
+  const bool failed = g->flags != 0u;
+  const bool any = g->n_insertable != 0u;
+  const bool use_win = g->tie_flag != 0u;
+  const bool committed = any && !failed;
+  if (phase_lo <= 2 && phase_hi >= 2 && committed && use_win) {
+    phase_resolve<T>(a);
+    grid.sync();
+  }
+  if (phase_lo <= 3 && phase_hi >= 3 && any) {
+    if (failed)
+      phase_cleanup<T>(a);
+    else
+      phase_select<T>(a, use_win, sh_u, &sh_base);
+    grid.sync();
+  }
+  if (phase_lo <= 4 && phase_hi >= 4 && committed) phase_update<T>(a, use_win, sh_d, sh_u, sh_k);
+  if (phase_lo <= 5 && phase_hi >= 5 && committed && fc.n > 0) phase_copy(fc, a.s);
+  if (phase_hi < 6) return;
+  if (phase_lo <= 5) grid.sync();
+  const unsigned long long gk = g->gbest_key, pk = g->obj_max_key;
+  const bool new_record = committed && gk != 0ull && (pk == 0ull || gk > pk);
+  const bool any_new = committed && g->n_new != 0u;
+  if (new_record || any_new) {
+    phase_best_and_count<T>(a, new_record, any_new, sh_u);
+    grid.sync();
+  }
+  phase_publish<T>(a, fc, committed, new_record, any_new, n_before, sh_u, &sh_base);
 }
 
 static int pick_vec(const void* a, const void* b, int64_t row_bytes) {
@@ -560,67 +720,78 @@ struct GridSpec {  // non-null measures => fused grid index
 };
 
 template <typename T, typename MT, int D, bool FUSED>
-static void launch_classify(int grid, cudaStream_t stream, int64_t B, int32_t* idx, const GridSpec& gs, const T* obj,
-                            const qd_store* st, T tmin, bool cma_me, bool mae, int32_t* status, T* value, Scratch s) {
-  classify_kernel<T, MT, D, FUSED><<<grid, 256, 0, stream>>>(B, idx, (const MT*)gs.measures, gs.gp, obj, st->occupied,
-                                                             (const T*)st->threshold, tmin, cma_me, mae, status,
-                                                             value, s);
+static int launch_insert(const InsertArgs<T>& a, const GridParams& gp, const FieldCopy& fc, int64_t work,
+                         int part, cudaStream_t stream) {
+  static int max_ctas = 0;  // per instantiation
+  if (max_ctas == 0) {
+    int per_sm = 0, dev = 0, sms = kNumSMs;
+    QD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel<T, MT, D, FUSED>, kThreads, 0));
+    QD_CHECK_CUDA(cudaGetDevice(&dev));
+    QD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (per_sm < 1) {
+      set_error("insert_kernel cannot be made resident");
+      return QD_ERR_CUDA;
+    }
+    int64_t m = (int64_t)per_sm * sms;
+    max_ctas = (int)(m < kMaxCtas ? m : kMaxCtas);
+  }
+  int64_t want = (work + kThreads - 1) / kThreads;
+  if (want < 8) want = 8;
+  const int grid = (int)(want < max_ctas ? want : max_ctas);
+  int lo = part == QD_INSERT_COMMIT ? 5 : 0, hi = part == QD_INSERT_CLASSIFY ? 4 : 7;
+  void* params[] = {(void*)&a, (void*)&gp, (void*)&fc, (void*)&lo, (void*)&hi};
+  QD_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)insert_kernel<T, MT, D, FUSED>, dim3(grid), dim3(kThreads),
+                                            params, 0, stream));
+  return check_launch("insert_kernel");
 }
 
 template <typename T>
 int insert_impl(const qd_store* st, int64_t B, int32_t* idx, const GridSpec& gs, const void* objective,
-                const void* const* field_src, double lr, double tmin, int64_t n_before, double prev_obj_max,
-                int32_t* status, void* value, qd_add_result* result, cudaStream_t stream) {
+                const void* const* field_src, double lr, double tmin, int32_t* status, void* value,
+                qd_add_result* result, int part, cudaStream_t stream) {
   const int64_t N = st->capacity;
-  Scratch s = carve(st->scratch, N);
-  const bool cma_me = (tmin == -INFINITY);
-  const bool mae = !cma_me;
+  InsertArgs<T> a;
+  a.B = B;
+  a.N = N;
+  a.idx = idx;
+  a.measures = gs.measures;
+  a.obj = (const T*)objective;
+  a.occupied = st->occupied;
+  a.occupied_list = st->occupied_list;
+  a.store_obj = (T*)st->objective;
+  a.store_thr = (T*)st->threshold;
+  a.tmin = (T)tmin;
+  a.lr = (T)lr;
+  a.mae = (tmin == -INFINITY) ? 0 : 1;
+  a.status = status;
+  a.value = (T*)value;
+  a.snapshot = (char*)st->best_snapshot;
+  a.result = result;
+  a.s = carve(st->scratch, N);
   FieldCopy fc;
   fc.n = st->n_fields;
+  int64_t max_row = 0;
+  int64_t off = 32;  // snapshot header: objective, threshold, cell
   for (int f = 0; f < fc.n; ++f) {
     fc.src[f] = (const char*)field_src[f];
     fc.dst[f] = (char*)st->field_dst[f];
     fc.row_bytes[f] = st->field_row_bytes[f];
     fc.vec[f] = pick_vec(fc.src[f], fc.dst[f], fc.row_bytes[f]);
+    fc.snap_off[f] = off;
+    off += (int64_t)align_up((size_t)fc.row_bytes[f], 16);
+    max_row += fc.row_bytes[f];
   }
-  const T* obj = (const T*)objective;
-  const int grid = grid_for(B, 256, 8);
-  if (gs.measures == nullptr) {
-    launch_classify<T, double, 0, false>(grid, stream, B, idx, gs, obj, st, (T)tmin, cma_me, mae, status, (T*)value, s);
-  } else if (gs.meas_dtype == QD_F64) {
-    if (gs.gp.d == 2)
-      launch_classify<T, double, 2, true>(grid, stream, B, idx, gs, obj, st, (T)tmin, cma_me, mae, status, (T*)value, s);
-    else
-      launch_classify<T, double, 0, true>(grid, stream, B, idx, gs, obj, st, (T)tmin, cma_me, mae, status, (T*)value, s);
-  } else {
-    if (gs.gp.d == 2)
-      launch_classify<T, float, 2, true>(grid, stream, B, idx, gs, obj, st, (T)tmin, cma_me, mae, status, (T*)value, s);
-    else
-      launch_classify<T, float, 0, true>(grid, stream, B, idx, gs, obj, st, (T)tmin, cma_me, mae, status, (T*)value, s);
+  // enough CTAs for the row passes and for the copy of up to min(B, N) winner rows
+  const int64_t wmax = B < N ? B : N;
+  int64_t work = B;
+  if (wmax * (max_row / 16) > work) work = wmax * (max_row / 16);
+  if (gs.measures == nullptr) return launch_insert<T, double, 0, false>(a, gs.gp, fc, work, part, stream);
+  if (gs.meas_dtype == QD_F64) {
+    if (gs.gp.d == 2) return launch_insert<T, double, 2, true>(a, gs.gp, fc, work, part, stream);
+    return launch_insert<T, double, 0, true>(a, gs.gp, fc, work, part, stream);
   }
-  int rc = check_launch("classify_kernel");
-  if (rc) return rc;
-  resolve_kernel<T><<<grid, 256, 0, stream>>>(B, idx, obj, status, mae, s);
-  if ((rc = check_launch("resolve_kernel"))) return rc;
-  select_kernel<T><<<grid, 256, 0, stream>>>(B, idx, obj, status, mae, s);
-  if ((rc = check_launch("select_kernel"))) return rc;
-  update_kernel<T><<<grid_for(B < N ? B : N, 256, 8), 256, 0, stream>>>(B, obj, st->occupied, (T*)st->objective,
-                                                                       (T*)st->threshold, (T)tmin, (T)lr, mae, s);
-  if ((rc = check_launch("update_kernel"))) return rc;
-  if (fc.n > 0) {
-    copy_rows_kernel<<<kNumSMs * 8, 256, 0, stream>>>(fc, s);
-    if ((rc = check_launch("copy_rows_kernel"))) return rc;
-  }
-  bestcell_kernel<T><<<grid_for(N, 256, 4), 256, 0, stream>>>(N, st->occupied, (const T*)st->objective, prev_obj_max, s);
-  if ((rc = check_launch("bestcell_kernel"))) return rc;
-  const int64_t words = (N + 31) / 32;
-  const int nblk = (int)((words + kWordsPerBlock - 1) / kWordsPerBlock);
-  if (nblk > 1) {
-    append_count_kernel<<<nblk, kAppendThreads, 0, stream>>>(words, s);
-    if ((rc = check_launch("append_count_kernel"))) return rc;
-  }
-  append_emit_kernel<<<nblk, kAppendThreads, 0, stream>>>(words, st->occupied_list, n_before, B, s, result);
-  return check_launch("append_emit_kernel");
+  if (gs.gp.d == 2) return launch_insert<T, float, 2, true>(a, gs.gp, fc, work, part, stream);
+  return launch_insert<T, float, 0, true>(a, gs.gp, fc, work, part, stream);
 }
 
 static int check_insert_args(const qd_store* store, int64_t B, const void* objective, const int32_t* status_out,
@@ -634,6 +805,54 @@ static int check_insert_args(const qd_store* store, int64_t B, const void* objec
              "null store pointer");
   if (B > 0) QD_REQUIRE(objective && status_out && value_out, "null batch pointer");
   return QD_OK;
+}
+
+// ---- store state helpers -------------------------------------------------------------------------
+template <typename T>
+__global__ void store_clear_kernel(int64_t N, uint8_t* occupied, T* thr, Scratch s) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t c = i; c < N; c += (int64_t)gridDim.x * blockDim.x) {
+    occupied[c] = 0;
+    thr[c] = (T)NAN;
+  }
+  if (i == 0) {
+    InsertState* g = s.g;
+    g->n_occupied = 0;
+    g->obj_max_key = 0ull;
+    g->objective_sum = 0.0;
+    g->store_absmax = 0.0;
+  }
+}
+
+template <typename T>
+__global__ void store_mask_thresholds_kernel(int64_t N, const uint8_t* occupied, T* thr) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < N; c += (int64_t)gridDim.x * blockDim.x)
+    if (!occupied[c]) thr[c] = (T)NAN;
+}
+
+__global__ void store_set_state_kernel(Scratch s, long long n_occupied, double objective_sum, int has_max,
+                                       double obj_max, double absmax) {
+  InsertState* g = s.g;
+  g->n_occupied = n_occupied;
+  g->objective_sum = objective_sum;
+  g->obj_max_key = has_max ? ord_key(obj_max) : 0ull;
+  g->store_absmax = absmax;
+}
+
+__global__ void store_read_state_kernel(Scratch s, qd_add_result* out) {
+  InsertState* g = s.g;
+  qd_add_result r;
+  memset(&r, 0, sizeof(r));
+  r.best_cell = -1;
+  r.n_occupied = g->n_occupied;
+  r.objective_sum = g->objective_sum;
+  r.obj_max = g->obj_max_key ? ord_unkey(g->obj_max_key) : 0.0;
+  r.has_obj_max = g->obj_max_key ? 1 : 0;
+  r.last_failed_flags = g->last_failed_flags;
+  r.n_commits = g->n_commits;
+  r.best_serial = g->best_serial;
+  r.n_failed = g->n_failed;
+  *out = r;
 }
 
 }  // namespace qd
@@ -652,32 +871,82 @@ extern "C" int qd_insert_scratch_init(void* scratch, int64_t capacity, void* str
   return check_launch("scratch_init_kernel");
 }
 
+extern "C" size_t qd_best_snapshot_bytes(const qd_store* store) {
+  if (!store) return 0;
+  size_t off = 32;
+  for (int f = 0; f < store->n_fields; ++f) off += qd::align_up((size_t)store->field_row_bytes[f], 16);
+  return off;
+}
+
+extern "C" int qd_store_clear(const qd_store* store, void* stream) {
+  using namespace qd;
+  QD_REQUIRE(store && store->scratch && store->occupied && store->threshold, "null store pointer");
+  Scratch s = carve(store->scratch, store->capacity);
+  const int grid = grid_for(store->capacity, 256);
+  if (store->obj_dtype == QD_F64)
+    store_clear_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(store->capacity, store->occupied,
+                                                                       (double*)store->threshold, s);
+  else
+    store_clear_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(store->capacity, store->occupied,
+                                                                      (float*)store->threshold, s);
+  return check_launch("store_clear_kernel");
+}
+
+extern "C" int qd_store_set_state(const qd_store* store, int64_t n_occupied, double objective_sum, int has_obj_max,
+                                  double obj_max, double objective_absmax, void* stream) {
+  using namespace qd;
+  QD_REQUIRE(store && store->scratch && store->occupied && store->threshold, "null store pointer");
+  Scratch s = carve(store->scratch, store->capacity);
+  const int grid = grid_for(store->capacity, 256);
+  if (store->obj_dtype == QD_F64)
+    store_mask_thresholds_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(store->capacity, store->occupied,
+                                                                                 (double*)store->threshold);
+  else
+    store_mask_thresholds_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(store->capacity, store->occupied,
+                                                                                (float*)store->threshold);
+  int rc = check_launch("store_mask_thresholds_kernel");
+  if (rc) return rc;
+  store_set_state_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(s, (long long)n_occupied, objective_sum, has_obj_max,
+                                                          obj_max, objective_absmax);
+  return check_launch("store_set_state_kernel");
+}
+
+extern "C" int qd_store_read_state(const qd_store* store, qd_add_result* out, void* stream) {
+  using namespace qd;
+  QD_REQUIRE(store && store->scratch && out, "null pointer");
+  Scratch s = carve(store->scratch, store->capacity);
+  store_read_state_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(s, out);
+  return check_launch("store_read_state_kernel");
+}
+
 extern "C" int qd_insert(const qd_store* store, int64_t B, const int32_t* idx, const void* objective,
                          const void* const* field_src, double learning_rate, double threshold_min,
-                         int64_t n_occupied_before, double prev_obj_max, int32_t* status_out, void* value_out,
-                         qd_add_result* result, void* stream) {
+                         int32_t* status_out, void* value_out, qd_add_result* result, int part, void* stream) {
   using namespace qd;
   int rc = check_insert_args(store, B, objective, status_out, value_out, result);
   if (rc) return rc;
+  QD_REQUIRE(part >= QD_INSERT_WHOLE && part <= QD_INSERT_COMMIT, "part must be QD_INSERT_WHOLE/CLASSIFY/COMMIT");
   if (B > 0) QD_REQUIRE(idx, "null idx");
   GridSpec gs;
+  gs.gp.d = 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (store->obj_dtype == QD_F64)
     return insert_impl<double>(store, B, const_cast<int32_t*>(idx), gs, objective, field_src, learning_rate,
-                               threshold_min, n_occupied_before, prev_obj_max, status_out, value_out, result, s);
+                               threshold_min, status_out, value_out, result, part, s);
   return insert_impl<float>(store, B, const_cast<int32_t*>(idx), gs, objective, field_src, learning_rate,
-                            threshold_min, n_occupied_before, prev_obj_max, status_out, value_out, result, s);
+                            threshold_min, status_out, value_out, result, part, s);
 }
 
 extern "C" int qd_grid_insert(const qd_store* store, int64_t B, const void* measures, int meas_dtype, int d,
                               const int32_t* dims, const double* lower, const double* interval, double epsilon,
                               const void* objective, const void* const* field_src, double learning_rate,
-                              double threshold_min, int64_t n_occupied_before, double prev_obj_max, int32_t* idx_out,
-                              int32_t* status_out, void* value_out, qd_add_result* result, void* stream) {
+                              double threshold_min, int32_t* idx_out, int32_t* status_out, void* value_out,
+                              qd_add_result* result, int part, void* stream) {
   using namespace qd;
   int rc = check_insert_args(store, B, objective, status_out, value_out, result);
   if (rc) return rc;
   QD_REQUIRE(meas_dtype == QD_F32 || meas_dtype == QD_F64, "measures dtype must be f32/f64");
+  QD_REQUIRE(part >= QD_INSERT_WHOLE && part <= QD_INSERT_COMMIT, "part must be QD_INSERT_WHOLE/CLASSIFY/COMMIT");
   if (B > 0) QD_REQUIRE(measures && idx_out, "null measures / idx_out");
   GridSpec gs;
   if ((rc = fill_grid_params(gs.gp, d, dims, lower, interval, epsilon))) return rc;
@@ -685,8 +954,8 @@ extern "C" int qd_grid_insert(const qd_store* store, int64_t B, const void* meas
   gs.meas_dtype = meas_dtype;
   cudaStream_t s = (cudaStream_t)stream;
   if (store->obj_dtype == QD_F64)
-    return insert_impl<double>(store, B, idx_out, gs, objective, field_src, learning_rate, threshold_min,
-                               n_occupied_before, prev_obj_max, status_out, value_out, result, s);
-  return insert_impl<float>(store, B, idx_out, gs, objective, field_src, learning_rate, threshold_min,
-                            n_occupied_before, prev_obj_max, status_out, value_out, result, s);
+    return insert_impl<double>(store, B, idx_out, gs, objective, field_src, learning_rate, threshold_min, status_out,
+                               value_out, result, part, s);
+  return insert_impl<float>(store, B, idx_out, gs, objective, field_src, learning_rate, threshold_min, status_out,
+                            value_out, result, part, s);
 }

@@ -24,14 +24,34 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/qd_b200.h but not exported"
     assert set(_lib.PROTOTYPES) == set(names), set(_lib.PROTOTYPES) ^ set(names)
-    assert _lib.lib().qd_abi_version() == 1
+    assert _lib.lib().qd_abi_version() == 2
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors in pyribs_b200/_lib.py against the header as gcc lays it out."""
+    import subprocess
+
     from pyribs_b200 import _lib
 
-    assert ctypes.sizeof(_lib.AddResult) == 56
-    assert _lib.lib().qd_insert_scratch_bytes(1000) > 1000 * 40
+    fields = {"qd_add_result": [f[0] for f in _lib.AddResult._fields_],
+              "qd_store": [f[0] for f in _lib.Store._fields_],
+              "qd_cma_scalars": [f[0] for f in _lib.CmaScalars._fields_]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "qd_b200.h"', 'int main(void) {']
+    for st, names in fields.items():
+        lines.append(f'printf("{st} %zu\\n", sizeof({st}));')
+        for n in names:
+            lines.append(f'printf("{st}.{n} %zu\\n", offsetof({st}, {n}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for st, cls in (("qd_add_result", _lib.AddResult), ("qd_store", _lib.Store), ("qd_cma_scalars", _lib.CmaScalars)):
+        assert int(got[st]) == ctypes.sizeof(cls), st
+        for n in fields[st]:
+            assert int(got[f"{st}.{n}"]) == getattr(cls, n).offset, f"{st}.{n}"
+    assert _lib.lib().qd_insert_scratch_bytes(1000) >= 1000 * 40
 
 
 def test_product_does_not_import_oracle():

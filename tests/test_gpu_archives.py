@@ -284,6 +284,65 @@ def test_retrieve_and_iteration():
     assert len(a) == 0 and a.stats.obj_max is None
 
 
+def test_device_adds_are_asynchronous_and_state_lives_on_device():
+    """CUDA-tensor insertions are only enqueued: len / stats / best_elite / occupied_list read the
+    device-side running state back lazily and must equal what the same NumPy batches give (which
+    wait after every call); a non-finite batch is dropped on the device and surfaces as the
+    reference's ValueError at the next read, leaving the archive untouched."""
+    import torch
+
+    from pyribs_b200.archives import CVTArchive, GridArchive
+
+    rng = np.random.default_rng(7)
+    cen = rng.uniform(-1, 1, (500, 2))
+    for make in (lambda: GridArchive(solution_dim=5, dims=[20, 20], ranges=[(-1, 1)] * 2, learning_rate=0.1,
+                                     threshold_min=-1.0),
+                 lambda: GridArchive(solution_dim=5, dims=[20, 20], ranges=[(-1, 1)] * 2),
+                 lambda: CVTArchive(solution_dim=5, centroids=cen, ranges=[(-1, 1)] * 2)):
+        a, b = make(), make()
+        batches = [dict(solution=rng.standard_normal((3000, 5)), objective=rng.normal(j, 2.0, 3000),
+                        measures=rng.uniform(-1.1, 1.1, (3000, 2))) for j in range(6)]
+        outs = []
+        for bt in batches:  # no host read in between
+            outs.append(a.add(*(torch.from_numpy(bt[k]).cuda() for k in ("solution", "objective", "measures"))))
+        assert a._store._pending
+        for bt, o in zip(batches, outs):
+            r = b.add(**bt)
+            np.testing.assert_array_equal(o["status"].cpu().numpy(), r["status"])
+            np.testing.assert_array_equal(o["value"].cpu().numpy(), r["value"])
+        assert len(a) == len(b) and not a._store._pending
+        sa, sb = a.stats, b.stats
+        assert sa.num_elites == sb.num_elites and sa.qd_score == sb.qd_score and sa.obj_max == sb.obj_max
+        assert sa.obj_mean == sb.obj_mean
+        for k in a.best_elite:
+            np.testing.assert_array_equal(a.best_elite[k], b.best_elite[k])
+        np.testing.assert_array_equal(a._store.occupied_list, b._store.occupied_list)
+        da, db = a.data(), b.data()
+        for k in da:
+            np.testing.assert_array_equal(da[k], db[k])
+        # a bad batch between good ones: dropped, reported once, later batches still land
+        bad = {k: torch.from_numpy(v).cuda() for k, v in batches[0].items()}
+        bad["objective"] = bad["objective"].clone()
+        bad["objective"][17] = float("nan")
+        n0 = len(a)
+        a.add(bad["solution"], bad["objective"], bad["measures"])
+        good = dict(batches[5])
+        good["objective"] = good["objective"] + 50.0
+        a.add(*(torch.from_numpy(good[k]).cuda() for k in ("solution", "objective", "measures")))
+        with pytest.raises(ValueError, match="objective"):
+            len(a)
+        b.add(**good)
+        assert len(a) == len(b) >= n0
+        np.testing.assert_array_equal(a.data("objective"), b.data("objective"))
+        a.clear()
+        assert len(a) == 0 and a.stats.obj_max is None and a.best_elite is None
+        a.add(**batches[0])
+        c = make()
+        c.add(**batches[0])
+        np.testing.assert_array_equal(a.data("threshold"), c.data("threshold"))
+        assert a.stats.qd_score == c.stats.qd_score
+
+
 @pytest.mark.parametrize("shape", [(200_000, 10_000, 2), (60_000, 100_000, 8), (30_000, 50_000, 5), (3_000, 300_000, 3),
                                    (20_000, 20_000, 13), (20_000, 20_000, 24)])
 def test_cvt_tensor_equals_scan(shape):
