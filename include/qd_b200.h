@@ -160,6 +160,11 @@ uint32_t* qd_insert_flags_ptr(void* scratch /*[dev]*/, int64_t capacity);
 /* *out = OR of in[0..n): merges the validation flags gathered from all ranks of a data-parallel add. */
 int qd_flags_or(const uint32_t* in /*[dev] n*/, int n, uint32_t* out /*[dev] 1*/, void* stream);
 
+/* Diagnostics: %globaltimer (ns) at the phase boundaries of the last insertion on this store
+ * (absmax, classify, resolve, select, update, copy, best/count, publish start, publish end).
+ * Blocks until the stream is idle. */
+int qd_insert_phase_times(const void* scratch /*[dev]*/, int64_t capacity, uint64_t* out_ns /*[host] 10*/,
+                          void* stream);
 size_t qd_best_snapshot_bytes(const qd_store* store);
 /* ArrayStore.clear (_array_store.py:610-616) + _stats_reset: occupancy 0, thresholds NaN, element
  * count / objective sum / best objective reset. Also the initialiser of a fresh store. */

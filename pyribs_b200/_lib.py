@@ -82,6 +82,7 @@ PROTOTYPES = {
     "qd_insert_scratch_init": (_int, [_vp, _i64, _vp]),
     "qd_insert_flags_ptr": (_vp, [_vp, _i64]),
     "qd_flags_or": (_int, [_vp, _int, _vp, _vp]),
+    "qd_insert_phase_times": (_int, [_vp, _i64, C.POINTER(_u64), _vp]),
     "qd_best_snapshot_bytes": (_sz, [C.POINTER(Store)]),
     "qd_store_clear": (_int, [C.POINTER(Store), _vp]),
     "qd_store_set_state": (_int, [C.POINTER(Store), _i64, _dbl, _int, _dbl, _dbl, _vp]),

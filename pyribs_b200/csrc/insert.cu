@@ -59,7 +59,7 @@ struct InsertState {
   uint32_t n_insertable;
   uint32_t n_new;
   uint32_t flags;
-  uint32_t tie_flag;  // two insertable rows of one cell share the cell's best objective
+  uint32_t pad0;
   uint32_t n_winners;
   double dsum[3];
   // ---- persistent ----
@@ -72,6 +72,7 @@ struct InsertState {
   unsigned long long n_failed;    // calls dropped by validation
   uint32_t last_failed_flags;     // flags of the most recent such call
   uint32_t pad;
+  unsigned long long t_phase[10]; // %globaltimer at the phase boundaries of the last call (diagnostics)
 };
 
 struct Scratch {
@@ -227,77 +228,141 @@ __device__ __forceinline__ bool is_finite_t(T o) {
   return sizeof(T) == 8 ? finite_d((double)o) : finite_f((float)o);
 }
 
+// Row passes keep kRows independent rows in flight per thread (rows tid, tid+S, tid+2S, ... of one
+// sweep, S = threads in the grid): with 1024 threads per SM a single outstanding load per thread
+// cannot cover the HBM / L2 latency.
+constexpr int kRows = 4;
+
 // ---- phase 0 ----------------------------------------------------------------------------------
-template <typename T>
-__device__ void phase_absmax(const InsertArgs<T>& a) {
-  double amax = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x) {
-    const T o = a.obj[i];
-    if (is_finite_t(o)) amax = fmax(amax, fabs((double)o));
+// block-wide max of non-negative doubles through `sh` (kThreads / 32 entries); result valid in thread 0
+__device__ __forceinline__ double block_max(double v, double* sh) {
+  for (int o2 = 16; o2 > 0; o2 >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o2));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.0;
+    for (int o2 = 16; o2 > 0; o2 >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o2));
   }
-  for (int o2 = 16; o2 > 0; o2 >>= 1) amax = fmax(amax, __shfl_down_sync(0xffffffffu, amax, o2));
-  if ((threadIdx.x & 31) == 0 && amax > 0.0)
+  return v;
+}
+
+template <typename T>
+__device__ void phase_absmax(const InsertArgs<T>& a, double* sh_d) {
+  double amax = 0.0;
+  const int64_t S = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < a.B; base += 8 * S) {
+    T o[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t i = base + u * S;
+      o[u] = i < a.B ? a.obj[i] : (T)0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (is_finite_t(o[u])) amax = fmax(amax, fabs((double)o[u]));
+  }
+  amax = block_max(amax, sh_d);
+  if (threadIdx.x == 0 && amax > 0.0)
     atomicMax(&a.s.g->absmax_bits, (unsigned long long)__double_as_longlong(amax));
 }
 
 // ---- phase 1 ----------------------------------------------------------------------------------
 template <typename T, typename MT, int D, bool FUSED>
-__device__ void phase_classify(const InsertArgs<T>& a, const GridParams& gp) {
+__device__ void phase_classify(const InsertArgs<T>& a, const GridParams& gp, double* sh_d, uint32_t* sh_u) {
   const bool mae = a.mae;
   const bool cma_me = !mae;
   FxConst fx;
   if (mae) fx = make_fx(__longlong_as_double((long long)a.s.g->absmax_bits), a.B);
   uint32_t ncan = 0;
   double amax = 0.0;
-  bool bad = false, bad_meas = false, tie = false;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x) {
-    int32_t c;
-    if constexpr (FUSED) {
-      c = grid_cell_of<MT, D>((const MT*)a.measures, i, gp, bad_meas);  // A2 fused into the first pass
-      a.idx[i] = c;
-    } else {
-      c = a.idx[i];
+  bool bad = false, bad_meas = false;
+  const int64_t S = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < a.B; base += kRows * S) {
+    int32_t c[kRows];
+    T o[kRows], tc[kRows];
+#pragma unroll
+    for (int u = 0; u < kRows; ++u) {
+      const int64_t i = base + u * S;
+      c[u] = -1;
+      if (i < a.B) {
+        if constexpr (FUSED)
+          c[u] = grid_cell_of<MT, D>((const MT*)a.measures, i, gp, bad_meas);  // A2 fused into the first pass
+        else
+          c[u] = a.idx[i];
+        o[u] = a.obj[i];
+      }
     }
-    const T o = a.obj[i];
-    const bool fin = is_finite_t(o);
-    bad |= !fin;
-    const T tc = a.store_thr[c];
-    const bool occ = (tc == tc);      // unoccupied cells hold NaN
-    const T t = occ ? tc : a.tmin;    // _grid_archive.py:628-630
-    const bool can = fin && (o > t);  // :636
-    a.status[i] = can ? (occ ? 1 : 2) : 0;
-    const T tval = (can && !occ) ? (cma_me ? (T)0 : a.tmin) : t;  // :646-648
-    a.value[i] = o - tval;                                        // :649
-    if (can) {
-      Cell* cell = &a.s.cell[c];
-      const unsigned long long key = ord_key((double)o);
-      const unsigned long long old = atomicMax(&cell->best, key);
-      tie |= (old == key);
-      if (mae) fx_add(cell, (double)o, fx);
-      ++ncan;
+#pragma unroll
+    for (int u = 0; u < kRows; ++u)
+      if (c[u] >= 0) tc[u] = a.store_thr[c[u]];
+#pragma unroll
+    for (int u = 0; u < kRows; ++u) {
+      if (c[u] < 0) continue;
+      const int64_t i = base + u * S;
+      if constexpr (FUSED) a.idx[i] = c[u];
+      const bool fin = is_finite_t(o[u]);
+      bad |= !fin;
+      const bool occ = (tc[u] == tc[u]);   // unoccupied cells hold NaN
+      const T t = occ ? tc[u] : a.tmin;    // _grid_archive.py:628-630
+      const bool can = fin && (o[u] > t);  // :636
+      a.status[i] = can ? (occ ? 1 : 2) : 0;
+      const T tval = (can && !occ) ? (cma_me ? (T)0 : a.tmin) : t;  // :646-648
+      a.value[i] = o[u] - tval;                                     // :649
+      if (can) {
+        Cell* cell = &a.s.cell[c[u]];
+        atomicMax(&cell->best, ord_key((double)o[u]));  // result unused: a fire-and-forget RED
+        if (mae) fx_add(cell, (double)o[u], fx);
+        ++ncan;
+      }
+      if (!mae && fin) amax = fmax(amax, fabs((double)o[u]));
     }
-    if (!mae && fin) amax = fmax(amax, fabs((double)o));
   }
-  if (tie) a.s.g->tie_flag = 1u;
-  if (bad_meas) atomicOr(&a.s.g->flags, QD_FLAG_NONFINITE_MEASURES);
-  if (bad) atomicOr(&a.s.g->flags, QD_FLAG_NONFINITE_OBJECTIVE);
-  for (int o2 = 16; o2 > 0; o2 >>= 1) {
-    ncan += __shfl_down_sync(0xffffffffu, ncan, o2);
-    amax = fmax(amax, __shfl_down_sync(0xffffffffu, amax, o2));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (ncan) atomicAdd(&a.s.g->n_insertable, ncan);
+  // one set of global atomics per CTA (per-warp same-address atomics serialise in L2)
+  const int any_bad_meas = __syncthreads_or(bad_meas), any_bad = __syncthreads_or(bad);
+  amax = block_max(amax, sh_d);
+  ncan = __reduce_add_sync(0xffffffffu, ncan);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh_u[threadIdx.x >> 5] = ncan;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t n = 0;
+    for (int k = 0; k < kThreads / 32; ++k) n += sh_u[k];
+    if (n) atomicAdd(&a.s.g->n_insertable, n);
     if (amax > 0.0) atomicMax(&a.s.g->absmax_bits, (unsigned long long)__double_as_longlong(amax));
+    if (any_bad_meas) atomicOr(&a.s.g->flags, QD_FLAG_NONFINITE_MEASURES);
+    if (any_bad) atomicOr(&a.s.g->flags, QD_FLAG_NONFINITE_OBJECTIVE);
   }
+  __syncthreads();
 }
 
-// ---- phase 2 (only after a tie) ------------------------------------------------------------------
+// ---- phase 2 ----------------------------------------------------------------------------------
+// Every row whose objective equals its cell's maximum competes for the cell: the lowest row wins
+// (first in batch wins ties, _grid_archive.py:693-696). A row holding the maximum of its cell is
+// insertable by construction (insertability depends on (objective, cell) only), and cells without
+// insertable rows keep best == 0, which is no finite objective's key -- so `status` is not read.
 template <typename T>
-__device__ void phase_resolve(const InsertArgs<T>& a) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x) {
-    if (a.status[i] == 0) continue;
-    Cell* cell = &a.s.cell[a.idx[i]];
-    if (ord_key((double)a.obj[i]) == cell->best) atomicMin(&cell->win, (int32_t)i);  // first in batch wins
+__device__ void phase_mark_winner(const InsertArgs<T>& a) {
+  const int64_t S = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < a.B; base += kRows * S) {
+    int32_t c[kRows];
+    T o[kRows];
+    unsigned long long best[kRows];
+#pragma unroll
+    for (int u = 0; u < kRows; ++u) {
+      const int64_t i = base + u * S;
+      c[u] = -1;
+      if (i < a.B) {
+        c[u] = a.idx[i];
+        o[u] = a.obj[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRows; ++u)
+      if (c[u] >= 0) best[u] = a.s.cell[c[u]].best;
+#pragma unroll
+    for (int u = 0; u < kRows; ++u)
+      if (c[u] >= 0 && ord_key((double)o[u]) == best[u]) atomicMin(&a.s.cell[c[u]].win, (int32_t)(base + u * S));
   }
 }
 
@@ -314,19 +379,19 @@ __device__ void phase_cleanup(const InsertArgs<T>& a) {  // validation failed: l
   }
 }
 
+// list mode (cells >> rows): winners append (row, cell) to the compact list, one global atomic per
+// kThreads rows
 template <typename T>
-__device__ void phase_select(const InsertArgs<T>& a, bool use_win, uint32_t* s_cnt, uint32_t* s_base) {
+__device__ void phase_select(const InsertArgs<T>& a, uint32_t* s_cnt, uint32_t* s_base) {
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   constexpr int NW = kThreads / 32;
-  // block-wide append: one global atomic per kThreads rows
   for (int64_t b0 = (int64_t)blockIdx.x * kThreads; b0 < a.B; b0 += (int64_t)gridDim.x * kThreads) {
     const int64_t i = b0 + threadIdx.x;
     int32_t c = 0;
     bool iswin = false;
     if (i < a.B && a.status[i] != 0) {
       c = a.idx[i];
-      const Cell* cell = &a.s.cell[c];
-      iswin = use_win ? (cell->win == (int32_t)i) : (ord_key((double)a.obj[i]) == cell->best);
+      iswin = a.s.cell[c].win == (int32_t)i;
     }
     const unsigned m = __ballot_sync(0xffffffffu, iswin);
     if (lane == 0) s_cnt[wi] = __popc(m);
@@ -347,147 +412,316 @@ __device__ void phase_select(const InsertArgs<T>& a, bool use_win, uint32_t* s_c
   }
 }
 
-// ---- phase 4: one thread per winner --------------------------------------------------------------
+// ---- phase 4 ----------------------------------------------------------------------------------
+// What a winner does to its cell (threshold, objective, occupancy, objective-sum delta); returns through
+// the accumulators. `cell` is the record before cleaning.
 template <typename T>
-__device__ void phase_update(const InsertArgs<T>& a, bool use_win, double (*sh_d)[kThreads / 32], uint32_t* sh_n,
-                             unsigned long long* sh_k) {
-  const InsertState* g = a.s.g;
-  const int64_t W = g->n_winners;
-  const bool mae = a.mae;
-  const int lane = threadIdx.x & 31;
-  const double batch_absmax = __longlong_as_double((long long)g->absmax_bits);
-  const BinConst bc = make_bins(batch_absmax + g->store_absmax, a.B);
-  FxConst fx;
-  if (mae) fx = make_fx(batch_absmax, a.B);
+struct UpdateAcc {
   double d0 = 0.0, d1 = 0.0, d2 = 0.0;
   uint32_t nnew = 0;
   unsigned long long kbest = 0ull;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < W; t += (int64_t)gridDim.x * blockDim.x) {
-    const int2 rc = a.s.wlist[t];
-    const int32_t c = rc.y;
-    const T o = a.obj[rc.x];
-    const T tc = a.store_thr[c];
-    const bool occ = (tc == tc);
-    const T old_obj = occ ? a.store_obj[c] : (T)0;
-    T newthr;
-    if (!mae) {
-      newthr = o;  // :663-665
-    } else {       // _compute_thresholds, :473-516 (fp64 arithmetic after NumPy promotion)
-      const Cell cell = a.s.cell[c];
-      double S;
-      uint32_t kc;
-      fx_read(cell, fx, S, kc);
-      S = (double)(T)S;
-      const double k = (double)kc;
-      const double tcell = (double)(occ ? tc : a.tmin);
-      const double ratio = powi((double)((T)1 - a.lr), kc);
-      newthr = (T)__dadd_rn(__dmul_rn(ratio, tcell), __dmul_rn(__ddiv_rn(S, k), __dsub_rn(1.0, ratio)));
-    }
-    a.store_thr[c] = newthr;
-    a.store_obj[c] = o;
-    if (!occ) {
-      a.occupied[c] = 1;
-      atomicOr(&a.s.newmask[c >> 5], 1u << (c & 31));
-      ++nnew;
-    }
-    double h0, h1, h2;
-    bin_split((double)(T)(o - old_obj), bc, h0, h1, h2);  // :707-710
-    d0 += h0;
-    d1 += h1;
-    d2 += h2;
-    const unsigned long long k2 = ord_key((double)o);
-    kbest = k2 > kbest ? k2 : kbest;
-    // scratch back to its clean state
-    Cell z;
-    z.best = 0ull;
-    z.w0 = z.w1 = 0ll;
-    z.win = INT32_MAX;
-    z.cnt = 0u;
-    a.s.cell[c] = z;
+};
+
+template <typename T>
+__device__ __forceinline__ void update_cell(const InsertArgs<T>& a, int32_t c, T o, const Cell& cell, bool mae,
+                                            const FxConst& fx, const BinConst& bc, UpdateAcc<T>& acc) {
+  const T tc = a.store_thr[c];
+  const bool occ = (tc == tc);
+  const T old_obj = occ ? a.store_obj[c] : (T)0;
+  T newthr;
+  if (!mae) {
+    newthr = o;  // :663-665
+  } else {       // _compute_thresholds, :473-516 (fp64 arithmetic after NumPy promotion)
+    double S;
+    uint32_t kc;
+    fx_read(cell, fx, S, kc);
+    S = (double)(T)S;
+    const double k = (double)kc;
+    const double tcell = (double)(occ ? tc : a.tmin);
+    const double ratio = powi((double)((T)1 - a.lr), kc);
+    newthr = (T)__dadd_rn(__dmul_rn(ratio, tcell), __dmul_rn(__ddiv_rn(S, k), __dsub_rn(1.0, ratio)));
   }
-  // warp -> block -> global accumulation (bins add exactly, so the grouping does not matter)
+  a.store_thr[c] = newthr;
+  a.store_obj[c] = o;
+  if (!occ) {
+    a.occupied[c] = 1;
+    atomicOr(&a.s.newmask[c >> 5], 1u << (c & 31));
+    ++acc.nnew;
+  }
+  double h0, h1, h2;
+  bin_split((double)(T)(o - old_obj), bc, h0, h1, h2);  // :707-710
+  acc.d0 += h0;
+  acc.d1 += h1;
+  acc.d2 += h2;
+  const unsigned long long k2 = ord_key((double)o);
+  acc.kbest = k2 > acc.kbest ? k2 : acc.kbest;
+  Cell z;  // scratch back to its clean state
+  z.best = 0ull;
+  z.w0 = z.w1 = 0ll;
+  z.win = INT32_MAX;
+  z.cnt = 0u;
+  a.s.cell[c] = z;
+}
+
+// warp -> block -> global accumulation (bins add exactly, so the grouping does not matter)
+template <typename T>
+__device__ void update_reduce(const InsertArgs<T>& a, UpdateAcc<T> acc, double (*sh_d)[kThreads / 32], uint32_t* sh_n,
+                              unsigned long long* sh_k) {
+  const int lane = threadIdx.x & 31;
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
-    d0 += __shfl_down_sync(0xffffffffu, d0, o2);
-    d1 += __shfl_down_sync(0xffffffffu, d1, o2);
-    d2 += __shfl_down_sync(0xffffffffu, d2, o2);
-    nnew += __shfl_down_sync(0xffffffffu, nnew, o2);
-    unsigned long long ok = __shfl_down_sync(0xffffffffu, kbest, o2);
-    kbest = ok > kbest ? ok : kbest;
+    acc.d0 += __shfl_down_sync(0xffffffffu, acc.d0, o2);
+    acc.d1 += __shfl_down_sync(0xffffffffu, acc.d1, o2);
+    acc.d2 += __shfl_down_sync(0xffffffffu, acc.d2, o2);
+    acc.nnew += __shfl_down_sync(0xffffffffu, acc.nnew, o2);
+    const unsigned long long ok = __shfl_down_sync(0xffffffffu, acc.kbest, o2);
+    acc.kbest = ok > acc.kbest ? ok : acc.kbest;
   }
   const int wi = threadIdx.x >> 5;
+  __syncthreads();
   if (lane == 0) {
-    sh_d[0][wi] = d0;
-    sh_d[1][wi] = d1;
-    sh_d[2][wi] = d2;
-    sh_n[wi] = nnew;
-    sh_k[wi] = kbest;
+    sh_d[0][wi] = acc.d0;
+    sh_d[1][wi] = acc.d1;
+    sh_d[2][wi] = acc.d2;
+    sh_n[wi] = acc.nnew;
+    sh_k[wi] = acc.kbest;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int k = 1; k < kThreads / 32; ++k) {
-      d0 += sh_d[0][k];
-      d1 += sh_d[1][k];
-      d2 += sh_d[2][k];
-      nnew += sh_n[k];
-      kbest = sh_k[k] > kbest ? sh_k[k] : kbest;
+      acc.d0 += sh_d[0][k];
+      acc.d1 += sh_d[1][k];
+      acc.d2 += sh_d[2][k];
+      acc.nnew += sh_n[k];
+      acc.kbest = sh_k[k] > acc.kbest ? sh_k[k] : acc.kbest;
     }
-    if (d0 != 0.0) atomicAdd(&a.s.g->dsum[0], d0);
-    if (d1 != 0.0) atomicAdd(&a.s.g->dsum[1], d1);
-    if (d2 != 0.0) atomicAdd(&a.s.g->dsum[2], d2);
-    if (nnew) atomicAdd(&a.s.g->n_new, nnew);
-    if (kbest) atomicMax(&a.s.g->gbest_key, kbest);
+    if (acc.d0 != 0.0) atomicAdd(&a.s.g->dsum[0], acc.d0);
+    if (acc.d1 != 0.0) atomicAdd(&a.s.g->dsum[1], acc.d1);
+    if (acc.d2 != 0.0) atomicAdd(&a.s.g->dsum[2], acc.d2);
+    if (acc.nnew) atomicAdd(&a.s.g->n_new, acc.nnew);
+    if (acc.kbest) atomicMax(&a.s.g->gbest_key, acc.kbest);
   }
   __syncthreads();
 }
 
-// ---- phase 5: row scatter of the winners (_array_store.py:605-608) --------------------------------
-// Every (winner, 16-byte chunk) pair is one work item of a flat grid-stride loop, four loads in
-// flight per thread: a plain HBM stream of 2 * row_bytes per winner.
-__device__ void phase_copy(const FieldCopy& fc, const Scratch& s) {
-  const int64_t W = s.g->n_winners;
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  for (int f = 0; f < fc.n; ++f) {
-    const int vec = fc.vec[f];
-    const int64_t rb = fc.row_bytes[f];
-    const char* __restrict__ src = fc.src[f];
-    char* __restrict__ dst = fc.dst[f];
-    const int64_t nch = rb / vec;
-    const int64_t total = W * nch;
-    if (vec == 16) {
-      for (int64_t base = tid; base < total; base += 4 * nthreads) {
-        uint4 v[4];
-        int64_t doff[4];
+// list mode: one thread per winner
+template <typename T>
+__device__ void phase_update_list(const InsertArgs<T>& a, double (*sh_d)[kThreads / 32], uint32_t* sh_n,
+                                  unsigned long long* sh_k) {
+  const InsertState* g = a.s.g;
+  const int64_t W = g->n_winners;
+  const bool mae = a.mae;
+  const double batch_absmax = __longlong_as_double((long long)g->absmax_bits);
+  const BinConst bc = make_bins(batch_absmax + g->store_absmax, a.B);
+  FxConst fx;
+  if (mae) fx = make_fx(batch_absmax, a.B);
+  UpdateAcc<T> acc;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < W; t += (int64_t)gridDim.x * blockDim.x) {
+    const int2 rc = a.s.wlist[t];
+    const Cell cell = a.s.cell[rc.y];
+    update_cell<T>(a, rc.y, a.obj[rc.x], cell, mae, fx, bc, acc);
+  }
+  update_reduce<T>(a, acc, sh_d, sh_n, sh_k);
+}
+
+// cell mode: one thread per CELL, everything coalesced. The winner's objective is decoded from the cell's
+// key, its row comes from `win`; the (row, cell) list it emits is sorted by cell within each CTA tile, so
+// the row copy writes the store in nearly ascending address order.
+template <typename T>
+__device__ void phase_update_cells(const InsertArgs<T>& a, double (*sh_d)[kThreads / 32], uint32_t* sh_n,
+                                   unsigned long long* sh_k, uint32_t* s_cnt, uint32_t* s_base) {
+  const InsertState* g = a.s.g;
+  const bool mae = a.mae;
+  const double batch_absmax = __longlong_as_double((long long)g->absmax_bits);
+  const BinConst bc = make_bins(batch_absmax + g->store_absmax, a.B);
+  FxConst fx;
+  if (mae) fx = make_fx(batch_absmax, a.B);
+  UpdateAcc<T> acc;
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  constexpr int NW = kThreads / 32;
+  for (int64_t c0 = (int64_t)blockIdx.x * kThreads; c0 < a.N; c0 += (int64_t)gridDim.x * kThreads) {
+    const int64_t c = c0 + threadIdx.x;
+    Cell cell;
+    cell.best = 0ull;
+    if (c < a.N) cell = a.s.cell[c];
+    const bool has = cell.best != 0ull;
+    if (has) update_cell<T>(a, (int32_t)c, (T)ord_unkey(cell.best), cell, mae, fx, bc, acc);
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    if (lane == 0) s_cnt[wi] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int64_t item = base + u * nthreads;
-          doff[u] = -1;
-          if (item < total) {
-            const int64_t wn = item / nch, ch = item - wn * nch;
-            const int2 rc = s.wlist[wn];
-            v[u] = __ldcs(reinterpret_cast<const uint4*>(src + (int64_t)rc.x * rb + ch * 16));
-            doff[u] = (int64_t)rc.y * rb + ch * 16;
-          }
-        }
+      for (int k = 0; k < NW; ++k) {
+        const uint32_t n = s_cnt[k];
+        s_cnt[k] = tot;
+        tot += n;
+      }
+      *s_base = tot ? atomicAdd(&a.s.g->n_winners, tot) : 0u;
+    }
+    __syncthreads();
+    if (has) a.s.wlist[*s_base + s_cnt[wi] + __popc(m & ((1u << lane) - 1u))] = make_int2(cell.win, (int32_t)c);
+    __syncthreads();
+  }
+  update_reduce<T>(a, acc, sh_d, sh_n, sh_k);
+}
+
+// ---- phase 5: row scatter of the winners (_array_store.py:605-608) --------------------------------
+// TMA bulk copies: a lane moves one piece of a winner row (a whole row up to 2 KB) global -> shared
+// (cp.async.bulk, completion on the warp's mbarrier) and shared -> global (bulk store group). No
+// registers hold data in flight, so each SM keeps kCopyWarps x kSlotBytes per CTA outstanding --
+// about three times what register staging at this occupancy could -- and the phase is a plain HBM
+// stream of 2 * row_bytes per winner. Fields whose rows are not 16-byte aligned take the scalar path.
+constexpr int kCopyWarps = 4;
+constexpr int kSlotBytes = 24 * 1024;
+constexpr int kPieceMax = 2048;
+constexpr int kCopySmem = kCopyWarps * kSlotBytes;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+
+constexpr int kBulkMinRow = 256;  // rows shorter than this are cheaper through registers
+
+__device__ __forceinline__ bool is_bulk_field(const FieldCopy& fc, int f) {
+  return fc.vec[f] == 16 && fc.row_bytes[f] >= kBulkMinRow;
+}
+
+// small / unaligned rows: a group of 2^k threads (the smallest power of two covering the row's chunks, at
+// most a warp) moves one row, four rows in flight per thread; `tid` of `nthreads` is the caller's team
+__device__ void copy_rows_small(const FieldCopy& fc, int f, const Scratch& s, int64_t W, int64_t tid,
+                                int64_t nthreads) {
+  const int vec = fc.vec[f];
+  const int64_t rb = fc.row_bytes[f];
+  const char* __restrict__ src = fc.src[f];
+  char* __restrict__ dst = fc.dst[f];
+  const int64_t nch = rb / vec;
+  int lg = 0;
+  while ((1 << lg) < nch && lg < 5) ++lg;
+  const int gsz = 1 << lg;
+  const int sub = (int)(tid & (gsz - 1));
+  const int64_t grp = tid >> lg, ngrp = nthreads >> lg;
+  if (ngrp == 0) return;
+  for (int64_t w0 = grp; w0 < W; w0 += 4 * ngrp) {
+    int2 rc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t w = w0 + u * ngrp;
+      rc[u] = w < W ? s.wlist[w] : make_int2(-1, -1);
+    }
+    for (int64_t ch = sub; ch < nch; ch += gsz) {
+      if (vec == 16) {
+        uint4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (doff[u] >= 0) *reinterpret_cast<uint4*>(dst + doff[u]) = v[u];
-      }
-    } else {
-      for (int64_t item = tid; item < total; item += nthreads) {
-        const int64_t wn = item / nch, ch = item - wn * nch;
-        const int2 rc = s.wlist[wn];
-        const char* sp = src + (int64_t)rc.x * rb + ch * vec;
-        char* dp = dst + (int64_t)rc.y * rb + ch * vec;
-        if (vec == 8)
-          *reinterpret_cast<uint2*>(dp) = *reinterpret_cast<const uint2*>(sp);
-        else if (vec == 4)
-          *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
-        else
-          *dp = *sp;
+          if (rc[u].x >= 0) v[u] = __ldcs(reinterpret_cast<const uint4*>(src + (int64_t)rc[u].x * rb) + ch);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (rc[u].x >= 0) __stcs(reinterpret_cast<uint4*>(dst + (int64_t)rc[u].y * rb) + ch, v[u]);
+      } else if (vec == 8) {
+        uint2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (rc[u].x >= 0) v[u] = *(reinterpret_cast<const uint2*>(src + (int64_t)rc[u].x * rb) + ch);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (rc[u].x >= 0) *(reinterpret_cast<uint2*>(dst + (int64_t)rc[u].y * rb) + ch) = v[u];
+      } else if (vec == 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (rc[u].x >= 0)
+            *(reinterpret_cast<uint32_t*>(dst + (int64_t)rc[u].y * rb) + ch) =
+                *(reinterpret_cast<const uint32_t*>(src + (int64_t)rc[u].x * rb) + ch);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (rc[u].x >= 0) dst[(int64_t)rc[u].y * rb + ch] = src[(int64_t)rc[u].x * rb + ch];
       }
     }
   }
+}
+
+__device__ void phase_copy(const FieldCopy& fc, const Scratch& s, unsigned char* slots, uint64_t* mbar,
+                           uint32_t& parity) {
+  const int64_t W = s.g->n_winners;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bool any_bulk = false;
+  for (int f = 0; f < fc.n; ++f) any_bulk |= is_bulk_field(fc, f);
+  if (!any_bulk || warp >= kCopyWarps) {
+    // the register path: every warp when no field is bulk, otherwise the warps the bulk copy leaves idle
+    const int team = any_bulk ? kThreads - 32 * kCopyWarps : kThreads;
+    const int64_t tid = (int64_t)blockIdx.x * team + (threadIdx.x - (any_bulk ? 32 * kCopyWarps : 0));
+    for (int f = 0; f < fc.n; ++f)
+      if (!is_bulk_field(fc, f)) copy_rows_small(fc, f, s, W, tid, (int64_t)gridDim.x * team);
+    return;
+  }
+  for (int f = 0; f < fc.n; ++f) {
+    if (!is_bulk_field(fc, f)) continue;
+    const int64_t rb = fc.row_bytes[f];
+    const char* __restrict__ src = fc.src[f];
+    char* __restrict__ dst = fc.dst[f];
+    const int piece = (int)(rb < kPieceMax ? rb : kPieceMax);
+    const int64_t ppr = (rb + piece - 1) / piece;  // pieces per row
+    const int L = kSlotBytes / piece < 32 ? kSlotBytes / piece : 32;
+    const int64_t total = W * ppr;
+    unsigned char* slot = slots + warp * kSlotBytes + lane * piece;
+    uint64_t* bar = &mbar[warp];
+    const int64_t gw = (int64_t)blockIdx.x * kCopyWarps + warp, ngw = (int64_t)gridDim.x * kCopyWarps;
+    for (int64_t it0 = gw * L; it0 < total; it0 += ngw * L) {
+      const int64_t item = it0 + lane;
+      const bool active = lane < L && item < total;
+      uint32_t len = 0;
+      const char* sp = nullptr;
+      char* dp = nullptr;
+      if (active) {
+        const int64_t w = ppr == 1 ? item : item / ppr;
+        const int64_t off = (item - w * ppr) * piece;
+        len = (uint32_t)(rb - off < piece ? rb - off : piece);
+        const int2 rc = s.wlist[w];
+        sp = src + (int64_t)rc.x * rb + off;
+        dp = dst + (int64_t)rc.y * rb + off;
+      }
+      const uint32_t round_bytes = __reduce_add_sync(0xffffffffu, len);
+      if (lane == 0) mbar_expect_tx(bar, round_bytes);
+      __syncwarp();
+      if (active) bulk_g2s(slot, sp, len, bar);
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      if (active) bulk_s2g(dp, slot, len);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the slot may be refilled
+      __syncwarp();
+    }
+  }
+  // bulk stores are complete (not just read) and ordered before the generic-proxy accesses that follow
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 // ---- phase 6 ----------------------------------------------------------------------------------
@@ -644,8 +878,9 @@ __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool 
     g.gbest_key = 0ull;
     g.absmax_bits = 0ull;
     g.best_cell = INT32_MAX;
-    g.n_insertable = g.n_new = g.flags = g.tie_flag = g.n_winners = 0u;
+    g.n_insertable = g.n_new = g.flags = g.n_winners = 0u;
     g.dsum[0] = g.dsum[1] = g.dsum[2] = 0.0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g.t_phase[8]));
     *gp = g;
   }
 }
@@ -659,42 +894,72 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
                                                            const __grid_constant__ FieldCopy fc, int phase_lo,
                                                            int phase_hi) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ uint32_t sh_u[kThreads / 32 + 32];
+  extern __shared__ __align__(128) unsigned char copy_slots[];
+  __shared__ uint64_t copy_bar[kCopyWarps];
+  uint32_t copy_parity = 0;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kCopyWarps; ++k) mbar_init(&copy_bar[k], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  __shared__ uint32_t sh_u[64];
   __shared__ uint32_t sh_base;
   __shared__ double sh_d[3][kThreads / 32];
   __shared__ unsigned long long sh_k[kThreads / 32];
   const InsertState* g = a.s.g;
   const bool mae = a.mae;
   const int64_t n_before = g->n_occupied;  // CTA 0 advances it in the publish phase
-
+  auto stamp = [&](int k) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.s.g->t_phase[k] = t;
+    }
+  };
+  if (phase_lo <= 0) stamp(0);
   if (phase_lo <= 0 && mae) {
-    phase_absmax<T>(a);
+    phase_absmax<T>(a, &sh_d[0][0]);
     grid.sync();
   }
+  if (phase_lo <= 0) stamp(1);
   if (phase_lo <= 1 && phase_hi >= 1) {
-    phase_classify<T, MT, D, FUSED>(a, gp);
+    phase_classify<T, MT, D, FUSED>(a, gp, &sh_d[0][0], sh_u);
     grid.sync();
   }
+  if (phase_lo <= 1) stamp(2);
   // the globals below were last written before a barrier / launch boundary: uniform over the grid
   const bool failed = g->flags != 0u;
   const bool any = g->n_insertable != 0u;
-  const bool use_win = g->tie_flag != 0u;
   const bool committed = any && !failed;
-  if (phase_lo <= 2 && phase_hi >= 2 && committed && use_win) {
-    phase_resolve<T>(a);
+  // cell mode: the update runs over the cells (coalesced) and emits a cell-sorted winner list; list mode
+  // (archives much larger than the batch) never touches cells the batch did not
+  const bool cell_mode = a.N <= 16 * a.B;
+  if (phase_lo <= 2 && phase_hi >= 2 && committed) {
+    phase_mark_winner<T>(a);
     grid.sync();
   }
-  if (phase_lo <= 3 && phase_hi >= 3 && any) {
+  if (phase_lo <= 2) stamp(3);
+  if (phase_lo <= 3 && phase_hi >= 3 && any && (failed || !cell_mode)) {
     if (failed)
       phase_cleanup<T>(a);
     else
-      phase_select<T>(a, use_win, sh_u, &sh_base);
+      phase_select<T>(a, sh_u, &sh_base);
     grid.sync();
   }
-  if (phase_lo <= 4 && phase_hi >= 4 && committed) phase_update<T>(a, use_win, sh_d, sh_u, sh_k);
-  if (phase_lo <= 5 && phase_hi >= 5 && committed && fc.n > 0) phase_copy(fc, a.s);
+  if (phase_lo <= 3) stamp(4);
+  if (phase_lo <= 4 && phase_hi >= 4 && committed) {
+    if (cell_mode) {
+      phase_update_cells<T>(a, sh_d, sh_u + 32, sh_k, sh_u, &sh_base);
+      if (phase_hi >= 5) grid.sync();  // the winner list is complete only now
+    } else {
+      phase_update_list<T>(a, sh_d, sh_u + 32, sh_k);
+    }
+  }
+  if (phase_lo <= 4) stamp(5);
+  if (phase_lo <= 5 && phase_hi >= 5 && committed && fc.n > 0) phase_copy(fc, a.s, copy_slots, copy_bar, copy_parity);
   if (phase_hi < 6) return;
   if (phase_lo <= 5) grid.sync();
+  stamp(6);
   const unsigned long long gk = g->gbest_key, pk = g->obj_max_key;
   const bool new_record = committed && gk != 0ull && (pk == 0ull || gk > pk);
   const bool any_new = committed && g->n_new != 0u;
@@ -702,6 +967,7 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
     phase_best_and_count<T>(a, new_record, any_new, sh_u);
     grid.sync();
   }
+  stamp(7);
   phase_publish<T>(a, fc, committed, new_record, any_new, n_before, sh_u, &sh_base);
 }
 
@@ -725,7 +991,10 @@ static int launch_insert(const InsertArgs<T>& a, const GridParams& gp, const Fie
   static int max_ctas = 0;  // per instantiation
   if (max_ctas == 0) {
     int per_sm = 0, dev = 0, sms = kNumSMs;
-    QD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel<T, MT, D, FUSED>, kThreads, 0));
+    QD_CHECK_CUDA(cudaFuncSetAttribute(insert_kernel<T, MT, D, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kCopySmem));
+    QD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel<T, MT, D, FUSED>, kThreads,
+                                                                kCopySmem));
     QD_CHECK_CUDA(cudaGetDevice(&dev));
     QD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (per_sm < 1) {
@@ -741,7 +1010,7 @@ static int launch_insert(const InsertArgs<T>& a, const GridParams& gp, const Fie
   int lo = part == QD_INSERT_COMMIT ? 5 : 0, hi = part == QD_INSERT_CLASSIFY ? 4 : 7;
   void* params[] = {(void*)&a, (void*)&gp, (void*)&fc, (void*)&lo, (void*)&hi};
   QD_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)insert_kernel<T, MT, D, FUSED>, dim3(grid), dim3(kThreads),
-                                            params, 0, stream));
+                                            params, kCopySmem, stream));
   return check_launch("insert_kernel");
 }
 
@@ -861,6 +1130,16 @@ extern "C" size_t qd_insert_scratch_bytes(int64_t capacity) { return qd::scratch
 
 extern "C" uint32_t* qd_insert_flags_ptr(void* scratch, int64_t capacity) {
   return &qd::carve(scratch, capacity).g->flags;
+}
+
+extern "C" int qd_insert_phase_times(const void* scratch, int64_t capacity, uint64_t* out_ns, void* stream) {
+  using namespace qd;
+  QD_REQUIRE(scratch && out_ns && capacity >= 1, "bad arguments");
+  Scratch s = carve(const_cast<void*>(scratch), capacity);
+  QD_CHECK_CUDA(cudaMemcpyAsync(out_ns, s.g->t_phase, 10 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                (cudaStream_t)stream));
+  QD_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return QD_OK;
 }
 
 extern "C" int qd_insert_scratch_init(void* scratch, int64_t capacity, void* stream) {
