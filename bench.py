@@ -38,6 +38,9 @@ WORKLOAD = {
     "batch": 100_000,
 }
 N_RESIDENT = 16  # distinct batches cycled through: 16 x 10.4 MB = 166 MB > 126 MB L2
+OBJ_DRIFT = 0.05  # objective offset per step: every step keeps inserting (a stationary stream would stop
+                  # improving the archive after the first pass over the resident batches)
+MAX_OBJ_STEPS = 2048  # distinct per-step objective vectors kept resident (0.8 MB each)
 
 
 def make_inputs(seed, n_batches, B=None):
@@ -48,8 +51,7 @@ def make_inputs(seed, n_batches, B=None):
     for j in range(n_batches):
         batches.append(dict(
             solution=rng.uniform(-1, 1, (B, WORKLOAD["solution_dim"])),
-            # rising objectives: a realistic share of every batch keeps inserting
-            objective=rng.standard_normal(B) + 0.05 * j,
+            objective=rng.standard_normal(B),  # + OBJ_DRIFT * step at use
             measures=rng.uniform(-1, 1, (B, WORKLOAD["measure_dim"])),
         ))
     return cen, batches
@@ -102,17 +104,62 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+NCU_TRAFFIC = {"cvt_bucket_kernel": 1_833_984, "insert_kernel_grid_2M": 311_130_624 + 205_896_704}
+
+
+def grid_insert_roofline(torch, dev, peak_hbm):
+    """GridArchive insertion against the HBM roofline (north_star: >= 60 % of HBM peak at 1 GPU): CMA-MAE
+    lr=0.01, 500x500 cells (the grid of configs[2]), n=100, 2M-row batches of uniform measures -- the size at
+    which the insertion is throughput- rather than latency-bound. Algorithmic bytes per SURVEY 8(d):
+    45 B/row + 1 648 B per winner."""
+    from pyribs_b200.archives import GridArchive
+
+    Bg, n = 2_000_000, 100
+    a = GridArchive(solution_dim=n, dims=(500, 500), ranges=[(-1, 1)] * 2, learning_rate=0.01, threshold_min=0.0)
+    g = torch.Generator(device=dev).manual_seed(1)
+    bs = [dict(solution=torch.randn(Bg, n, dtype=torch.float64, device=dev, generator=g),
+               objective=torch.rand(Bg, dtype=torch.float64, device=dev, generator=g) * 100 + 5.0 * j,
+               measures=torch.rand(Bg, 2, dtype=torch.float64, device=dev, generator=g) * 2 - 1) for j in range(3)]
+    for j in range(3):
+        a.add(**bs[j])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 12
+    e0.record()
+    for j in range(iters):
+        a.add(**bs[j % 3])  # 3 x 1.65 GB of inputs: nothing survives in the 126 MB L2 between calls
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    st = a.add(**bs[0])["status"]
+    W = int(torch.unique(a.index_of(bs[0]["measures"])[st != 0]).numel())
+    alg = Bg * 45 + W * (2 * n * 8 + 2 * 2 * 8 + 2 * 8)
+    return {"kernel": "insert_kernel<double, double, 2, fused grid index> (GridArchive.add, one launch per add)",
+            "workload": "GridArchive 500x500, CMA-MAE lr=0.01, n=100, 2M-row batches, uniform measures",
+            "bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak_hbm, "unit": "GB/s", "frac": alg / ms / 1e6 / peak_hbm,
+            "ms_per_add": ms, "insertions_per_s": Bg / ms * 1e3, "winners_per_add": W, "algorithmic_bytes": alg,
+            "traffic": NCU_TRAFFIC.get("insert_kernel_grid_2M"),
+            "note": "row passes are bound by scattered L1/L2 accesses (threshold gather + 3 atomics per row, ~6 L1tex "
+                    "wavefront-cycles per row), the winner-row copy by HBM (TMA bulk, 5.3-5.9 TB/s); DESIGN.md 4.2"}
+
+
 def cpu_reference(cen, batches, steps, warmup, workers):
     """The oracle port (reference algorithm on the CPU). Returns (insertions/s, seconds)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import qd_oracle as O
 
     a = O.make_cvt_oracle(solution_dim=WORKLOAD["solution_dim"], centroids=cen, workers=workers)
+
+    def add(j):  # same drifting objectives as the GPU arm (the vector add is <1 % of a step)
+        b = batches[j % len(batches)]
+        a.add(solution=b["solution"], objective=b["objective"] + OBJ_DRIFT * j, measures=b["measures"])
+
     for j in range(warmup):
-        a.add(**batches[j % len(batches)])
+        add(j)
     t0 = time.perf_counter()
     for j in range(steps):
-        a.add(**batches[(warmup + j) % len(batches)])
+        add(warmup + j)
     dt = time.perf_counter() - t0
     return steps * WORKLOAD["batch"] / dt, dt
 
@@ -143,6 +190,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--search", default="auto", choices=["auto", "tensor", "scan", "bucket"])
+    ap.add_argument("--no-grid", action="store_true", help="skip the GridArchive 2M-row insertion roofline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -174,6 +222,13 @@ def main():
                          data_parallel=world > 1)
     dev_batches = [{k: torch.from_numpy(v).to(dev) for k, v in b.items()} for b in batches]
     pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in batches]
+    # one objective vector per step (drifting upwards), resident on the device and in page-locked host memory
+    n_obj = min(MAX_OBJ_STEPS, args.steps + args.warmup)
+    obj_host = torch.empty((n_obj, B), dtype=torch.float64).pin_memory()
+    for j in range(n_obj):
+        obj_host[j] = torch.from_numpy(batches[j % N_RESIDENT]["objective"]) + OBJ_DRIFT * j
+    obj_dev = obj_host.to(dev)
+    obj_np = obj_host.numpy()
 
     def barrier():
         if world > 1:
@@ -202,7 +257,7 @@ def main():
     # ---- device-resident throughput -------------------------------------------------------
     def step_dev(j):
         b = dev_batches[j % N_RESIDENT]
-        archive.add(b["solution"], b["objective"], b["measures"])
+        archive.add(b["solution"], obj_dev[j % n_obj], b["measures"])
 
     with ClockSampler(local_rank) as clk:
         ms_dev, launches = timed(step_dev, args.steps, args.warmup)
@@ -214,7 +269,7 @@ def main():
 
     def step_e2e(j):
         b = host_batches[j % N_RESIDENT]
-        out = archive.add(b["solution"], b["objective"], b["measures"])
+        out = archive.add(b["solution"], obj_np[j % n_obj], b["measures"])
         assert out["status"].shape[0] == B
 
     ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
@@ -234,23 +289,70 @@ def main():
     except Exception:
         pass
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
-    flops = 2.0 * B * WORKLOAD["centroids"] * WORKLOAD["measure_dim"]
-    ach = flops / (ms_k / args.steps * 1e-3) / 1e12
-    # dram bytes of one cvt_tc_kernel launch from the committed `ncu --set full` capture
-    # (profiles/r01_top_kernels_ncu_full.txt: 2.375 MB read + 768 B written)
-    ncu_traffic = 2_375_424 + 768
-    pairs = float(B) * WORKLOAD["centroids"]
-    roofline = {
-        "kernel": "cvt nearest-centroid search (cvt_tc_kernel + rescoring)", "bound": "tensor", "achieved": ach,
-        "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": ncu_traffic,
-        "note": "d=2: 4 GFLOP of useful contraction per launch; the kernel is bound by the TMEM->register epilogue "
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    C_, d_ = WORKLOAD["centroids"], WORKLOAD["measure_dim"]
+    flops = 2.0 * B * C_ * d_  # the contraction an exhaustive search performs
+    s_k = ms_k / args.steps * 1e-3
+    ach = flops / s_k / 1e12
+    method = {0: "tensor", 1: "scan", 2: "bucket"}[archive._pick_method(B, C_)]
+    if method == "bucket":
+        kernel = "cvt_bucket_kernel<double, 2> (exact nearest centroid through a bucket grid, csrc/cvt_bucket.cu)"
+        note = ("achieved = algorithmic flops of SURVEY 8(d) (2*B*C*d, what an exhaustive search computes) / measured "
+                "kernel time. The bucket grid evaluates ~20 of the 10 000 centroids per query in fp64, so this is work "
+                "avoided, not tensor-pipe utilisation; the kernel itself is a latency-bound gather over an L1/L2-resident "
+                "220 KB structure (hbm view below). The tcgen05 search (--search tensor, the path of the 8-D / 1M-centroid "
+                "configuration) measures 23.7 TFLOP/s algorithmic on this shape (profiles/r01_bench_line_n1.json).")
+        # dram bytes of one launch: profiles/r01_cvt_bucket_insert_ncu_full.txt
+        ncu_traffic = NCU_TRAFFIC.get("cvt_bucket_kernel")
+    else:
+        kernel = "cvt nearest-centroid search (cvt_tc_kernel + rescoring)" if method == "tensor" else "cvt_scan_fp64_kernel"
+        note = ("d=2: 4 GFLOP of useful contraction per launch; the tcgen05 kernel is bound by the TMEM->register epilogue "
                 "that must inspect every one of the B*C accumulators (measured tcgen05.ld ceiling 96 fp32/clk/SM, "
-                "tools/tmem_bw.cu), not by the tensor pipe",
-        "pairs_per_s": pairs / (ms_k / args.steps * 1e-3),
-        "tmem_read_ceiling_pairs_per_s": 96 * 148 * 1.965e9,
+                "tools/tmem_bw.cu), not by the tensor pipe")
+        ncu_traffic = 2_375_424 + 768 if method == "tensor" else None
+    alg_bytes = (B + C_) * d_ * 8 + 4 * B
+    roofline = {
+        "kernel": kernel, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+        "traffic": ncu_traffic, "note": note,
         "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1590",
         "flops_per_launch": flops, "ms_per_search": ms_k / args.steps, "launches_per_search": k_launches / args.steps,
+        "queries_per_s": B / s_k,
+        "hbm_view": {"algorithmic_bytes": alg_bytes, "achieved_GBps": alg_bytes / s_k / 1e9, "peak_GBps": peak_hbm,
+                     "frac": alg_bytes / s_k / 1e9 / peak_hbm},
     }
+
+    # ---- the other kernel of the step (insert_kernel) on this workload, from its own phase timers ----
+    secondary = []
+    try:
+        import ctypes as C_t
+
+        from pyribs_b200.archives._device_store import current_stream_ptr
+
+        archive.clear()
+        for j in range(8):
+            step_dev(j)
+        st = archive.add(dev_batches[8]["solution"], obj_dev[8 % n_obj], dev_batches[8]["measures"])["status"]
+        t = (C_t.c_uint64 * 10)()
+        _lib.check(_lib.lib().qd_insert_phase_times(archive._store._scratch.data_ptr(), archive._store.capacity, t,
+                                                    current_stream_ptr()))
+        ins_us = (t[8] - t[0]) / 1e3
+        idx4 = archive.index_of(dev_batches[8]["measures"])
+        W = int(torch.unique(idx4[st != 0]).numel())
+        n_ = WORKLOAD["solution_dim"]
+        ins_bytes = B * (4 + 8) + B * (8 + 1) + B * (4 + 8) + W * (2 * n_ * 8 + 2 * d_ * 8) + W * 16
+        secondary.append({"kernel": "insert_kernel (persistent cooperative, csrc/insert.cu) on this workload",
+                          "bound": "hbm", "achieved": ins_bytes / ins_us / 1e3, "peak": peak_hbm, "unit": "GB/s",
+                          "frac": ins_bytes / ins_us / 1e3 / peak_hbm, "us_per_launch": ins_us, "winners": W,
+                          "algorithmic_bytes": ins_bytes,
+                          "note": "100k rows are far too few to fill a B200: 8 phases + grid barriers in 6-8 us"})
+    except Exception as e:  # noqa: BLE001
+        secondary.append({"kernel": "insert_kernel", "error": f"{type(e).__name__}: {e}"})
+    if world == 1 and rank == 0 and not args.no_grid:
+        try:
+            secondary.append(grid_insert_roofline(torch, dev, peak_hbm))
+        except Exception as e:  # noqa: BLE001
+            secondary.append({"kernel": "insert_kernel (GridArchive 2M rows)", "error": f"{type(e).__name__}: {e}"})
+    roofline["secondary"] = secondary
 
     line = {
         "metric": "archive insertions/sec (batch add)",
@@ -268,7 +370,8 @@ def main():
         "config": {**WORKLOAD, "global_batch": world * B, "search": args.search,
                    "parallelism": f"dp{world}: batch-sharded search + all-gather + replicated insert" if world > 1
                    else "single GPU",
-                   "l2": f"{N_RESIDENT} resident batches cycled (166 MB > 126 MB L2)"},
+                   "l2": f"{N_RESIDENT} resident batches cycled (166 MB > 126 MB L2)",
+                   "objective": f"standard normal + {OBJ_DRIFT} per step (every step keeps inserting)"},
         "clocks": clocks,
         "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "insertions/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},

@@ -58,9 +58,11 @@ def c2():
     ph2, tot2 = phase_times(a)
     print(json.dumps({"case": "C2 add", "e2e_us": e2e_us, "device_in_sync_us": dev_sync_us, "device_in_async_us": dev_async_us,
                       "host_enqueue_us": t_enq, "insert_phases_us_host_batch": ph, "insert_phases_us_device_batch": ph2, "insert_total_us": tot2}))
-    pr = cProfile.Profile(); pr.enable()
-    for j in range(300): a.add(**host[j % 8])
-    pr.disable(); s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(18); print(s.getvalue()[:3500])
+    for label, bs in (("numpy", host), ("device", dev)):
+        pr = cProfile.Profile(); pr.enable()
+        for j in range(300): a.add(**bs[j % 8])
+        pr.disable(); torch.cuda.synchronize(); s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(22)
+        print("== cProfile", label); print(s.getvalue()[:4200])
 
 def grid_large():
     rng = np.random.default_rng(0); B, n = 2_000_000, 100
