@@ -21,12 +21,13 @@
 //
 // Phases (B rows, W winners, N cells):
 //   0 absmax    CMA-MAE only: max |objective| fixes the fixed-point scale of the sums
-//   1 classify  (grid: fused with index_of) status / value vs the PRE-batch store; best; sums;
-//               an equal-objective collision in a cell raises the tie flag
-//   2 resolve   only after a tie: first-in-batch wins (_grid_archive.py:693-696)
-//   3 select    winner of every touched cell -> compact (row, cell) list
-//   4 update    one thread per winner: threshold, objective, occupancy, objective-sum delta
-//   5 copy      flat HBM stream of the winners' row fields into the store
+//   1 classify  (grid: fused with index_of) status / value vs the PRE-batch store; best; sums
+//   2 mark      rows holding their cell's maximum: atomicMin(row) = first in batch wins
+//               (_grid_archive.py:693-696)
+//   3 select    list mode only (cells >> rows): winners -> compact (row, cell) list
+//   4 update    cell mode: one thread per cell, coalesced, emits the winner list sorted by cell;
+//               list mode: one thread per winner. Threshold, objective, occupancy, sum delta
+//   5 copy      TMA bulk copies of the winners' row fields into the store (HBM stream)
 //   6 best/cnt  lowest winning cell holding the new best objective; new-cell bitmap counts
 //   7 publish   occupied_list append in ascending cell order (_array_store.py:586-600), stats,
 //               best-elite snapshot, qd_add_result; re-arms the per-call globals
