@@ -257,6 +257,39 @@ int qd_sym_max(int64_t n, double* A /*[dev] n x n*/, void* stream);          /* 
 int qd_sym_eigh_batched(int64_t n, int64_t batch, const double* A /*[dev] batch x n x n*/,
                         double* eig /*[dev] batch x n*/, double* V /*[dev] batch x n x n*/,
                         int* sweeps /*[dev] batch or NULL*/, void* stream);
+/* CMA-ES pool: E strategies of identical (n, lambda) whose state is stacked in device memory; every
+ * kernel is batched over the emitters (the many-emitter regime: ribs/schedulers/_scheduler.py:180-213,
+ * 361-412 loops ask/tell over the emitters in Python). Arithmetic identical to the single-strategy entry
+ * points below, so a pooled strategy and a stand-alone one fed the same normals agree bit for bit.
+ * The covariance is updated in place. `ids` selects the emitters an operation applies to. */
+typedef struct qd_cma_pool {
+  int64_t E, n, lam;
+  double* mean;     /* [dev] E x n */
+  double* pc;       /* [dev] E x n */
+  double* ps;       /* [dev] E x n */
+  double* C;        /* [dev] E x n x n */
+  double* B;        /* [dev] E x n x n eigenvectors (columns) */
+  double* eig;      /* [dev] E x n */
+  double* T;        /* [dev] E x n x n  B sqrt(eig) */
+  double* invsqrt;  /* [dev] E x n x n */
+  double* status;   /* [dev] E x 8 */
+  double* new_mean; /* [dev] E x n scratch */
+  double* ws;       /* [dev] E x ws_stride scratch, ws_stride >= n + 8 */
+  double* X;        /* [dev] E x lam x n samples of the last ask */
+  double* z;        /* [dev] E x lam x n unit normals of the last ask */
+  int64_t ws_stride;
+} qd_cma_pool;
+/* lazy eigensystem refresh (_cma_es.py:51-82) of the listed emitters, n <= 150 */
+int qd_cma_pool_refresh(const qd_cma_pool* pool /*[host]*/, const int32_t* ids /*[dev] n_ids*/, int n_ids,
+                        void* stream);
+/* ask of every emitter; emitter e draws from Philox stream (seeds[e], offsets[e]) -- the stream a
+ * stand-alone strategy with that seed would use. seeds == NULL: pool->z was filled by the caller. */
+int qd_cma_pool_ask(const qd_cma_pool* pool /*[host]*/, const uint64_t* seeds /*[dev] E*/,
+                    const uint64_t* offsets /*[dev] E*/, void* stream);
+/* tell of the listed emitters: rank / w are E x lam (first mu[e] entries of row e used), sc E entries */
+int qd_cma_pool_tell(const qd_cma_pool* pool /*[host]*/, const int32_t* ids /*[dev] n_ids*/, int n_ids,
+                     const int64_t* rank /*[dev]*/, const double* w /*[dev]*/, const int64_t* mu /*[dev] E*/,
+                     const qd_cma_scalars* sc /*[dev] E*/, void* stream);
 int qd_cma_transform(int64_t n, const double* Bmat, const double* eigvals, double* T, void* stream); /* T = B*sqrt(eig) */
 int qd_cma_invsqrt(int64_t n, const double* Bmat, const double* eigvals, double* invsqrt, void* stream);
 int qd_cma_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,

@@ -56,6 +56,12 @@ class Store(C.Structure):
     ]
 
 
+class CmaPool(C.Structure):
+    _fields_ = [("E", C.c_int64), ("n", C.c_int64), ("lam", C.c_int64)] + [
+        (k, C.c_void_p) for k in ("mean", "pc", "ps", "C", "B", "eig", "T", "invsqrt", "status", "new_mean", "ws", "X", "z")
+    ] + [("ws_stride", C.c_int64)]
+
+
 class CmaScalars(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("cc", "cs", "c1", "cmu", "mueff", "damps", "wsum", "hsig_exp")]
 
@@ -101,6 +107,9 @@ PROTOTYPES = {
     "qd_sep_tell": (_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(CmaScalars), _vp, _vp]),
     "qd_sym_max": (_int, [_i64, _vp, _vp]),
     "qd_sym_eigh_batched": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "qd_cma_pool_refresh": (_int, [C.POINTER(CmaPool), _vp, _int, _vp]),
+    "qd_cma_pool_ask": (_int, [C.POINTER(CmaPool), _vp, _vp, _vp]),
+    "qd_cma_pool_tell": (_int, [C.POINTER(CmaPool), _vp, _int, _vp, _vp, _vp, _vp, _vp]),
     "qd_cma_transform": (_int, [_i64, _vp, _vp, _vp, _vp]),
     "qd_cma_invsqrt": (_int, [_i64, _vp, _vp, _vp, _vp]),
     "qd_cma_ask": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -470,7 +470,8 @@ class DeviceArchive:
                 insert(_lib.INSERT_COMMIT)
             store._pending = True
             lo, hi = self._dp_rank * B_local, (self._dp_rank + 1) * B_local  # this rank's slice of the batch
-            if dev_in and not self._sync_device_adds and not self._needs_flag_check:
+            mixed = any(not is_device_tensor(v) for v in data.values())  # host arrays ride on reusable staging buffers
+            if dev_in and not mixed and not self._sync_device_adds and not self._needs_flag_check:
                 # CUDA tensors in, CUDA tensors out: nothing to wait for. Stats / len / the finite
                 # check are read back lazily (_sync).
                 self._inflight = dev  # keeps the batch alive until the stream has consumed it

@@ -18,7 +18,9 @@ constexpr int kEighMaxN = 150;  // A must fit in shared memory (n (n+1) doubles)
 __global__ void __launch_bounds__(kEighThreads) jacobi_eigh_kernel(int n, const double* __restrict__ Ain,
                                                                    double* __restrict__ eig_out,
                                                                    double* __restrict__ Vout, int v_in_smem,
-                                                                   int max_sweeps, int* __restrict__ sweeps_out) {
+                                                                   int max_sweeps, int* __restrict__ sweeps_out,
+                                                                   const int32_t* __restrict__ ids) {
+  const size_t mat = ids ? (size_t)ids[blockIdx.x] : (size_t)blockIdx.x;  // which matrix of the stack
   extern __shared__ double sm[];
   const int m = n + (n & 1);   // even number of players; index n (if any) is a bye
   const int ld = n + 1;        // odd-ish stride: no bank conflicts on column walks
@@ -26,9 +28,9 @@ __global__ void __launch_bounds__(kEighThreads) jacobi_eigh_kernel(int n, const 
   double* cs = A + (size_t)n * ld;      // m/2 (c, s) pairs
   int* pq = reinterpret_cast<int*>(cs + m);  // m/2 (p, q) pairs
   double* red = reinterpret_cast<double*>(pq + m);  // 32 reduction slots
-  double* V = v_in_smem ? red + 32 : Vout + (size_t)blockIdx.x * n * n;
+  double* V = v_in_smem ? red + 32 : Vout + mat * n * n;
   const int ldv = v_in_smem ? ld : n;
-  const double* Ab = Ain + (size_t)blockIdx.x * n * n;
+  const double* Ab = Ain + mat * n * n;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int e = tid; e < n * n; e += nt) {
     const int i = e / n, j = e - i * n;
@@ -134,8 +136,8 @@ __global__ void __launch_bounds__(kEighThreads) jacobi_eigh_kernel(int n, const 
   }
   if (sweeps_out && tid == 0) sweeps_out[blockIdx.x] = sweep;
   // ascending order (ties by original position) and output
-  double* eb = eig_out + (size_t)blockIdx.x * n;
-  double* Vb = Vout + (size_t)blockIdx.x * n * n;
+  double* eb = eig_out + mat * n;
+  double* Vb = Vout + mat * n * n;
   int* rank = pq;  // reuse (n <= m ints available? pq holds m ints) -- m >= n
   for (int i = tid; i < n; i += nt) {
     const double li = A[i * ld + i];
@@ -169,8 +171,8 @@ __global__ void __launch_bounds__(kEighThreads) jacobi_eigh_kernel(int n, const 
 
 }  // namespace qd
 
-extern "C" int qd_sym_eigh_batched(int64_t n, int64_t batch, const double* A, double* eig, double* V, int* sweeps,
-                                   void* stream) {
+static int launch_eigh(int64_t n, int64_t batch, const int32_t* ids, const double* A, double* eig, double* V,
+                       int* sweeps, cudaStream_t stream) {
   using namespace qd;
   QD_REQUIRE(A && eig && V, "null pointer");
   QD_REQUIRE(n >= 1 && n <= kEighMaxN, "qd_sym_eigh_batched supports 1 <= n <= 150");
@@ -186,7 +188,17 @@ extern "C" int qd_sym_eigh_batched(int64_t n, int64_t batch, const double* A, do
     QD_CHECK_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = 220 * 1024;
   }
-  jacobi_eigh_kernel<<<(unsigned)batch, kEighThreads, smem, (cudaStream_t)stream>>>((int)n, A, eig, V, v_in_smem, 40,
-                                                                                  sweeps);
+  jacobi_eigh_kernel<<<(unsigned)batch, kEighThreads, smem, stream>>>((int)n, A, eig, V, v_in_smem, 40, sweeps, ids);
   return check_launch("jacobi_eigh_kernel");
+}
+
+// matrices ids[0..batch) of a stack (CMA-ES pool refresh, es.cu)
+int qd_sym_eigh_indexed(int64_t n, int64_t batch, const int32_t* ids, const double* A, double* eig, double* V,
+                        cudaStream_t stream) {
+  return launch_eigh(n, batch, ids, A, eig, V, nullptr, stream);
+}
+
+extern "C" int qd_sym_eigh_batched(int64_t n, int64_t batch, const double* A, double* eig, double* V, int* sweeps,
+                                   void* stream) {
+  return launch_eigh(n, batch, nullptr, A, eig, V, sweeps, (cudaStream_t)stream);
 }

@@ -470,6 +470,391 @@ static CmaScalars to_dev(const qd_cma_scalars* s) {
   return c;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CMA-ES pool: E strategies of identical (n, lambda) stacked in HBM, every kernel batched over the
+// emitters through blockIdx.z (the many-emitter regime of configs[0] and
+// configs[2], where a launch sequence per emitter is pure launch latency). The arithmetic of each
+// kernel repeats its single-strategy counterpart above operation for operation, so a pooled strategy
+// and a stand-alone one fed the same normals stay bit-identical (tests/test_gpu_es.py).
+// ---------------------------------------------------------------------------------------------
+struct PoolView {
+  int64_t E, n, lam;
+  double *mean, *pc, *ps, *C, *B, *eig, *T, *invsqrt, *status, *new_mean, *ws, *X, *z;
+  int64_t ws_stride;
+};
+
+__device__ __forceinline__ int pool_slot(const int32_t* ids) { return ids ? ids[blockIdx.z] : (int)blockIdx.z; }
+
+__global__ void __launch_bounds__(256) pool_fill_normal_kernel(PoolView pv, const uint64_t* __restrict__ seeds,
+                                                               const uint64_t* __restrict__ offsets) {
+  const int e = blockIdx.z;
+  const int64_t count = pv.lam * pv.n;
+  double* out = pv.z + (int64_t)e * count;
+  const uint64_t seed = seeds[e], offset = offsets[e];
+  const int64_t pairs = (count + 1) / 2;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t ctr = offset + (uint64_t)p;
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x243F6A88u, 0x85A308D3u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    const double u1 = ((double)(((uint64_t)(c[0] >> 5) << 26) | (c[1] >> 6)) + 1.0) * 0x1p-53;
+    const double u2 = (double)(((uint64_t)(c[2] >> 5) << 26) | (c[3] >> 6)) * 0x1p-53;
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    out[2 * p] = rad * cs;
+    if (2 * p + 1 < count) out[2 * p + 1] = rad * sn;
+  }
+}
+
+// batched "NT" GEMM: the tile code of gemm_nt_kernel with an emitter index threaded through the functors
+template <class KF, class AF, class BF, class EF>
+__global__ void __launch_bounds__(256) gemm_nt_pool_kernel(int64_t M, int64_t N, const int32_t* __restrict__ ids,
+                                                           KF k_of, AF a_of, BF b_of, EF epilogue) {
+  __shared__ double sA[16][64 + 1];
+  __shared__ double sB[16][64 + 1];
+  const int e = pool_slot(ids);
+  const int64_t K = k_of(e);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t i0 = (int64_t)blockIdx.y * 64, j0 = (int64_t)blockIdx.x * 64;
+  double acc[4][4] = {};
+  for (int64_t k0 = 0; k0 < K; k0 += 16) {
+    for (int t = threadIdx.x; t < 64 * 16; t += 256) {
+      const int r = t >> 4, kk = t & 15;
+      sA[kk][r] = (i0 + r < M && k0 + kk < K) ? a_of(e, i0 + r, k0 + kk) : 0.0;
+      sB[kk][r] = (j0 + r < N && k0 + kk < K) ? b_of(e, j0 + r, k0 + kk) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = sA[kk][ty * 4 + u];
+        b[u] = sB[kk][tx * 4 + u];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int64_t i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
+      if (i < M && j < N) epilogue(e, i, j, acc[u][v]);
+    }
+}
+
+template <class KF, class AF, class BF, class EF>
+int launch_gemm_nt_pool(int64_t M, int64_t N, int batch, const int32_t* ids, KF kf, AF a, BF b, EF ep, cudaStream_t s,
+                        const char* what) {
+  dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64), (unsigned)batch);
+  gemm_nt_pool_kernel<<<grid, 256, 0, s>>>(M, N, ids, kf, a, b, ep);
+  return check_launch(what);
+}
+
+__global__ void pool_sym_max_kernel(PoolView pv, const int32_t* __restrict__ ids, int which) {
+  const int e = pool_slot(ids);
+  const int64_t n = pv.n;
+  double* A = (which == 0 ? pv.C : pv.invsqrt) + (int64_t)e * n * n;
+  const int64_t total = n * n;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / n, j = t - i * n;
+    if (i < j) {
+      const double m = fmax(A[i * n + j], A[j * n + i]);
+      A[i * n + j] = m;
+      A[j * n + i] = m;
+    }
+  }
+}
+
+// |eig|, T = B * sqrt(eig), eigenvalue extrema into the status block
+__global__ void __launch_bounds__(256) pool_transform_kernel(PoolView pv, const int32_t* __restrict__ ids) {
+  const int e = pool_slot(ids);
+  const int64_t n = pv.n;
+  double* eig = pv.eig + (int64_t)e * n;
+  const double* Bm = pv.B + (int64_t)e * n * n;
+  double* T = pv.T + (int64_t)e * n * n;
+  __shared__ double sh_mx[8], sh_mn[8];
+  double mx = -INFINITY, mn = INFINITY;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    const double v = fabs(eig[j]);
+    mx = fmax(mx, v);
+    mn = fmin(mn, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh_mx[threadIdx.x >> 5] = mx;
+    sh_mn[threadIdx.x >> 5] = mn;
+  }
+  __syncthreads();
+  const int64_t total = n * n;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+    T[t] = __dmul_rn(Bm[t], sqrt(fabs(eig[t % n])));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      mx = fmax(mx, sh_mx[w]);
+      mn = fmin(mn, sh_mn[w]);
+    }
+    pv.status[(int64_t)e * 8 + kStatusMax] = mx;
+    pv.status[(int64_t)e * 8 + kStatusMin] = mn;
+  }
+}
+
+__global__ void pool_abs_eig_kernel(PoolView pv, const int32_t* __restrict__ ids) {
+  const int e = pool_slot(ids);
+  double* eig = pv.eig + (int64_t)e * pv.n;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < pv.n; j += (int64_t)gridDim.x * blockDim.x)
+    eig[j] = fabs(eig[j]);
+}
+
+// weighted parent mean: the split-then-sum order of wsum_partial_kernel + wsum_final_kernel in one kernel
+__global__ void __launch_bounds__(kWsumCols) pool_wsum_kernel(PoolView pv, const int32_t* __restrict__ ids,
+                                                              const int64_t* __restrict__ rank,
+                                                              const double* __restrict__ w,
+                                                              const int64_t* __restrict__ mu_arr) {
+  const int e = pool_slot(ids);
+  const int64_t n = pv.n, lam = pv.lam, mu = mu_arr[e];
+  const double* X = pv.X + (int64_t)e * lam * n;
+  const int64_t* rk = rank + (int64_t)e * lam;
+  const double* we = w + (int64_t)e * lam;
+  const int64_t j = blockIdx.x * (int64_t)kWsumCols + threadIdx.x;
+  __shared__ int64_t s_rank[kWsumRowsPerSplit];
+  __shared__ double s_w[kWsumRowsPerSplit];
+  double total = 0.0;
+  for (int64_t k0 = 0; k0 < mu; k0 += kWsumRowsPerSplit) {
+    const int64_t k1 = min(mu, k0 + kWsumRowsPerSplit);
+    __syncthreads();
+    for (int t = threadIdx.x; t < k1 - k0; t += kWsumCols) {
+      s_rank[t] = rk[k0 + t];
+      s_w[t] = we[k0 + t];
+    }
+    __syncthreads();
+    if (j < n) {
+      double a = 0.0;
+      for (int t = 0; t < k1 - k0; ++t) a = __dadd_rn(a, __dmul_rn(X[s_rank[t] * n + j], s_w[t]));
+      total = __dadd_rn(total, a);
+    }
+  }
+  if (j < n) pv.new_mean[(int64_t)e * n + j] = total;
+}
+
+__global__ void __launch_bounds__(256) pool_tell_ps_kernel(PoolView pv, const int32_t* __restrict__ ids,
+                                                           const CmaScalars* __restrict__ sc_arr) {
+  const int e = pool_slot(ids);
+  const int64_t n = pv.n;
+  const CmaScalars sc = sc_arr[e];
+  const double* new_mean = pv.new_mean + (int64_t)e * n;
+  const double* mean = pv.mean + (int64_t)e * n;
+  const double* invsqrt = pv.invsqrt + (int64_t)e * n * n;
+  double* ps = pv.ps + (int64_t)e * n;
+  double* rowsq = pv.ws + (int64_t)e * pv.ws_stride;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  double acc = 0.0;
+  for (int64_t k = lane; k < n; k += 32) acc = fma(invsqrt[row * n + k], __dsub_rn(new_mean[k], mean[k]), acc);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const double sigma = pv.status[(int64_t)e * 8 + kStatusSigma];
+    const double coef = sqrt(sc.cs * (2.0 - sc.cs) * sc.mueff) / sigma;
+    const double p = (1.0 - sc.cs) * ps[row] + coef * acc;
+    ps[row] = p;
+    rowsq[row] = p * p;
+  }
+}
+
+__global__ void __launch_bounds__(256) pool_tell_pc_kernel(PoolView pv, const int32_t* __restrict__ ids,
+                                                           const CmaScalars* __restrict__ sc_arr) {
+  const int e = pool_slot(ids);
+  const int64_t n = pv.n;
+  const CmaScalars sc = sc_arr[e];
+  const double* new_mean = pv.new_mean + (int64_t)e * n;
+  const double* mean = pv.mean + (int64_t)e * n;
+  double* pc = pv.pc + (int64_t)e * n;
+  double* status = pv.status + (int64_t)e * 8;
+  const double* rowsq = pv.ws + (int64_t)e * pv.ws_stride;
+  double* scal = pv.ws + (int64_t)e * pv.ws_stride + n;
+  __shared__ double s_ssq;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int64_t r = 0; r < n; ++r) s += rowsq[r];
+    s_ssq = s;
+  }
+  __syncthreads();
+  const double ssq = s_ssq;
+  const double sigma = status[kStatusSigma];
+  const double left = ssq / (double)n / (1.0 - pow(1.0 - sc.cs, sc.hsig_exp));
+  const double hsig = left < 2.0 + 4.0 / ((double)n + 1.0) ? 1.0 : 0.0;
+  const double c1a = sc.c1 * (1.0 - (1.0 - hsig * hsig) * sc.cc * (2.0 - sc.cc));
+  const double pc_coef = hsig * sqrt(sc.cc * (2.0 - sc.cc) * sc.mueff);
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+    pc[j] = (1.0 - sc.cc) * pc[j] + pc_coef * __dsub_rn(new_mean[j], mean[j]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[0] = 1.0 - c1a - sc.cmu * sc.wsum;
+    scal[1] = sc.c1 * sc.c1;
+    scal[2] = sc.cmu / (sigma * sigma);
+    scal[3] = sigma * exp(fmin(1.0, (sc.cs / sc.damps) * (ssq / (double)n - 1.0) / 2.0));  // new sigma
+    status[kStatusSsq] = ssq;
+  }
+}
+
+__global__ void pool_tell_finish_kernel(PoolView pv, const int32_t* __restrict__ ids) {
+  const int e = pool_slot(ids);
+  const int64_t n = pv.n;
+  const double* new_mean = pv.new_mean + (int64_t)e * n;
+  double* mean = pv.mean + (int64_t)e * n;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+    mean[j] = new_mean[j];
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    pv.status[(int64_t)e * 8 + kStatusSigma] = pv.ws[(int64_t)e * pv.ws_stride + n + 3];
+}
+
+static int to_view(const qd_cma_pool* p, PoolView& v) {
+  QD_REQUIRE(p, "null pool");
+  QD_REQUIRE(p->E >= 1 && p->n >= 1 && p->lam >= 1, "bad pool shape");
+  QD_REQUIRE(p->mean && p->pc && p->ps && p->C && p->B && p->eig && p->T && p->invsqrt && p->status && p->new_mean &&
+                 p->ws && p->X && p->z,
+             "null pool pointer");
+  QD_REQUIRE(p->ws_stride >= p->n + 8, "pool workspace stride must be >= n + 8 doubles");
+  v.E = p->E;
+  v.n = p->n;
+  v.lam = p->lam;
+  v.mean = p->mean;
+  v.pc = p->pc;
+  v.ps = p->ps;
+  v.C = p->C;
+  v.B = p->B;
+  v.eig = p->eig;
+  v.T = p->T;
+  v.invsqrt = p->invsqrt;
+  v.status = p->status;
+  v.new_mean = p->new_mean;
+  v.ws = p->ws;
+  v.X = p->X;
+  v.z = p->z;
+  v.ws_stride = p->ws_stride;
+  return QD_OK;
+}
+
+}  // namespace qd
+
+using namespace qd;
+
+int qd_sym_eigh_indexed(int64_t n, int64_t batch, const int32_t* ids, const double* A, double* eig, double* V,
+                        cudaStream_t stream);  // eigh.cu
+
+extern "C" int qd_cma_pool_refresh(const qd_cma_pool* pool, const int32_t* ids, int n_ids, void* stream) {
+  PoolView pv;
+  int rc = to_view(pool, pv);
+  if (rc) return rc;
+  if (n_ids == 0) return QD_OK;
+  QD_REQUIRE(ids && n_ids > 0 && n_ids <= pool->E, "bad ids");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = pv.n;
+  const dim3 gnn((unsigned)grid_for(n * n, 256), 1, (unsigned)n_ids);
+  pool_sym_max_kernel<<<gnn, 256, 0, s>>>(pv, ids, 0);  // C = max(C, C^T)   (_cma_es.py:67)
+  if ((rc = check_launch("pool_sym_max_kernel"))) return rc;
+  if ((rc = qd_sym_eigh_indexed(n, n_ids, ids, pv.C, pv.eig, pv.B, s))) return rc;
+  pool_transform_kernel<<<gnn, 256, 0, s>>>(pv, ids);
+  if ((rc = check_launch("pool_transform_kernel"))) return rc;
+  pool_abs_eig_kernel<<<dim3((unsigned)grid_for(n, 256), 1, (unsigned)n_ids), 256, 0, s>>>(pv, ids);
+  if ((rc = check_launch("pool_abs_eig_kernel"))) return rc;
+  // invsqrt = (B * (1/sqrt(eig))) @ B^T, then max with its transpose   (_cma_es.py:76-80)
+  const double* Bm = pv.B;
+  const double* eig = pv.eig;
+  double* inv = pv.invsqrt;
+  auto kf = [=] __device__(int) { return n; };
+  auto a_of = [=] __device__(int e, int64_t i, int64_t k) {
+    return __dmul_rn(Bm[(int64_t)e * n * n + i * n + k], 1.0 / sqrt(eig[(int64_t)e * n + k]));
+  };
+  auto b_of = [=] __device__(int e, int64_t j, int64_t k) { return Bm[(int64_t)e * n * n + j * n + k]; };
+  auto epi = [=] __device__(int e, int64_t i, int64_t j, double v) { inv[(int64_t)e * n * n + i * n + j] = v; };
+  if ((rc = launch_gemm_nt_pool(n, n, n_ids, ids, kf, a_of, b_of, epi, s, "pool_invsqrt_gemm"))) return rc;
+  pool_sym_max_kernel<<<gnn, 256, 0, s>>>(pv, ids, 1);
+  return check_launch("pool_sym_max_kernel");
+}
+
+extern "C" int qd_cma_pool_ask(const qd_cma_pool* pool, const uint64_t* seeds, const uint64_t* offsets, void* stream) {
+  PoolView pv;
+  int rc = to_view(pool, pv);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = pv.n, lam = pv.lam;
+  if (seeds) {  // NULL: the caller filled pool->z itself (parity runs)
+    QD_REQUIRE(offsets, "null offsets");
+    const dim3 g((unsigned)grid_for((lam * n + 1) / 2, 256, 2), 1, (unsigned)pv.E);
+    pool_fill_normal_kernel<<<g, 256, 0, s>>>(pv, seeds, offsets);
+    if ((rc = check_launch("pool_fill_normal_kernel"))) return rc;
+  }
+  // X[e][k][i] = mean[e][i] + sum_j T[e][i][j] * (sigma_e z[e][k][j])      (_cma_es.py:181-189)
+  const double *z = pv.z, *T = pv.T, *status = pv.status, *mean = pv.mean;
+  double* X = pv.X;
+  auto kf = [=] __device__(int) { return n; };
+  auto a_of = [=] __device__(int e, int64_t k, int64_t j) {
+    return __dmul_rn(status[(int64_t)e * 8 + kStatusSigma], z[((int64_t)e * lam + k) * n + j]);
+  };
+  auto b_of = [=] __device__(int e, int64_t i, int64_t j) { return T[(int64_t)e * n * n + i * n + j]; };
+  auto epi = [=] __device__(int e, int64_t k, int64_t i, double v) {
+    X[((int64_t)e * lam + k) * n + i] = v + mean[(int64_t)e * n + i];
+  };
+  return launch_gemm_nt_pool(lam, n, (int)pv.E, nullptr, kf, a_of, b_of, epi, s, "pool_ask_gemm");
+}
+
+extern "C" int qd_cma_pool_tell(const qd_cma_pool* pool, const int32_t* ids, int n_ids, const int64_t* rank,
+                                const double* w, const int64_t* mu, const qd_cma_scalars* sc, void* stream) {
+  PoolView pv;
+  int rc = to_view(pool, pv);
+  if (rc) return rc;
+  if (n_ids == 0) return QD_OK;
+  QD_REQUIRE(ids && n_ids > 0 && n_ids <= pool->E && rank && w && mu && sc, "null pointer");
+  static_assert(sizeof(qd_cma_scalars) == sizeof(CmaScalars), "scalar block layouts differ");
+  const CmaScalars* sca = reinterpret_cast<const CmaScalars*>(sc);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = pv.n, lam = pv.lam;
+  pool_wsum_kernel<<<dim3((unsigned)((n + kWsumCols - 1) / kWsumCols), 1, (unsigned)n_ids), kWsumCols, 0, s>>>(
+      pv, ids, rank, w, mu);
+  if ((rc = check_launch("pool_wsum_kernel"))) return rc;
+  pool_tell_ps_kernel<<<dim3((unsigned)((n * 32 + 255) / 256), 1, (unsigned)n_ids), 256, 0, s>>>(pv, ids, sca);
+  if ((rc = check_launch("pool_tell_ps_kernel"))) return rc;
+  pool_tell_pc_kernel<<<dim3((unsigned)grid_for(n, 256), 1, (unsigned)n_ids), 256, 0, s>>>(pv, ids, sca);
+  if ((rc = check_launch("pool_tell_pc_kernel"))) return rc;
+  // rank-mu, in place: C[i][j] = C[i][j]*decay + c1^2 pc_i pc_j + (cmu/sigma^2) sum_k w_k ys_ki ys_kj   (:261-270, :318-323)
+  const double *X = pv.X, *old_mean = pv.mean, *pc = pv.pc, *ws = pv.ws;
+  double* Cm = pv.C;
+  const int64_t wss = pv.ws_stride;
+  auto kf = [=] __device__(int e) { return mu[e]; };
+  auto a_of = [=] __device__(int e, int64_t i, int64_t k) {
+    return (X[((int64_t)e * lam + rank[(int64_t)e * lam + k]) * n + i] - old_mean[(int64_t)e * n + i]) *
+           w[(int64_t)e * lam + k];
+  };
+  auto b_of = [=] __device__(int e, int64_t j, int64_t k) {
+    return X[((int64_t)e * lam + rank[(int64_t)e * lam + k]) * n + j] - old_mean[(int64_t)e * n + j];
+  };
+  auto epi = [=] __device__(int e, int64_t i, int64_t j, double v) {
+    const double* scal = ws + (int64_t)e * wss + n;
+    double* c = Cm + (int64_t)e * n * n + i * n + j;
+    *c = *c * scal[0] + (pc[(int64_t)e * n + i] * pc[(int64_t)e * n + j]) * scal[1] + v * scal[2];
+  };
+  if ((rc = launch_gemm_nt_pool(n, n, n_ids, ids, kf, a_of, b_of, epi, s, "pool_rank_mu_gemm"))) return rc;
+  pool_tell_finish_kernel<<<dim3((unsigned)grid_for(n, 256), 1, (unsigned)n_ids), 256, 0, s>>>(pv, ids);
+  return check_launch("pool_tell_finish_kernel");
+}
+
+namespace qd {
 }  // namespace qd
 
 using namespace qd;

@@ -122,6 +122,8 @@ class CMAEvolutionStrategy(DeviceES):
         """DecompMatrix.update_eigensystem, _cma_es.py:51-82."""
         if not force and self.current_eval <= self.updated_eval + self.lazy_gap_evals:
             return False
+        if self._pool is not None:
+            raise RuntimeError("the eigensystem of a pooled strategy is refreshed by its pool")
         if force:
             self._cancel_prefetch()
             with torch.cuda.stream(self._es_stream()):
@@ -154,6 +156,8 @@ class CMAEvolutionStrategy(DeviceES):
 
     def tell(self, ranking_indices, ranking_values, num_parents):
         """_cma_es.py:274-328."""
+        if self._pool is not None:
+            return self._pool.tell_many([self._slot], [ranking_indices], [num_parents])
         n = self.solution_dim
         self.current_eval += len(ranking_indices)
         num_parents = int(num_parents)

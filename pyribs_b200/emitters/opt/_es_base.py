@@ -79,6 +79,8 @@ class DeviceES:
         self._pending = None
         self._host_ready = False
         self._rng_mark = 0
+        self._pool = None  # set when a CMAPool adopts this strategy (emitters/_emitter_pool.py)
+        self._slot = -1
 
     # ---- helpers ------------------------------------------------------------------------------
     def _normals(self, rows):
@@ -157,7 +159,7 @@ class DeviceES:
         that by the time the scheduler asks, the samples of all emitters have been produced
         concurrently. Identical results: `ask` is a pure function of the ES state and the RNG
         counter, and nothing changes either between this call and the next `ask`."""
-        if self._pending is None and not self._bounded:
+        if self._pending is None and not self._bounded and self._pool is None:
             self._rng_mark = self._rng_offset
             # small batches also start their device->host copy now; big ones wait to see what ask() wants
             self._enqueue_ask(self.batch_size, None, want_host=self.batch_size * self.solution_dim * 8 <= (8 << 20))
@@ -175,6 +177,10 @@ class DeviceES:
         CUDA tensor that `tell` will re-read, without a device->host copy.
         """
         lam = self.batch_size if batch_size is None else int(batch_size)
+        if self._pool is not None:
+            if z is not None or lam != self.batch_size:
+                raise ValueError("a pooled strategy samples batch_size solutions from its own stream")
+            return self._pool.ask_one(self._slot, return_device)
         if self._pending is not None and (z is not None or lam != self._pending):
             self._cancel_prefetch()
         if self._pending is None:

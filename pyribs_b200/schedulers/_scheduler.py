@@ -13,7 +13,7 @@ import numpy as np
 
 
 class Scheduler:
-    def __init__(self, archive, emitters, result_archive=None, *, add_mode="batch"):
+    def __init__(self, archive, emitters, result_archive=None, *, add_mode="batch", pool_emitters=True):
         if len(emitters) == 0:
             raise ValueError("Pass in at least one emitter to the scheduler.")
         if add_mode not in ("single", "batch"):
@@ -28,6 +28,13 @@ class Scheduler:
         self._last_called = None
         self._cur_solutions = None
         self._num_emitted = [None] * len(self._emitters)
+        # fast path: homogeneous CMA-ES emitters run as one batched pool --
+        # same results, one launch sequence per ask / tell instead of one per emitter
+        self._pool = None
+        if pool_emitters and add_mode == "batch":
+            from pyribs_b200.emitters._emitter_pool import EmitterPool
+
+            self._pool = EmitterPool.try_build(self._emitters, archive)
 
     @property
     def archive(self):
@@ -41,10 +48,18 @@ class Scheduler:
     def result_archive(self):
         return self._archive if self._result_archive is None else self._result_archive
 
-    def ask(self):
+    def ask(self, return_device=False):
+        """`return_device=True` (pooled emitters only) hands out the CUDA tensor of the samples, for
+        evaluators that run on the GPU; `tell` then also accepts CUDA tensors."""
         if self._last_called == "ask":
             raise RuntimeError("ask cannot be called immediately after ask")
         self._last_called = "ask"
+        if self._pool is not None:
+            self._cur_solutions = self._pool.ask(return_device)
+            self._num_emitted = [self._pool.lam] * len(self._emitters)
+            return self._cur_solutions
+        if return_device:
+            raise ValueError("return_device=True needs pooled emitters (homogeneous CMA-ES emitters, add_mode='batch')")
         sols = []
         for i, emitter in enumerate(self._emitters):
             s = emitter.ask()
@@ -75,12 +90,22 @@ class Scheduler:
         if self._last_called != "ask":
             raise RuntimeError("tell() was called without calling ask().")
         self._last_called = "tell"
-        data = {"solution": self._cur_solutions, "objective": np.asarray(objective), "measures": np.asarray(measures),
-                **{k: np.asarray(v) for k, v in fields.items()}}
+        def host_or_device(v):
+            return v if hasattr(v, "is_cuda") else np.asarray(v)
+
+        data = {"solution": self._cur_solutions, "objective": host_or_device(objective),
+                "measures": host_or_device(measures), **{k: host_or_device(v) for k, v in fields.items()}}
         for name, arr in data.items():
             if len(arr) != len(self._cur_solutions):
                 raise ValueError(f"{name} should have length {len(self._cur_solutions)} (this is the number of "
                                  f"solutions output by ask()) but has length {len(arr)}")
+        if self._pool is not None:
+            # the samples are still on the device: insert from there, rank on the host, update every strategy at once
+            data["solution"] = self._pool.solutions_device()
+            add_info = self._add_to_archives(data)
+            host_info = {k: (v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v)) for k, v in add_info.items()}
+            self._pool.tell(data["objective"], host_info)
+            return
         add_info = self._add_to_archives(data)
         pos = 0
         for emitter, n in zip(self._emitters, self._num_emitted):
