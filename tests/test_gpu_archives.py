@@ -373,3 +373,38 @@ def test_cvt_tensor_equals_scan(shape):
     sub = rng.choice(B, 200, replace=False)
     dd = ((meas[sub, None, :] - cen[None, :, :]) ** 2).sum(-1)
     np.testing.assert_array_equal(out["tensor"][sub], dd.argmin(1))
+
+
+def test_cma_mae_batch_beyond_packed_count_range():
+    """Batches of >= 2^24 rows take the separate-counter variant of the fixed-point cell sums
+    (csrc/insert.cu make_fx): 16.8M rows into 64 cells, checked against NumPy's sequential per-cell
+    sums (np.bincount adds in batch order, like the reference's numba loop) and first-wins argmax."""
+    import torch
+
+    from pyribs_b200.archives import GridArchive
+
+    B, lr = (1 << 24) + 3, 1e-6
+    rng = np.random.default_rng(5)
+    meas = rng.uniform(-1, 1, (B, 2))
+    obj = np.round(rng.uniform(0.5, 100, B), 3)  # rounded: exact ties inside cells do occur
+    a = GridArchive(solution_dim=1, dims=(8, 8), ranges=[(-1, 1)] * 2, learning_rate=lr, threshold_min=0.0)
+    sol = np.arange(B, dtype=np.float64)[:, None]
+    out = a.add(torch.from_numpy(sol).cuda(), torch.from_numpy(obj).cuda(), torch.from_numpy(meas).cuda())
+    idx = a.index_of(meas)
+    assert len(a) == 64
+    assert bool((out["status"] == 2).all().item())
+    np.testing.assert_array_equal(out["value"].cpu().numpy(), obj)  # threshold_min = 0
+    k = np.bincount(idx, minlength=64).astype(np.float64)
+    S = np.bincount(idx, weights=obj, minlength=64)
+    ratio = (1.0 - lr) ** k
+    thr = ratio * 0.0 + (S / k) * (1.0 - ratio)
+    d = a.data()
+    order = np.argsort(d["index"])
+    np.testing.assert_allclose(d["threshold"][order], thr, rtol=1e-9)
+    best = np.full(64, -np.inf)
+    np.maximum.at(best, idx, obj)
+    np.testing.assert_array_equal(d["objective"][order], best)
+    first = np.full(64, B, dtype=np.int64)
+    cand = np.nonzero(obj == best[idx])[0]
+    np.minimum.at(first, idx[cand], cand)
+    np.testing.assert_array_equal(d["solution"][order, 0], first.astype(np.float64))

@@ -94,3 +94,66 @@ def test_two_gpu_insertion():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def _emitter_worker(rank, world, port, q):
+    """Emitters sharded over the ranks: every rank owns E/world emitters and a replica of
+    a data-parallel archive; `add` all-gathers the ranks' batches. With restart rule "basic" nothing depends
+    on rank-local randomness, so the replicas must equal a single-process run of all emitters."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from pyribs_b200.archives import GridArchive
+    from pyribs_b200.emitters import EvolutionStrategyEmitter
+    from pyribs_b200.schedulers import Scheduler
+
+    n, E, lam = 12, 6, 10
+    mb = n / 2 * 5.12
+
+    def sphere(sol):
+        worst = (5.12 + 2.048) ** 2 * n
+        obj = (worst - np.sum((sol - 2.048) ** 2, axis=1)) / worst * 100
+        c = np.clip(sol, -5.12, 5.12)
+        return obj, np.stack((c[:, : n // 2].sum(1), c[:, n // 2:].sum(1)), axis=1)
+
+    def run(data_parallel, emitter_ids):
+        a = GridArchive(solution_dim=n, dims=(30, 30), ranges=[(-mb, mb)] * 2, learning_rate=0.05, threshold_min=0.0,
+                        data_parallel=data_parallel)
+        seeds = np.random.SeedSequence(5).spawn(E)
+        ems = [EvolutionStrategyEmitter(a, x0=np.zeros(n), sigma0=0.5, batch_size=lam, seed=seeds[i], ranker="imp",
+                                        selection_rule="mu", restart_rule="basic") for i in emitter_ids]
+        s = Scheduler(a, ems)
+        for _ in range(25):
+            s.tell(*sphere(s.ask()))
+        return a
+
+    per = E // world
+    sharded = run(True, range(rank * per, (rank + 1) * per))
+    whole = run(False, range(E))
+    ds, dw = sharded.data(), whole.data()
+    ok = len(sharded) == len(whole) and all(np.array_equal(ds[k], dw[k]) for k in ds)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_emitters():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_emitter_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

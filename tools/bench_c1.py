@@ -14,7 +14,16 @@ def sphere(sol):
     meas = np.stack((c[:, : n // 2].sum(1), c[:, n // 2:].sum(1)), axis=1)
     return obj, meas
 
-def run_gpu(iters, n=100, E=15, lam=36, c3=False):
+def sphere_torch(sol):
+    import torch
+    n = sol.shape[1]
+    worst = (5.12 + 2.048) ** 2 * n
+    obj = (worst - ((sol - 2.048) ** 2).sum(1)) / worst * 100
+    c = sol.clamp(-5.12, 5.12)
+    return obj, torch.stack((c[:, : n // 2].sum(1), c[:, n // 2:].sum(1)), dim=1)
+
+
+def run_gpu(iters, n=100, E=15, lam=36, c3=False, device_eval=False, pooled=True):
     from pyribs_b200.archives import GridArchive
     from pyribs_b200.emitters import EvolutionStrategyEmitter
     from pyribs_b200.schedulers import Scheduler
@@ -27,7 +36,17 @@ def run_gpu(iters, n=100, E=15, lam=36, c3=False):
     kw = dict(ranker="imp", selection_rule="mu", restart_rule="basic") if c3 else dict(
         ranker="2imp", selection_rule="filter", restart_rule="no_improvement")
     ems = [EvolutionStrategyEmitter(a, x0=np.zeros(n), sigma0=0.5, batch_size=lam, seed=s, **kw) for s in seeds]
-    s = Scheduler(a, ems)
+    s = Scheduler(a, ems, pool_emitters=pooled)
+    if device_eval:
+        import torch
+        for _ in range(10):
+            s.tell(*sphere_torch(s.ask(return_device=True)))
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(iters):
+            s.tell(*sphere_torch(s.ask(return_device=True)))
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        return dict(it_per_s=iters / dt, solutions_per_s=iters * E * lam / dt, elites=len(a), qd=float(a.stats.qd_score),
+                    restarts=sum(e.restarts for e in ems), evaluator="torch sphere on the GPU (ask/tell exchange CUDA tensors)")
     for _ in range(10):
         sol = s.ask(); s.tell(*sphere(sol))
     t0 = time.perf_counter(); t_ask = t_tell = 0.0
@@ -72,6 +91,9 @@ if __name__ == "__main__":
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     if len(sys.argv) > 2 and sys.argv[2] == "c3":
         print(json.dumps({"case": "C3 sphere CMA-MAE 100x512 n=100, grid 500x500", "gpu": run_gpu(iters, E=100, lam=512, c3=True),
+                          "gpu_device_eval": run_gpu(iters, E=100, lam=512, c3=True, device_eval=True),
+                          "gpu_unpooled": run_gpu(max(3, iters // 5), E=100, lam=512, c3=True, pooled=False),
                           "cpu_oracle_port": run_cpu(max(3, iters // 5), E=100, lam=512, c3=True), "cores": os.cpu_count()}))
     else:
-        print(json.dumps({"case": "C1 sphere CMA-ME 15x36 n=100", "gpu": run_gpu(iters), "cpu_oracle_port": run_cpu(iters), "cores": os.cpu_count()}))
+        print(json.dumps({"case": "C1 sphere CMA-ME 15x36 n=100", "gpu": run_gpu(iters), "gpu_device_eval": run_gpu(iters, device_eval=True),
+                          "gpu_unpooled": run_gpu(iters, pooled=False), "cpu_oracle_port": run_cpu(iters), "cores": os.cpu_count()}))
