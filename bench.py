@@ -105,6 +105,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+C_SIZEOF_RESULT = 120  # sizeof(qd_add_result)
 NCU_TRAFFIC = {"cvt_bucket_kernel": 1_833_984, "insert_kernel_grid_2M": 311_130_624 + 205_896_704}
 
 
@@ -272,9 +273,16 @@ def main():
         out = archive.add(b["solution"], obj_np[j % n_obj], b["measures"])
         assert out["status"].shape[0] == B
 
+    zc0 = archive._zero_copy_bytes
     ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
-    h2d = sum(v.nbytes for v in batches[0].values())
-    d2h = B * (4 + 8) + 56
+    # bytes that crossed PCIe per step, counted from what was copied: measures + objective by DMA; the
+    # solution rows either by DMA (all of them) or, for page-locked inputs when at most cells << batch rows
+    # can win, only the winners' rows, read by the insert kernel straight from host memory (zero-copy)
+    zc = (archive._zero_copy_bytes - zc0) / (args.steps + args.warmup)
+    e2e_zero_copy = bool(archive._last_zero_copy)
+    h2d = (batches[0]["measures"].nbytes + batches[0]["objective"].nbytes
+           + (zc if e2e_zero_copy else batches[0]["solution"].nbytes))
+    d2h = B * (4 + 8) + C_SIZEOF_RESULT
 
     # ---- dominant kernel alone: nearest-centroid search -------------------------------------
     flags = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -374,7 +382,11 @@ def main():
                    "objective": f"standard normal + {OBJ_DRIFT} per step (every step keeps inserting)"},
         "clocks": clocks,
         "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "insertions/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                "transfers": "measures streamed by the search kernel and winners' rows gathered by the insert kernel "
+                             "straight from the page-locked inputs (zero-copy over PCIe), objective by DMA, status / "
+                             "value written by the kernel into page-locked result buffers"
+                if e2e_zero_copy else "whole batch by DMA (H2D), status / value by DMA (D2H)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }

@@ -51,6 +51,11 @@ const char* qd_last_error(void);
 int64_t qd_launch_count(void);
 /* cudaStreamSynchronize(stream): the one blocking call of add() (the host needs qd_add_result). */
 int qd_stream_synchronize(void* stream);
+/* cudaMemcpyAsync / cudaEventRecord / cudaStreamWaitEvent on raw handles (kind: 1 H2D, 2 D2H, 3 D2D, else
+ * default), so that a binding can order its copies around the kernels with one foreign call each. */
+int qd_memcpy_async(void* dst, const void* src, size_t nbytes, int kind, void* stream);
+int qd_event_record(void* event /*cudaEvent_t*/, void* stream);
+int qd_stream_wait_event(void* stream, void* event /*cudaEvent_t*/);
 
 /* ------------------------------------------------------------------------------------
  * A2  GridArchive.index_of      ribs/archives/_grid_archive.py:362-410, 432-450
@@ -129,6 +134,7 @@ typedef struct qd_add_result {
   uint64_t best_serial;   /* bumps whenever the best-elite snapshot was replaced */
   uint64_t n_failed;      /* calls dropped because of a non-finite objective / measure: a host that
                              did not wait for every call raises ValueError when this advances */
+  uint64_t n_winners;     /* rows of THIS call written into the store (= cells that received an elite) */
 } qd_add_result;
 
 typedef struct qd_store {
@@ -175,6 +181,15 @@ int qd_store_set_state(const qd_store* store, int64_t n_occupied, double objecti
                        double obj_max, double objective_absmax, void* stream);
 /* Writes the store-state half of qd_add_result (per-call fields zero) to out [dev]. */
 int qd_store_read_state(const qd_store* store, qd_add_result* out /*[dev]*/, void* stream);
+
+/* Exchange step of the data-parallel add(): rank `rank` writes its slice of every batch
+ * field (src[f], slice_bytes[f] bytes) into the global field array of EVERY peer, at
+ * peer_bases[p] + dst_off[f] + rank * slice_bytes[f] -- P2P stores over NVLink into symmetric memory
+ * (peer_bases[rank] is the local buffer). The caller follows it with a cross-rank barrier before any
+ * rank reads its global arrays. */
+int qd_dp_push(int n_fields, const void* const* src /*[host] dev ptrs*/, const int64_t* slice_bytes /*[host]*/,
+               const int64_t* dst_off /*[host]*/, void* const* peer_bases /*[host] n_peers dev ptrs*/, int n_peers,
+               int rank, void* stream);
 
 /* One batched insertion = ONE persistent cooperative kernel. `idx` comes from qd_grid_index_of /
  * qd_cvt_index_of. New cells are appended to occupied_list in ascending cell order after the

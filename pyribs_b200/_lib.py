@@ -37,6 +37,7 @@ class AddResult(C.Structure):
         ("n_commits", C.c_uint64),
         ("best_serial", C.c_uint64),
         ("n_failed", C.c_uint64),
+        ("n_winners", C.c_uint64),
     ]
 
 
@@ -74,6 +75,9 @@ PROTOTYPES = {
     "qd_last_error": (C.c_char_p, []),
     "qd_launch_count": (_i64, []),
     "qd_stream_synchronize": (_int, [_vp]),
+    "qd_memcpy_async": (_int, [_vp, _vp, _sz, _int, _vp]),
+    "qd_event_record": (_int, [_vp, _vp]),
+    "qd_stream_wait_event": (_int, [_vp, _vp]),
     "qd_grid_index_of": (_int, [_vp, _int, _i64, _int, C.POINTER(_i32), C.POINTER(_dbl), C.POINTER(_dbl), _dbl,
                                 _vp, _vp, _vp]),
     "qd_cvt_prepared_bytes": (_sz, [_i64, _int]),
@@ -93,6 +97,7 @@ PROTOTYPES = {
     "qd_store_clear": (_int, [C.POINTER(Store), _vp]),
     "qd_store_set_state": (_int, [C.POINTER(Store), _i64, _dbl, _int, _dbl, _dbl, _vp]),
     "qd_store_read_state": (_int, [C.POINTER(Store), _vp, _vp]),
+    "qd_dp_push": (_int, [_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_vp), _int, _int, _vp]),
     "qd_insert": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _dbl, _dbl, _vp, _vp, _vp, _int, _vp]),
     "qd_grid_insert": (_int, [C.POINTER(Store), _i64, _vp, _int, _int, C.POINTER(_i32), C.POINTER(_dbl),
                               C.POINTER(_dbl), _dbl, _vp, C.POINTER(_vp), _dbl, _dbl, _vp, _vp, _vp, _vp, _int,

@@ -140,6 +140,8 @@ class DeviceArchive:
         self._tmin_f = float(self._threshold_min)
         self._best_elite = None
         self._best_serial = 0
+        self._st = (0, 0.0, None, 0)
+        self._stats_dirty = False
         self._objective_sum = None
         self._stats = None
         self._stats_reset()
@@ -151,6 +153,13 @@ class DeviceArchive:
         self._sync_device_adds = False    # True: add() of CUDA tensors also waits and validates like NumPy input
         self._inflight = None
         self._needs_flag_check = False
+        self._dp_symm = None  # {batch signature: symmetric-memory exchange state}; False = unavailable
+        self._zero_copy_rows = True   # read winners' rows straight from page-locked host arrays when that saves PCIe traffic
+        self._last_zero_copy = False
+        self._zero_copy_bytes = 0
+        self._zc = None
+        self._pin_cache = {}
+        self._row_bytes_total = sum(self._store._row_bytes(n) for n in self._store.row_fields)
         self._force_scan = False
         self._overflow_fallbacks = 0
 
@@ -178,6 +187,8 @@ class DeviceArchive:
     @property
     def stats(self):
         self._sync()
+        if self._stats_dirty:
+            self._build_stats()
         return self._stats
 
     @property
@@ -187,6 +198,9 @@ class DeviceArchive:
     @property
     def best_elite(self):
         self._sync()
+        if self._st[3] != self._best_serial:  # the device replaced its best-elite snapshot since the last read
+            self._best_serial = self._st[3]
+            self._best_elite = self._store.read_snapshot()
         return self._best_elite
 
     @property
@@ -240,22 +254,26 @@ class DeviceArchive:
         self._raise_for_flags(flags)
 
     def _apply_state(self, res):
+        """Adopts the device-side running state; the ArchiveStats record / best elite are built on access."""
+        self._st = (int(res.n_occupied), float(res.objective_sum), float(res.obj_max) if res.has_obj_max else None,
+                    int(res.best_serial))
+        self._stats_dirty = True
+
+    def _build_stats(self):
         """_stats_update (_grid_archive.py:325-360) from the device-side running state."""
-        odt = self.dtypes["objective"]
-        if res.best_serial != self._best_serial:
-            self._best_serial = int(res.best_serial)
-            self._best_elite = self._store.read_snapshot()
-        n = int(res.n_occupied)
-        if n == 0 or not res.has_obj_max:
+        self._stats_dirty = False
+        n, osum, omax, _ = self._st
+        if n == 0 or omax is None:
             return
-        self._objective_sum = np.asarray(res.objective_sum, dtype=odt)
+        odt = self.dtypes["objective"]
+        self._objective_sum = np.asarray(osum, dtype=odt)
         qd = self._objective_sum - np.asarray(n, dtype=odt) * self._qd_score_offset
         self._stats = ArchiveStats(
             num_elites=n,
             coverage=np.asarray(n / self.cells, dtype=odt),
             qd_score=qd,
             norm_qd_score=np.asarray(qd / self.cells, dtype=odt),
-            obj_max=self._best_elite["objective"] if self._best_elite is not None else np.asarray(res.obj_max, odt),
+            obj_max=np.dtype(odt).type(omax),
             obj_mean=np.asarray(self._objective_sum / n, dtype=odt),
         )
 
@@ -263,6 +281,8 @@ class DeviceArchive:
     def _stats_reset(self):
         odt = self.dtypes["objective"]
         self._best_elite = None
+        self._best_serial = self._st[3]
+        self._stats_dirty = False
         self._objective_sum = np.asarray(0.0, dtype=odt)
         self._stats = ArchiveStats(
             num_elites=0,
@@ -278,8 +298,10 @@ class DeviceArchive:
         """Host array -> device tensor through a reusable pinned staging buffer (one per
         field, so that in-flight async copies of one add() never share a buffer)."""
         if isinstance(arr, torch.Tensor):
-            t = arr.to(device=self._device, dtype=torch_dtype(np_dtype))
-            return t.contiguous()
+            want = torch_dtype(np_dtype)
+            if arr.device == self._device and arr.dtype == want and arr.is_contiguous():
+                return arr
+            return arr.to(device=self._device, dtype=want).contiguous()
         arr = np.ascontiguousarray(arr, dtype=np_dtype)
         if arr.size == 0:
             return torch.empty(arr.shape, dtype=torch_dtype(np_dtype), device=self._device)
@@ -300,6 +322,11 @@ class DeviceArchive:
     def _index_of_device(self, measures: torch.Tensor, flags_ptr: int) -> torch.Tensor:
         raise NotImplementedError
 
+    def _host_measures_ok(self):
+        """True when the index kernel of the next add() may read the measures straight from page-locked host
+        memory (one coalesced pass over them): the fused grid index and the CVT bucket search."""
+        return self._fused_index_insert
+
     def _all_gather_many(self, tensors):
         """All-gathers several equally-sharded tensors over NCCL."""
         import torch.distributed as dist
@@ -310,6 +337,66 @@ class DeviceArchive:
         for o, t in zip(outs, ins):  # (torch's coalescing manager measured slower than separate launches)
             dist.all_gather_into_tensor(o, t, group=self._dp_group)
         return outs
+
+    # ---- exchange step of the data-parallel add() over NVLink peer memory --------------------------
+    def _symm_exchange(self, idx, dev, B_local):
+        """Push all-gather: every rank writes its slice of (flags, idx, every batch field) straight into
+        the global arrays of every peer (torch symmetric memory = P2P-mapped cudaMalloc; csrc/abi.cu
+        qd_dp_push), then one cross-rank barrier. Two buffer sets alternate so that a rank running ahead
+        never overwrites arrays a slower peer's insert kernel is still reading. Returns None when
+        symmetric memory cannot be set up (the NCCL all-gathers below are used instead)."""
+        if self._dp_symm is False:
+            return None
+        import torch.distributed as dist
+
+        store = self._store
+        names = list(dev)
+        key = (B_local, tuple((n, tuple(dev[n].shape[1:]), dev[n].dtype) for n in names))
+        st = self._dp_symm.get(key) if self._dp_symm else None
+        R = self._dp_world
+        if st is None:
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                group = self._dp_group if self._dp_group is not None else dist.group.WORLD
+                slices = [4, 4 * B_local] + [dev[n][0].numel() * dev[n].element_size() * B_local if dev[n].dim() > 1
+                                             else dev[n].element_size() * B_local for n in names]
+                offs, total = [], 0
+                for nb in slices:
+                    offs.append(total)
+                    total += (R * nb + 255) // 256 * 256
+                bufs, handles = [], []
+                for _ in range(2):
+                    t = symm.empty(total, dtype=torch.uint8, device=self._device)
+                    handles.append(symm.rendezvous(t, group))
+                    bufs.append(t)
+                peers = [(C.c_void_p * R)(*[int(p) for p in h.buffer_ptrs]) for h in handles]
+                st = dict(slices=slices, offs=offs, bufs=bufs, handles=handles, peers=peers, turn=0,
+                          c_slices=(C.c_int64 * len(slices))(*slices), c_offs=(C.c_int64 * len(offs))(*offs))
+                if self._dp_symm is None:
+                    self._dp_symm = {}
+                self._dp_symm[key] = st
+            except Exception:  # noqa: BLE001  (no P2P / IPC on this box)
+                self._dp_symm = False
+                return None
+        turn = st["turn"]
+        st["turn"] = 1 - turn
+        off = store._flags_ptr - store._scratch.data_ptr()
+        flags = store._scratch[off:off + 4]
+        srcs = [flags, idx] + [dev[n] for n in names]
+        c_src = (C.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+        _lib.check(_lib.lib().qd_dp_push(len(srcs), c_src, st["c_slices"], st["c_offs"], st["peers"][turn], R,
+                                         self._dp_rank, current_stream_ptr()))
+        st["handles"][turn].barrier()
+        G = st["bufs"][turn]
+        o, sl = st["offs"], st["slices"]
+        _lib.check(_lib.lib().qd_flags_or(G[o[0]:o[0] + 4 * R].data_ptr(), R, store._flags_ptr, current_stream_ptr()))
+        g_idx = G[o[1]:o[1] + R * sl[1]].view(torch.int32)
+        g_dev = {}
+        for k, n in enumerate(names):
+            t = dev[n]
+            g_dev[n] = G[o[2 + k]:o[2 + k] + R * sl[2 + k]].view(t.dtype).view(R * B_local, *t.shape[1:])
+        return g_idx, g_dev, R * B_local
 
     def _gather_global_batch(self, idx, dev, B_local, skip=()):
         """All-gathers the per-rank slices (equal sizes on every rank) into the global batch and
@@ -413,18 +500,24 @@ class DeviceArchive:
                         "value": torch.empty(0, dtype=torch_dtype(odt), device=self._device)}
             return {"status": np.empty(0, dtype=np.int32), "value": np.empty(0, dtype=odt)}
         store = self._store
+        if (not dev_in and self._dp_world == 1 and self.cells * 2 <= B and self._zero_copy_rows
+                and self._host_measures_ok() and torch.cuda.current_device() == self._device.index):
+            out = self._add_zero_copy(data, B)
+            if out is not None:
+                return out
         with torch.cuda.device(self._device):
+            fused = self._dp_world == 1 and self._fused_index_insert
+            global_search = self._dp_world > 1 and getattr(self, "_world", 1) > 1  # centroid-sharded CVT
+            rows_event = None
+            self._last_zero_copy = False
             # measures + objective first: the index kernels only need those, so the (much larger)
             # solution / extra-field rows travel host->device on a side stream while the search runs
             dev = {name: self._to_device(data[name], store.dtypes[name], name) for name in ("measures", "objective")}
-            fused = self._dp_world == 1 and self._fused_index_insert
-            global_search = self._dp_world > 1 and getattr(self, "_world", 1) > 1  # centroid-sharded CVT
             if global_search:
                 # every rank searches ALL queries against its centroid shard: gather the measures first
                 dev["measures"] = self._all_gather_many([dev["measures"]])[0]
             idx = None if fused else self._index_of_device(dev["measures"], store._flags_ptr)
             rest = [n for n in data if n not in dev]
-            rows_event = None
             if dev_in or all(isinstance(data[n], torch.Tensor) for n in rest):
                 for n in rest:
                     dev[n] = self._to_device(data[n], store.dtypes[n], n)
@@ -445,8 +538,11 @@ class DeviceArchive:
                 if global_search:  # idx and measures are already global
                     _, dev, B = self._gather_global_batch(None, dev, B_local, skip=("measures",))
                 else:
-                    idx, dev, B = self._gather_global_batch(idx, dev, B_local)
+                    dev = {n: dev[n].contiguous() for n in dev}
+                    got = self._symm_exchange(idx, dev, B_local)
+                    idx, dev, B = got if got is not None else self._gather_global_batch(idx, dev, B_local)
             status, value, status_h, value_h, pooled = self._out_buffers(B, dev_in)
+            host_out = False
             names = store.row_fields
             src = (C.c_void_p * max(len(names), 1))(*[dev[n].data_ptr() for n in names])
             def insert(part):
@@ -478,7 +574,7 @@ class DeviceArchive:
                 return {"status": status[lo:hi], "value": value[lo:hi]} if self._dp_world > 1 else \
                     {"status": status, "value": value}
             store._result_host.copy_(store._result_dev, non_blocking=True)
-            if not dev_in and rows_event is None:
+            if not dev_in and rows_event is None and not host_out:
                 status_h.copy_(status, non_blocking=True)
                 value_h.copy_(value, non_blocking=True)
             _lib.check(_lib.lib().qd_stream_synchronize(current_stream_ptr()))
@@ -501,6 +597,93 @@ class DeviceArchive:
         if pooled is not None:  # views of a pooled page-locked buffer (see _out_buffers)
             return {"status": pooled[2][lo:hi], "value": pooled[3][lo:hi]}
         return {"status": status_h.numpy()[lo:hi].copy(), "value": value_h.numpy()[lo:hi].copy()}
+
+    # ---- add() of page-locked host batches: zero-copy plan ----------------------------------------------
+    class _HostRows:
+        """A page-locked host array seen by the kernels: just an address and a shape."""
+        __slots__ = ("ptr", "shape")
+
+        def __init__(self, ptr, shape):
+            self.ptr, self.shape = ptr, shape
+
+        def data_ptr(self):
+            return self.ptr
+
+    def _is_pinned(self, arr):
+        key = (arr.__array_interface__["data"][0], arr.nbytes)
+        hit = self._pin_cache.get(key)
+        if hit is None:
+            if len(self._pin_cache) > 512:
+                self._pin_cache.clear()
+            hit = self._pin_cache[key] = bool(torch.from_numpy(arr).is_pinned())
+        return hit
+
+    def _add_zero_copy(self, data, B):
+        """At most `cells` rows of a batch can win, so shipping every solution row to the GPU is wasted PCIe
+        traffic. With page-locked inputs: the search / classify phases stream the measures straight from host
+        memory (coalesced zero-copy reads, no DMA set-up latency) while the objective vector travels by DMA
+        next to them; the copy phase of the insert kernel gathers just the winners' rows of the solution /
+        extra fields from host memory; status / value are written by the kernel directly into the page-locked
+        buffers the caller receives. Returns None when the batch is not eligible (pageable / strided arrays)."""
+        store = self._store
+        dts = store._np_dtypes
+        for n, arr in data.items():
+            if (not isinstance(arr, np.ndarray) or not arr.flags.c_contiguous or arr.dtype != dts[n]
+                    or not self._is_pinned(arr)):
+                return None
+        L = _lib.lib()
+        zc = self._zc
+        if zc is None:
+            cs = torch.cuda.Stream(device=self._device)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            zc = self._zc = {"stream": cs, "sp": cs.cuda_stream, "ev": ev, "ep": ev.cuda_event, "obj": {},
+                             "res": _lib.AddResult.from_address(store._result_host.data_ptr()), "store": store}
+        elif zc["store"] is not store:  # retessellate / resize replaced the store
+            zc["res"] = _lib.AddResult.from_address(store._result_host.data_ptr())
+            zc["store"] = store
+        sp = current_stream_ptr()
+        obj_h = data["objective"]
+        obj_d = zc["obj"].get(B)
+        if obj_d is None:
+            if len(zc["obj"]) > 8:
+                zc["obj"].clear()
+            obj_d = zc["obj"][B] = torch.empty(B, dtype=torch_dtype(store.dtypes["objective"]), device=self._device)
+        _lib.check(L.qd_memcpy_async(obj_d.data_ptr(), obj_h.__array_interface__["data"][0], obj_h.nbytes, 1, zc["sp"]))
+        _lib.check(L.qd_event_record(zc["ep"], zc["sp"]))
+        meas = data["measures"]
+        host_meas = self._HostRows(meas.__array_interface__["data"][0], meas.shape)
+        fused = self._fused_index_insert
+        idx = None if fused else self._index_of_device(host_meas, store._flags_ptr)
+        _lib.check(L.qd_stream_wait_event(sp, zc["ep"]))
+        status, value, status_h, value_h, pooled = self._out_buffers(B, False)
+        if pooled is not None:  # the kernel writes straight into the buffers the caller gets
+            status, value = status_h, value_h
+        dev = {"measures": host_meas, "objective": obj_d}
+        names = store.row_fields
+        src = (C.c_void_p * max(len(names), 1))(*[data[n].__array_interface__["data"][0] for n in names])
+        if fused:
+            self._grid_insert(dev, B, src, status, value, _lib.INSERT_WHOLE)
+        else:
+            _lib.check(L.qd_insert(C.byref(store.abi_store()), B, idx.data_ptr(), obj_d.data_ptr(), src, self._lr_f,
+                                   self._tmin_f, status.data_ptr(), value.data_ptr(), store._result_dev.data_ptr(),
+                                   _lib.INSERT_WHOLE, sp))
+        store._pending = True
+        if pooled is None:
+            status_h.copy_(status, non_blocking=True)
+            value_h.copy_(value, non_blocking=True)
+        _lib.check(L.qd_memcpy_async(store._result_host.data_ptr(), store._result_dev.data_ptr(),
+                                     C.sizeof(_lib.AddResult), 2, sp))
+        _lib.check(L.qd_stream_synchronize(sp))
+        res = zc["res"]  # a live view of the page-locked result block
+        flags = store.consume(res) | res.flags
+        self._raise_for_flags(flags)
+        self._apply_state(res)
+        self._last_zero_copy = True
+        self._zero_copy_bytes += int(res.n_winners) * self._row_bytes_total
+        if pooled is not None:
+            return {"status": pooled[2][0:B], "value": pooled[3][0:B]}
+        return {"status": status_h.numpy().copy(), "value": value_h.numpy().copy()}
 
     def add_single(self, solution, objective, measures, **fields):
         """Scalar rule of _grid_archive.py:716-848, run as a batch of one (identical statuses;

@@ -158,6 +158,9 @@ class CVTArchive(DeviceArchive):
     def interval_size(self):
         return self._interval_size
 
+    def _host_measures_ok(self):
+        return self._buckets is not None and not self._force_scan and self._search_method != "scan"
+
     def _pick_method(self, B, C):
         if self._force_scan or self._search_method == "scan":
             return 1

@@ -191,6 +191,7 @@ struct FieldCopy {
   int64_t row_bytes[QD_MAX_FIELDS];
   int64_t snap_off[QD_MAX_FIELDS];  // offset of the field inside the best-elite snapshot
   int vec[QD_MAX_FIELDS];           // 16, 8, 4 or 1
+  int host_src[QD_MAX_FIELDS];      // source rows live in page-locked HOST memory (read over PCIe)
 };
 
 template <typename T>
@@ -390,7 +391,7 @@ __device__ void phase_select(const InsertArgs<T>& a, uint32_t* s_cnt, uint32_t* 
     const int64_t i = b0 + threadIdx.x;
     int32_t c = 0;
     bool iswin = false;
-    if (i < a.B && a.status[i] != 0) {
+    if (i < a.B) {  // `win` stays INT32_MAX for cells without an insertable row: no need to read status
       c = a.idx[i];
       iswin = a.s.cell[c].win == (int32_t)i;
     }
@@ -611,7 +612,7 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
 constexpr int kBulkMinRow = 256;  // rows shorter than this are cheaper through registers
 
 __device__ __forceinline__ bool is_bulk_field(const FieldCopy& fc, int f) {
-  return fc.vec[f] == 16 && fc.row_bytes[f] >= kBulkMinRow;
+  return fc.vec[f] == 16 && fc.row_bytes[f] >= kBulkMinRow && !fc.host_src[f];
 }
 
 // small / unaligned rows: a group of 2^k threads (the smallest power of two covering the row's chunks, at
@@ -875,6 +876,7 @@ __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool 
     r.n_commits = g.n_commits;
     r.best_serial = g.best_serial;
     r.n_failed = g.n_failed;
+    r.n_winners = committed ? g.n_winners : 0;
     *a.result = r;
     g.gbest_key = 0ull;
     g.absmax_bits = 0ull;
@@ -1046,6 +1048,17 @@ int insert_impl(const qd_store* st, int64_t B, int32_t* idx, const GridSpec& gs,
     fc.src[f] = (const char*)field_src[f];
     fc.dst[f] = (char*)st->field_dst[f];
     fc.row_bytes[f] = st->field_row_bytes[f];
+    fc.host_src[f] = 0;
+    // A source in page-locked host memory (zero-copy: only the winners' rows cross PCIe, read by the copy
+    // phase itself) is addressed through its device alias.
+    cudaPointerAttributes pa;
+    if (fc.src[f] && cudaPointerGetAttributes(&pa, fc.src[f]) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+      QD_REQUIRE(pa.devicePointer != nullptr, "host field source is not mapped into the device address space");
+      fc.src[f] = (const char*)pa.devicePointer;
+      fc.host_src[f] = 1;
+    } else {
+      cudaGetLastError();  // unregistered host pointers make the query fail: not ours to handle here
+    }
     fc.vec[f] = pick_vec(fc.src[f], fc.dst[f], fc.row_bytes[f]);
     fc.snap_off[f] = off;
     off += (int64_t)align_up((size_t)fc.row_bytes[f], 16);

@@ -408,3 +408,37 @@ def test_cma_mae_batch_beyond_packed_count_range():
     cand = np.nonzero(obj == best[idx])[0]
     np.minimum.at(first, idx[cand], cand)
     np.testing.assert_array_equal(d["solution"][order, 0], first.astype(np.float64))
+
+
+def test_zero_copy_rows_from_pinned_host_arrays():
+    """When at most cells << batch rows can win, add() of page-locked NumPy arrays does not ship the solution /
+    extra-field rows: the insert kernel reads the winners' rows straight from host memory. Same archive as the
+    DMA path and as device inputs."""
+    import torch
+
+    from pyribs_b200.archives import CVTArchive, GridArchive
+
+    rng = np.random.default_rng(3)
+    cen = rng.uniform(-1, 1, (300, 2))
+    for make in (lambda: CVTArchive(solution_dim=7, centroids=cen, ranges=[(-1, 1)] * 2, extra_fields={"tag": ((), np.int32)}),
+                 lambda: GridArchive(solution_dim=7, dims=[12, 12], ranges=[(-1, 1)] * 2, learning_rate=0.2,
+                                     threshold_min=-2.0, extra_fields={"tag": ((), np.int32)})):
+        a, b = make(), make()
+        b._zero_copy_rows = False
+        for j in range(4):
+            B = 5000
+            pin = dict(solution=torch.from_numpy(rng.standard_normal((B, 7))).pin_memory(),
+                       objective=torch.from_numpy(rng.normal(j, 1.0, B)).pin_memory(),
+                       measures=torch.from_numpy(rng.uniform(-1, 1, (B, 2))).pin_memory(),
+                       tag=torch.from_numpy(rng.integers(0, 1000, B).astype(np.int32)).pin_memory())
+            host = {k: v.numpy() for k, v in pin.items()}
+            ra, rb = a.add(**host), b.add(**host)
+            assert a._last_zero_copy and not b._last_zero_copy
+            np.testing.assert_array_equal(ra["status"], rb["status"])
+            np.testing.assert_array_equal(ra["value"], rb["value"])
+        da, db = a.data(), b.data()
+        for k in da:
+            np.testing.assert_array_equal(da[k], db[k], err_msg=k)
+        assert a._zero_copy_bytes > 0
+        for k in a.best_elite:
+            np.testing.assert_array_equal(a.best_elite[k], b.best_elite[k])

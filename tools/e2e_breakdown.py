@@ -58,6 +58,19 @@ def c2():
     ph2, tot2 = phase_times(a)
     print(json.dumps({"case": "C2 add", "e2e_us": e2e_us, "device_in_sync_us": dev_sync_us, "device_in_async_us": dev_async_us,
                       "host_enqueue_us": t_enq, "insert_phases_us_host_batch": ph, "insert_phases_us_device_batch": ph2, "insert_total_us": tot2}))
+    # search kernel: measures in HBM vs streamed from page-locked host memory; DMA of the same arrays
+    flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+    def ev_time(fn, n=50):
+        for _ in range(5): fn()
+        torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n): fn()
+        e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / n * 1e3
+    md = torch.empty_like(dev[0]["measures"]); od = torch.empty_like(dev[0]["objective"])
+    print(json.dumps({"search_us_measures_in_hbm": ev_time(lambda: a._index_of_device(dev[0]["measures"], flags.data_ptr())),
+                      "search_us_measures_in_pinned_host": ev_time(lambda: a._index_of_device(pin[0]["measures"], flags.data_ptr())),
+                      "dma_measures_us": ev_time(lambda: md.copy_(pin[0]["measures"], non_blocking=True)),
+                      "dma_objective_us": ev_time(lambda: od.copy_(pin[0]["objective"], non_blocking=True))}))
     for label, bs in (("numpy", host), ("device", dev)):
         pr = cProfile.Profile(); pr.enable()
         for j in range(300): a.add(**bs[j % 8])
