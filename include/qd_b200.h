@@ -210,6 +210,15 @@ int qd_insert(const qd_store* store, int64_t B, const int32_t* idx /*[dev] B*/,
               double learning_rate, double threshold_min,
               int32_t* status_out /*[dev] B*/, void* value_out /*[dev] B*/,
               qd_add_result* result /*[dev]*/, int part, void* stream);
+/* Data-parallel variant: the batch is the concatenation of every rank's rows_per_rank rows;
+ * idx / objective are global arrays (exchanged beforehand, 12 B per row), but the row fields stay where they
+ * were produced: peer_field_src [dev] is an (n_ranks x n_fields) table of device pointers -- rank r's slice of
+ * field f, mapped into this GPU's address space (NVLink peer memory) -- and the copy phase of the insert kernel
+ * gathers just the WINNERS' rows from their owners. peer_field_src == NULL: plain qd_insert (field_src used). */
+int qd_insert_sharded_rows(const qd_store* store, int64_t B, const int32_t* idx, const void* objective,
+                           const void* const* field_src, const void* const* peer_field_src /*[dev]*/,
+                           int64_t rows_per_rank, double learning_rate, double threshold_min,
+                           int32_t* status_out, void* value_out, qd_add_result* result, int part, void* stream);
 /* GridArchive.add with A2 fused into the first pass (measures are read once, idx_out is
  * written for the later passes and for the caller). Arguments as qd_grid_index_of + qd_insert. */
 int qd_grid_insert(const qd_store* store, int64_t B, const void* measures /*[dev] B x d*/, int meas_dtype,

@@ -99,6 +99,8 @@ PROTOTYPES = {
     "qd_store_read_state": (_int, [C.POINTER(Store), _vp, _vp]),
     "qd_dp_push": (_int, [_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_vp), _int, _int, _vp]),
     "qd_insert": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _dbl, _dbl, _vp, _vp, _vp, _int, _vp]),
+    "qd_insert_sharded_rows": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _vp, _i64, _dbl, _dbl, _vp, _vp,
+                                      _vp, _int, _vp]),
     "qd_grid_insert": (_int, [C.POINTER(Store), _i64, _vp, _int, _int, C.POINTER(_i32), C.POINTER(_dbl),
                               C.POINTER(_dbl), _dbl, _vp, C.POINTER(_vp), _dbl, _dbl, _vp, _vp, _vp, _vp, _int,
                               _vp]),

@@ -340,18 +340,22 @@ class DeviceArchive:
 
     # ---- exchange step of the data-parallel add() over NVLink peer memory --------------------------
     def _symm_exchange(self, idx, dev, B_local):
-        """Push all-gather: every rank writes its slice of (flags, idx, every batch field) straight into
-        the global arrays of every peer (torch symmetric memory = P2P-mapped cudaMalloc; csrc/abi.cu
-        qd_dp_push), then one cross-rank barrier. Two buffer sets alternate so that a rank running ahead
-        never overwrites arrays a slower peer's insert kernel is still reading. Returns None when
-        symmetric memory cannot be set up (the NCCL all-gathers below are used instead)."""
+        """Exchange step of the data-parallel add() over NVLink peer memory (torch symmetric memory = P2P-mapped
+        cudaMalloc). Every rank pushes its slice of (flags, idx, objective) -- 12 B per row -- straight into the
+        global arrays of every peer (csrc/abi.cu qd_dp_push) and parks its row fields (solutions, measures,
+        extras) in its own symmetric buffer; one cross-rank barrier. The row fields are NOT exchanged: at most
+        `cells` rows can win, and the copy phase of the insert kernel gathers exactly the winners' rows from their
+        owners' buffers (qd_insert_sharded_rows). Two buffer sets alternate so that a rank running ahead never
+        overwrites memory a slower peer's insert kernel is still reading. Returns (global idx, global objective,
+        device pointer of the peer table, global batch size), or None when symmetric memory cannot be set up
+        (the NCCL all-gathers below are used instead)."""
         if self._dp_symm is False:
             return None
         import torch.distributed as dist
 
         store = self._store
-        names = list(dev)
-        key = (B_local, tuple((n, tuple(dev[n].shape[1:]), dev[n].dtype) for n in names))
+        rows = store.row_fields
+        key = B_local  # field shapes / dtypes are fixed per archive
         st = self._dp_symm.get(key) if self._dp_symm else None
         R = self._dp_world
         if st is None:
@@ -359,20 +363,36 @@ class DeviceArchive:
                 import torch.distributed._symmetric_memory as symm
 
                 group = self._dp_group if self._dp_group is not None else dist.group.WORLD
-                slices = [4, 4 * B_local] + [dev[n][0].numel() * dev[n].element_size() * B_local if dev[n].dim() > 1
-                                             else dev[n].element_size() * B_local for n in names]
+                osz = dev["objective"].element_size()
+                small = [4, 4 * B_local, osz * B_local]           # flags, idx, objective: replicated R times
+                local = [store._row_bytes(n) * B_local for n in rows]  # row fields: this rank's slice only
                 offs, total = [], 0
-                for nb in slices:
+                for nb in small:
                     offs.append(total)
                     total += (R * nb + 255) // 256 * 256
+                loffs = []
+                for nb in local:
+                    loffs.append(total)
+                    total += (nb + 255) // 256 * 256
                 bufs, handles = [], []
                 for _ in range(2):
                     t = symm.empty(total, dtype=torch.uint8, device=self._device)
                     handles.append(symm.rendezvous(t, group))
                     bufs.append(t)
-                peers = [(C.c_void_p * R)(*[int(p) for p in h.buffer_ptrs]) for h in handles]
-                st = dict(slices=slices, offs=offs, bufs=bufs, handles=handles, peers=peers, turn=0,
-                          c_slices=(C.c_int64 * len(slices))(*slices), c_offs=(C.c_int64 * len(offs))(*offs))
+                peers, own, tabs, views = [], [], [], []
+                for G, h in zip(bufs, handles):
+                    ptrs = [int(p) for p in h.buffer_ptrs]
+                    peers.append((C.c_void_p * R)(*ptrs))
+                    own.append((C.c_void_p * 1)(ptrs[self._dp_rank]))
+                    tab = np.array([[ptrs[r] + lo for lo in loffs] for r in range(R)], dtype=np.int64)
+                    tabs.append(torch.from_numpy(tab).to(self._device))
+                    views.append((G[offs[1]:offs[1] + R * small[1]].view(torch.int32),
+                                  G[offs[2]:offs[2] + R * small[2]].view(dev["objective"].dtype),
+                                  G[offs[0]:offs[0] + 4 * R].data_ptr()))
+                st = dict(handles=handles, peers=peers, own=own, tabs=tabs, views=views, bufs=bufs, turn=0,
+                          c_small=(C.c_int64 * 3)(*small), c_offs=(C.c_int64 * 3)(*offs),
+                          c_local=(C.c_int64 * max(len(local), 1))(*local),
+                          c_loffs=(C.c_int64 * max(len(loffs), 1))(*loffs))
                 if self._dp_symm is None:
                     self._dp_symm = {}
                 self._dp_symm[key] = st
@@ -381,22 +401,17 @@ class DeviceArchive:
                 return None
         turn = st["turn"]
         st["turn"] = 1 - turn
-        off = store._flags_ptr - store._scratch.data_ptr()
-        flags = store._scratch[off:off + 4]
-        srcs = [flags, idx] + [dev[n] for n in names]
-        c_src = (C.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
-        _lib.check(_lib.lib().qd_dp_push(len(srcs), c_src, st["c_slices"], st["c_offs"], st["peers"][turn], R,
-                                         self._dp_rank, current_stream_ptr()))
+        L = _lib.lib()
+        sp = current_stream_ptr()
+        c_small = (C.c_void_p * 3)(store._flags_ptr, idx.data_ptr(), dev["objective"].data_ptr())
+        _lib.check(L.qd_dp_push(3, c_small, st["c_small"], st["c_offs"], st["peers"][turn], R, self._dp_rank, sp))
+        if rows:
+            c_rows = (C.c_void_p * len(rows))(*[dev[n].data_ptr() for n in rows])
+            _lib.check(L.qd_dp_push(len(rows), c_rows, st["c_local"], st["c_loffs"], st["own"][turn], 1, 0, sp))
         st["handles"][turn].barrier()
-        G = st["bufs"][turn]
-        o, sl = st["offs"], st["slices"]
-        _lib.check(_lib.lib().qd_flags_or(G[o[0]:o[0] + 4 * R].data_ptr(), R, store._flags_ptr, current_stream_ptr()))
-        g_idx = G[o[1]:o[1] + R * sl[1]].view(torch.int32)
-        g_dev = {}
-        for k, n in enumerate(names):
-            t = dev[n]
-            g_dev[n] = G[o[2 + k]:o[2 + k] + R * sl[2 + k]].view(t.dtype).view(R * B_local, *t.shape[1:])
-        return g_idx, g_dev, R * B_local
+        g_idx, g_obj, flags_ptr = st["views"][turn]
+        _lib.check(L.qd_flags_or(flags_ptr, R, store._flags_ptr, sp))
+        return g_idx, g_obj, st["tabs"][turn].data_ptr(), R * B_local
 
     def _gather_global_batch(self, idx, dev, B_local, skip=()):
         """All-gathers the per-rank slices (equal sizes on every rank) into the global batch and
@@ -534,24 +549,30 @@ class DeviceArchive:
                 else:  # only the row-copy phase of the insertion waits for the solutions (qd_insert)
                     rows_event = self._copy_event
             B_local = B
+            peer_tab = None
             if self._dp_world > 1:
                 if global_search:  # idx and measures are already global
                     _, dev, B = self._gather_global_batch(None, dev, B_local, skip=("measures",))
                 else:
                     dev = {n: dev[n].contiguous() for n in dev}
                     got = self._symm_exchange(idx, dev, B_local)
-                    idx, dev, B = got if got is not None else self._gather_global_batch(idx, dev, B_local)
+                    if got is not None:  # row fields stay on their ranks: the insert kernel gathers the winners' rows
+                        idx, g_obj, peer_tab, B = got
+                        dev = {"objective": g_obj}
+                    else:
+                        idx, dev, B = self._gather_global_batch(idx, dev, B_local)
             status, value, status_h, value_h, pooled = self._out_buffers(B, dev_in)
             host_out = False
             names = store.row_fields
-            src = (C.c_void_p * max(len(names), 1))(*[dev[n].data_ptr() for n in names])
+            src = None if peer_tab else (C.c_void_p * max(len(names), 1))(*[dev[n].data_ptr() for n in names])
+
             def insert(part):
                 if fused:
                     self._grid_insert(dev, B, src, status, value, part)
                 else:
-                    _lib.check(_lib.lib().qd_insert(
-                        C.byref(store.abi_store()), B, idx.data_ptr(), dev["objective"].data_ptr(), src,
-                        self._lr_f, self._tmin_f, status.data_ptr(), value.data_ptr(),
+                    _lib.check(_lib.lib().qd_insert_sharded_rows(
+                        C.byref(store.abi_store()), B, idx.data_ptr(), dev["objective"].data_ptr(), src, peer_tab,
+                        B_local, self._lr_f, self._tmin_f, status.data_ptr(), value.data_ptr(),
                         store._result_dev.data_ptr(), part, current_stream_ptr()))
 
             if rows_event is None:

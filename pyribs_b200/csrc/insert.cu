@@ -192,7 +192,18 @@ struct FieldCopy {
   int64_t snap_off[QD_MAX_FIELDS];  // offset of the field inside the best-elite snapshot
   int vec[QD_MAX_FIELDS];           // 16, 8, 4 or 1
   int host_src[QD_MAX_FIELDS];      // source rows live in page-locked HOST memory (read over PCIe)
+  // data-parallel add(): batch row g lives on rank g / rows_per_rank; peer_tab[rank * n + f] is that rank's
+  // slice of field f, mapped into this GPU's address space (NVLink peer memory). NULL: src[] holds all rows.
+  const char* const* peer_tab;
+  int64_t rows_per_rank;
 };
+
+__device__ __forceinline__ const char* src_row(const FieldCopy& fc, int f, int row, int64_t rb) {
+  if (fc.peer_tab == nullptr) return fc.src[f] + (int64_t)row * rb;
+  const int r = (int)(row / fc.rows_per_rank);
+  const int64_t l = row - (int64_t)r * fc.rows_per_rank;
+  return fc.peer_tab[r * fc.n + f] + l * rb;
+}
 
 template <typename T>
 struct InsertArgs {
@@ -612,7 +623,7 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
 constexpr int kBulkMinRow = 256;  // rows shorter than this are cheaper through registers
 
 __device__ __forceinline__ bool is_bulk_field(const FieldCopy& fc, int f) {
-  return fc.vec[f] == 16 && fc.row_bytes[f] >= kBulkMinRow && !fc.host_src[f];
+  return fc.vec[f] == 16 && fc.row_bytes[f] >= kBulkMinRow && !fc.host_src[f] && fc.peer_tab == nullptr;
 }
 
 // small / unaligned rows: a group of 2^k threads (the smallest power of two covering the row's chunks, at
@@ -621,7 +632,6 @@ __device__ void copy_rows_small(const FieldCopy& fc, int f, const Scratch& s, in
                                 int64_t nthreads) {
   const int vec = fc.vec[f];
   const int64_t rb = fc.row_bytes[f];
-  const char* __restrict__ src = fc.src[f];
   char* __restrict__ dst = fc.dst[f];
   const int64_t nch = rb / vec;
   int lg = 0;
@@ -637,12 +647,15 @@ __device__ void copy_rows_small(const FieldCopy& fc, int f, const Scratch& s, in
       const int64_t w = w0 + u * ngrp;
       rc[u] = w < W ? s.wlist[w] : make_int2(-1, -1);
     }
+    const char* sp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sp[u] = rc[u].x >= 0 ? src_row(fc, f, rc[u].x, rb) : nullptr;
     for (int64_t ch = sub; ch < nch; ch += gsz) {
       if (vec == 16) {
         uint4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (rc[u].x >= 0) v[u] = __ldcs(reinterpret_cast<const uint4*>(src + (int64_t)rc[u].x * rb) + ch);
+          if (rc[u].x >= 0) v[u] = __ldcs(reinterpret_cast<const uint4*>(sp[u]) + ch);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (rc[u].x >= 0) __stcs(reinterpret_cast<uint4*>(dst + (int64_t)rc[u].y * rb) + ch, v[u]);
@@ -650,7 +663,7 @@ __device__ void copy_rows_small(const FieldCopy& fc, int f, const Scratch& s, in
         uint2 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (rc[u].x >= 0) v[u] = *(reinterpret_cast<const uint2*>(src + (int64_t)rc[u].x * rb) + ch);
+          if (rc[u].x >= 0) v[u] = *(reinterpret_cast<const uint2*>(sp[u]) + ch);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (rc[u].x >= 0) *(reinterpret_cast<uint2*>(dst + (int64_t)rc[u].y * rb) + ch) = v[u];
@@ -659,11 +672,11 @@ __device__ void copy_rows_small(const FieldCopy& fc, int f, const Scratch& s, in
         for (int u = 0; u < 4; ++u)
           if (rc[u].x >= 0)
             *(reinterpret_cast<uint32_t*>(dst + (int64_t)rc[u].y * rb) + ch) =
-                *(reinterpret_cast<const uint32_t*>(src + (int64_t)rc[u].x * rb) + ch);
+                *(reinterpret_cast<const uint32_t*>(sp[u]) + ch);
       } else {
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (rc[u].x >= 0) dst[(int64_t)rc[u].y * rb + ch] = src[(int64_t)rc[u].x * rb + ch];
+          if (rc[u].x >= 0) dst[(int64_t)rc[u].y * rb + ch] = sp[u][ch];
       }
     }
   }
@@ -1020,7 +1033,8 @@ static int launch_insert(const InsertArgs<T>& a, const GridParams& gp, const Fie
 template <typename T>
 int insert_impl(const qd_store* st, int64_t B, int32_t* idx, const GridSpec& gs, const void* objective,
                 const void* const* field_src, double lr, double tmin, int32_t* status, void* value,
-                qd_add_result* result, int part, cudaStream_t stream) {
+                qd_add_result* result, int part, cudaStream_t stream, const void* const* peer_tab = nullptr,
+                int64_t rows_per_rank = 0) {
   const int64_t N = st->capacity;
   InsertArgs<T> a;
   a.B = B;
@@ -1042,10 +1056,12 @@ int insert_impl(const qd_store* st, int64_t B, int32_t* idx, const GridSpec& gs,
   a.s = carve(st->scratch, N);
   FieldCopy fc;
   fc.n = st->n_fields;
+  fc.peer_tab = reinterpret_cast<const char* const*>(peer_tab);
+  fc.rows_per_rank = rows_per_rank;
   int64_t max_row = 0;
   int64_t off = 32;  // snapshot header: objective, threshold, cell
   for (int f = 0; f < fc.n; ++f) {
-    fc.src[f] = (const char*)field_src[f];
+    fc.src[f] = peer_tab ? nullptr : (const char*)field_src[f];
     fc.dst[f] = (char*)st->field_dst[f];
     fc.row_bytes[f] = st->field_row_bytes[f];
     fc.host_src[f] = 0;
@@ -1215,19 +1231,29 @@ extern "C" int qd_store_read_state(const qd_store* store, qd_add_result* out, vo
 extern "C" int qd_insert(const qd_store* store, int64_t B, const int32_t* idx, const void* objective,
                          const void* const* field_src, double learning_rate, double threshold_min,
                          int32_t* status_out, void* value_out, qd_add_result* result, int part, void* stream) {
+  return qd_insert_sharded_rows(store, B, idx, objective, field_src, nullptr, 0, learning_rate, threshold_min,
+                                status_out, value_out, result, part, stream);
+}
+
+extern "C" int qd_insert_sharded_rows(const qd_store* store, int64_t B, const int32_t* idx, const void* objective,
+                                      const void* const* field_src, const void* const* peer_field_src,
+                                      int64_t rows_per_rank, double learning_rate, double threshold_min,
+                                      int32_t* status_out, void* value_out, qd_add_result* result, int part,
+                                      void* stream) {
   using namespace qd;
   int rc = check_insert_args(store, B, objective, status_out, value_out, result);
   if (rc) return rc;
   QD_REQUIRE(part >= QD_INSERT_WHOLE && part <= QD_INSERT_COMMIT, "part must be QD_INSERT_WHOLE/CLASSIFY/COMMIT");
   if (B > 0) QD_REQUIRE(idx, "null idx");
+  if (peer_field_src) QD_REQUIRE(rows_per_rank >= 1, "rows_per_rank must be positive");
   GridSpec gs;
   gs.gp.d = 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (store->obj_dtype == QD_F64)
     return insert_impl<double>(store, B, const_cast<int32_t*>(idx), gs, objective, field_src, learning_rate,
-                               threshold_min, status_out, value_out, result, part, s);
+                               threshold_min, status_out, value_out, result, part, s, peer_field_src, rows_per_rank);
   return insert_impl<float>(store, B, const_cast<int32_t*>(idx), gs, objective, field_src, learning_rate,
-                            threshold_min, status_out, value_out, result, part, s);
+                            threshold_min, status_out, value_out, result, part, s, peer_field_src, rows_per_rank);
 }
 
 extern "C" int qd_grid_insert(const qd_store* store, int64_t B, const void* measures, int meas_dtype, int d,
