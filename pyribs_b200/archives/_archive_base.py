@@ -9,6 +9,7 @@ _cvt_archive.py:713-909); see SURVEY.md appendix A for the restatement.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import sys
 
@@ -30,6 +31,7 @@ from pyribs_b200.archives._archive_stats import ArchiveStats
 from pyribs_b200.archives._device_store import DeviceStore, current_stream_ptr
 
 _RESERVED = {"solution", "objective", "measures", "threshold", "index"}
+_NULL_CTX = contextlib.nullcontext()
 
 
 def parse_all_dtypes(dtype, solution_dtype, objective_dtype, measures_dtype):
@@ -158,6 +160,7 @@ class DeviceArchive:
         self._last_zero_copy = False
         self._zero_copy_bytes = 0
         self._zc = None
+        self._extra_names = {n for n in self._store.field_list if n not in ("solution", "objective", "measures", "threshold")}
         self._pin_cache = {}
         self._row_bytes_total = sum(self._store._row_bytes(n) for n in self._store.row_fields)
         self._force_scan = False
@@ -500,8 +503,7 @@ class DeviceArchive:
     def add(self, solution, objective, measures, **fields):
         dev_in = is_device_tensor(solution)
         data = validate_batch(self, {"solution": solution, "objective": objective, "measures": measures, **fields})
-        extra_names = [n for n in self._store.field_list if n not in ("solution", "objective", "measures", "threshold")]
-        if set(extra_names) != set(fields):
+        if self._extra_names != set(fields):
             raise ValueError(
                 f"`data` has keys {list(data)} but should have the same keys as this archive's store, i.e., "
                 f"{[n for n in self._store.field_list if n != 'threshold']}. This error may occur if the archive "
@@ -520,7 +522,8 @@ class DeviceArchive:
             out = self._add_zero_copy(data, B)
             if out is not None:
                 return out
-        with torch.cuda.device(self._device):
+        # (entering a device context costs more than the launches below: only when it is not current already)
+        with (_NULL_CTX if torch.cuda.current_device() == self._device.index else torch.cuda.device(self._device)):
             fused = self._dp_world == 1 and self._fused_index_insert
             global_search = self._dp_world > 1 and getattr(self, "_world", 1) > 1  # centroid-sharded CVT
             rows_event = None

@@ -227,19 +227,52 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(BucketView v, int64_t
 
 // ---- search ------------------------------------------------------------------------------
 template <int D>
+__device__ __forceinline__ void consider(const double* __restrict__ x, const BucketView& v, int p, const double (&c)[D],
+                                         double& best, int32_t& bi) {
+  const double dd = sqdist_np<D>(x, c, D);
+  if (dd < best) {  // the id is only fetched for a candidate that matters
+    best = dd;
+    bi = __ldg(v.ids + p);
+  } else if (dd == best) {
+    const int32_t id = __ldg(v.ids + p);
+    if (id < bi) bi = id;
+  }
+}
+
+// points [p0, p1) of the bucket-major array, two at a time so that their loads overlap
+template <int D>
 __device__ __forceinline__ void scan_range(const double* __restrict__ x, const BucketView& v, int p0, int p1,
                                            double& best, int32_t& bi) {
-  for (int p = p0; p < p1; ++p) {
-    double c[D];
+  int p = p0;
+  for (; p + 1 < p1; p += 2) {
+    double c0[D], c1[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) c[k] = __ldg(v.pts + (int64_t)p * D + k);
-    const double dd = sqdist_np<D>(x, c, D);
-    const int32_t id = __ldg(v.ids + p);
-    if (dd < best || (dd == best && id < bi)) {
-      best = dd;
-      bi = id;
+    for (int k = 0; k < D; ++k) {
+      c0[k] = __ldg(v.pts + (int64_t)p * D + k);
+      c1[k] = __ldg(v.pts + (int64_t)(p + 1) * D + k);
     }
+    consider<D>(x, v, p, c0, best, bi);
+    consider<D>(x, v, p + 1, c1, best, bi);
   }
+  if (p < p1) {
+    double c0[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) c0[k] = __ldg(v.pts + (int64_t)p * D + k);
+    consider<D>(x, v, p, c0, best, bi);
+  }
+}
+
+// conservative lower bound on the distance to anything outside the (2r+1)-box around the query's bucket
+template <int D>
+__device__ __forceinline__ double ring_bound(const double* x, const int* bx, int r, const BucketHeader& h) {
+  double lb = INFINITY;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    if (bx[k] - r > 0) lb = fmin(lb, x[k] - (h.lo[k] + (double)(bx[k] - r) * h.w[k]));
+    if (bx[k] + r < h.G[k] - 1) lb = fmin(lb, (h.lo[k] + (double)(bx[k] + r + 1) * h.w[k]) - x[k]);
+  }
+  if (lb == INFINITY) return lb;                  // the box covers the whole grid
+  return lb * (1.0 - 1e-11) - h.margin;           // far larger than any rounding of the faces / the binning
 }
 
 template <typename T, int D>
@@ -250,6 +283,7 @@ __global__ void __launch_bounds__(256) cvt_bucket_kernel(const T* __restrict__ m
   if (threadIdx.x == 0) h = *v.h;
   __syncthreads();
   bool bad = false;
+  constexpr int kRows = D == 1 ? 1 : (D == 2 ? 3 : 9);  // rows of the 3^D start box (last axis contiguous)
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < B; q += (int64_t)gridDim.x * blockDim.x) {
     double x[D];
     int bx[D];
@@ -266,44 +300,58 @@ __global__ void __launch_bounds__(256) cvt_bucket_kernel(const T* __restrict__ m
     int maxG = 0;
 #pragma unroll
     for (int k = 0; k < D; ++k) maxG = max(maxG, h.G[k]);
-    for (int r = 0; r < maxG && !qbad; ++r) {
-      // rows over the leading D-1 axes; the last axis is contiguous in the CSR layout
-      const int lo1 = D >= 2 ? max(bx[0] - r, 0) : 0, hi1 = D >= 2 ? min(bx[0] + r, h.G[0] - 1) : 0;
-      for (int a = lo1; a <= hi1; ++a) {
-        const int lo2 = D >= 3 ? max(bx[1] - r, 0) : 0, hi2 = D >= 3 ? min(bx[1] + r, h.G[1] - 1) : 0;
-        for (int b2 = lo2; b2 <= hi2; ++b2) {
-          int row = 0;
-          bool shell = false;  // some leading axis already sits at Chebyshev distance r
-          if (D >= 2) {
-            row = a;
-            shell |= (abs(a - bx[0]) == r);
-          }
-          if (D >= 3) {
-            row = row * h.G[1] + b2;
-            shell |= (abs(b2 - bx[1]) == r);
-          }
-          const int GL = h.G[D - 1];
-          const int c0 = bx[D - 1] - r, c1 = bx[D - 1] + r;
-          const int rowbase = row * GL;
-          if (shell || r == 0) {
-            const int s0 = max(c0, 0), s1 = min(c1, GL - 1);
-            scan_range<D>(x, v, __ldg(v.start + rowbase + s0), __ldg(v.start + rowbase + s1 + 1), best, bi);
-          } else {
-            if (c0 >= 0) scan_range<D>(x, v, __ldg(v.start + rowbase + c0), __ldg(v.start + rowbase + c0 + 1), best, bi);
-            if (c1 < GL) scan_range<D>(x, v, __ldg(v.start + rowbase + c1), __ldg(v.start + rowbase + c1 + 1), best, bi);
+    if (!qbad) {
+      // rings 0 and 1 together: the whole 3^D box. All row extents are fetched before any point is touched.
+      const int GL = h.G[D - 1];
+      const int s0 = max(bx[D - 1] - 1, 0), s1 = min(bx[D - 1] + 1, GL - 1);
+      int p0[kRows], p1[kRows];
+#pragma unroll
+      for (int t = 0; t < kRows; ++t) {
+        int row = 0;
+        bool in = true;
+        if (D == 2) {
+          row = bx[0] + t - 1;
+          in = row >= 0 && row < h.G[0];
+        } else if (D == 3) {
+          const int a = bx[0] + t / 3 - 1, b2 = bx[1] + t % 3 - 1;
+          in = a >= 0 && a < h.G[0] && b2 >= 0 && b2 < h.G[1];
+          row = a * h.G[1] + b2;
+        }
+        p0[t] = in ? __ldg(v.start + row * GL + s0) : 0;
+        p1[t] = in ? __ldg(v.start + row * GL + s1 + 1) : 0;
+      }
+#pragma unroll
+      for (int t = 0; t < kRows; ++t) scan_range<D>(x, v, p0[t], p1[t], best, bi);
+      double lb = ring_bound<D>(x, bx, 1, h);
+      for (int r = 2; r < maxG && !(lb == INFINITY) && !(lb > 0.0 && best < lb * lb); ++r) {
+        // shell of Chebyshev radius r: rows over the leading D-1 axes; the last axis is contiguous in the CSR layout
+        const int lo1 = D >= 2 ? max(bx[0] - r, 0) : 0, hi1 = D >= 2 ? min(bx[0] + r, h.G[0] - 1) : 0;
+        for (int a = lo1; a <= hi1; ++a) {
+          const int lo2 = D >= 3 ? max(bx[1] - r, 0) : 0, hi2 = D >= 3 ? min(bx[1] + r, h.G[1] - 1) : 0;
+          for (int b2 = lo2; b2 <= hi2; ++b2) {
+            int row = 0;
+            bool shell = false;  // some leading axis already sits at Chebyshev distance r
+            if (D >= 2) {
+              row = a;
+              shell |= (abs(a - bx[0]) == r);
+            }
+            if (D >= 3) {
+              row = row * h.G[1] + b2;
+              shell |= (abs(b2 - bx[1]) == r);
+            }
+            const int c0 = bx[D - 1] - r, c1 = bx[D - 1] + r;
+            const int rowbase = row * GL;
+            if (shell) {
+              const int t0 = max(c0, 0), t1 = min(c1, GL - 1);
+              scan_range<D>(x, v, __ldg(v.start + rowbase + t0), __ldg(v.start + rowbase + t1 + 1), best, bi);
+            } else {
+              if (c0 >= 0) scan_range<D>(x, v, __ldg(v.start + rowbase + c0), __ldg(v.start + rowbase + c0 + 1), best, bi);
+              if (c1 < GL) scan_range<D>(x, v, __ldg(v.start + rowbase + c1), __ldg(v.start + rowbase + c1 + 1), best, bi);
+            }
           }
         }
+        lb = ring_bound<D>(x, bx, r, h);
       }
-      // everything not visited yet lies beyond one of the faces of the (2r+1)-box
-      double lb = INFINITY;
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        if (bx[k] - r > 0) lb = fmin(lb, x[k] - (h.lo[k] + (double)(bx[k] - r) * h.w[k]));
-        if (bx[k] + r < h.G[k] - 1) lb = fmin(lb, (h.lo[k] + (double)(bx[k] + r + 1) * h.w[k]) - x[k]);
-      }
-      if (lb == INFINITY) break;  // the box covers the whole grid
-      lb = lb * (1.0 - 1e-11) - h.margin;  // far larger than any rounding of the faces / the binning
-      if (lb > 0.0 && best < lb * lb) break;
     }
     idx[q] = qbad ? base : ((bi == INT32_MAX ? 0 : bi) + base);
     if (dist_out) dist_out[q] = qbad ? INFINITY : best;
