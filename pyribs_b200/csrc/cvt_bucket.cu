@@ -239,6 +239,20 @@ __device__ __forceinline__ void consider(const double* __restrict__ x, const Buc
   }
 }
 
+// one point of the bucket-major array; 2-D points are 16-byte aligned: one vector load (scattered loads cost
+// L1 wavefronts per lane and per instruction, and this kernel is bound by them)
+template <int D>
+__device__ __forceinline__ void load_point(const BucketView& v, int p, double (&c)[D]) {
+  if constexpr (D == 2) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(v.pts) + p);
+    c[0] = t.x;
+    c[1] = t.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) c[k] = __ldg(v.pts + (int64_t)p * D + k);
+  }
+}
+
 // points [p0, p1) of the bucket-major array, two at a time so that their loads overlap
 template <int D>
 __device__ __forceinline__ void scan_range(const double* __restrict__ x, const BucketView& v, int p0, int p1,
@@ -246,18 +260,14 @@ __device__ __forceinline__ void scan_range(const double* __restrict__ x, const B
   int p = p0;
   for (; p + 1 < p1; p += 2) {
     double c0[D], c1[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      c0[k] = __ldg(v.pts + (int64_t)p * D + k);
-      c1[k] = __ldg(v.pts + (int64_t)(p + 1) * D + k);
-    }
+    load_point<D>(v, p, c0);
+    load_point<D>(v, p + 1, c1);
     consider<D>(x, v, p, c0, best, bi);
     consider<D>(x, v, p + 1, c1, best, bi);
   }
   if (p < p1) {
     double c0[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) c0[k] = __ldg(v.pts + (int64_t)p * D + k);
+    load_point<D>(v, p, c0);
     consider<D>(x, v, p, c0, best, bi);
   }
 }
@@ -275,7 +285,7 @@ __device__ __forceinline__ double ring_bound(const double* x, const int* bx, int
   return lb * (1.0 - 1e-11) - h.margin;           // far larger than any rounding of the faces / the binning
 }
 
-template <typename T, int D>
+template <typename T, int D, bool VEC>
 __global__ void __launch_bounds__(256) cvt_bucket_kernel(const T* __restrict__ meas, int64_t B, BucketView v,
                                                        int32_t base, int32_t* __restrict__ idx,
                                                        double* __restrict__ dist_out, uint32_t* flags) {
@@ -288,9 +298,16 @@ __global__ void __launch_bounds__(256) cvt_bucket_kernel(const T* __restrict__ m
     double x[D];
     int bx[D];
     bool qbad = false;
+    if constexpr (VEC) {  // 2-D fp64 rows on a 16-byte aligned base
+      const double2 t = reinterpret_cast<const double2*>(meas)[q];
+      x[0] = t.x;
+      x[1] = t.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; ++k) x[k] = (double)meas[q * D + k];
+    }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      x[k] = (double)meas[q * D + k];
       qbad |= !finite_d(x[k]);
       bx[k] = bucket_coord<D>(x[k], k, h);
     }
@@ -364,9 +381,14 @@ static int launch_bucket(const T* meas, int64_t B, int d, BucketView v, int32_t 
                          uint32_t* flags, cudaStream_t s) {
   const int grid = grid_for(B, 256, 8);
   switch (d) {
-    case 1: cvt_bucket_kernel<T, 1><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags); break;
-    case 2: cvt_bucket_kernel<T, 2><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags); break;
-    case 3: cvt_bucket_kernel<T, 3><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags); break;
+    case 1: cvt_bucket_kernel<T, 1, false><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags); break;
+    case 2:
+      if (sizeof(T) == 8 && ((uintptr_t)meas & 15) == 0)
+        cvt_bucket_kernel<T, 2, sizeof(T) == 8><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags);
+      else
+        cvt_bucket_kernel<T, 2, false><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags);
+      break;
+    case 3: cvt_bucket_kernel<T, 3, false><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags); break;
     default: set_error("bucket search supports measure_dim <= 3"); return QD_ERR_UNSUPPORTED;
   }
   return check_launch("cvt_bucket_kernel");
