@@ -226,36 +226,53 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(BucketView v, int64_t
 }
 
 // ---- search ------------------------------------------------------------------------------
-template <int D>
-__device__ __forceinline__ void consider(const double* __restrict__ x, const BucketView& v, int p, const double (&c)[D],
+// Where the search reads the structure from: global memory through the read-only path, or a copy the CTA
+// staged in shared memory (random 16-byte gathers cost ~2 L1 wavefront-cycles per lane from global memory,
+// a few bank conflicts from shared memory). ids stay in global memory: they are fetched for improving
+// candidates only.
+template <bool SMEM>
+struct BSrc {
+  const double* pts;
+  const int32_t* start;
+  const int32_t* ids;
+  __device__ __forceinline__ int32_t st(int i) const { return SMEM ? start[i] : __ldg(start + i); }
+  __device__ __forceinline__ int32_t id(int p) const { return __ldg(ids + p); }
+  __device__ __forceinline__ double pt(int64_t i) const { return SMEM ? pts[i] : __ldg(pts + i); }
+  __device__ __forceinline__ double2 pt2(int p) const {
+    return SMEM ? reinterpret_cast<const double2*>(pts)[p] : __ldg(reinterpret_cast<const double2*>(pts) + p);
+  }
+};
+
+template <int D, class S>
+__device__ __forceinline__ void consider(const double* __restrict__ x, const S& v, int p, const double (&c)[D],
                                          double& best, int32_t& bi) {
   const double dd = sqdist_np<D>(x, c, D);
   if (dd < best) {  // the id is only fetched for a candidate that matters
     best = dd;
-    bi = __ldg(v.ids + p);
+    bi = v.id(p);
   } else if (dd == best) {
-    const int32_t id = __ldg(v.ids + p);
+    const int32_t id = v.id(p);
     if (id < bi) bi = id;
   }
 }
 
 // one point of the bucket-major array; 2-D points are 16-byte aligned: one vector load (scattered loads cost
 // L1 wavefronts per lane and per instruction, and this kernel is bound by them)
-template <int D>
-__device__ __forceinline__ void load_point(const BucketView& v, int p, double (&c)[D]) {
+template <int D, class S>
+__device__ __forceinline__ void load_point(const S& v, int p, double (&c)[D]) {
   if constexpr (D == 2) {
-    const double2 t = __ldg(reinterpret_cast<const double2*>(v.pts) + p);
+    const double2 t = v.pt2(p);
     c[0] = t.x;
     c[1] = t.y;
   } else {
 #pragma unroll
-    for (int k = 0; k < D; ++k) c[k] = __ldg(v.pts + (int64_t)p * D + k);
+    for (int k = 0; k < D; ++k) c[k] = v.pt((int64_t)p * D + k);
   }
 }
 
 // points [p0, p1) of the bucket-major array, two at a time so that their loads overlap
-template <int D>
-__device__ __forceinline__ void scan_range(const double* __restrict__ x, const BucketView& v, int p0, int p1,
+template <int D, class S>
+__device__ __forceinline__ void scan_range(const double* __restrict__ x, const S& v, int p0, int p1,
                                            double& best, int32_t& bi) {
   int p = p0;
   for (; p + 1 < p1; p += 2) {
@@ -285,13 +302,33 @@ __device__ __forceinline__ double ring_bound(const double* x, const int* bx, int
   return lb * (1.0 - 1e-11) - h.margin;           // far larger than any rounding of the faces / the binning
 }
 
-template <typename T, int D, bool VEC>
-__global__ void __launch_bounds__(256) cvt_bucket_kernel(const T* __restrict__ meas, int64_t B, BucketView v,
-                                                       int32_t base, int32_t* __restrict__ idx,
-                                                       double* __restrict__ dist_out, uint32_t* flags) {
+template <typename T, int D, bool VEC, bool SMEM>
+__global__ void __launch_bounds__(SMEM ? 1024 : 256) cvt_bucket_kernel(const T* __restrict__ meas, int64_t B,
+                                                                     BucketView bv, int32_t base,
+                                                                     int32_t* __restrict__ idx,
+                                                                     double* __restrict__ dist_out, uint32_t* flags,
+                                                                     int64_t C) {
   __shared__ BucketHeader h;
-  if (threadIdx.x == 0) h = *v.h;
+  extern __shared__ __align__(16) unsigned char bucket_smem[];
+  if (threadIdx.x == 0) h = *bv.h;
   __syncthreads();
+  BSrc<SMEM> v;
+  v.ids = bv.ids;
+  if constexpr (SMEM) {  // stage points + CSR offsets once per CTA (both 16-byte aligned, sizes padded by the host)
+    const int64_t pts16 = (C * D * 8 + 15) / 16, st16 = ((int64_t)(h.nb + 1) * 4 + 15) / 16;
+    uint4* sp = reinterpret_cast<uint4*>(bucket_smem);
+    uint4* ss = sp + pts16;
+    const uint4* gp = reinterpret_cast<const uint4*>(bv.pts);
+    const uint4* gs = reinterpret_cast<const uint4*>(bv.start);
+    for (int64_t t = threadIdx.x; t < pts16; t += blockDim.x) sp[t] = __ldg(gp + t);
+    for (int64_t t = threadIdx.x; t < st16; t += blockDim.x) ss[t] = __ldg(gs + t);
+    __syncthreads();
+    v.pts = reinterpret_cast<const double*>(sp);
+    v.start = reinterpret_cast<const int32_t*>(ss);
+  } else {
+    v.pts = bv.pts;
+    v.start = bv.start;
+  }
   bool bad = false;
   constexpr int kRows = D == 1 ? 1 : (D == 2 ? 3 : 9);  // rows of the 3^D start box (last axis contiguous)
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < B; q += (int64_t)gridDim.x * blockDim.x) {
@@ -334,8 +371,8 @@ __global__ void __launch_bounds__(256) cvt_bucket_kernel(const T* __restrict__ m
           in = a >= 0 && a < h.G[0] && b2 >= 0 && b2 < h.G[1];
           row = a * h.G[1] + b2;
         }
-        p0[t] = in ? __ldg(v.start + row * GL + s0) : 0;
-        p1[t] = in ? __ldg(v.start + row * GL + s1 + 1) : 0;
+        p0[t] = in ? v.st(row * GL + s0) : 0;
+        p1[t] = in ? v.st(row * GL + s1 + 1) : 0;
       }
 #pragma unroll
       for (int t = 0; t < kRows; ++t) scan_range<D>(x, v, p0[t], p1[t], best, bi);
@@ -360,10 +397,10 @@ __global__ void __launch_bounds__(256) cvt_bucket_kernel(const T* __restrict__ m
             const int rowbase = row * GL;
             if (shell) {
               const int t0 = max(c0, 0), t1 = min(c1, GL - 1);
-              scan_range<D>(x, v, __ldg(v.start + rowbase + t0), __ldg(v.start + rowbase + t1 + 1), best, bi);
+              scan_range<D>(x, v, v.st(rowbase + t0), v.st(rowbase + t1 + 1), best, bi);
             } else {
-              if (c0 >= 0) scan_range<D>(x, v, __ldg(v.start + rowbase + c0), __ldg(v.start + rowbase + c0 + 1), best, bi);
-              if (c1 < GL) scan_range<D>(x, v, __ldg(v.start + rowbase + c1), __ldg(v.start + rowbase + c1 + 1), best, bi);
+              if (c0 >= 0) scan_range<D>(x, v, v.st(rowbase + c0), v.st(rowbase + c0 + 1), best, bi);
+              if (c1 < GL) scan_range<D>(x, v, v.st(rowbase + c1), v.st(rowbase + c1 + 1), best, bi);
             }
           }
         }
@@ -376,30 +413,55 @@ __global__ void __launch_bounds__(256) cvt_bucket_kernel(const T* __restrict__ m
   if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, QD_FLAG_NONFINITE_MEASURES);
 }
 
-template <typename T>
-static int launch_bucket(const T* meas, int64_t B, int d, BucketView v, int32_t base, int32_t* idx, double* dist,
-                         uint32_t* flags, cudaStream_t s) {
+constexpr size_t kBucketSmemMax = 200 * 1024;
+
+template <typename T, int D>
+static int launch_bucket_d(const T* meas, int64_t B, int64_t C, BucketView v, int32_t base, int32_t* idx, double* dist,
+                           uint32_t* flags, cudaStream_t s) {
+  const bool vec = D == 2 && sizeof(T) == 8 && ((uintptr_t)meas & 15) == 0;
+  // points + CSR offsets of small shards fit in shared memory: one CTA per SM stages them and serves a slice
+  // of the queries from there
+  const int64_t nb = bucket_count(C, D);
+  const size_t smem = (size_t)((C * D * 8 + 15) / 16 + ((nb + 1) * 4 + 15) / 16) * 16;
+  if (smem <= kBucketSmemMax && B >= 4096) {
+    const int grid = (int)((B + 1023) / 1024 < kNumSMs ? (B + 1023) / 1024 : kNumSMs);
+    if (vec) {
+      QD_CHECK_CUDA(cudaFuncSetAttribute(cvt_bucket_kernel<T, D, D == 2 && sizeof(T) == 8, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBucketSmemMax));
+      cvt_bucket_kernel<T, D, D == 2 && sizeof(T) == 8, true><<<grid, 1024, smem, s>>>(meas, B, v, base, idx, dist,
+                                                                                     flags, C);
+    } else {
+      QD_CHECK_CUDA(cudaFuncSetAttribute(cvt_bucket_kernel<T, D, false, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBucketSmemMax));
+      cvt_bucket_kernel<T, D, false, true><<<grid, 1024, smem, s>>>(meas, B, v, base, idx, dist, flags, C);
+    }
+    return check_launch("cvt_bucket_kernel(smem)");
+  }
   const int grid = grid_for(B, 256, 8);
+  if (vec)
+    cvt_bucket_kernel<T, D, D == 2 && sizeof(T) == 8, false><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags, C);
+  else
+    cvt_bucket_kernel<T, D, false, false><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags, C);
+  return check_launch("cvt_bucket_kernel");
+}
+
+template <typename T>
+static int launch_bucket(const T* meas, int64_t B, int d, int64_t C, BucketView v, int32_t base, int32_t* idx,
+                         double* dist, uint32_t* flags, cudaStream_t s) {
   switch (d) {
-    case 1: cvt_bucket_kernel<T, 1, false><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags); break;
-    case 2:
-      if (sizeof(T) == 8 && ((uintptr_t)meas & 15) == 0)
-        cvt_bucket_kernel<T, 2, sizeof(T) == 8><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags);
-      else
-        cvt_bucket_kernel<T, 2, false><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags);
-      break;
-    case 3: cvt_bucket_kernel<T, 3, false><<<grid, 256, 0, s>>>(meas, B, v, base, idx, dist, flags); break;
+    case 1: return launch_bucket_d<T, 1>(meas, B, C, v, base, idx, dist, flags, s);
+    case 2: return launch_bucket_d<T, 2>(meas, B, C, v, base, idx, dist, flags, s);
+    case 3: return launch_bucket_d<T, 3>(meas, B, C, v, base, idx, dist, flags, s);
     default: set_error("bucket search supports measure_dim <= 3"); return QD_ERR_UNSUPPORTED;
   }
-  return check_launch("cvt_bucket_kernel");
 }
 
 int cvt_bucket_index_of(const void* measures, int dtype, int64_t B, int d, int64_t C, const void* buckets,
                         int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags, cudaStream_t s) {
   BucketView v = carve_bucket(const_cast<void*>(buckets), C, d);
   if (dtype == QD_F64)
-    return launch_bucket<double>((const double*)measures, B, d, v, index_base, idx_out, dist_out, flags, s);
-  return launch_bucket<float>((const float*)measures, B, d, v, index_base, idx_out, dist_out, flags, s);
+    return launch_bucket<double>((const double*)measures, B, d, C, v, index_base, idx_out, dist_out, flags, s);
+  return launch_bucket<float>((const float*)measures, B, d, C, v, index_base, idx_out, dist_out, flags, s);
 }
 
 }  // namespace qd
