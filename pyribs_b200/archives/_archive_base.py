@@ -160,6 +160,8 @@ class DeviceArchive:
         self._last_zero_copy = False
         self._zero_copy_bytes = 0
         self._zc = None
+        self._shared_idx = None  # (device idx tensor, B) handed over by an archive of the same geometry (result_archive)
+        self._last_idx = None    # (device idx tensor, B) of the last completed, waited-for add()
         self._extra_names = {n for n in self._store.field_list if n not in ("solution", "objective", "measures", "threshold")}
         self._pin_cache = {}
         self._row_bytes_total = sum(self._store._row_bytes(n) for n in self._store.row_fields)
@@ -324,6 +326,11 @@ class DeviceArchive:
 
     def _index_of_device(self, measures: torch.Tensor, flags_ptr: int) -> torch.Tensor:
         raise NotImplementedError
+
+    def same_geometry(self, other):
+        """True when `other` maps every measure vector to the same cell index as this archive (then a batch
+        indexed for one of them needs no second index_of: Scheduler's result_archive, _scheduler.py:260-264)."""
+        return False
 
     def _host_measures_ok(self):
         """True when the index kernel of the next add() may read the measures straight from page-locked host
@@ -511,6 +518,10 @@ class DeviceArchive:
             )
         B = int(data["solution"].shape[0])
         odt = self.dtypes["objective"]
+        self._last_idx = None
+        preset, self._shared_idx = self._shared_idx, None
+        if preset is not None and preset[1] != B:
+            preset = None
         if B == 0:
             if dev_in:
                 return {"status": torch.empty(0, dtype=torch.int32, device=self._device),
@@ -518,14 +529,17 @@ class DeviceArchive:
             return {"status": np.empty(0, dtype=np.int32), "value": np.empty(0, dtype=odt)}
         store = self._store
         if (not dev_in and self._dp_world == 1 and self.cells * 2 <= B and self._zero_copy_rows
-                and self._host_measures_ok() and torch.cuda.current_device() == self._device.index):
-            out = self._add_zero_copy(data, B)
+                and (preset is not None or self._host_measures_ok())
+                and torch.cuda.current_device() == self._device.index):
+            out = self._add_zero_copy(data, B, preset)
             if out is not None:
                 return out
         # (entering a device context costs more than the launches below: only when it is not current already)
         with (_NULL_CTX if torch.cuda.current_device() == self._device.index else torch.cuda.device(self._device)):
-            fused = self._dp_world == 1 and self._fused_index_insert
+            fused = self._dp_world == 1 and self._fused_index_insert and preset is None
             global_search = self._dp_world > 1 and getattr(self, "_world", 1) > 1  # centroid-sharded CVT
+            if self._dp_world > 1:
+                preset = None
             rows_event = None
             self._last_zero_copy = False
             # measures + objective first: the index kernels only need those, so the (much larger)
@@ -534,7 +548,10 @@ class DeviceArchive:
             if global_search:
                 # every rank searches ALL queries against its centroid shard: gather the measures first
                 dev["measures"] = self._all_gather_many([dev["measures"]])[0]
-            idx = None if fused else self._index_of_device(dev["measures"], store._flags_ptr)
+            if preset is not None:  # an archive of the same geometry has just indexed this very batch
+                idx = preset[0]
+            else:
+                idx = None if fused else self._index_of_device(dev["measures"], store._flags_ptr)
             rest = [n for n in data if n not in dev]
             if dev_in or all(isinstance(data[n], torch.Tensor) for n in rest):
                 for n in rest:
@@ -615,6 +632,8 @@ class DeviceArchive:
                 self._force_scan = False
         self._raise_for_flags(flags)
         self._apply_state(res)
+        if self._dp_world == 1:
+            self._last_idx = (idx if idx is not None else self._idx_buf[:B], B)
         if dev_in:
             return {"status": status[lo:hi], "value": value[lo:hi]} if self._dp_world > 1 else \
                 {"status": status, "value": value}
@@ -642,7 +661,7 @@ class DeviceArchive:
             hit = self._pin_cache[key] = bool(torch.from_numpy(arr).is_pinned())
         return hit
 
-    def _add_zero_copy(self, data, B):
+    def _add_zero_copy(self, data, B, preset=None):
         """At most `cells` rows of a batch can win, so shipping every solution row to the GPU is wasted PCIe
         traffic. With page-locked inputs: the search / classify phases stream the measures straight from host
         memory (coalesced zero-copy reads, no DMA set-up latency) while the objective vector travels by DMA
@@ -677,8 +696,11 @@ class DeviceArchive:
         _lib.check(L.qd_event_record(zc["ep"], zc["sp"]))
         meas = data["measures"]
         host_meas = self._HostRows(meas.__array_interface__["data"][0], meas.shape)
-        fused = self._fused_index_insert
-        idx = None if fused else self._index_of_device(host_meas, store._flags_ptr)
+        fused = self._fused_index_insert and preset is None
+        if preset is not None:
+            idx = preset[0]
+        else:
+            idx = None if fused else self._index_of_device(host_meas, store._flags_ptr)
         _lib.check(L.qd_stream_wait_event(sp, zc["ep"]))
         status, value, status_h, value_h, pooled = self._out_buffers(B, False)
         if pooled is not None:  # the kernel writes straight into the buffers the caller gets
@@ -705,6 +727,7 @@ class DeviceArchive:
         self._apply_state(res)
         self._last_zero_copy = True
         self._zero_copy_bytes += int(res.n_winners) * self._row_bytes_total
+        self._last_idx = (idx if idx is not None else self._idx_buf[:B], B)
         if pooled is not None:
             return {"status": pooled[2][0:B], "value": pooled[3][0:B]}
         return {"status": status_h.numpy().copy(), "value": value_h.numpy().copy()}

@@ -140,6 +140,7 @@ class CVTArchive(DeviceArchive):
                                                      self._measure_dim, self._prepared.data_ptr(),
                                                      current_stream_ptr()))
         self._cvt_scratch = None
+        self._geom_cache = {}
         self._force_scan = False
 
     @property
@@ -157,6 +158,17 @@ class CVTArchive(DeviceArchive):
     @property
     def interval_size(self):
         return self._interval_size
+
+    def same_geometry(self, other):
+        key = id(other)
+        hit = self._geom_cache.get(key)
+        if hit is None:
+            hit = self._geom_cache[key] = bool(
+                type(other) is type(self) and self._device == other._device
+                and self._centroids.shape == other._centroids.shape and self._centroids.dtype == other._centroids.dtype
+                and getattr(other, "_world", 1) == 1 and self._world == 1
+                and np.array_equal(self._centroids, other._centroids))
+        return hit
 
     def _host_measures_ok(self):
         return self._buckets is not None and not self._force_scan and self._search_method != "scan"

@@ -94,6 +94,12 @@ class GridArchive(DeviceArchive):
             float(self._epsilon), idx.data_ptr(), flags_ptr, current_stream_ptr()))
         return idx
 
+    def same_geometry(self, other):
+        return (type(other) is type(self) and np.array_equal(self._dims, other._dims)
+                and np.array_equal(self._lower_bounds, other._lower_bounds)
+                and np.array_equal(self._upper_bounds, other._upper_bounds) and self._epsilon == other._epsilon
+                and self.dtypes["measures"] == other.dtypes["measures"] and self._device == other._device)
+
     def _grid_insert(self, dev, B, src, status, value, part):
         """A2 + A4-A8 in one ABI call (qd_grid_insert): measures are read once."""
         store = self._store

@@ -72,6 +72,12 @@ class Scheduler:
         if self._add_mode == "batch":
             add_info = self._archive.add(**data)
             if self._result_archive is not None:
+                # both archives index the same measures: when their geometry is identical the cell indices
+                # computed for `archive` are handed to `result_archive` (one index_of for the double insert)
+                last = getattr(self._archive, "_last_idx", None)
+                if last is not None and hasattr(self._result_archive, "same_geometry") and \
+                        self._result_archive.same_geometry(self._archive):
+                    self._result_archive._shared_idx = last
                 self._result_archive.add(**data)
         else:
             infos = []

@@ -442,3 +442,48 @@ def test_zero_copy_rows_from_pinned_host_arrays():
         assert a._zero_copy_bytes > 0
         for k in a.best_elite:
             np.testing.assert_array_equal(a.best_elite[k], b.best_elite[k])
+
+
+@pytest.mark.parametrize("kind", ["grid", "cvt"])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_result_archive_shares_the_index_of_the_main_archive(kind, pinned):
+    """Scheduler(archive, emitters, result_archive=...) inserts every batch into two archives of the same
+    geometry (CMA-MAE: _scheduler.py:260-264). The second insertion reuses the cell indices of the first;
+    the result archive must equal one that indexed the batch itself."""
+    import torch
+
+    from pyribs_b200.archives import CVTArchive, GridArchive
+    from pyribs_b200.schedulers import Scheduler
+
+    rng = np.random.default_rng(17)
+    cen = rng.uniform(-1, 1, (400, 2))
+
+    def make(lr):
+        kw = dict(learning_rate=lr, threshold_min=0.0) if lr is not None else {}
+        if kind == "grid":
+            return GridArchive(solution_dim=6, dims=[15, 15], ranges=[(-1, 1)] * 2, **kw)
+        return CVTArchive(solution_dim=6, centroids=cen, ranges=[(-1, 1)] * 2, **kw)
+
+    main, shared, alone = make(0.05), make(None), make(None)
+    assert shared.same_geometry(main) and not shared.same_geometry(GridArchive(solution_dim=6, dims=[15, 16],
+                                                                               ranges=[(-1, 1)] * 2))
+
+    class _Stub:  # Scheduler only needs something emitter-shaped to be constructed
+        pass
+
+    sched = Scheduler(main, [_Stub()], result_archive=shared, pool_emitters=False)
+    for j in range(4):
+        B = 3000
+        b = dict(solution=rng.standard_normal((B, 6)), objective=rng.uniform(0, 10, B) + j,
+                 measures=rng.uniform(-1.1, 1.1, (B, 2)))
+        if pinned:
+            keep = {k: torch.from_numpy(v).pin_memory() for k, v in b.items()}
+            b = {k: v.numpy() for k, v in keep.items()}
+        sched._add_to_archives(dict(b))
+        assert shared._last_idx is not None and main._last_idx is not None
+        alone.add(**b)
+    ds, da = shared.data(), alone.data()
+    assert len(shared) == len(alone) > 100
+    for k in ds:
+        np.testing.assert_array_equal(ds[k], da[k], err_msg=k)
+    assert shared.stats.qd_score == alone.stats.qd_score
