@@ -281,6 +281,21 @@ int qd_sym_max(int64_t n, double* A /*[dev] n x n*/, void* stream);          /* 
 int qd_sym_eigh_batched(int64_t n, int64_t batch, const double* A /*[dev] batch x n x n*/,
                         double* eig /*[dev] batch x n*/, double* V /*[dev] batch x n x n*/,
                         int* sweeps /*[dev] batch or NULL*/, void* stream);
+/* ------------------------------------------------------------------------------------
+ * Variation operators of the MAP-Elites emitters (next rows of the scope table)
+ *   GaussianEmitter.ask   ribs/emitters/_gaussian_emitter.py:139-166
+ *   IsoLineEmitter.ask    ribs/emitters/_iso_line_emitter.py:156-201
+ * X[k] = clip(P[a_k] + sigma * z[k] (+ line_sigma * line_z[k] * (P[b_k] - P[a_k])), lower, upper), P = the
+ * archive's solution field; parent lists NULL: every parent is x0 (empty archive). iso_sigma holds one value
+ * or n values (sigma_is_vector) in the solution dtype. line_z == NULL selects the Gaussian operator.
+ * ---------------------------------------------------------------------------------- */
+int qd_emit_variation(const void* store_solution /*[dev] capacity x n*/, int dtype, int64_t n, int64_t B,
+                      const int32_t* parent_a /*[dev] B or NULL*/, const int32_t* parent_b /*[dev] B or NULL*/,
+                      const void* x0 /*[dev] n or NULL*/, const double* z /*[dev] B x n unit normals*/,
+                      const double* line_z /*[dev] B or NULL*/, const void* iso_sigma /*[dev] 1 or n*/,
+                      int sigma_is_vector, double line_sigma, const void* lower /*[dev] n*/,
+                      const void* upper /*[dev] n*/, void* X_out /*[dev] B x n*/, void* stream);
+
 /* CMA-ES pool: E strategies of identical (n, lambda) whose state is stacked in device memory; every
  * kernel is batched over the emitters (the many-emitter regime: ribs/schedulers/_scheduler.py:180-213,
  * 361-412 loops ask/tell over the emitters in Python). Arithmetic identical to the single-strategy entry

@@ -381,6 +381,41 @@ def gen_rankers():
     save("rankers", out)
 
 
+# ---------------------------------------------------------------------------------------
+# 6. GaussianEmitter / IsoLineEmitter asks (MAP-Elites variation operators)
+# ---------------------------------------------------------------------------------------
+def gen_emitters():
+    from ribs.emitters import GaussianEmitter, IsoLineEmitter
+
+    out = {}
+    for tag, dtype, bounded in (("f64", np.float64, False), ("f64_bounds", np.float64, True), ("f32", np.float32, False)):
+        rng = np.random.default_rng(21)
+        n, B = 7, 48
+        arch = GridArchive(solution_dim=n, dims=(12, 12), ranges=[(-1, 1)] * 2, seed=77, dtype=dtype)
+        fill = dict(solution=rng.standard_normal((600, n)).astype(dtype), objective=rng.standard_normal(600).astype(dtype),
+                    measures=rng.uniform(-1, 1, (600, 2)).astype(dtype))
+        lo = np.full(n, -0.8, dtype=dtype) if bounded else None
+        hi = np.full(n, 0.9, dtype=dtype) if bounded else None
+        sig = np.linspace(0.05, 0.3, n).astype(dtype)
+        ge = GaussianEmitter(arch, sigma=sig, x0=np.full(n, 0.25), lower_bounds=lo, upper_bounds=hi, batch_size=B, seed=5)
+        ie = IsoLineEmitter(arch, iso_sigma=0.02, line_sigma=0.3, x0=np.full(n, -0.1), lower_bounds=lo, upper_bounds=hi,
+                            batch_size=B, seed=6)
+        g_rng, i_rng = np.random.default_rng(5), np.random.default_rng(6)  # replay the emitters' normal streams
+        case = {"cfg": {"n": n, "B": B, "f32": int(dtype == np.float32), "bounded": int(bounded), "sigma": sig,
+                        "iso_sigma": 0.02, "line_sigma": 0.3, "gx0": np.full(n, 0.25), "ix0": np.full(n, -0.1)},
+                "fill": fill}
+        for step in range(3):  # step 0: empty archive (parents = x0); then two asks on the filled archive
+            if step == 1:
+                arch.add(**fill)
+            zg = g_rng.standard_normal((B, n))
+            xg = ge.ask()
+            zi, zl = i_rng.standard_normal((B, n)), i_rng.standard_normal((B, 1))
+            xi = ie.ask()
+            case[f"s{step}"] = {"gauss_z": zg, "gauss_x": xg, "iso_z": zi, "line_z": zl, "iso_x": xi}
+        out[tag] = case
+    save("emitters", out)
+
+
 if __name__ == "__main__":
     print("reference", ribs.__version__, "from", os.path.dirname(ribs.__file__))
     gen_grid_index()
@@ -388,3 +423,4 @@ if __name__ == "__main__":
     gen_add()
     gen_es()
     gen_rankers()
+    gen_emitters()

@@ -654,3 +654,58 @@ class OracleLMMAES:
 
 
 ORACLE_ES = {"cma_es": OracleCMAES, "sep_cma_es": OracleSepCMAES, "lm_ma_es": OracleLMMAES}
+
+
+# ---------------------------------------------------------------------------------------
+# MAP-Elites variation emitters (next rows of the scope table)
+# ---------------------------------------------------------------------------------------
+class OracleGaussianEmitter:
+    """ribs/emitters/_gaussian_emitter.py:139-166 with the unit normals injectable:
+    rng.normal(scale=sigma, size) == sigma * rng.standard_normal(size) on the same stream."""
+
+    def __init__(self, archive, sigma, x0, batch_size, lower=-np.inf, upper=np.inf, seed=None, dtype=np.float64):
+        self.archive, self.dtype = archive, dtype
+        self.sigma = np.asarray(sigma, dtype=dtype)
+        self.x0 = np.array(x0, dtype=dtype)
+        self.batch_size = batch_size
+        self.lower, self.upper = lower, upper
+        self.rng = np.random.default_rng(seed)
+
+    def ask(self, z=None):
+        B = self.batch_size
+        if len(self.archive) == 0:
+            parents = np.repeat(self.x0[None], repeats=B, axis=0)  # :158
+        else:
+            parents = self.archive.sample_elites(B)["solution"]  # :160
+        shape = (B, len(self.x0))
+        z = self.rng.standard_normal(shape) if z is None else np.asarray(z, dtype=np.float64).reshape(shape)
+        noise = (self.sigma.astype(np.float64) * z).astype(self.dtype)  # :162-165
+        return np.clip(parents + noise, self.lower, self.upper)  # :166
+
+
+class OracleIsoLineEmitter:
+    """ribs/emitters/_iso_line_emitter.py:156-201."""
+
+    def __init__(self, archive, iso_sigma, line_sigma, x0, batch_size, lower=-np.inf, upper=np.inf, seed=None,
+                 dtype=np.float64):
+        self.archive, self.dtype = archive, dtype
+        self.iso_sigma = np.asarray(iso_sigma, dtype=dtype)
+        self.line_sigma = np.asarray(line_sigma, dtype=dtype)
+        self.x0 = np.array(x0, dtype=dtype)
+        self.batch_size = batch_size
+        self.lower, self.upper = lower, upper
+        self.rng = np.random.default_rng(seed)
+
+    def ask(self, z=None, line_z=None):
+        B, n = self.batch_size, len(self.x0)
+        if len(self.archive) == 0:
+            parents = np.repeat(self.x0[None], repeats=2 * B, axis=0)  # :182
+        else:
+            parents = self.archive.sample_elites(2 * B)["solution"]  # :184
+        parents = parents.reshape(2, B, n)  # :186
+        elites, directions = parents[0], parents[1] - parents[0]  # :187-188
+        z = self.rng.standard_normal((B, n)) if z is None else np.asarray(z, dtype=np.float64).reshape(B, n)
+        iso = (float(self.iso_sigma) * z).astype(self.dtype)  # :190-193
+        lz = self.rng.standard_normal((B, 1)) if line_z is None else np.asarray(line_z, dtype=np.float64).reshape(B, 1)
+        line = (float(self.line_sigma) * lz).astype(self.dtype)  # :194-198
+        return np.clip(elites + iso + line * directions, self.lower, self.upper)  # :200-201

@@ -114,6 +114,7 @@ PROTOTYPES = {
     "qd_sep_tell": (_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(CmaScalars), _vp, _vp]),
     "qd_sym_max": (_int, [_i64, _vp, _vp]),
     "qd_sym_eigh_batched": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "qd_emit_variation": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _dbl, _vp, _vp, _vp, _vp]),
     "qd_cma_pool_refresh": (_int, [C.POINTER(CmaPool), _vp, _int, _vp]),
     "qd_cma_pool_ask": (_int, [C.POINTER(CmaPool), _vp, _vp, _vp]),
     "qd_cma_pool_tell": (_int, [C.POINTER(CmaPool), _vp, _int, _vp, _vp, _vp, _vp, _vp]),

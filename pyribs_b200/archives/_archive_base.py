@@ -766,6 +766,17 @@ class DeviceArchive:
     def data(self, fields=None, return_type="dict"):
         return self._store.data(fields, return_type)
 
+    def sample_elite_cells(self, n, replace=True):
+        """The cell indices `sample_elites(n)` would retrieve (same draw from the archive's generator,
+        _grid_archive.py:912-924), without fetching the rows: device-side consumers gather them in place."""
+        if self.empty:
+            raise IndexError("No elements in archive.")
+        if not replace and n > len(self._store):
+            raise ValueError(
+                "Cannot take a larger sample than the number of elites in the archive when 'replace=False'")
+        random_indices = self._rng.choice(len(self._store), size=n, replace=replace)
+        return np.ascontiguousarray(self._store._sync_occupied_list()[random_indices])
+
     def sample_elites(self, n, replace=True):
         if self.empty:
             raise IndexError("No elements in archive.")

@@ -122,6 +122,31 @@ def test_rankers_golden():
         np.testing.assert_array_equal(O.rank_two_stage(c["status"], proj)[0], c["2rd"]["indices"])
 
 
+@pytest.mark.parametrize("tag", ["f64", "f64_bounds", "f32"])
+def test_variation_emitters_golden(tag):
+    """GaussianEmitter / IsoLineEmitter asks (ribs/emitters/_gaussian_emitter.py:139-166,
+    _iso_line_emitter.py:156-201): the oracle replays the reference's parent draws (archive seed 77) and
+    normals; the asked solutions are bit-identical."""
+    case = load_golden("emitters")[tag]
+    cfg = case["cfg"]
+    dtype = np.float32 if int(cfg["f32"]) else np.float64
+    n, B = int(cfg["n"]), int(cfg["B"])
+    a = O.make_grid_oracle(solution_dim=n, dims=(12, 12), ranges=[(-1, 1)] * 2, dtype=dtype, seed=77)
+    lo, hi = ((np.full(n, -0.8, dtype=dtype), np.full(n, 0.9, dtype=dtype)) if int(cfg["bounded"])
+              else (-np.inf, np.inf))
+    ge = O.OracleGaussianEmitter(a, cfg["sigma"], cfg["gx0"], B, lo, hi, dtype=dtype)
+    ie = O.OracleIsoLineEmitter(a, float(cfg["iso_sigma"]), float(cfg["line_sigma"]), cfg["ix0"], B, lo, hi,
+                                dtype=dtype)
+    for j, s in enumerate(steps_of(case)):
+        if j == 1:
+            a.add(**case["fill"])
+        xg = ge.ask(s["gauss_z"])
+        xi = ie.ask(s["iso_z"], s["line_z"])
+        assert xg.dtype == dtype and xi.dtype == dtype
+        np.testing.assert_array_equal(xg, s["gauss_x"], err_msg=f"{tag} s{j} gaussian")
+        np.testing.assert_array_equal(xi, s["iso_x"], err_msg=f"{tag} s{j} isoline")
+
+
 # ---- live reference (authoring container only) ----------------------------------------
 def _import_reference():
     ref = os.environ.get("QD_REFERENCE", "/root/reference")
