@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 2
+#define QD_ABI_VERSION 3
 
 #define QD_OK 0
 #define QD_ERR_INVALID_ARG (-1)
@@ -249,6 +249,10 @@ int qd_store_gather(int64_t M, const int32_t* idx /*[dev] M*/, int n_fields,
  * re-asks only the rows that fell outside the bounds.
  * ---------------------------------------------------------------------------------- */
 int qd_fill_normal(double* out /*[dev] count*/, int64_t count, uint64_t seed, uint64_t offset, void* stream);
+/* Same contract with a cheaper generator for the bandwidth-bound strategies (sep-CMA-ES, LM-MA-ES at
+ * solution_dim ~ 10^4): Philox4x32-10 bits through a 256-layer ziggurat (the method of NumPy's
+ * Generator.standard_normal); out[4q..4q+3] are drawn from counter offset + q. */
+int qd_fill_normal_zig(double* out /*[dev] count*/, int64_t count, uint64_t seed, uint64_t offset, void* stream);
 /* oob[k] = any coordinate of X[row_ids[k]] outside [lower, upper]   (_cma_es.py:190-194) */
 int qd_es_out_of_bounds(const double* X, int64_t rows, int64_t n, const int32_t* row_ids,
                         const double* lower /*[dev] n*/, const double* upper /*[dev] n*/,
@@ -270,6 +274,12 @@ size_t qd_es_workspace_doubles(int64_t n);
 /* sep-CMA-ES   (_sep_cma_es.py:140-191 ask, :257-311 tell) */
 int qd_sep_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
                const double* C /*[dev] n diagonal*/, const double* status, double* X, void* stream);
+/* ask with the generator fused in (no z round trip through HBM): sample k, columns 4q..4q+3 draw from
+ * counter offset + k * ceil(n / 4) + q of qd_fill_normal_zig's stream family; z_out (optional, rows x n)
+ * receives the unit normals. */
+int qd_sep_ask_rng(int64_t rows, int64_t n, const int32_t* row_ids, const double* mean, const double* C,
+                   const double* status, uint64_t seed, uint64_t offset, double* X, double* z_out /*or NULL*/,
+                   void* stream);
 int qd_sep_tell(int64_t n, const double* new_mean, const double* rank_mu /*[dev] n*/, double* mean, double* pc,
                 double* ps, double* C, double* status, const qd_cma_scalars* sc /*[host]*/,
                 double* workspace /*[dev] qd_es_workspace_doubles(n)*/, void* stream);
@@ -339,9 +349,13 @@ int qd_cma_tell(int64_t n, const double* X, const int64_t* rank, const double* w
                 const double* Cmat, double* Cnext, double* status, const qd_cma_scalars* sc /*[host]*/,
                 double* workspace, void* stream);
 /* LM-MA-ES     (_lm_ma_es.py:126-194 ask, :209-239 tell) */
+/* `workspace`: qd_lmma_ask_workspace_doubles(rows, n, itrs) doubles of device scratch. The `itrs` rank-one
+ * transforms of :136-144 are evaluated as Z M^T, M M^T (tall-skinny products), a forward substitution per
+ * sample and one pass X = mean + sigma Q (Z + T M): same arithmetic up to rounding order. */
+size_t qd_lmma_ask_workspace_doubles(int64_t rows, int64_t n, int64_t itrs);
 int qd_lmma_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
                 const double* status, const double* M /*[dev] n_vectors x n*/, const double* cd /*[dev]*/,
-                int64_t itrs, double* X, void* stream);
+                int64_t itrs, double* X, double* workspace, void* stream);
 int qd_lmma_tell(int64_t n, int64_t n_vectors, const double* new_mean, const double* z_mean, double* mean,
                  double* ps, double* M, const double* cc /*[dev] n_vectors*/, double csigma, double mueff,
                  double* status, double* workspace, void* stream);

@@ -385,40 +385,7 @@ __global__ void sym_max_kernel(int64_t n, double* __restrict__ A) {  // A = max(
 // ---------------------------------------------------------------------------------------------
 // A14: LM-MA-ES
 // ---------------------------------------------------------------------------------------------
-// ask (_lm_ma_es.py:126-152): one CTA per sample row; d lives in shared memory.
-__global__ void __launch_bounds__(512) lmma_ask_kernel(const double* __restrict__ z, int64_t rows, int64_t n,
-                                                       const int32_t* __restrict__ row_ids,
-                                                       const double* __restrict__ mean,
-                                                       const double* __restrict__ status, const double* __restrict__ Mv,
-                                                       const double* __restrict__ cd, int itrs,
-                                                       double* __restrict__ X) {
-  extern __shared__ double s_d[];  // n doubles + 16 reduction slots
-  double* s_red = s_d + n;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const double sigma = status[kStatusSigma];
-  for (int64_t k = blockIdx.x; k < rows; k += gridDim.x) {
-    const int64_t row = row_ids ? row_ids[k] : k;
-    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) s_d[j] = z[k * n + j];
-    __syncthreads();
-    for (int it = 0; it < itrs; ++it) {
-      const double* m = Mv + (int64_t)it * n;
-      double acc = 0.0;
-      for (int64_t j = threadIdx.x; j < n; j += blockDim.x) acc = fma(m[j], s_d[j], acc);
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-      if (lane == 0) s_red[warp] = acc;
-      __syncthreads();
-      double dot = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) dot += s_red[w];
-      const double c = cd[it];
-      for (int64_t j = threadIdx.x; j < n; j += blockDim.x)
-        s_d[j] = __dadd_rn(__dmul_rn(1.0 - c, s_d[j]), __dmul_rn(__dmul_rn(c, m[j]), dot));
-      __syncthreads();
-    }
-    for (int64_t j = threadIdx.x; j < n; j += blockDim.x)
-      X[row * n + j] = __dadd_rn(mean[j], __dmul_rn(sigma, s_d[j]));
-    __syncthreads();
-  }
-}
+// ask (_lm_ma_es.py:126-152): es_stream.cu (tall-skinny products + forward substitution)
 
 // tell (_lm_ma_es.py:224-239): ps, M rows, mean, sigma
 __global__ void __launch_bounds__(256) lmma_tell_ps_kernel(int64_t n, const double* __restrict__ z_mean,
@@ -980,23 +947,6 @@ extern "C" int qd_cma_tell(int64_t n, const double* X, const int64_t* rank, cons
   if ((rc = launch_gemm_nt(n, n, mu, a_of, b_of, epi, s, "cma_rank_mu_gemm"))) return rc;
   cma_tell_finish_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, new_mean, mean, status, scal);
   return check_launch("cma_tell_finish_kernel");
-}
-
-extern "C" int qd_lmma_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
-                           const double* status, const double* M, const double* cd, int64_t itrs, double* X,
-                           void* stream) {
-  if (rows == 0) return QD_OK;
-  QD_REQUIRE(z && mean && status && X && (itrs == 0 || (M && cd)), "null pointer");
-  const size_t smem = (size_t)(n + 16) * sizeof(double);
-  QD_REQUIRE(smem <= 220 * 1024, "solution_dim too large for the LM-MA ask kernel (n <= 28000)");
-  static bool attr = false;
-  if (!attr) {
-    QD_CHECK_CUDA(cudaFuncSetAttribute(lmma_ask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr = true;
-  }
-  const int grid = (int)(rows < (int64_t)kNumSMs * 8 ? rows : (int64_t)kNumSMs * 8);
-  lmma_ask_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(z, rows, n, row_ids, mean, status, M, cd, (int)itrs, X);
-  return check_launch("lmma_ask_kernel");
 }
 
 extern "C" int qd_lmma_tell(int64_t n, int64_t n_vectors, const double* new_mean, const double* z_mean, double* mean,

@@ -1,0 +1,689 @@
+// A13 / A14 at configs[3] scale (solution_dim = 10 000, batch 4096): the streaming side of the evolution
+// strategies (reference ribs/emitters/opt/_sep_cma_es.py:140-191, _lm_ma_es.py:126-194).
+//
+//   * unit normals: Philox4x32-10 bits through a ziggurat (the method NumPy's Generator.standard_normal
+//     uses, numpy/random/src/distributions: one table look-up, one multiply and one compare for almost all
+//     samples; wedges and the tail by rejection in fp64). 52-bit uniforms, exact N(0,1) law, at a fraction
+//     of the instruction count of a double-precision Box-Muller, which made the fill kernel compute-bound
+//     (213 us for 41 M normals against 50 us of HBM time).
+//   * sep-CMA ask: generator fused with the transform -- X is the only HBM traffic (lambda * n * 8 bytes).
+//   * LM-MA ask: the reference applies `itrs` rank-one transforms d <- (1-c_j) d + c_j m_j (m_j . d) one
+//     after the other to every sample row (:136-144). With d_j = Q_j (z + sum_{i<j} t_i m_i),
+//     Q_j = prod_{l<j} (1-c_l), the coefficients obey
+//         t_j = c_j / (1-c_j) * (m_j . z + sum_{i<j} t_i (m_j . m_i)),
+//     so the whole ask is P = Z M^T and G = M M^T (tall-skinny products, Z read once), a forward
+//     substitution per row, and X = mean + sigma Q_m (Z + T M) (Z read once, X written once). Same
+//     arithmetic up to rounding order (1e-15 relative; tests hold it to the oracle at 1e-9); the
+//     row-by-row version re-read every m_j for every row out of L2 and took 2.1 ms at 20 vectors.
+#include <cmath>
+#include <mutex>
+
+#include "qd_common.cuh"
+
+namespace qd {
+
+// ---------------------------------------------------------------------------------------------
+// ziggurat tables (Marsaglia & Tsang 2000): kZigLayers layers of equal area V under exp(-x^2/2). Layer 0 is
+// the base strip [0, R] x [0, f(R)] plus the tail beyond R; layer i >= 1 is the rectangle
+// [0, x_i] x [f(x_i), f(x_{i-1})], x_0 = 0 < x_1 < ... < x_{N-1} = R. 2048 layers (R = 4.2164) instead of the
+// usual 256: a candidate misses the accept-at-once region of its layer with probability 0.23 % instead of
+// 1.2 %, so a warp of 32 draws enters the divergent wedge / tail code 7 % of the time instead of 32 %.
+// ---------------------------------------------------------------------------------------------
+constexpr int kZigLayers = 2048;
+constexpr int kZigBits = 11;
+
+struct ZigTables {
+  double2 wb[kZigLayers];  // (width of layer i, accept-at-once bound x_{i-1}); layer 0: (V / f(R), R)
+  double f[kZigLayers];    // density at the layer's right edge; f[0] = 1 (x = 0)
+  double r, inv_r;
+};
+
+__device__ ZigTables g_zig;
+
+static int zig_tables_ready() {
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  QD_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 64 && done[dev]) return QD_OK;
+  auto dens = [](double x) { return std::exp(-0.5 * x * x); };
+  auto area = [&](double R) { return R * dens(R) + std::sqrt(M_PI / 2.0) * std::erfc(R / std::sqrt(2.0)); };
+  static double x[kZigLayers];
+  // edges for a trial R; returns how far the top layer is from closing at the mode (V / x_1 + f(x_1) = f(0) = 1)
+  auto closure = [&](double R) {
+    const double V = area(R);
+    x[kZigLayers - 1] = R;
+    for (int i = kZigLayers - 2; i >= 1; --i) {
+      const double a = V / x[i + 1] + dens(x[i + 1]);
+      if (a >= 1.0) return 1.0;  // the layers pass the mode before the last one: R too small
+      x[i] = std::sqrt(-2.0 * std::log(a));
+    }
+    return V / x[1] + dens(x[1]) - 1.0;
+  };
+  double lo = 2.0, hi = 7.0;
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    (closure(mid) > 0.0 ? lo : hi) = mid;
+  }
+  const double R = 0.5 * (lo + hi);
+  QD_REQUIRE(std::fabs(closure(R)) < 1e-9, "ziggurat tables do not close");
+  x[0] = 0.0;
+  static ZigTables t;
+  const double q = area(R) / dens(R);  // virtual width of the base layer (rectangle + tail)
+  t.wb[0] = make_double2(q, R);
+  t.f[0] = 1.0;
+  for (int i = 1; i < kZigLayers; ++i) {
+    t.wb[i] = make_double2(x[i], x[i - 1]);
+    t.f[i] = dens(x[i]);
+  }
+  t.r = R;
+  t.inv_r = 1.0 / R;
+  QD_CHECK_CUDA(cudaMemcpyToSymbol(g_zig, &t, sizeof(t)));
+  if (dev < 64) done[dev] = true;
+  return QD_OK;
+}
+
+__device__ __forceinline__ void philox_round4(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const unsigned long long p0 = (unsigned long long)0xD2511F53u * c[0];  // one IMAD.WIDE for hi and lo
+  const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c[2];
+  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+  c[0] = n0;
+  c[1] = (uint32_t)p1;
+  c[2] = n2;
+  c[3] = (uint32_t)p0;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round4(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__device__ __forceinline__ double open01(uint32_t lo, uint32_t hi) {  // (0, 1) from 64 bits
+  return ((double)(long long)((((unsigned long long)hi << 32) | lo) >> 11) + 0.5) * 0x1p-53;
+}
+
+// A candidate's 64 bits: 11 layer index | 1 sign | 52 uniform (the mantissa of a double in [1, 2)).
+__device__ __forceinline__ int zig_layer(unsigned long long r) { return (int)(r & (kZigLayers - 1)); }
+__device__ __forceinline__ double zig_uniform(unsigned long long r) {  // [0, 1)
+  return __longlong_as_double((long long)((r >> 12) | 0x3FF0000000000000ull)) - 1.0;
+}
+__device__ __forceinline__ double zig_signed(unsigned long long r, double x) { return (r >> kZigBits) & 1u ? -x : x; }
+
+// The 0.23 % of candidates that miss the accept-at-once region of their layer: the wedge test, or the tail
+// beyond R for the base layer; a rejected candidate is replaced by fresh ones until one is accepted. Pure
+// function of its arguments -- its random words come from Philox sub-streams of the same counter, keyed by
+// the candidate's slot -- and out of line, so that the common path is straight-line code.
+__device__ __noinline__ double zig_fix(unsigned long long r, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                       uint32_t slot) {
+  for (uint32_t attempt = 0;; ++attempt) {
+    uint32_t c[4] = {c0, c1, slot + 4u * attempt, 0x534C4F57u};  // uniforms of this attempt + the next candidate
+    philox4x32_10(c, k0, k1);
+    const int idx = zig_layer(r);
+    const double2 wb = g_zig.wb[idx];
+    const double x = zig_uniform(r) * wb.x;
+    if (x < wb.y) return zig_signed(r, x);  // (only replacement candidates can land here)
+    if (idx == 0) {
+      const double R = g_zig.r, inv_r = g_zig.inv_r;
+      for (uint32_t t = 0;; ++t) {
+        uint32_t d[4] = {c0, c1, slot + 4u * attempt, 0x5441494Cu + t};
+        philox4x32_10(d, k0, k1);
+        const double xx = -log(open01(d[0], d[1])) * inv_r;
+        const double yy = -log(open01(d[2], d[3]));
+        if (yy + yy > xx * xx) return zig_signed(r, R + xx);
+      }
+    }
+    const double fi = g_zig.f[idx], fa = g_zig.f[idx - 1];
+    if (fi + open01(c[0], c[1]) * (fa - fi) < exp(-0.5 * x * x)) return zig_signed(r, x);
+    r = ((unsigned long long)c[3] << 32) | c[2];
+  }
+}
+
+// Four unit normals from (seed, counter): two Philox calls give four candidates; all four take the
+// accept-at-once path without a branch, and one test sends the warp to the fix-up code when any missed.
+__device__ __forceinline__ void zig_quad(uint64_t seed, uint64_t ctr, const double2* __restrict__ swb, double (&z)[4]) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32);
+  uint32_t a[4] = {c0, c1, 0u, 0x5A494731u}, b[4] = {c0, c1, 1u, 0x5A494731u};
+  philox4x32_10(a, k0, k1);
+  philox4x32_10(b, k0, k1);
+  const unsigned long long r[4] = {((unsigned long long)a[1] << 32) | a[0], ((unsigned long long)a[3] << 32) | a[2],
+                                   ((unsigned long long)b[1] << 32) | b[0], ((unsigned long long)b[3] << 32) | b[2]};
+  bool miss[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double2 wb = swb[zig_layer(r[i])];
+    const double x = zig_uniform(r[i]) * wb.x;
+    miss[i] = !(x < wb.y);
+    z[i] = zig_signed(r[i], x);
+  }
+  if (miss[0] | miss[1] | miss[2] | miss[3]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (miss[i]) z[i] = zig_fix(r[i], k0, k1, c0, c1, (uint32_t)i);
+  }
+}
+
+__device__ __forceinline__ void store4_cs(double* p, const double (&v)[4]) {  // 32-byte aligned, streaming
+  __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
+  __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(v[2], v[3]));
+}
+
+__device__ __forceinline__ void zig_stage_tables(double2* swb) {
+  for (int i = threadIdx.x; i < kZigLayers; i += blockDim.x) swb[i] = g_zig.wb[i];
+  __syncthreads();
+}
+
+// out[4q .. 4q+3] come from counter offset + q
+__global__ void __launch_bounds__(256) fill_normal_zig_kernel(double* __restrict__ out, int64_t count, uint64_t seed,
+                                                              uint64_t offset) {
+  __shared__ double2 swb[kZigLayers];
+  zig_stage_tables(swb);
+  const int64_t quads = (count + 3) / 4;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
+    double z[4];
+    zig_quad(seed, offset + (uint64_t)q, swb, z);
+    if (4 * q + 3 < count) {
+      store4_cs(out + 4 * q, z);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (4 * q + i < count) out[4 * q + i] = z[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A13 ask with the generator fused in: X[row] = sqrt(C) * (sigma z) + mean   (_sep_cma_es.py:160-179)
+// A thread owns four columns and walks down the rows: sqrt(C) and mean stay in registers.
+// Sample k, quad jq draws from counter offset + k * ceil(n / 4) + jq.
+// ---------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256) sep_ask_rng_kernel(int64_t rows, int64_t n, const int32_t* __restrict__ row_ids,
+                                                          const double* __restrict__ mean, const double* __restrict__ C,
+                                                          const double* __restrict__ sigma_p, uint64_t seed,
+                                                          uint64_t offset, double* __restrict__ X,
+                                                          double* __restrict__ z_out) {
+  __shared__ double2 swb[kZigLayers];
+  zig_stage_tables(swb);
+  const int64_t qpr = (n + 3) / 4;
+  const int64_t jq = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (jq >= qpr) return;
+  const int64_t j0 = jq * 4;
+  const double sigma = *sigma_p;
+  double sd[4], mu[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool ok = j0 + i < n;
+    sd[i] = ok ? sqrt(C[j0 + i]) : 0.0;
+    mu[i] = ok ? mean[j0 + i] : 0.0;
+  }
+  for (int64_t k = blockIdx.y; k < rows; k += gridDim.y) {
+    double z[4], x[4];
+    zig_quad(seed, offset + (uint64_t)(k * qpr + jq), swb, z);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      x[i] = __dadd_rn(__dmul_rn(sd[i], __dmul_rn(sigma, z[i])), mu[i]);  // rng.normal(0, sigma) = 0 + sigma z
+    const int64_t row = row_ids ? row_ids[k] : k;
+    if (VEC) {  // n % 4 == 0: every quad is whole and 32-byte aligned
+      store4_cs(X + row * n + j0, x);
+      if (z_out) store4_cs(z_out + k * n + j0, z);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (j0 + i < n) {
+          X[row * n + j0 + i] = x[i];
+          if (z_out) z_out[k * n + j0 + i] = z[i];
+        }
+    }
+  }
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool pred) {  // !pred: zero fill
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// tall-skinny product: part[split][j][k] = sum over the split's columns c of A[k][c] * M[j][c]
+// (A: rows x n, M: m x n, both row-major with leading dimension n) on the fp64 tensor pipe
+// (mma.sync m8n8k4: 63.9 FMA/clk/SM measured against 56.9 for DFMA, tools/fp64_peak.cu, and a seventh of
+// the shared-memory wavefronts the broadcast-FMA form needed, which is what bounded that one). A CTA owns
+// 32 rows x 24 vectors; chunks of 64 columns arrive through a three-stage cp.async ring; each of the eight
+// warps multiplies eight columns of every chunk (two k-steps of 4 x 3 MMAs) and the warps' accumulators
+// are summed in warp order at the end (deterministic).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTdRows = 32, kTdCols = 64, kTdVecs = 24, kTdStages = 3;
+constexpr int kTdLd = kTdCols + 4;  // 68: the 8 x 4 fragment reads of a half-warp fall on distinct banks
+constexpr int kTdStageDoubles = (kTdRows + kTdVecs) * kTdLd;
+constexpr size_t kTdSmem = kTdStages * (size_t)kTdStageDoubles * sizeof(double);
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 2) tall_dots_kernel(const double* __restrict__ A, int64_t rows, int64_t n,
+                                                           const double* __restrict__ M, int m, int64_t cols_per_split,
+                                                           double* __restrict__ part) {
+  extern __shared__ __align__(16) double td_smem[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * kTdRows;
+  const int split = blockIdx.y;
+  const int j0 = blockIdx.z * kTdVecs;
+  const int64_t cbeg = split * cols_per_split;
+  const int64_t cend = cbeg + cols_per_split < n ? cbeg + cols_per_split : n;
+  const int nch = (int)((cend - cbeg + kTdCols - 1) / kTdCols);
+  auto issue = [&](int ch) {
+    double* As = td_smem + (ch % kTdStages) * kTdStageDoubles;
+    double* Ms = As + kTdRows * kTdLd;
+    const int64_t c0 = cbeg + (int64_t)ch * kTdCols;
+#pragma unroll
+    for (int i = 0; i < kTdRows * kTdCols / 256; ++i) {  // a warp copies 32 consecutive doubles of one row
+      const int idx = i * 256 + t, r = idx >> 6, c = idx & 63;
+      const bool ok = row0 + r < rows && c0 + c < cend;
+      cp_async8(&As[r * kTdLd + c], ok ? A + (row0 + r) * n + c0 + c : A, ok);
+    }
+#pragma unroll
+    for (int i = 0; i < kTdVecs * kTdCols / 256; ++i) {
+      const int idx = i * 256 + t, j = idx >> 6, c = idx & 63;
+      const bool ok = j0 + j < m && c0 + c < cend;
+      cp_async8(&Ms[j * kTdLd + c], ok ? M + (int64_t)(j0 + j) * n + c0 + c : M, ok);
+    }
+  };
+  double acc[kTdRows / 8][kTdVecs / 8][2];
+#pragma unroll
+  for (int rb = 0; rb < kTdRows / 8; ++rb)
+#pragma unroll
+    for (int nb = 0; nb < kTdVecs / 8; ++nb) acc[rb][nb][0] = acc[rb][nb][1] = 0.0;
+#pragma unroll
+  for (int st = 0; st < kTdStages - 1; ++st) {
+    if (st < nch) issue(st);
+    cp_async_commit();
+  }
+  const int fg = lane >> 2, ft = lane & 3;  // fragment coordinates: A[row fg][col ft], B[k ft][n fg]
+  for (int ch = 0; ch < nch; ++ch) {
+    cp_async_wait<kTdStages - 2>();
+    __syncthreads();  // chunk ch has landed for every thread; the stage chunk ch-1 used is free again
+    if (ch + kTdStages - 1 < nch) issue(ch + kTdStages - 1);
+    cp_async_commit();
+    const double* As = td_smem + (ch % kTdStages) * kTdStageDoubles;
+    const double* Ms = As + kTdRows * kTdLd;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int c = warp * 8 + ks * 4 + ft;
+      double a[kTdRows / 8], b[kTdVecs / 8];
+#pragma unroll
+      for (int rb = 0; rb < kTdRows / 8; ++rb) a[rb] = As[(rb * 8 + fg) * kTdLd + c];
+#pragma unroll
+      for (int nb = 0; nb < kTdVecs / 8; ++nb) b[nb] = Ms[(nb * 8 + fg) * kTdLd + c];
+#pragma unroll
+      for (int rb = 0; rb < kTdRows / 8; ++rb)
+#pragma unroll
+        for (int nb = 0; nb < kTdVecs / 8; ++nb) dmma884(acc[rb][nb], a[rb], b[nb]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  double* buf = td_smem;  // [vector j][row]: kTdVecs x 32 sums; C fragment: row fg, vectors 2 ft, 2 ft + 1
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int rb = 0; rb < kTdRows / 8; ++rb)
+#pragma unroll
+        for (int nb = 0; nb < kTdVecs / 8; ++nb)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int o = (nb * 8 + 2 * ft + e) * 32 + rb * 8 + fg;
+            buf[o] = (w ? buf[o] : 0.0) + acc[rb][nb][e];
+          }
+    }
+    __syncthreads();
+  }
+  for (int idx = t; idx < kTdVecs * 32; idx += 256) {
+    const int j = idx >> 5, r = idx & 31;
+    if (j0 + j < m && row0 + r < rows) part[((int64_t)split * m + j0 + j) * rows + row0 + r] = buf[idx];
+  }
+}
+
+// out[i] = sum over splits of part[split][i]: one warp per element, fixed reduction tree (deterministic)
+__global__ void __launch_bounds__(256) sum_splits_kernel(const double* __restrict__ part, int nsplit, int64_t count,
+                                                         double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = w0; i < count; i += nw) {
+    double s = 0.0;
+    for (int k = lane; k < nsplit; k += 32) s += part[(int64_t)k * count + i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[i] = s;
+  }
+}
+
+// the same for many elements: one thread per element, the splits' loads issued together
+__global__ void __launch_bounds__(256) sum_splits_wide_kernel(const double* __restrict__ part, int nsplit, int64_t count,
+                                                              double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < nsplit; ++k) s += part[(int64_t)k * count + i];
+    out[i] = s;
+  }
+}
+
+// forward substitution, one thread per sample row: t_j = c_j / (1 - c_j) * (p_j + sum_{i<j} t_i G[j][i]).
+// Tt is vector-major (m x rows), so the rows of a warp read and write consecutive addresses. SMEM: the
+// row's p / t values, the ratios and G sit in shared memory (m <= kCoefSmemMax), so the recurrence never
+// waits on global memory; larger m re-reads Tt and G through L1.
+constexpr int kCoefThreads = 128, kCoefSmemMax = 96;
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kCoefThreads) lmma_coef_kernel(const double* __restrict__ P /*[m][rows]*/,
+                                                                 const double* __restrict__ G,
+                                                                 const double* __restrict__ cd, int m, int64_t rows,
+                                                                 double* Tt, double* __restrict__ qm_out) {
+  extern __shared__ double coef_smem[];
+  double* ts = coef_smem;                              // [m][kCoefThreads]
+  double* rho = ts + (SMEM ? m * kCoefThreads : 0);    // [m]  c_j / (1 - c_j)
+  double* omc = rho + (SMEM ? m : 0);                  // [m]  1 - c_j
+  double* gs = omc + (SMEM ? m : 0);                   // [m][m]
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (SMEM) {
+    for (int j = threadIdx.x; j < m; j += kCoefThreads) {
+      const double c = cd[j];
+      omc[j] = 1.0 - c;
+      rho[j] = c / (1.0 - c);
+    }
+    for (int e = threadIdx.x; e < m * m; e += kCoefThreads) gs[e] = G[e];
+    if (k < rows) {
+#pragma unroll 8
+      for (int j = 0; j < m; ++j) ts[j * kCoefThreads + threadIdx.x] = P[(int64_t)j * rows + k];
+    }
+    __syncthreads();
+    if (k == 0) {
+      double q = 1.0;
+      for (int j = 0; j < m; ++j) q *= omc[j];
+      *qm_out = q;
+    }
+    if (k >= rows) return;
+    for (int j = 0; j < m; ++j) {
+      double a = ts[j * kCoefThreads + threadIdx.x], b = 0.0;
+      const double* g = gs + j * m;
+      int i = 0;
+      for (; i + 1 < j; i += 2) {
+        a = fma(ts[i * kCoefThreads + threadIdx.x], g[i], a);
+        b = fma(ts[(i + 1) * kCoefThreads + threadIdx.x], g[i + 1], b);
+      }
+      if (i < j) a = fma(ts[i * kCoefThreads + threadIdx.x], g[i], a);
+      const double tj = rho[j] * (a + b);
+      ts[j * kCoefThreads + threadIdx.x] = tj;
+      Tt[(int64_t)j * rows + k] = tj;
+    }
+    return;
+  }
+  if (k == 0) {
+    double q = 1.0;
+    for (int j = 0; j < m; ++j) q *= 1.0 - cd[j];
+    *qm_out = q;
+  }
+  if (k >= rows) return;
+  for (int j = 0; j < m; ++j) {
+    double a = P[(int64_t)j * rows + k], b = 0.0;
+    const double* __restrict__ g = G + (int64_t)j * m;
+    int i = 0;
+    for (; i + 1 < j; i += 2) {
+      a = fma(Tt[(int64_t)i * rows + k], __ldg(g + i), a);
+      b = fma(Tt[(int64_t)(i + 1) * rows + k], __ldg(g + i + 1), b);
+    }
+    if (i < j) a = fma(Tt[(int64_t)i * rows + k], __ldg(g + i), a);
+    const double c = cd[j];
+    Tt[(int64_t)j * rows + k] = c / (1.0 - c) * (a + b);
+  }
+}
+
+// X[row][c] = mean[c] + sigma * Q_m * (z[k][c] + sum_j T[k][j] M[j][c]) on the fp64 tensor pipe: a CTA owns
+// 16 sample rows x 512 columns, a warp 16 x 64 of them (2 x 8 accumulator tiles); k runs over the direction
+// vectors, four per MMA. Every m_j value of the CTA's columns is used by exactly one lane, so B fragments are
+// plain global loads (L2-resident M); the z tile streams in through cp.async while the MMAs run.
+constexpr int kLoRows = 16, kLoCols = 512, kLoLd = kLoCols + 8;  // 520: conflict-free 16-byte fragment reads
+
+template <bool VEC2>  // n even: rows stay 16-byte aligned, X leaves as double2
+__global__ void __launch_bounds__(256, 2) lmma_out_kernel(const double* __restrict__ z, int64_t rows, int64_t n,
+                                                          const int32_t* __restrict__ row_ids,
+                                                          const double* __restrict__ mean,
+                                                          const double* __restrict__ status, const double* __restrict__ M,
+                                                          int m, const double* __restrict__ Tt,
+                                                          const double* __restrict__ qm_p, double* __restrict__ X) {
+  extern __shared__ __align__(16) double zs[];  // [kLoRows][kLoLd]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t col0 = blockIdx.x * (int64_t)kLoCols;
+  const int64_t row0 = (int64_t)blockIdx.y * kLoRows;
+#pragma unroll
+  for (int r = 0; r < kLoRows; ++r) {
+    const bool okr = row0 + r < rows;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t c = col0 + h * 256 + t;
+      const bool ok = okr && c < n;
+      cp_async8(&zs[r * kLoLd + h * 256 + t], ok ? z + (row0 + r) * n + c : z, ok);
+    }
+  }
+  cp_async_commit();
+  const int fg = lane >> 2, ft = lane & 3;
+  double acc[2][8][2];
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+  const int64_t cw = col0 + warp * 64;  // first column of the warp
+  for (int j4 = 0; j4 < m; j4 += 4) {
+    const int j = j4 + ft;
+    const bool okj = j < m;
+    double a[2], b[8];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+      const int64_t row = row0 + mb * 8 + fg;
+      a[mb] = (okj && row < rows) ? __ldg(Tt + (int64_t)j * rows + row) : 0.0;  // A[row fg][k ft]
+    }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int64_t c = cw + nb * 8 + fg;
+      b[nb] = (okj && c < n) ? __ldg(M + (int64_t)j * n + c) : 0.0;  // B[k ft][n fg]
+    }
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) dmma884(acc[mb][nb], a[mb], b[nb]);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  const double sigma = status[0];
+  const double qm = m > 0 ? *qm_p : 1.0;
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb) {
+    const int r = mb * 8 + fg;
+    if (row0 + r >= rows) continue;
+    const int64_t row = row_ids ? row_ids[row0 + r] : row0 + r;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int cl = warp * 64 + nb * 8 + 2 * ft;  // C fragment: row fg, columns 2 ft, 2 ft + 1
+      const int64_t c = col0 + cl;
+      if (c >= n) continue;
+      const double2 zz = *reinterpret_cast<const double2*>(&zs[r * kLoLd + cl]);
+      const double d0 = m > 0 ? __dmul_rn(qm, __dadd_rn(zz.x, acc[mb][nb][0])) : zz.x;
+      const double d1 = m > 0 ? __dmul_rn(qm, __dadd_rn(zz.y, acc[mb][nb][1])) : zz.y;
+      const double x0 = __dadd_rn(mean[c], __dmul_rn(sigma, d0));  // mean + sigma * d  (:145)
+      if (VEC2) {
+        const double x1 = __dadd_rn(mean[c + 1], __dmul_rn(sigma, d1));
+        __stcs(reinterpret_cast<double2*>(X + row * n + c), make_double2(x0, x1));
+      } else {
+        X[row * n + c] = x0;
+        if (c + 1 < n) X[row * n + c + 1] = __dadd_rn(mean[c + 1], __dmul_rn(sigma, d1));
+      }
+    }
+  }
+}
+
+// launch geometry of the two tall-skinny products, shared by the workspace query and the launcher
+struct TdPlan {
+  int row_tiles, groups, nsplit;
+  int64_t cols_per_split;
+};
+
+static TdPlan td_plan(int64_t rows, int64_t n, int64_t m) {
+  TdPlan p;
+  p.row_tiles = (int)((rows + kTdRows - 1) / kTdRows);
+  p.groups = (int)((m + kTdVecs - 1) / kTdVecs);
+  const int64_t chunks = (n + kTdCols - 1) / kTdCols;
+  int64_t want = (4 * (int64_t)kNumSMs + (int64_t)p.row_tiles * p.groups - 1) / ((int64_t)p.row_tiles * p.groups);
+  if (want < 1) want = 1;
+  if (want > 64) want = 64;
+  if (want > chunks) want = chunks;
+  const int64_t cps = (chunks + want - 1) / want;  // chunks per split
+  p.nsplit = (int)((chunks + cps - 1) / cps);
+  p.cols_per_split = cps * kTdCols;
+  return p;
+}
+
+struct LmmaWs {  // doubles
+  size_t ppart, p, gpart, g, tt, qm, total;
+};
+
+static LmmaWs lmma_ws(int64_t rows, int64_t n, int64_t m) {
+  LmmaWs w;
+  const TdPlan pp = td_plan(rows, n, m), pg = td_plan(m, n, m);
+  size_t off = 0;
+  w.ppart = off;
+  off += (size_t)pp.nsplit * m * rows;
+  w.p = off;
+  off += (size_t)m * rows;
+  w.gpart = off;
+  off += (size_t)pg.nsplit * m * m;
+  w.g = off;
+  off += (size_t)m * m;
+  w.tt = off;
+  off += (size_t)m * rows;
+  w.qm = off;
+  off += 8;
+  w.total = off;
+  return w;
+}
+
+static int launch_tall_dots(const double* A, int64_t rows, int64_t n, const double* M, int64_t m, double* part,
+                            cudaStream_t s) {
+  const TdPlan p = td_plan(rows, n, m);
+  QD_REQUIRE(p.groups <= 65535 && p.nsplit <= 65535, "too many direction vectors");
+  static bool attr = false;
+  if (!attr) {
+    QD_CHECK_CUDA(cudaFuncSetAttribute(tall_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTdSmem));
+    attr = true;
+  }
+  tall_dots_kernel<<<dim3(p.row_tiles, p.nsplit, p.groups), 256, kTdSmem, s>>>(A, rows, n, M, (int)m,
+                                                                               p.cols_per_split, part);
+  return check_launch("tall_dots_kernel");
+}
+
+}  // namespace qd
+
+extern "C" int qd_fill_normal_zig(double* out, int64_t count, uint64_t seed, uint64_t offset, void* stream) {
+  using namespace qd;
+  if (count == 0) return QD_OK;
+  QD_REQUIRE(out && count > 0, "bad arguments");
+  int rc = zig_tables_ready();
+  if (rc) return rc;
+  fill_normal_zig_kernel<<<grid_for((count + 3) / 4, 256, 6), 256, 0, (cudaStream_t)stream>>>(out, count, seed, offset);
+  return check_launch("fill_normal_zig_kernel");
+}
+
+extern "C" int qd_sep_ask_rng(int64_t rows, int64_t n, const int32_t* row_ids, const double* mean, const double* C,
+                              const double* status, uint64_t seed, uint64_t offset, double* X, double* z_out,
+                              void* stream) {
+  using namespace qd;
+  if (rows == 0) return QD_OK;
+  QD_REQUIRE(mean && C && status && X && rows > 0 && n > 0, "bad arguments");
+  int rc = zig_tables_ready();
+  if (rc) return rc;
+  const int64_t qpr = (n + 3) / 4;
+  const unsigned gx = (unsigned)((qpr + 255) / 256);
+  // ~6 resident CTAs per SM (each stages the 32 KB layer table once); a thread then walks rows / gy samples with
+  // its columns' sqrt(C) and mean in registers
+  int64_t gy = (6 * (int64_t)kNumSMs + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  if (gy > 65535) gy = 65535;
+  const dim3 grid(gx, (unsigned)gy);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n % 4 == 0)
+    sep_ask_rng_kernel<true><<<grid, 256, 0, s>>>(rows, n, row_ids, mean, C, status, seed, offset, X, z_out);
+  else
+    sep_ask_rng_kernel<false><<<grid, 256, 0, s>>>(rows, n, row_ids, mean, C, status, seed, offset, X, z_out);
+  return check_launch("sep_ask_rng_kernel");
+}
+
+extern "C" size_t qd_lmma_ask_workspace_doubles(int64_t rows, int64_t n, int64_t itrs) {
+  if (rows <= 0 || n <= 0 || itrs <= 0) return 8;
+  return qd::lmma_ws(rows, n, itrs).total;
+}
+
+extern "C" int qd_lmma_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
+                           const double* status, const double* M, const double* cd, int64_t itrs, double* X,
+                           double* workspace, void* stream) {
+  using namespace qd;
+  if (rows == 0) return QD_OK;
+  QD_REQUIRE(z && mean && status && X && rows > 0 && n > 0 && itrs >= 0, "bad arguments");
+  QD_REQUIRE(itrs == 0 || (M && cd && workspace), "null pointer");
+  QD_REQUIRE(itrs < ((int64_t)1 << 20) && rows < ((int64_t)1 << 31), "sizes out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int m = (int)itrs;
+  const double* Tt = nullptr;
+  const double* qm = nullptr;
+  if (m > 0) {
+    const LmmaWs w = lmma_ws(rows, n, m);
+    double* ws = workspace;
+    int rc = launch_tall_dots(M, m, n, M, m, ws + w.gpart, s);  // G = M M^T
+    if (rc) return rc;
+    sum_splits_kernel<<<grid_for((int64_t)m * m * 32, 256), 256, 0, s>>>(ws + w.gpart, td_plan(m, n, m).nsplit,
+                                                                   (int64_t)m * m, ws + w.g);
+    if ((rc = check_launch("sum_splits_kernel"))) return rc;
+    if ((rc = launch_tall_dots(z, rows, n, M, m, ws + w.ppart, s))) return rc;  // P = Z M^T
+    const int nsp = td_plan(rows, n, m).nsplit;
+    sum_splits_wide_kernel<<<grid_for((int64_t)m * rows, 256), 256, 0, s>>>(ws + w.ppart, nsp, (int64_t)m * rows, ws + w.p);
+    if ((rc = check_launch("sum_splits_wide_kernel"))) return rc;
+    static bool attr = false;
+    if (!attr) {
+      QD_CHECK_CUDA(cudaFuncSetAttribute(lmma_coef_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    const unsigned cgrid = (unsigned)((rows + kCoefThreads - 1) / kCoefThreads);
+    const size_t tsm = ((size_t)m * kCoefThreads + 2 * m + (size_t)m * m) * sizeof(double);
+    if (m <= kCoefSmemMax)
+      lmma_coef_kernel<true><<<cgrid, kCoefThreads, tsm, s>>>(ws + w.p, ws + w.g, cd, m, rows, ws + w.tt, ws + w.qm);
+    else
+      lmma_coef_kernel<false><<<cgrid, kCoefThreads, 0, s>>>(ws + w.p, ws + w.g, cd, m, rows, ws + w.tt, ws + w.qm);
+    if ((rc = check_launch("lmma_coef_kernel"))) return rc;
+    Tt = ws + w.tt;
+    qm = ws + w.qm;
+  }
+  const dim3 grid((unsigned)((n + kLoCols - 1) / kLoCols), (unsigned)((rows + kLoRows - 1) / kLoRows));
+  QD_REQUIRE(grid.y <= 65535, "too many sample rows");
+  constexpr size_t zsm = (size_t)kLoRows * kLoLd * sizeof(double);
+  static bool out_attr = false;
+  if (!out_attr) {
+    QD_CHECK_CUDA(cudaFuncSetAttribute(lmma_out_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
+    QD_CHECK_CUDA(cudaFuncSetAttribute(lmma_out_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
+    out_attr = true;
+  }
+  if (n % 2 == 0)
+    lmma_out_kernel<true><<<grid, 256, zsm, s>>>(z, rows, n, row_ids, mean, status, M, m, Tt, qm, X);
+  else
+    lmma_out_kernel<false><<<grid, 256, zsm, s>>>(z, rows, n, row_ids, mean, status, M, m, Tt, qm, X);
+  return check_launch("lmma_out_kernel");
+}

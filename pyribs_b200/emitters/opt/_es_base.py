@@ -83,11 +83,21 @@ class DeviceES:
         self._slot = -1
 
     # ---- helpers ------------------------------------------------------------------------------
+    # Strategies whose ask is an HBM stream over (batch, n) draw from the ziggurat generator (one Philox
+    # counter per four normals); the GEMM-bound CMA-ES keeps the Box-Muller stream its pooled form shares.
+    _zig_normals = False
+    # ... and those that do not need z afterwards sample inside the ask kernel (`_sample_rows(None, ...)`).
+    _fused_rng = False
+
     def _normals(self, rows):
         z = torch.empty((rows, self.solution_dim), dtype=torch.float64, device=self._device)
         cnt = z.numel()
-        _lib.check(self._L.qd_fill_normal(z.data_ptr(), cnt, self._seed, self._rng_offset, stream_ptr()))
-        self._rng_offset += (cnt + 1) // 2
+        if self._zig_normals:
+            _lib.check(self._L.qd_fill_normal_zig(z.data_ptr(), cnt, self._seed, self._rng_offset, stream_ptr()))
+            self._rng_offset += (cnt + 3) // 4
+        else:
+            _lib.check(self._L.qd_fill_normal(z.data_ptr(), cnt, self._seed, self._rng_offset, stream_ptr()))
+            self._rng_offset += (cnt + 1) // 2
         return z
 
     def _as_z(self, z, rows):
@@ -128,7 +138,7 @@ class DeviceES:
         with torch.cuda.device(self._device), torch.cuda.stream(stream):
             self._solutions = torch.empty((lam, n), dtype=torch.float64, device=self._device)
             self._prepare_ask(lam)
-            zz = self._as_z(z, lam)
+            zz = None if (z is None and self._fused_rng) else self._as_z(z, lam)
             self._z = zz
             self._sample_rows(zz, lam, None)
             if self._bounded:  # resampling loop of the reference (needs the host to see the violations)
@@ -145,8 +155,9 @@ class DeviceES:
                         break
                     if itrs > BOUNDS_SAMPLING_THRESHOLD:
                         warnings.warn(BOUNDS_WARNING, stacklevel=3)
-                    znew = self._normals(remaining.numel())
-                    self._z[remaining.long()] = znew
+                    znew = None if self._fused_rng else self._normals(remaining.numel())
+                    if self._z is not None and znew is not None:
+                        self._z[remaining.long()] = znew
                     self._sample_rows(znew, remaining.numel(), remaining)
             self._ask_event.record(stream)
         self._host_ready = False
@@ -209,6 +220,16 @@ class DeviceES:
             X.data_ptr(), n, rank_d.data_ptr(), w_d.data_ptr(), mu, None if old_mean is None else old_mean.data_ptr(),
             None if out_mean is None else out_mean.data_ptr(), None if out_sq is None else out_sq.data_ptr(),
             self._partial.data_ptr(), stream_ptr()))
+
+    def _weights_device(self, mu):
+        """(w, mueff, w on the device) of `es_weights(mu)`, cached: the parent count rarely changes between
+        generations, and a pageable host->device copy per tell costs more than the kernels it feeds."""
+        hit = self.__dict__.get("_w_cache")
+        if hit is None or hit[0] != mu:
+            w, mueff = es_weights(mu)
+            hit = (mu, w, mueff, torch.from_numpy(w).to(self._device))
+            self._w_cache = hit
+        return hit[1], hit[2], hit[3]
 
     def _rank_to_device(self, ranking_indices, num_parents):
         if isinstance(ranking_indices, torch.Tensor):

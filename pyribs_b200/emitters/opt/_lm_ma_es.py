@@ -29,6 +29,7 @@ class LMMAEvolutionStrategy(DeviceES):
         self._ps = torch.zeros(n, **f64)
         self._m = torch.zeros((self.n_vectors, n), **f64)
         self._z_mean = torch.empty(n, **f64)
+        self._ask_ws = None
         self.current_gens = None
 
     def reset(self, x0):
@@ -56,12 +57,17 @@ class LMMAEvolutionStrategy(DeviceES):
     def m(self):
         return self._to_host(self._m)
 
+    _zig_normals = True  # z is kept: tell averages the parents' z (:224-226)
+
     def _sample_rows(self, z, rows, row_ids):
         itrs = min(self.current_gens, self.n_vectors)
+        need = int(self._L.qd_lmma_ask_workspace_doubles(rows, self.solution_dim, itrs))
+        if self._ask_ws is None or self._ask_ws.numel() < need:
+            self._ask_ws = torch.empty(need, dtype=torch.float64, device=self._device)
         _lib.check(self._L.qd_lmma_ask(
             z.data_ptr(), rows, self.solution_dim, None if row_ids is None else row_ids.data_ptr(),
             self._mean.data_ptr(), self._status.data_ptr(), self._m.data_ptr(), self._cd_d.data_ptr(), itrs,
-            self._solutions.data_ptr(), stream_ptr()))
+            self._solutions.data_ptr(), self._ask_ws.data_ptr(), stream_ptr()))
 
     def tell(self, ranking_indices, ranking_values, num_parents):
         """_lm_ma_es.py:209-239."""
@@ -70,10 +76,9 @@ class LMMAEvolutionStrategy(DeviceES):
         num_parents = int(num_parents)
         if num_parents == 0:
             return
-        w, mueff = es_weights(num_parents)
+        w, mueff, w_d = self._weights_device(num_parents)
         with torch.cuda.device(self._device), torch.cuda.stream(self._es_stream()):
             rank_d = self._rank_to_device(ranking_indices, num_parents)
-            w_d = torch.from_numpy(w).to(self._device)
             self._weighted(self._z, rank_d, w_d, num_parents, None, self._z_mean, None)
             self._weighted(self._solutions, rank_d, w_d, num_parents, None, self._new_mean, None)
             _lib.check(self._L.qd_lmma_tell(

@@ -28,7 +28,7 @@ class SeparableCMAEvolutionStrategy(DeviceES):
     def _calc_strat_params(self, mu):
         """_sep_cma_es.py:203-231."""
         n = self.solution_dim
-        w, mueff = es_weights(mu)
+        w, mueff, _ = self._weights_device(mu)
         cc = (1 + 1 / n + mueff / n) / (n**0.5 + 1 / n + 2 * mueff / n)
         cs = (mueff + 2) / (n + mueff + 5)
         c1 = 2 / ((n + 1.3) ** 2 + mueff)
@@ -69,7 +69,17 @@ class SeparableCMAEvolutionStrategy(DeviceES):
     def cov(self):
         return self._to_host(self._C)
 
+    _zig_normals = True
+    _fused_rng = True  # tell re-reads the solutions only (:281-303), so z never has to exist in HBM
+
     def _sample_rows(self, z, rows, row_ids):
+        if z is None:  # generator fused into the transform: X is the only HBM traffic of the ask
+            n = self.solution_dim
+            _lib.check(self._L.qd_sep_ask_rng(
+                rows, n, None if row_ids is None else row_ids.data_ptr(), self._mean.data_ptr(), self._C.data_ptr(),
+                self._status.data_ptr(), self._seed, self._rng_offset, self._solutions.data_ptr(), None, stream_ptr()))
+            self._rng_offset += rows * ((n + 3) // 4)
+            return
         _lib.check(self._L.qd_sep_ask(
             z.data_ptr(), rows, self.solution_dim, None if row_ids is None else row_ids.data_ptr(),
             self._mean.data_ptr(), self._C.data_ptr(), self._status.data_ptr(), self._solutions.data_ptr(),
@@ -86,7 +96,7 @@ class SeparableCMAEvolutionStrategy(DeviceES):
         damps = 1 + 2 * max(0, np.sqrt((mueff - 1) / (n + 1)) - 1) + cs
         with torch.cuda.device(self._device), torch.cuda.stream(self._es_stream()):
             rank_d = self._rank_to_device(ranking_indices, num_parents)
-            w_d = torch.from_numpy(w).to(self._device)
+            w_d = self._weights_device(num_parents)[2]
             self._weighted(self._solutions, rank_d, w_d, num_parents, self._mean, self._new_mean, self._rank_mu)
             sc = self._scalars(cc=cc, cs=cs, c1=c1, cmu=cmu, mueff=mueff, damps=damps, wsum=np.sum(w),
                                hsig_exp=2 * self.current_eval / self.batch_size)

@@ -246,3 +246,121 @@ def test_pooled_scheduler_matches_emitter_by_emitter(mode):
     s2.tell(torch.from_numpy(o).cuda(), torch.from_numpy(m).cuda())
     s1.tell(*_sphere(s1.ask()))
     np.testing.assert_array_equal(a1.data("objective"), a2.data("objective"))
+
+
+# ---- streaming strategies at scale: ziggurat normals, fused sep-CMA ask, LM-MA ask as tall-skinny products ----
+def _zig_fill(count, seed, offset=0):
+    import torch
+
+    from pyribs_b200 import _lib
+
+    out = torch.empty(count, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().qd_fill_normal_zig(out.data_ptr(), count, seed, offset,
+                                             torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def test_ziggurat_normals():
+    """qd_fill_normal_zig: a standard normal to the resolution 4M samples can see (moments, a Kolmogorov
+    distance, the wedge / tail regions the slow path produces), reproducible, and counter-addressed:
+    out[4q..4q+3] depend on (seed, offset + q) only."""
+    import torch
+    from scipy import stats
+
+    x = _zig_fill(4_000_003, 77).cpu().numpy()
+    assert np.all(np.isfinite(x))
+    assert abs(x.mean()) < 2.5e-3 and abs(x.var() - 1) < 4e-3
+    assert abs(stats.skew(x)) < 6e-3 and abs(stats.kurtosis(x)) < 1.5e-2
+    assert stats.kstest(x[:1_000_000], "norm").statistic < 2.0e-3
+    for t in (1.0, 2.0, 3.0, 4.0, 4.216370409511896):  # two-sided tail masses, incl. beyond the base layer's edge
+        p, got = 2 * stats.norm.sf(t), np.mean(np.abs(x) > t)
+        assert abs(got - p) < 6 * np.sqrt(p / x.size) + 1e-7, (t, got, p)
+    assert abs(np.mean(x > 0) - 0.5) < 1.5e-3
+    assert np.unique(x).size > 0.999 * x.size  # 53-bit variates: no visible lattice
+    a = _zig_fill(4096, 5)
+    assert torch.equal(a, _zig_fill(4096, 5)) and not torch.equal(a, _zig_fill(4096, 6))
+    assert torch.equal(a[400:1000], _zig_fill(600, 5, offset=100))  # quad 100 onwards
+    assert torch.equal(_zig_fill(4001, 5)[:4000], _zig_fill(4000, 5))  # ragged tail does not disturb the rest
+
+
+@pytest.mark.parametrize("n,lam", [(1000, 64), (10, 7), (37, 50)])
+def test_sep_ask_fused_generator(n, lam):
+    """qd_sep_ask_rng == qd_sep_ask applied to the normals it reports (bit for bit), and for n % 4 == 0 those
+    are the stream qd_fill_normal_zig produces from the same counters; row_ids redirect rows."""
+    import torch
+
+    from pyribs_b200 import _lib
+
+    L, s = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(0)
+    dev = dict(dtype=torch.float64, device="cuda")
+    mean = torch.from_numpy(rng.standard_normal(n)).cuda()
+    C = torch.from_numpy(rng.uniform(0.1, 3.0, n)).cuda()
+    status = torch.zeros(8, **dev)
+    status[0] = 0.37
+    X, z, X2 = torch.zeros(lam, n, **dev), torch.zeros(lam, n, **dev), torch.zeros(lam, n, **dev)
+    _lib.check(L.qd_sep_ask_rng(lam, n, None, mean.data_ptr(), C.data_ptr(), status.data_ptr(), 99, 1000, X.data_ptr(),
+                                z.data_ptr(), s))
+    _lib.check(L.qd_sep_ask(z.data_ptr(), lam, n, None, mean.data_ptr(), C.data_ptr(), status.data_ptr(),
+                            X2.data_ptr(), s))
+    assert torch.equal(X, X2)
+    ref = np.sqrt(C.cpu().numpy()) * (0.37 * z.cpu().numpy()) + mean.cpu().numpy()  # _sep_cma_es.py:160-179
+    np.testing.assert_array_equal(X.cpu().numpy(), ref)
+    if n % 4 == 0:
+        assert torch.equal(z.reshape(-1), _zig_fill(lam * n, 99, offset=1000))
+    zz = z.cpu().numpy()
+    assert abs(zz.mean()) < 5 / np.sqrt(zz.size) and abs(zz.var() - 1) < 8 / np.sqrt(zz.size)
+    # without z_out, and with redirected rows
+    ids = torch.from_numpy(rng.permutation(lam).astype(np.int32)).cuda()
+    X3 = torch.zeros(lam, n, **dev)
+    _lib.check(L.qd_sep_ask_rng(lam, n, ids.data_ptr(), mean.data_ptr(), C.data_ptr(), status.data_ptr(), 99, 1000,
+                                X3.data_ptr(), None, s))
+    assert torch.equal(X3[ids.long()], X)
+
+
+def test_sep_cma_default_ask_is_reproducible_and_normal():
+    from pyribs_b200.emitters.opt import SeparableCMAEvolutionStrategy
+
+    def run(seed):
+        es = SeparableCMAEvolutionStrategy(0.5, 2000, 128, seed=seed)
+        es.reset(np.full(2000, 0.25))
+        a = es.ask()
+        es.tell(np.arange(128), None, 64)
+        return a, es.ask()
+
+    (a1, b1), (a2, b2), (a3, _) = run(4), run(4), run(5)
+    np.testing.assert_array_equal(a1, a2)
+    np.testing.assert_array_equal(b1, b2)
+    assert not np.array_equal(a1, a3) and not np.array_equal(a1, b1)
+    zz = (a1 - 0.25) / 0.5
+    assert abs(zz.mean()) < 0.01 and abs(zz.var() - 1) < 0.02
+
+
+@pytest.mark.parametrize("n,lam,nv,gens", [(1003, 77, 37, 40), (256, 33, None, 6), (64, 5, 3, 5), (2048, 128, 70, 72)])
+def test_lmma_ask_matches_the_sequential_transforms(n, lam, nv, gens):
+    """LM-MA ask as Z M^T, M M^T, forward substitution and one output pass against the oracle's rank-one
+    transforms applied one after the other (_lm_ma_es.py:136-144), with ragged sizes and more direction vectors
+    than one register group; the strategies are driven in lockstep so the vectors are realistic."""
+    from pyribs_b200.emitters.opt import LMMAEvolutionStrategy
+
+    kw = {} if nv is None else {"n_vectors": nv}
+    gpu = LMMAEvolutionStrategy(0.8, n, lam, seed=2, **kw)
+    ora = O.OracleLMMAES(0.8, n, lam, seed=2, **kw)
+    x0 = np.linspace(-1, 1, n)
+    gpu.reset(x0), ora.reset(x0)
+    # the reference's cd (1 / (1.5^j n)) makes the transforms nearly the identity; scale it up so that an error in
+    # the coefficients would be visible at the tolerance
+    boost = np.minimum(0.3, ora.cd * n * 0.2)
+    ora.cd = boost
+    gpu._cd_d.copy_(__import__("torch").from_numpy(boost))
+    rng = np.random.default_rng(n + lam)
+    for g in range(gens):
+        z = rng.standard_normal((lam, n))
+        so, sg = ora.ask(z), gpu.ask(z=z)
+        assert_close(sg, so, 1e-9, f"gen {g} solutions")
+        if g == 0:
+            np.testing.assert_array_equal(sg, so)  # no transform yet: mean + sigma z, bit for bit
+        rank = np.argsort(-(-np.sum((so - 0.5) ** 2, axis=1)))[::-1].copy()
+        ora.tell(rank, lam // 2), gpu.tell(rank, None, lam // 2)
+    assert_close(gpu.m, ora.m, 1e-9, "direction vectors")
+    assert_close(gpu.mean, ora.mean, 1e-9, "mean")
