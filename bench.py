@@ -145,6 +145,62 @@ def grid_insert_roofline(torch, dev, peak_hbm):
                     "wavefront-cycles per row), the winner-row copy by HBM (TMA bulk, 5.3-5.9 TB/s); DESIGN.md 4.2"}
 
 
+def es_roofline(torch, dev, peak_hbm):
+    """BASELINE.json's second metric (emitter ask+tell solutions/sec) on configs[3]: sep-CMA-ES and LM-MA-ES,
+    solution_dim 10 000, batch 4096, mu = 2048, device-resident (ask hands out the CUDA tensor, the ranking is a
+    CUDA tensor), on-device ziggurat normals. CUDA events on the caller's stream, which waits for the strategy's
+    own stream on both sides; median of 10 generations after 12 (LM-MA: all 20 direction vectors in use).
+    Algorithmic bytes per SURVEY 8(d): sep ask lam*n*8 + 3*n*8, tell mu*n*8 + 8*n*8; LM-MA ask 2*lam*n*8 +
+    m*n*8 (+ 4*lam*n*m flops on the fp64 tensor pipe), tell 2*mu*n*8 + 2*m*n*8."""
+    import numpy as np
+
+    from pyribs_b200.emitters.opt import _get_es
+
+    n, lam, mu = 10_000, 4096, 2048
+    out = []
+    for es_name, kw, warm in (("sep_cma_es", {}, 4), ("lm_ma_es", {"n_vectors": 20}, 22)):
+        es = _get_es(es_name, sigma0=0.5, solution_dim=n, batch_size=lam, seed=1, dtype=np.float64,
+                     lower_bounds=np.full(n, -np.inf), upper_bounds=np.full(n, np.inf), **kw)
+        es.reset(np.zeros(n))
+        cur = torch.cuda.current_stream()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        t_ask, t_tell = [], []
+        for g in range(warm + 10):
+            torch.cuda.synchronize()
+            ev[0].record()
+            X = es.ask(return_device=True)  # the caller's stream waits for the strategy's stream
+            ev[1].record()
+            rank = torch.argsort((X - 1.0).pow(2).sum(1))  # sphere objective, best first
+            es._es_stream().wait_stream(cur)
+            ev[2].record(es._es_stream())
+            es.tell(rank, None, mu)
+            ev[3].record(es._es_stream())
+            torch.cuda.synchronize()
+            if g >= warm:
+                t_ask.append(ev[0].elapsed_time(ev[1]))
+                t_tell.append(ev[2].elapsed_time(ev[3]))
+        a, t = float(np.median(t_ask)), float(np.median(t_tell))
+        m = kw.get("n_vectors", 0)
+        ask_b = lam * n * 8 + 3 * n * 8 if es_name == "sep_cma_es" else 2 * lam * n * 8 + m * n * 8
+        tell_b = mu * n * 8 + 8 * n * 8 if es_name == "sep_cma_es" else 2 * mu * n * 8 + 2 * m * n * 8
+        e = {"kernel": {"sep_cma_es": "sep_ask_rng_kernel (Philox + ziggurat fused with the transform) / "
+                                      "wsum_partial_kernel + sep_tell_*",
+                        "lm_ma_es": "fill_normal_zig + tall_dots (fp64 mma) + lmma_coef + lmma_out (fp64 mma) / "
+                                    "wsum_partial_kernel x2 + lmma_tell_*"}[es_name] + ", csrc/es_stream.cu, es.cu",
+             "workload": f"{es_name} n={n} lambda={lam} mu={mu}" + (f" n_vectors={m}" if m else ""),
+             "metric": "emitter ask+tell solutions/sec", "solutions_per_s": lam / ((a + t) * 1e-3),
+             "bound": "hbm", "achieved": (ask_b + tell_b) / ((a + t) * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+             "frac": (ask_b + tell_b) / ((a + t) * 1e-3) / 1e9 / peak_hbm,
+             "ask_ms": a, "tell_ms": t, "ask_GBps": ask_b / a / 1e6, "tell_GBps": tell_b / t / 1e6,
+             "algorithmic_bytes": ask_b + tell_b}
+        if m:
+            e["ask_fp64_TFLOPs"] = 4.0 * lam * n * m / (a * 1e-3) / 1e12
+        out.append(e)
+        del es, X
+        torch.cuda.empty_cache()
+    return out
+
+
 def cpu_reference(cen, batches, steps, warmup, workers):
     """The oracle port (reference algorithm on the CPU). Returns (insertions/s, seconds)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -192,6 +248,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--search", default="auto", choices=["auto", "tensor", "scan", "bucket"])
     ap.add_argument("--no-grid", action="store_true", help="skip the GridArchive 2M-row insertion roofline")
+    ap.add_argument("--no-es", action="store_true", help="skip the configs[3] ask/tell measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -360,6 +417,11 @@ def main():
             secondary.append(grid_insert_roofline(torch, dev, peak_hbm))
         except Exception as e:  # noqa: BLE001
             secondary.append({"kernel": "insert_kernel (GridArchive 2M rows)", "error": f"{type(e).__name__}: {e}"})
+    if world == 1 and rank == 0 and not args.no_es:
+        try:
+            secondary.extend(es_roofline(torch, dev, peak_hbm))
+        except Exception as e:  # noqa: BLE001
+            secondary.append({"kernel": "evolution strategies (configs[3])", "error": f"{type(e).__name__}: {e}"})
     roofline["secondary"] = secondary
 
     line = {

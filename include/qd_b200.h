@@ -353,9 +353,17 @@ int qd_cma_tell(int64_t n, const double* X, const int64_t* rank, const double* w
  * transforms of :136-144 are evaluated as Z M^T, M M^T (tall-skinny products), a forward substitution per
  * sample and one pass X = mean + sigma Q (Z + T M): same arithmetic up to rounding order. */
 size_t qd_lmma_ask_workspace_doubles(int64_t rows, int64_t n, int64_t itrs);
+/* A large ask runs as row blocks of at most this many bytes of z, alternating between two internal streams
+ * (default 160 MB; <= 0 restores it). Returns the previous value; call before sizing the workspace. */
+int64_t qd_lmma_set_block_bytes(int64_t bytes);
 int qd_lmma_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
                 const double* status, const double* M /*[dev] n_vectors x n*/, const double* cd /*[dev]*/,
                 int64_t itrs, double* X, double* workspace, void* stream);
+/* the same with the unit normals generated on the way: z_out (rows x n, needed by tell) receives exactly what
+ * qd_fill_normal_zig(z_out, rows * n, seed, offset) produces */
+int qd_lmma_ask_rng(int64_t rows, int64_t n, const int32_t* row_ids, const double* mean, const double* status,
+                    const double* M, const double* cd, int64_t itrs, uint64_t seed, uint64_t offset,
+                    double* z_out, double* X, double* workspace, void* stream);
 int qd_lmma_tell(int64_t n, int64_t n_vectors, const double* new_mean, const double* z_mean, double* mean,
                  double* ps, double* M, const double* cc /*[dev] n_vectors*/, double csigma, double mueff,
                  double* status, double* workspace, void* stream);

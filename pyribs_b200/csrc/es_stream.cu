@@ -16,6 +16,7 @@
 //     arithmetic up to rounding order (1e-15 relative; tests hold it to the oracle at 1e-9); the
 //     row-by-row version re-read every m_j for every row out of L2 and took 2.1 ms at 20 vectors.
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 #include "qd_common.cuh"
@@ -84,14 +85,21 @@ static int zig_tables_ready() {
   return QD_OK;
 }
 
+// 32 x 32 -> (hi, lo) as one IMAD.WIDE; spelled in PTX so that the front end cannot promote the round's
+// xors and key additions to 64-bit arithmetic (which costs two extra adds per multiply after ptxas)
+__device__ __forceinline__ void mul_wide(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+  asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1, %0}, p;\n\t}" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
+}
+
 __device__ __forceinline__ void philox_round4(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const unsigned long long p0 = (unsigned long long)0xD2511F53u * c[0];  // one IMAD.WIDE for hi and lo
-  const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c[2];
-  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+  uint32_t hi0, lo0, hi1, lo1;
+  mul_wide(0xD2511F53u, c[0], hi0, lo0);
+  mul_wide(0xCD9E8D57u, c[2], hi1, lo1);
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
   c[0] = n0;
-  c[1] = (uint32_t)p1;
+  c[1] = lo1;
   c[2] = n2;
-  c[3] = (uint32_t)p0;
+  c[3] = lo0;
 }
 
 __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
@@ -146,7 +154,8 @@ __device__ __noinline__ double zig_fix(unsigned long long r, uint32_t k0, uint32
 // Four unit normals from (seed, counter): two Philox calls give four candidates; all four take the
 // accept-at-once path without a branch, and one test sends the warp to the fix-up code when any missed.
 __device__ __forceinline__ void zig_quad(uint64_t seed, uint64_t ctr, const double2* __restrict__ swb, double (&z)[4]) {
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32);
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32);
   uint32_t a[4] = {c0, c1, 0u, 0x5A494731u}, b[4] = {c0, c1, 1u, 0x5A494731u};
   philox4x32_10(a, k0, k1);
   philox4x32_10(b, k0, k1);
@@ -284,21 +293,35 @@ __global__ void __launch_bounds__(256, 2) tall_dots_kernel(const double* __restr
   const int64_t cbeg = split * cols_per_split;
   const int64_t cend = cbeg + cols_per_split < n ? cbeg + cols_per_split : n;
   const int nch = (int)((cend - cbeg + kTdCols - 1) / kTdCols);
-  auto issue = [&](int ch) {
-    double* As = td_smem + (ch % kTdStages) * kTdStageDoubles;
-    double* Ms = As + kTdRows * kTdLd;
-    const int64_t c0 = cbeg + (int64_t)ch * kTdCols;
+  // a thread copies the same (row, column) slots of every chunk: 8 of A, 6 of M. Slot i: element i * 256 + t of
+  // the 64-wide tile, i.e. row i * 4 + t / 64, column t % 64; pointers and row predicates are loop invariants
+  const int lc = t & 63, lr = t >> 6;
+  const double* a_src[kTdRows / 4];
+  const double* m_src[kTdVecs / 4];
 #pragma unroll
-    for (int i = 0; i < kTdRows * kTdCols / 256; ++i) {  // a warp copies 32 consecutive doubles of one row
-      const int idx = i * 256 + t, r = idx >> 6, c = idx & 63;
-      const bool ok = row0 + r < rows && c0 + c < cend;
-      cp_async8(&As[r * kTdLd + c], ok ? A + (row0 + r) * n + c0 + c : A, ok);
+  for (int i = 0; i < kTdRows / 4; ++i) {
+    const int64_t row = row0 + i * 4 + lr;
+    a_src[i] = row < rows ? A + row * n + cbeg + lc : nullptr;
+  }
+#pragma unroll
+  for (int i = 0; i < kTdVecs / 4; ++i) {
+    const int j = j0 + i * 4 + lr;
+    m_src[i] = j < m ? M + (int64_t)j * n + cbeg + lc : nullptr;
+  }
+  auto issue = [&](int ch) {
+    double* As = td_smem + (ch % kTdStages) * kTdStageDoubles + lr * kTdLd + lc;
+    double* Ms = As + kTdRows * kTdLd;
+    const int64_t off = (int64_t)ch * kTdCols;
+    const bool okc = cbeg + off + lc < cend;  // false only in the ragged last chunk
+#pragma unroll
+    for (int i = 0; i < kTdRows / 4; ++i) {
+      const bool ok = okc && a_src[i] != nullptr;
+      cp_async8(As + i * 4 * kTdLd, ok ? a_src[i] + off : A, ok);
     }
 #pragma unroll
-    for (int i = 0; i < kTdVecs * kTdCols / 256; ++i) {
-      const int idx = i * 256 + t, j = idx >> 6, c = idx & 63;
-      const bool ok = j0 + j < m && c0 + c < cend;
-      cp_async8(&Ms[j * kTdLd + c], ok ? M + (int64_t)(j0 + j) * n + c0 + c : M, ok);
+    for (int i = 0; i < kTdVecs / 4; ++i) {
+      const bool ok = okc && m_src[i] != nullptr;
+      cp_async8(Ms + i * 4 * kTdLd, ok ? m_src[i] + off : M, ok);
     }
   };
   double acc[kTdRows / 8][kTdVecs / 8][2];
@@ -450,14 +473,16 @@ __global__ void __launch_bounds__(kCoefThreads) lmma_coef_kernel(const double* _
   }
 }
 
-// X[row][c] = mean[c] + sigma * Q_m * (z[k][c] + sum_j T[k][j] M[j][c]) on the fp64 tensor pipe: a CTA owns
-// 16 sample rows x 512 columns, a warp 16 x 64 of them (2 x 8 accumulator tiles); k runs over the direction
+// X[row][c] = mean[c] + sigma * Q_m * (z[k][c] + sum_j T[k][j] M[j][c]) on the fp64 tensor pipe: a CTA (four
+// warps, four resident per SM so that their load / MMA / store phases interleave) owns 16 sample rows x 256
+// columns, a warp 16 x 64 of them (2 x 8 accumulator tiles); k runs over the direction
 // vectors, four per MMA. Every m_j value of the CTA's columns is used by exactly one lane, so B fragments are
 // plain global loads (L2-resident M); the z tile streams in through cp.async while the MMAs run.
-constexpr int kLoRows = 16, kLoCols = 512, kLoLd = kLoCols + 8;  // 520: conflict-free 16-byte fragment reads
+constexpr int kLoRows = 16, kLoThreads = 128, kLoCols = 2 * kLoThreads;
+constexpr int kLoLd = kLoCols + 8;  // 264: conflict-free 16-byte fragment reads
 
 template <bool VEC2>  // n even: rows stay 16-byte aligned, X leaves as double2
-__global__ void __launch_bounds__(256, 2) lmma_out_kernel(const double* __restrict__ z, int64_t rows, int64_t n,
+__global__ void __launch_bounds__(kLoThreads, 4) lmma_out_kernel(const double* __restrict__ z, int64_t rows, int64_t n,
                                                           const int32_t* __restrict__ row_ids,
                                                           const double* __restrict__ mean,
                                                           const double* __restrict__ status, const double* __restrict__ M,
@@ -472,9 +497,9 @@ __global__ void __launch_bounds__(256, 2) lmma_out_kernel(const double* __restri
     const bool okr = row0 + r < rows;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int64_t c = col0 + h * 256 + t;
+      const int64_t c = col0 + h * kLoThreads + t;
       const bool ok = okr && c < n;
-      cp_async8(&zs[r * kLoLd + h * 256 + t], ok ? z + (row0 + r) * n + c : z, ok);
+      cp_async8(&zs[r * kLoLd + h * kLoThreads + t], ok ? z + (row0 + r) * n + c : z, ok);
     }
   }
   cp_async_commit();
@@ -485,24 +510,35 @@ __global__ void __launch_bounds__(256, 2) lmma_out_kernel(const double* __restri
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
   const int64_t cw = col0 + warp * 64;  // first column of the warp
-  for (int j4 = 0; j4 < m; j4 += 4) {
+  // fragments of k-step j4: A[row fg][k ft] = T, B[k ft][n fg] = M; the next step's loads are issued before
+  // this step's MMAs (the loop bound is a run-time value, so the compiler does not pipeline it itself)
+  auto load_frags = [&](int j4, double (&a)[2], double (&b)[8]) {
     const int j = j4 + ft;
     const bool okj = j < m;
-    double a[2], b[8];
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) {
       const int64_t row = row0 + mb * 8 + fg;
-      a[mb] = (okj && row < rows) ? __ldg(Tt + (int64_t)j * rows + row) : 0.0;  // A[row fg][k ft]
+      a[mb] = (okj && row < rows) ? __ldg(Tt + (int64_t)j * rows + row) : 0.0;
     }
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
       const int64_t c = cw + nb * 8 + fg;
-      b[nb] = (okj && c < n) ? __ldg(M + (int64_t)j * n + c) : 0.0;  // B[k ft][n fg]
+      b[nb] = (okj && c < n) ? __ldg(M + (int64_t)j * n + c) : 0.0;
     }
+  };
+  double a0[2], b0[8];
+  if (m > 0) load_frags(0, a0, b0);
+  for (int j4 = 0; j4 < m; j4 += 4) {
+    double a1[2], b1[8];
+    load_frags(j4 + 4, a1, b1);  // past the end: all predicates false, zeros
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb) dmma884(acc[mb][nb], a[mb], b[nb]);
+      for (int nb = 0; nb < 8; ++nb) dmma884(acc[mb][nb], a0[mb], b0[nb]);
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) a0[mb] = a1[mb];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) b0[nb] = b1[nb];
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -554,28 +590,85 @@ static TdPlan td_plan(int64_t rows, int64_t n, int64_t m) {
   return p;
 }
 
-struct LmmaWs {  // doubles
-  size_t ppart, p, gpart, g, tt, qm, total;
+// Sample rows are independent given G = M M^T, so a large ask runs as row blocks that alternate between two
+// side streams: the ALU-bound generator, the tensor-bound product and the HBM-bound output pass of
+// neighbouring blocks overlap. Measured at n = 10 000, lambda = 4096 (327 MB of z): blocks of 160 MB (two
+// blocks) 0.39-0.45 ms per ask, one block 0.40-0.46 ms, 40 MB blocks (L2-sized, eight blocks) 0.49-0.56 ms --
+// the extra launches cost more than reading z back from L2 instead of HBM saves.
+constexpr int64_t kLmmaBlockBytes = 160ll << 20;
+constexpr int kLmmaSlots = 2;
+
+static std::atomic<int64_t> g_lmma_block_bytes{0};  // 0: not set yet
+
+static int64_t lmma_block_bytes() {  // QD_LMMA_BLOCK_MB / qd_lmma_set_block_bytes override the default
+  int64_t v = g_lmma_block_bytes.load(std::memory_order_relaxed);
+  if (v == 0) {
+    const char* e = getenv("QD_LMMA_BLOCK_MB");
+    const long mb = e ? atol(e) : 0;
+    v = mb > 0 ? (int64_t)mb << 20 : kLmmaBlockBytes;
+    g_lmma_block_bytes.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+static int64_t lmma_block_rows(int64_t rows, int64_t n) {
+  int64_t rb = lmma_block_bytes() / (n * (int64_t)sizeof(double)) / 32 * 32;
+  if (rb < 32) rb = 32;
+  return rb < rows ? rb : rows;
+}
+
+struct LmmaWs {  // offsets in doubles; the block part repeats once per slot
+  size_t gpart, g, block0, ppart, p, tt, qm, block_stride, total;
 };
 
 static LmmaWs lmma_ws(int64_t rows, int64_t n, int64_t m) {
   LmmaWs w;
-  const TdPlan pp = td_plan(rows, n, m), pg = td_plan(m, n, m);
+  const int64_t rb = lmma_block_rows(rows, n);
+  const TdPlan pg = td_plan(m, n, m);
+  const int64_t last = rows - (rows - 1) / rb * rb;  // rows of the final (possibly partial) block
+  const size_t pp_full = (size_t)td_plan(rb, n, m).nsplit * rb, pp_last = (size_t)td_plan(last, n, m).nsplit * last;
   size_t off = 0;
-  w.ppart = off;
-  off += (size_t)pp.nsplit * m * rows;
-  w.p = off;
-  off += (size_t)m * rows;
   w.gpart = off;
   off += (size_t)pg.nsplit * m * m;
   w.g = off;
   off += (size_t)m * m;
-  w.tt = off;
-  off += (size_t)m * rows;
-  w.qm = off;
-  off += 8;
-  w.total = off;
+  w.block0 = off;
+  size_t b = 0;
+  w.ppart = b;
+  b += (pp_full > pp_last ? pp_full : pp_last) * m;
+  w.p = b;
+  b += (size_t)m * rb;
+  w.tt = b;
+  b += (size_t)m * rb;
+  w.qm = b;
+  b += 8;
+  w.block_stride = b;
+  w.total = off + kLmmaSlots * b;
   return w;
+}
+
+struct SideStreams {
+  cudaStream_t s[kLmmaSlots];
+  cudaEvent_t fork, join[kLmmaSlots];
+  bool ready = false;
+};
+
+static int side_streams(SideStreams** out) {
+  static SideStreams pool[64];
+  int dev = 0;
+  QD_CHECK_CUDA(cudaGetDevice(&dev));
+  QD_REQUIRE(dev < 64, "device ordinal out of range");
+  SideStreams& p = pool[dev];
+  if (!p.ready) {
+    for (int i = 0; i < kLmmaSlots; ++i) {
+      QD_CHECK_CUDA(cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking));
+      QD_CHECK_CUDA(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming));
+    }
+    QD_CHECK_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    p.ready = true;
+  }
+  *out = &p;
+  return QD_OK;
 }
 
 static int launch_tall_dots(const double* A, int64_t rows, int64_t n, const double* M, int64_t m, double* part,
@@ -628,34 +721,31 @@ extern "C" int qd_sep_ask_rng(int64_t rows, int64_t n, const int32_t* row_ids, c
   return check_launch("sep_ask_rng_kernel");
 }
 
+extern "C" int64_t qd_lmma_set_block_bytes(int64_t bytes) {
+  const int64_t prev = qd::lmma_block_bytes();
+  qd::g_lmma_block_bytes.store(bytes > 0 ? bytes : qd::kLmmaBlockBytes, std::memory_order_relaxed);
+  return prev;
+}
+
 extern "C" size_t qd_lmma_ask_workspace_doubles(int64_t rows, int64_t n, int64_t itrs) {
   if (rows <= 0 || n <= 0 || itrs <= 0) return 8;
   return qd::lmma_ws(rows, n, itrs).total;
 }
 
-extern "C" int qd_lmma_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
-                           const double* status, const double* M, const double* cd, int64_t itrs, double* X,
-                           double* workspace, void* stream) {
-  using namespace qd;
-  if (rows == 0) return QD_OK;
-  QD_REQUIRE(z && mean && status && X && rows > 0 && n > 0 && itrs >= 0, "bad arguments");
-  QD_REQUIRE(itrs == 0 || (M && cd && workspace), "null pointer");
-  QD_REQUIRE(itrs < ((int64_t)1 << 20) && rows < ((int64_t)1 << 31), "sizes out of range");
-  cudaStream_t s = (cudaStream_t)stream;
-  const int m = (int)itrs;
+namespace qd {
+
+// P, forward substitution and the output pass for one block of sample rows (G is ready in ws_g)
+static int lmma_block(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
+                      const double* status, const double* M, const double* cd, int m, double* X, const double* ws_g,
+                      double* wb, const LmmaWs& w, cudaStream_t s) {
   const double* Tt = nullptr;
   const double* qm = nullptr;
+  int rc;
   if (m > 0) {
-    const LmmaWs w = lmma_ws(rows, n, m);
-    double* ws = workspace;
-    int rc = launch_tall_dots(M, m, n, M, m, ws + w.gpart, s);  // G = M M^T
-    if (rc) return rc;
-    sum_splits_kernel<<<grid_for((int64_t)m * m * 32, 256), 256, 0, s>>>(ws + w.gpart, td_plan(m, n, m).nsplit,
-                                                                   (int64_t)m * m, ws + w.g);
-    if ((rc = check_launch("sum_splits_kernel"))) return rc;
-    if ((rc = launch_tall_dots(z, rows, n, M, m, ws + w.ppart, s))) return rc;  // P = Z M^T
+    if ((rc = launch_tall_dots(z, rows, n, M, m, wb + w.ppart, s))) return rc;  // P = Z M^T
     const int nsp = td_plan(rows, n, m).nsplit;
-    sum_splits_wide_kernel<<<grid_for((int64_t)m * rows, 256), 256, 0, s>>>(ws + w.ppart, nsp, (int64_t)m * rows, ws + w.p);
+    sum_splits_wide_kernel<<<grid_for((int64_t)m * rows, 256), 256, 0, s>>>(wb + w.ppart, nsp, (int64_t)m * rows,
+                                                                            wb + w.p);
     if ((rc = check_launch("sum_splits_wide_kernel"))) return rc;
     static bool attr = false;
     if (!attr) {
@@ -665,12 +755,12 @@ extern "C" int qd_lmma_ask(const double* z, int64_t rows, int64_t n, const int32
     const unsigned cgrid = (unsigned)((rows + kCoefThreads - 1) / kCoefThreads);
     const size_t tsm = ((size_t)m * kCoefThreads + 2 * m + (size_t)m * m) * sizeof(double);
     if (m <= kCoefSmemMax)
-      lmma_coef_kernel<true><<<cgrid, kCoefThreads, tsm, s>>>(ws + w.p, ws + w.g, cd, m, rows, ws + w.tt, ws + w.qm);
+      lmma_coef_kernel<true><<<cgrid, kCoefThreads, tsm, s>>>(wb + w.p, ws_g, cd, m, rows, wb + w.tt, wb + w.qm);
     else
-      lmma_coef_kernel<false><<<cgrid, kCoefThreads, 0, s>>>(ws + w.p, ws + w.g, cd, m, rows, ws + w.tt, ws + w.qm);
+      lmma_coef_kernel<false><<<cgrid, kCoefThreads, 0, s>>>(wb + w.p, ws_g, cd, m, rows, wb + w.tt, wb + w.qm);
     if ((rc = check_launch("lmma_coef_kernel"))) return rc;
-    Tt = ws + w.tt;
-    qm = ws + w.qm;
+    Tt = wb + w.tt;
+    qm = wb + w.qm;
   }
   const dim3 grid((unsigned)((n + kLoCols - 1) / kLoCols), (unsigned)((rows + kLoRows - 1) / kLoRows));
   QD_REQUIRE(grid.y <= 65535, "too many sample rows");
@@ -682,8 +772,76 @@ extern "C" int qd_lmma_ask(const double* z, int64_t rows, int64_t n, const int32
     out_attr = true;
   }
   if (n % 2 == 0)
-    lmma_out_kernel<true><<<grid, 256, zsm, s>>>(z, rows, n, row_ids, mean, status, M, m, Tt, qm, X);
+    lmma_out_kernel<true><<<grid, kLoThreads, zsm, s>>>(z, rows, n, row_ids, mean, status, M, m, Tt, qm, X);
   else
-    lmma_out_kernel<false><<<grid, 256, zsm, s>>>(z, rows, n, row_ids, mean, status, M, m, Tt, qm, X);
+    lmma_out_kernel<false><<<grid, kLoThreads, zsm, s>>>(z, rows, n, row_ids, mean, status, M, m, Tt, qm, X);
   return check_launch("lmma_out_kernel");
+}
+
+// generate != 0: z (rows x n) is filled first, block by block, with the stream qd_fill_normal_zig(z, rows * n, seed,
+// offset) produces
+static int lmma_ask_impl(double* z, int generate, uint64_t seed, uint64_t offset, int64_t rows, int64_t n,
+                         const int32_t* row_ids, const double* mean, const double* status, const double* M,
+                         const double* cd, int64_t itrs, double* X, double* workspace, cudaStream_t s) {
+  if (rows == 0) return QD_OK;
+  QD_REQUIRE(z && mean && status && X && rows > 0 && n > 0 && itrs >= 0, "bad arguments");
+  QD_REQUIRE(itrs == 0 || (M && cd && workspace), "null pointer");
+  QD_REQUIRE(itrs < ((int64_t)1 << 20) && rows < ((int64_t)1 << 31), "sizes out of range");
+  int rc;
+  if (generate && (rc = zig_tables_ready())) return rc;
+  const int m = (int)itrs;
+  LmmaWs w = {};
+  double* ws = workspace;
+  if (m > 0) {
+    w = lmma_ws(rows, n, m);
+    if ((rc = launch_tall_dots(M, m, n, M, m, ws + w.gpart, s))) return rc;  // G = M M^T
+    sum_splits_kernel<<<grid_for((int64_t)m * m * 32, 256), 256, 0, s>>>(ws + w.gpart, td_plan(m, n, m).nsplit,
+                                                                   (int64_t)m * m, ws + w.g);
+    if ((rc = check_launch("sum_splits_kernel"))) return rc;
+  }
+  const int64_t rb = lmma_block_rows(rows, n);
+  const int64_t nblocks = (rows + rb - 1) / rb;
+  SideStreams* side = nullptr;
+  if (nblocks > 1) {
+    if ((rc = side_streams(&side))) return rc;
+    QD_CHECK_CUDA(cudaEventRecord(side->fork, s));
+    for (int i = 0; i < kLmmaSlots; ++i) QD_CHECK_CUDA(cudaStreamWaitEvent(side->s[i], side->fork, 0));
+  }
+  for (int64_t b = 0; b < nblocks; ++b) {
+    const int64_t r0 = b * rb, nr = rows - r0 < rb ? rows - r0 : rb;
+    const int slot = (int)(b % kLmmaSlots);
+    cudaStream_t bs = side ? side->s[slot] : s;
+    double* zb = z + r0 * n;
+    if (generate) {  // r0 * n is a multiple of 4 (r0 of 32): the block's quads are the flat fill's quads
+      fill_normal_zig_kernel<<<grid_for((nr * n + 3) / 4, 256, 6), 256, 0, bs>>>(zb, nr * n, seed,
+                                                                               offset + (uint64_t)(r0 * n / 4));
+      if ((rc = check_launch("fill_normal_zig_kernel"))) return rc;
+    }
+    rc = lmma_block(zb, nr, n, row_ids ? row_ids + r0 : nullptr, mean, status, M, cd, m, row_ids ? X : X + r0 * n,
+                    m > 0 ? ws + w.g : nullptr, m > 0 ? ws + w.block0 + slot * w.block_stride : nullptr, w, bs);
+    if (rc) return rc;
+  }
+  if (side) {
+    for (int i = 0; i < kLmmaSlots; ++i) {
+      QD_CHECK_CUDA(cudaEventRecord(side->join[i], side->s[i]));
+      QD_CHECK_CUDA(cudaStreamWaitEvent(s, side->join[i], 0));
+    }
+  }
+  return QD_OK;
+}
+
+}  // namespace qd
+
+extern "C" int qd_lmma_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
+                           const double* status, const double* M, const double* cd, int64_t itrs, double* X,
+                           double* workspace, void* stream) {
+  return qd::lmma_ask_impl(const_cast<double*>(z), 0, 0, 0, rows, n, row_ids, mean, status, M, cd, itrs, X, workspace,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int qd_lmma_ask_rng(int64_t rows, int64_t n, const int32_t* row_ids, const double* mean,
+                               const double* status, const double* M, const double* cd, int64_t itrs, uint64_t seed,
+                               uint64_t offset, double* z_out, double* X, double* workspace, void* stream) {
+  return qd::lmma_ask_impl(z_out, 1, seed, offset, rows, n, row_ids, mean, status, M, cd, itrs, X, workspace,
+                           (cudaStream_t)stream);
 }

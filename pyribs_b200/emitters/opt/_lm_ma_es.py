@@ -57,17 +57,33 @@ class LMMAEvolutionStrategy(DeviceES):
     def m(self):
         return self._to_host(self._m)
 
-    _zig_normals = True  # z is kept: tell averages the parents' z (:224-226)
+    _zig_normals = True
+    _fused_rng = True  # the ask entry point fills z itself (tell averages the parents' z, :224-226)
 
     def _sample_rows(self, z, rows, row_ids):
+        n = self.solution_dim
         itrs = min(self.current_gens, self.n_vectors)
-        need = int(self._L.qd_lmma_ask_workspace_doubles(rows, self.solution_dim, itrs))
+        need = int(self._L.qd_lmma_ask_workspace_doubles(rows, n, itrs))
         if self._ask_ws is None or self._ask_ws.numel() < need:
             self._ask_ws = torch.empty(need, dtype=torch.float64, device=self._device)
-        _lib.check(self._L.qd_lmma_ask(
-            z.data_ptr(), rows, self.solution_dim, None if row_ids is None else row_ids.data_ptr(),
-            self._mean.data_ptr(), self._status.data_ptr(), self._m.data_ptr(), self._cd_d.data_ptr(), itrs,
-            self._solutions.data_ptr(), self._ask_ws.data_ptr(), stream_ptr()))
+        ids = None if row_ids is None else row_ids.data_ptr()
+        if z is not None:
+            _lib.check(self._L.qd_lmma_ask(
+                z.data_ptr(), rows, n, ids, self._mean.data_ptr(), self._status.data_ptr(), self._m.data_ptr(),
+                self._cd_d.data_ptr(), itrs, self._solutions.data_ptr(), self._ask_ws.data_ptr(), stream_ptr()))
+            return
+        # unit normals generated block by block inside the call (the block's z is still in L2 when the product and
+        # the output pass read it); the stream is the one `_normals(rows)` would have produced
+        znew = torch.empty((rows, n), dtype=torch.float64, device=self._device)
+        _lib.check(self._L.qd_lmma_ask_rng(
+            rows, n, ids, self._mean.data_ptr(), self._status.data_ptr(), self._m.data_ptr(), self._cd_d.data_ptr(),
+            itrs, self._seed, self._rng_offset, znew.data_ptr(), self._solutions.data_ptr(), self._ask_ws.data_ptr(),
+            stream_ptr()))
+        self._rng_offset += (rows * n + 3) // 4
+        if row_ids is None:
+            self._z = znew
+        else:
+            self._z[row_ids.long()] = znew
 
     def tell(self, ranking_indices, ranking_values, num_parents):
         """_lm_ma_es.py:209-239."""

@@ -364,3 +364,65 @@ def test_lmma_ask_matches_the_sequential_transforms(n, lam, nv, gens):
         ora.tell(rank, lam // 2), gpu.tell(rank, None, lam // 2)
     assert_close(gpu.m, ora.m, 1e-9, "direction vectors")
     assert_close(gpu.mean, ora.mean, 1e-9, "mean")
+
+
+def test_lmma_default_ask_blocks_and_streams():
+    """The default LM-MA ask generates its normals inside the call, row block by row block on two side streams
+    (blocks of 40 MB of z set through qd_lmma_set_block_bytes: three blocks here). z must be the flat ziggurat stream of the strategy's counters,
+    and the solutions must equal, bit for bit, the single-stream ask applied to that z afterwards."""
+    import torch
+
+    from pyribs_b200 import _lib
+    from pyribs_b200.emitters.opt import LMMAEvolutionStrategy
+
+    n, lam = 8192, 1280
+    prev = _lib.lib().qd_lmma_set_block_bytes(40 << 20)
+    try:
+        _lmma_blocks_body(n, lam)
+    finally:
+        _lib.lib().qd_lmma_set_block_bytes(prev)
+
+
+def _lmma_blocks_body(n, lam):
+    import torch
+
+    from pyribs_b200 import _lib
+    from pyribs_b200.emitters.opt import LMMAEvolutionStrategy
+
+    es = LMMAEvolutionStrategy(0.3, n, lam, seed=7, n_vectors=10)
+    es.reset(np.zeros(n))
+    for g in range(3):
+        off = es._rng_offset
+        X = es.ask(return_device=True)
+        torch.cuda.synchronize()
+        z = es._z
+        assert es._rng_offset == off + lam * n // 4
+        assert torch.equal(z.reshape(-1), _zig_fill(lam * n, es._seed, offset=off))
+        # replay with the normals injected: same kernels, one block at a time on the caller's stream
+        X2 = torch.empty_like(X)
+        itrs = min(es.current_gens, es.n_vectors)
+        ws = torch.empty(int(_lib.lib().qd_lmma_ask_workspace_doubles(lam, n, itrs)), dtype=torch.float64, device="cuda")
+        with torch.cuda.stream(es._es_stream()):
+            _lib.check(_lib.lib().qd_lmma_ask(z.data_ptr(), lam, n, None, es._mean.data_ptr(), es._status.data_ptr(),
+                                              es._m.data_ptr(), es._cd_d.data_ptr(), itrs, X2.data_ptr(), ws.data_ptr(),
+                                              es._es_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(X, X2)
+        fit = -(X - 0.1).pow(2).sum(1)
+        es.tell(torch.argsort(fit, descending=True), None, lam // 2)
+    assert es.sigma > 0 and np.all(np.isfinite(es.mean)) and np.any(es.m != 0)
+
+
+def test_lmma_bounds_with_fused_generator():
+    from pyribs_b200.emitters.opt import LMMAEvolutionStrategy
+
+    n = 40
+    es = LMMAEvolutionStrategy(0.8, n, 24, seed=3, lower_bounds=np.full(n, -2.0), upper_bounds=np.full(n, 2.0))
+    es.reset(np.zeros(n))
+    for g in range(3):
+        sol = es.ask()
+        assert sol.shape == (24, n) and np.all(sol >= -2.0) and np.all(sol <= 2.0)
+        # the retained normals belong to the accepted samples: generation 0 has no transform, x = sigma z
+        if g == 0:
+            np.testing.assert_array_equal(sol, 0.8 * es._z.cpu().numpy())
+        es.tell(np.argsort(np.sum(sol ** 2, axis=1)), None, 12)
