@@ -416,6 +416,25 @@ def gen_emitters():
     save("emitters", out)
 
 
+# ---------------------------------------------------------------------------------------
+# 7. BanditScheduler (UCB1 emitter selection) driven by deterministic stub emitters
+# ---------------------------------------------------------------------------------------
+def gen_bandit():
+    import warnings
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bandit_stubs as S
+    from ribs.schedulers import BanditScheduler
+
+    out = {}
+    for case, reselect, k in S.CASES:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            masks, success, selection = S.run_bandit(BanditScheduler, case, reselect, k)
+        out[f"{case}_{reselect}_{k}"] = {"active": masks, "success": success, "selection": selection}
+    save("bandit", out)
+
+
 if __name__ == "__main__":
     print("reference", ribs.__version__, "from", os.path.dirname(ribs.__file__))
     gen_grid_index()
@@ -424,3 +443,4 @@ if __name__ == "__main__":
     gen_es()
     gen_rankers()
     gen_emitters()
+    gen_bandit()

@@ -117,3 +117,31 @@ def test_map_elites_runs_on_the_scheduler():
         sched.tell(obj, meas)
         hist.append(len(a))
     assert hist[-1] > hist[5] > hist[0] >= 1
+
+
+def test_bandit_scheduler_over_device_emitters():
+    """The reference's `me_map_elites` configuration in small (examples/sphere.py): a UCB1 bandit over a pool of
+    ES and variation emitters, all inserting into one device archive."""
+    from pyribs_b200.archives import GridArchive
+    from pyribs_b200.emitters import EvolutionStrategyEmitter, GaussianEmitter, IsoLineEmitter
+    from pyribs_b200.schedulers import BanditScheduler
+
+    n = 12
+    a = GridArchive(solution_dim=n, dims=(30, 30), ranges=[(-30.72, 30.72)] * 2, seed=4)
+    pool = ([EvolutionStrategyEmitter(a, x0=np.zeros(n), sigma0=0.5, ranker="2imp", batch_size=16, seed=s)
+             for s in range(3)] +
+            [GaussianEmitter(a, sigma=0.3, x0=np.zeros(n), batch_size=16, seed=10 + s) for s in range(2)] +
+            [IsoLineEmitter(a, x0=np.zeros(n), batch_size=16, seed=20 + s) for s in range(2)])
+    sched = BanditScheduler(a, pool, num_active=3, reselect="terminated")
+    sizes = []
+    for it in range(30):
+        x = sched.ask()
+        assert x.shape == (48, n) and sched.active.sum() == 3
+        obj = -np.sum((x - 2.0) ** 2, axis=1)
+        clipped = np.where(np.abs(x) <= 5.12, x, 5.12 / np.where(x == 0, 1, x))
+        meas = np.stack([clipped[:, : n // 2].sum(1), clipped[:, n // 2:].sum(1)], axis=1)
+        sched.tell(obj, meas)
+        sizes.append(len(a))
+    assert sizes[-1] > sizes[3] > 0
+    assert sched._selection.sum() == 30 * 48 and 0 < sched._success.sum() <= sched._selection.sum()
+    assert np.count_nonzero(sched._selection) >= 4  # the variation emitters (no restart counter) rotate
