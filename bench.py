@@ -109,7 +109,7 @@ C_SIZEOF_RESULT = 120  # sizeof(qd_add_result)
 NCU_TRAFFIC = {"cvt_bucket_kernel": 1_833_984, "insert_kernel_grid_2M": 311_130_624 + 205_896_704}
 
 
-def grid_insert_roofline(torch, dev, peak_hbm):
+def grid_insert_roofline(torch, dev, peak_hbm, pipelined=False):
     """GridArchive insertion against the HBM roofline (north_star: >= 60 % of HBM peak at 1 GPU): CMA-MAE
     lr=0.01, 500x500 cells (the grid of configs[2]), n=100, 2M-row batches of uniform measures -- the size at
     which the insertion is throughput- rather than latency-bound. Algorithmic bytes per SURVEY 8(d):
@@ -118,6 +118,7 @@ def grid_insert_roofline(torch, dev, peak_hbm):
 
     Bg, n = 2_000_000, 100
     a = GridArchive(solution_dim=n, dims=(500, 500), ranges=[(-1, 1)] * 2, learning_rate=0.01, threshold_min=0.0)
+    a.pipeline_commit = pipelined
     g = torch.Generator(device=dev).manual_seed(1)
     bs = [dict(solution=torch.randn(Bg, n, dtype=torch.float64, device=dev, generator=g),
                objective=torch.rand(Bg, dtype=torch.float64, device=dev, generator=g) * 100 + 5.0 * j,
@@ -130,14 +131,18 @@ def grid_insert_roofline(torch, dev, peak_hbm):
     e0.record()
     for j in range(iters):
         a.add(**bs[j % 3])  # 3 x 1.65 GB of inputs: nothing survives in the 126 MB L2 between calls
+    a.join()  # pipelined: the last row copy belongs to the timed region
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     st = a.add(**bs[0])["status"]
     W = int(torch.unique(a.index_of(bs[0]["measures"])[st != 0]).numel())
     alg = Bg * 45 + W * (2 * n * 8 + 2 * 2 * 8 + 2 * 8)
-    return {"kernel": "insert_kernel<double, double, 2, fused grid index> (GridArchive.add, one launch per add)",
-            "workload": "GridArchive 500x500, CMA-MAE lr=0.01, n=100, 2M-row batches, uniform measures",
+    return {"kernel": "insert_kernel<double, double, 2, fused grid index> (GridArchive.add, "
+                      + ("row phases and row copy as two launches on two streams: the copy of add k overlaps the row "
+                         "phases of add k+1; archive.pipeline_commit = True)" if pipelined else "one launch per add)"),
+            "workload": "GridArchive 500x500, CMA-MAE lr=0.01, n=100, 2M-row batches, uniform measures"
+                        + (", back-to-back adds" if pipelined else ""),
             "bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak_hbm, "unit": "GB/s", "frac": alg / ms / 1e6 / peak_hbm,
             "ms_per_add": ms, "insertions_per_s": Bg / ms * 1e3, "winners_per_add": W, "algorithmic_bytes": alg,
             "traffic": NCU_TRAFFIC.get("insert_kernel_grid_2M"),
@@ -415,6 +420,8 @@ def main():
     if world == 1 and rank == 0 and not args.no_grid:
         try:
             secondary.append(grid_insert_roofline(torch, dev, peak_hbm))
+            torch.cuda.empty_cache()
+            secondary.append(grid_insert_roofline(torch, dev, peak_hbm, pipelined=True))
         except Exception as e:  # noqa: BLE001
             secondary.append({"kernel": "insert_kernel (GridArchive 2M rows)", "error": f"{type(e).__name__}: {e}"})
     if world == 1 and rank == 0 and not args.no_es:

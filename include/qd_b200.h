@@ -205,6 +205,17 @@ int qd_dp_push(int n_fields, const void* const* src /*[host] dev ptrs*/, const i
 #define QD_INSERT_WHOLE 0
 #define QD_INSERT_CLASSIFY 1
 #define QD_INSERT_COMMIT 2
+/* Pipelined commit: QD_INSERT_ROWS does everything except the row copy (status / value, thresholds, objectives,
+ * occupancy, occupied_list, stats, result, best-elite snapshot taken from the batch) and leaves the winner list
+ * in one of two buffers; QD_INSERT_COPY, issued afterwards with the same arguments on ANOTHER stream (ordered
+ * after the ROWS launch by an event), copies the winners' rows into the store. It has no grid barrier and shares
+ * the SMs with the ROWS launch of the next add(): the HBM-bound copy hides behind the scattered-access-bound
+ * row passes. The caller alternates the buffers (OR in QD_INSERT_BUF1 for every other add), keeps the batch
+ * alive until the copy has run, issues copies in order on one stream, and joins that stream before anything reads
+ * the store's row fields or before a QD_INSERT_WHOLE / _COMMIT launch. */
+#define QD_INSERT_ROWS 3
+#define QD_INSERT_COPY 4
+#define QD_INSERT_BUF1 0x100
 int qd_insert(const qd_store* store, int64_t B, const int32_t* idx /*[dev] B*/,
               const void* objective /*[dev] B*/, const void* const* field_src /*[host] n_fields dev ptrs*/,
               double learning_rate, double threshold_min,

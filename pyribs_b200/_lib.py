@@ -13,7 +13,7 @@ QD_MAX_FIELDS = 16
 FLAG_NONFINITE_MEASURES = 1
 FLAG_NONFINITE_OBJECTIVE = 2
 FLAG_CVT_OVERFLOW = 4
-INSERT_WHOLE, INSERT_CLASSIFY, INSERT_COMMIT = 0, 1, 2
+INSERT_WHOLE, INSERT_CLASSIFY, INSERT_COMMIT, INSERT_ROWS, INSERT_COPY, INSERT_BUF1 = 0, 1, 2, 3, 4, 0x100
 
 
 class QdError(RuntimeError):

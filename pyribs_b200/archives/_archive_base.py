@@ -167,6 +167,12 @@ class DeviceArchive:
         self._row_bytes_total = sum(self._store._row_bytes(n) for n in self._store.row_fields)
         self._force_scan = False
         self._overflow_fallbacks = 0
+        # pipelined commit (see `pipeline_commit`)
+        self._pipeline_commit = False
+        self._pipe = None          # (side stream, rows-done event, [copy-done event of list buffer 0, 1])
+        self._pipe_calls = 0
+        self._pipe_pending = None  # copy-done event nobody has waited for yet
+        self._store._copy_join = self._join_copy
 
     # ---- properties ---------------------------------------------------------------------
     @property
@@ -239,6 +245,42 @@ class DeviceArchive:
     # ---- device-resident state -> host mirror ------------------------------------------------
     _ERR_OBJ = "All elements of objective must be finite (infinity and NaN values are not supported)."
     _ERR_MEAS = "All elements of measures must be finite (infinity and NaN values are not supported)."
+
+    # ---- pipelined commit -------------------------------------------------------------------------------
+    @property
+    def pipeline_commit(self):
+        """Opt-in software pipelining of back-to-back `add()` calls on CUDA tensors (single process). When set,
+        `add()` runs every phase except the copy of the winners' rows on the caller's stream (QD_INSERT_ROWS:
+        status / value, thresholds, objectives, occupancy, stats, best elite) and the row copy on a side stream
+        (QD_INSERT_COPY), where it overlaps the row phases of the next `add()`: the copy is HBM-bound, the row
+        passes are bound by scattered accesses, and together they fill the machine. Results are identical to the
+        default mode. Contract: like any asynchronous copy, the batch tensors must not be overwritten until the
+        copy has run -- until the next read of the archive (`data`, `retrieve*`, `sample_elites`, iteration,
+        `clear`, pickling; they wait for it) or an explicit `archive.join()`; freeing them is safe (their memory
+        is tied to the side stream)."""
+        return self._pipeline_commit
+
+    @pipeline_commit.setter
+    def pipeline_commit(self, on):
+        if not on:
+            self._join_copy()
+        self._pipeline_commit = bool(on)
+
+    def join(self):
+        """Makes the current stream wait for a row copy still running on the side stream."""
+        self._join_copy()
+
+    def _join_copy(self):
+        ev = self._pipe_pending
+        if ev is not None:
+            self._pipe_pending = None
+            torch.cuda.current_stream(self._device).wait_event(ev)
+
+    def _pipe_state(self):
+        if self._pipe is None:
+            self._pipe = (torch.cuda.Stream(device=self._device), torch.cuda.Event(),
+                          [torch.cuda.Event(), torch.cuda.Event()])
+        return self._pipe
 
     def _raise_for_flags(self, flags):
         if flags & _lib.FLAG_NONFINITE_OBJECTIVE:
@@ -595,9 +637,41 @@ class DeviceArchive:
                         B_local, self._lr_f, self._tmin_f, status.data_ptr(), value.data_ptr(),
                         store._result_dev.data_ptr(), part, current_stream_ptr()))
 
-            if rows_event is None:
+            pipelined = (self._pipeline_commit and rows_event is None and dev_in and self._dp_world == 1
+                         and all(is_device_tensor(v) for v in data.values()))
+            if pipelined:
+                side, rows_done, copy_done = self._pipe_state()
+                cur = torch.cuda.current_stream()
+                buf = self._pipe_calls & 1
+                bits = _lib.INSERT_BUF1 if buf else 0
+                if self._pipe_calls >= 2:  # the copy that read this list buffer two calls ago
+                    cur.wait_event(copy_done[buf])
+                probe = self.__dict__.get("_pipe_probe")  # tools/pipe_probe.py: timed events around both launches
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if probe is not None else None
+                if ev:
+                    ev[0].record(cur)
+                insert(_lib.INSERT_ROWS | bits)
+                rows_done.record(cur)
+                if ev:
+                    ev[1].record(cur)
+                side.wait_event(rows_done)
+                with torch.cuda.stream(side):
+                    if ev:
+                        ev[2].record(side)
+                    insert(_lib.INSERT_COPY | bits)
+                    copy_done[buf].record(side)
+                    if ev:
+                        ev[3].record(side)
+                        probe.append(ev)
+                for t in dev.values():  # the allocator must not hand the batch out again before the copy has read it
+                    t.record_stream(side)
+                self._pipe_calls += 1
+                self._pipe_pending = copy_done[buf]
+            elif rows_event is None:
+                self._join_copy()
                 insert(_lib.INSERT_WHOLE)
             else:
+                self._join_copy()
                 # status / value are final after the first part: they travel back while the solutions
                 # are still travelling in (full-duplex PCIe); only the row copy waits for them
                 insert(_lib.INSERT_CLASSIFY)
@@ -674,6 +748,7 @@ class DeviceArchive:
             if (not isinstance(arr, np.ndarray) or not arr.flags.c_contiguous or arr.dtype != dts[n]
                     or not self._is_pinned(arr)):
                 return None
+        self._join_copy()
         L = _lib.lib()
         zc = self._zc
         if zc is None:

@@ -148,9 +148,17 @@ class DeviceStore:
             return int(res.last_failed_flags) or int(res.flags)
         return 0
 
+    def join_row_copy(self):
+        """A pipelined add() (DeviceArchive.pipeline_commit) copies the winners' rows on a side stream; anything that
+        reads or rewrites the row fields first makes the current stream wait for it."""
+        hook = self.__dict__.get("_copy_join")
+        if hook is not None:
+            hook()
+
     def sync(self):
         """Reads the device-side store state back if insertions are still in flight. Returns the
         unreported validation flags (see consume)."""
+        self.join_row_copy()
         if not self._pending:
             return 0
         with torch.cuda.device(self._device):
@@ -254,6 +262,7 @@ class DeviceStore:
         src = (C.c_void_p * max(nf, 1))(*[self._fields[n].data_ptr() for n in names])
         dst = (C.c_void_p * max(nf, 1))(*[out[n].data_ptr() for n in names])
         rb = (C.c_int64 * max(nf, 1))(*[self._row_bytes(n) for n in names])
+        self.join_row_copy()
         with torch.cuda.device(self._device):
             _lib.check(_lib.lib().qd_store_gather(M, indices.data_ptr(), nf, src, dst, rb, self._occupied.data_ptr(),
                                                   occ.data_ptr(), current_stream_ptr()))

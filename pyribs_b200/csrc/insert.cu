@@ -74,6 +74,10 @@ struct InsertState {
   uint32_t last_failed_flags;     // flags of the most recent such call
   uint32_t pad;
   unsigned long long t_phase[10]; // %globaltimer at the phase boundaries of the last call (diagnostics)
+  // ---- per call, re-armed by publish ----
+  unsigned long long best_pack;   // (cell << 32 | batch row) of the lowest winning cell holding the new maximum
+  // ---- pipelined commit (QD_INSERT_ROWS / QD_INSERT_COPY): winners of the row phases, one count per list buffer
+  uint32_t copy_w[2];
 };
 
 struct Scratch {
@@ -96,8 +100,8 @@ static Scratch carve(void* base, int64_t N) {
   p += align_up((size_t)words * 4, 256);
   s.ctacnt = (uint32_t*)p;
   p += align_up((size_t)kMaxCtas * 4, 256);
-  s.wlist = (int2*)p;
-  p += align_up((size_t)N * 8, 256);
+  s.wlist = (int2*)p;  // two buffers of N entries (a pipelined row copy reads one while the next call fills the other)
+  p += 2 * align_up((size_t)N * 8, 256);
   s.g = (InsertState*)p;
   return s;
 }
@@ -105,7 +109,7 @@ static Scratch carve(void* base, int64_t N) {
 static size_t scratch_bytes(int64_t N) {
   const int64_t words = (N + 31) / 32;
   return align_up((size_t)N * sizeof(Cell), 256) + align_up((size_t)words * 4, 256) +
-         align_up((size_t)kMaxCtas * 4, 256) + align_up((size_t)N * 8, 256) + align_up(sizeof(InsertState), 256);
+         align_up((size_t)kMaxCtas * 4, 256) + 2 * align_up((size_t)N * 8, 256) + align_up(sizeof(InsertState), 256);
 }
 
 __global__ void scratch_init_kernel(Scratch s, int64_t N) {
@@ -124,6 +128,7 @@ __global__ void scratch_init_kernel(Scratch s, int64_t N) {
     InsertState g;
     memset(&g, 0, sizeof(g));
     g.best_cell = INT32_MAX;
+    g.best_pack = ~0ull;
     *s.g = g;
   }
 }
@@ -682,9 +687,8 @@ __device__ void copy_rows_small(const FieldCopy& fc, int f, const Scratch& s, in
   }
 }
 
-__device__ void phase_copy(const FieldCopy& fc, const Scratch& s, unsigned char* slots, uint64_t* mbar,
+__device__ void phase_copy(const FieldCopy& fc, const Scratch& s, int64_t W, unsigned char* slots, uint64_t* mbar,
                            uint32_t& parity) {
-  const int64_t W = s.g->n_winners;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bool any_bulk = false;
   for (int f = 0; f < fc.n; ++f) any_bulk |= is_bulk_field(fc, f);
@@ -754,13 +758,19 @@ __device__ void phase_best_and_count(const InsertArgs<T>& a, bool new_record, bo
   if (new_record) {  // lowest winning cell holding the batch maximum (_stats_update's argmax, :331-341)
     const int64_t W = g->n_winners;
     const unsigned long long gk = g->gbest_key;
-    int32_t m = INT32_MAX;
+    unsigned long long m = ~0ull;  // (cell << 32 | batch row): the minimum is the lowest cell, and names its winner's row
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < W; t += (int64_t)gridDim.x * blockDim.x) {
       const int2 rc = a.s.wlist[t];
-      if (ord_key((double)a.obj[rc.x]) == gk) m = min(m, rc.y);
+      if (ord_key((double)a.obj[rc.x]) == gk) {
+        const unsigned long long pk = ((unsigned long long)(uint32_t)rc.y << 32) | (uint32_t)rc.x;
+        m = pk < m ? pk : m;
+      }
     }
-    m = __reduce_min_sync(0xffffffffu, m);
-    if ((threadIdx.x & 31) == 0 && m != INT32_MAX) atomicMin(&a.s.g->best_cell, m);
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+      const unsigned long long o = __shfl_down_sync(0xffffffffu, m, o2);
+      m = o < m ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&a.s.g->best_pack, m);
   }
   if (any_new) {
     int64_t w0, w1;
@@ -780,9 +790,12 @@ __device__ void phase_best_and_count(const InsertArgs<T>& a, bool new_record, bo
 }
 
 // ---- phase 7 ----------------------------------------------------------------------------------
+// from_source: the best elite's rows are taken from the batch (the row copy has not run yet: QD_INSERT_ROWS);
+// save_w >= 0: the winner count is kept in copy_w[save_w] for the QD_INSERT_COPY launch that follows
 template <typename T>
 __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool committed, bool new_record,
-                              bool any_new, int64_t n_before, uint32_t* sh, uint32_t* sh_base) {
+                              bool any_new, int64_t n_before, uint32_t* sh, uint32_t* sh_base, bool from_source,
+                              int save_w) {
   InsertState* gp = a.s.g;
   const int lane = threadIdx.x & 31;
   if (any_new) {
@@ -839,15 +852,18 @@ __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool 
   }
   if (blockIdx.x != 0) return;
   // CTA 0: best-elite snapshot, then stats + result + re-arm
-  const int32_t best_cell = gp->best_cell;
+  const unsigned long long best_pack = gp->best_pack;
+  const int32_t best_cell = best_pack != ~0ull ? (int32_t)(best_pack >> 32) : INT32_MAX;
   const bool snap = committed && new_record && best_cell != INT32_MAX && a.snapshot != nullptr;
   if (snap) {
     for (int f = 0; f < fc.n; ++f) {
-      const char* sp = fc.dst[f] + (int64_t)best_cell * fc.row_bytes[f];
+      const char* sp = from_source ? src_row(fc, f, (int)(uint32_t)best_pack, fc.row_bytes[f])
+                                   : fc.dst[f] + (int64_t)best_cell * fc.row_bytes[f];
       char* dp = a.snapshot + fc.snap_off[f];
       for (int64_t o = threadIdx.x; o < fc.row_bytes[f]; o += blockDim.x) dp[o] = sp[o];
     }
   }
+  __syncthreads();  // every warp has read best_pack before thread 0 re-arms it
   if (threadIdx.x == 0) {
     InsertState g = *gp;
     const double delta = (double)(T)__dadd_rn(__dadd_rn(g.dsum[0], g.dsum[1]), g.dsum[2]);
@@ -891,9 +907,11 @@ __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool 
     r.n_failed = g.n_failed;
     r.n_winners = committed ? g.n_winners : 0;
     *a.result = r;
+    if (save_w >= 0) g.copy_w[save_w] = committed ? g.n_winners : 0u;
     g.gbest_key = 0ull;
     g.absmax_bits = 0ull;
     g.best_cell = INT32_MAX;
+    g.best_pack = ~0ull;
     g.n_insertable = g.n_new = g.flags = g.n_winners = 0u;
     g.dsum[0] = g.dsum[1] = g.dsum[2] = 0.0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g.t_phase[8]));
@@ -908,7 +926,11 @@ template <typename T, typename MT, int D, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_constant__ InsertArgs<T> a,
                                                            const __grid_constant__ GridParams gp,
                                                            const __grid_constant__ FieldCopy fc, int phase_lo,
-                                                           int phase_hi) {
+                                                           int phase_hi, int mode, int buf) {
+  // mode 0: phases [phase_lo, phase_hi] in order. mode 1 (QD_INSERT_ROWS): everything but the row copy -- phases
+  // 0-4, then best / count and publish with the best elite taken from the batch; the winner list stays in list
+  // buffer `buf` (a.s.wlist points at it). mode 2 (QD_INSERT_COPY): only the row copy of that list, a plain
+  // launch on another stream that overlaps the row phases of the next add().
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(128) unsigned char copy_slots[];
   __shared__ uint64_t copy_bar[kCopyWarps];
@@ -923,6 +945,11 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
   __shared__ double sh_d[3][kThreads / 32];
   __shared__ unsigned long long sh_k[kThreads / 32];
   const InsertState* g = a.s.g;
+  if (mode == 2) {
+    const int64_t W = g->copy_w[buf];
+    if (W > 0 && fc.n > 0) phase_copy(fc, a.s, W, copy_slots, copy_bar, copy_parity);
+    return;
+  }
   const bool mae = a.mae;
   const int64_t n_before = g->n_occupied;  // CTA 0 advances it in the publish phase
   auto stamp = [&](int k) {
@@ -966,15 +993,16 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
   if (phase_lo <= 4 && phase_hi >= 4 && committed) {
     if (cell_mode) {
       phase_update_cells<T>(a, sh_d, sh_u + 32, sh_k, sh_u, &sh_base);
-      if (phase_hi >= 5) grid.sync();  // the winner list is complete only now
+      if (phase_hi >= 5 && mode == 0) grid.sync();  // the winner list is complete only now
     } else {
       phase_update_list<T>(a, sh_d, sh_u + 32, sh_k);
     }
   }
   if (phase_lo <= 4) stamp(5);
-  if (phase_lo <= 5 && phase_hi >= 5 && committed && fc.n > 0) phase_copy(fc, a.s, copy_slots, copy_bar, copy_parity);
-  if (phase_hi < 6) return;
-  if (phase_lo <= 5) grid.sync();
+  if (mode == 0 && phase_lo <= 5 && phase_hi >= 5 && committed && fc.n > 0)
+    phase_copy(fc, a.s, g->n_winners, copy_slots, copy_bar, copy_parity);
+  if (phase_hi < 6 && mode == 0) return;
+  if (phase_lo <= 5 || mode == 1) grid.sync();
   stamp(6);
   const unsigned long long gk = g->gbest_key, pk = g->obj_max_key;
   const bool new_record = committed && gk != 0ull && (pk == 0ull || gk > pk);
@@ -984,7 +1012,7 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
     grid.sync();
   }
   stamp(7);
-  phase_publish<T>(a, fc, committed, new_record, any_new, n_before, sh_u, &sh_base);
+  phase_publish<T>(a, fc, committed, new_record, any_new, n_before, sh_u, &sh_base, mode == 1, mode == 1 ? buf : -1);
 }
 
 static int pick_vec(const void* a, const void* b, int64_t row_bytes) {
@@ -1002,9 +1030,9 @@ struct GridSpec {  // non-null measures => fused grid index
 };
 
 template <typename T, typename MT, int D, bool FUSED>
-static int launch_insert(const InsertArgs<T>& a, const GridParams& gp, const FieldCopy& fc, int64_t work,
-                         int part, cudaStream_t stream) {
-  static int max_ctas = 0;  // per instantiation
+static int launch_insert(InsertArgs<T> a, const GridParams& gp, const FieldCopy& fc, int64_t work, int part,
+                         cudaStream_t stream) {
+  static int max_ctas = 0, sm_count = kNumSMs;  // per instantiation
   if (max_ctas == 0) {
     int per_sm = 0, dev = 0, sms = kNumSMs;
     QD_CHECK_CUDA(cudaFuncSetAttribute(insert_kernel<T, MT, D, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1019,14 +1047,26 @@ static int launch_insert(const InsertArgs<T>& a, const GridParams& gp, const Fie
     }
     int64_t m = (int64_t)per_sm * sms;
     max_ctas = (int)(m < kMaxCtas ? m : kMaxCtas);
+    sm_count = sms;
   }
+  const int kind = part & 0xff, buf = (part >> 8) & 1;
+  a.s.wlist += (int64_t)buf * (int64_t)(align_up((size_t)a.N * 8, 256) / 8);
   int64_t want = (work + kThreads - 1) / kThreads;
   if (want < 8) want = 8;
-  const int grid = (int)(want < max_ctas ? want : max_ctas);
-  int lo = part == QD_INSERT_COMMIT ? 5 : 0, hi = part == QD_INSERT_CLASSIFY ? 4 : 7;
-  void* params[] = {(void*)&a, (void*)&gp, (void*)&fc, (void*)&lo, (void*)&hi};
+  // the two halves of a pipelined add() share the SMs: one CTA per SM each
+  const int cap = (kind == QD_INSERT_ROWS || kind == QD_INSERT_COPY) ? (sm_count < max_ctas ? sm_count : max_ctas)
+                                                                     : max_ctas;
+  const int grid = (int)(want < cap ? want : cap);
+  int lo = kind == QD_INSERT_COMMIT ? 5 : 0, hi = (kind == QD_INSERT_CLASSIFY || kind == QD_INSERT_ROWS) ? 4 : 7;
+  int mode = kind == QD_INSERT_ROWS ? 1 : kind == QD_INSERT_COPY ? 2 : 0;
+  int bufi = buf;
+  if (mode == 2) {  // no grid barrier inside: a plain launch, free to run next to the following add()'s row phases
+    insert_kernel<T, MT, D, FUSED><<<grid, kThreads, kCopySmem, stream>>>(a, gp, fc, 5, 5, mode, bufi);
+    return check_launch("insert_kernel(copy)");
+  }
+  void* params[] = {(void*)&a, (void*)&gp, (void*)&fc, (void*)&lo, (void*)&hi, (void*)&mode, (void*)&bufi};
   QD_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)insert_kernel<T, MT, D, FUSED>, dim3(grid), dim3(kThreads),
-                                            params, kCopySmem, stream));
+                                            params, mode == 1 ? 0 : kCopySmem, stream));
   return check_launch("insert_kernel");
 }
 
@@ -1243,7 +1283,7 @@ extern "C" int qd_insert_sharded_rows(const qd_store* store, int64_t B, const in
   using namespace qd;
   int rc = check_insert_args(store, B, objective, status_out, value_out, result);
   if (rc) return rc;
-  QD_REQUIRE(part >= QD_INSERT_WHOLE && part <= QD_INSERT_COMMIT, "part must be QD_INSERT_WHOLE/CLASSIFY/COMMIT");
+  QD_REQUIRE((part & 0xff) >= QD_INSERT_WHOLE && (part & 0xff) <= QD_INSERT_COPY && (part & ~0x1ff) == 0, "bad part");
   if (B > 0) QD_REQUIRE(idx, "null idx");
   if (peer_field_src) QD_REQUIRE(rows_per_rank >= 1, "rows_per_rank must be positive");
   GridSpec gs;
@@ -1265,7 +1305,7 @@ extern "C" int qd_grid_insert(const qd_store* store, int64_t B, const void* meas
   int rc = check_insert_args(store, B, objective, status_out, value_out, result);
   if (rc) return rc;
   QD_REQUIRE(meas_dtype == QD_F32 || meas_dtype == QD_F64, "measures dtype must be f32/f64");
-  QD_REQUIRE(part >= QD_INSERT_WHOLE && part <= QD_INSERT_COMMIT, "part must be QD_INSERT_WHOLE/CLASSIFY/COMMIT");
+  QD_REQUIRE((part & 0xff) >= QD_INSERT_WHOLE && (part & 0xff) <= QD_INSERT_COPY && (part & ~0x1ff) == 0, "bad part");
   if (B > 0) QD_REQUIRE(measures && idx_out, "null measures / idx_out");
   GridSpec gs;
   if ((rc = fill_grid_params(gs.gp, d, dims, lower, interval, epsilon))) return rc;

@@ -139,6 +139,7 @@ class _VariationEmitter:
             lz = self._as_normals(line_z, (B,)) if n_parents == 2 else None
             sig = torch.from_numpy(np.ascontiguousarray(sigma).reshape(-1)).to(self._device)
             X = torch.empty((B, n), dtype=self._td, device=self._device)
+            arch._store.join_row_copy()  # a pipelined add() may still be writing the solution field
             sol = arch._store._fields["solution"]
             _lib.check(_lib.lib().qd_emit_variation(
                 sol.data_ptr(), self._dt_code, n, B, None if pa is None else pa.data_ptr(),

@@ -487,3 +487,72 @@ def test_result_archive_shares_the_index_of_the_main_archive(kind, pinned):
     for k in ds:
         np.testing.assert_array_equal(ds[k], da[k], err_msg=k)
     assert shared.stats.qd_score == alone.stats.qd_score
+
+
+@pytest.mark.parametrize("kind", ["grid_me", "grid_mae", "cvt_mae", "grid_list_mode"])
+def test_pipelined_commit_equals_default(kind):
+    """`archive.pipeline_commit = True` runs the row copy of add() k on a side stream next to the row phases of
+    add() k+1 (QD_INSERT_ROWS / QD_INSERT_COPY, two winner-list buffers). Everything observable must equal the
+    default single-launch mode: status / value of every call, stats, best elite, the stored rows -- also when the
+    batch tensors are dropped right after add() and when reads are interleaved."""
+    import torch
+
+    from pyribs_b200.archives import CVTArchive, GridArchive
+
+    rng = np.random.default_rng(31)
+    n = 24
+    cen = rng.uniform(-1, 1, (700, 2))
+
+    def make():
+        if kind == "grid_me":
+            return GridArchive(solution_dim=n, dims=[40, 30], ranges=[(-1, 1)] * 2, seed=3,
+                               extra_fields={"tag": ((2,), np.int32)})
+        if kind == "grid_mae":
+            return GridArchive(solution_dim=n, dims=[40, 30], ranges=[(-1, 1)] * 2, learning_rate=0.05, threshold_min=-1.0,
+                               seed=3)
+        if kind == "grid_list_mode":  # cells >> rows: the compact winner list path
+            return GridArchive(solution_dim=n, dims=[400, 300], ranges=[(-1, 1)] * 2, learning_rate=0.2, threshold_min=0.0,
+                               seed=3)
+        return CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * 2, learning_rate=0.1, threshold_min=0.0, seed=3)
+
+    a, b = make(), make()
+    b.pipeline_commit = True
+    assert b.pipeline_commit and not a.pipeline_commit
+    B = 5000
+    for j in range(9):
+        batch = dict(solution=rng.standard_normal((B, n)), objective=rng.uniform(0, 10, B) + 0.7 * j,
+                     measures=rng.uniform(-1.05, 1.05, (B, 2)))
+        if kind == "grid_me":
+            batch["tag"] = rng.integers(0, 1000, (B, 2)).astype(np.int32)
+        da = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
+        db = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
+        ra, rb = a.add(**da), b.add(**db)
+        del db  # freed while the side-stream copy may still be reading it
+        junk = torch.full((B, n), float("nan"), dtype=torch.float64, device="cuda")  # would land in the freed block
+        assert torch.equal(ra["status"], rb["status"]) and torch.equal(ra["value"], rb["value"])
+        del junk
+        if j in (3, 6):  # interleaved reads wait for the copy
+            assert len(a) == len(b)
+            xa, xb = a.data(), b.data()
+            for k in xa:
+                np.testing.assert_array_equal(xa[k], xb[k], err_msg=f"{kind} add {j} {k}")
+            ea, eb = a.sample_elites(5), b.sample_elites(5)
+            for k in ea:
+                np.testing.assert_array_equal(ea[k], eb[k])
+    assert len(a) == len(b) > 100
+    sa, sb = a.stats, b.stats
+    assert (sa.num_elites, sa.qd_score, sa.obj_max, sa.obj_mean) == (sb.num_elites, sb.qd_score, sb.obj_max, sb.obj_mean)
+    for k in a.best_elite:
+        np.testing.assert_array_equal(a.best_elite[k], b.best_elite[k], err_msg=f"best elite {k}")
+    xa, xb = a.data(), b.data()
+    for k in xa:
+        np.testing.assert_array_equal(xa[k], xb[k], err_msg=f"{kind} final {k}")
+    # back to the default mode, and a host batch after pipelined adds
+    b.pipeline_commit = False
+    h = dict(solution=rng.standard_normal((300, n)), objective=rng.uniform(20, 30, 300), measures=rng.uniform(-1, 1, (300, 2)))
+    if kind == "grid_me":
+        h["tag"] = np.zeros((300, 2), dtype=np.int32)
+    ra, rb = a.add(**h), b.add(**h)
+    np.testing.assert_array_equal(ra["status"], rb["status"])
+    for k in xa:
+        np.testing.assert_array_equal(a.data()[k], b.data()[k])
