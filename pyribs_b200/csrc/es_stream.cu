@@ -569,6 +569,17 @@ __global__ void __launch_bounds__(kLoThreads, 4) lmma_out_kernel(const double* _
   }
 }
 
+// cudaFuncSetAttribute is per device: remember which devices a kernel has been opted in on
+template <class K>
+static int opt_in_smem(K kernel, size_t bytes, bool (&done)[64]) {
+  int dev = 0;
+  QD_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && done[dev]) return QD_OK;
+  QD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (dev < 64) done[dev] = true;
+  return QD_OK;
+}
+
 // launch geometry of the two tall-skinny products, shared by the workspace query and the launcher
 struct TdPlan {
   int row_tiles, groups, nsplit;
@@ -675,11 +686,9 @@ static int launch_tall_dots(const double* A, int64_t rows, int64_t n, const doub
                             cudaStream_t s) {
   const TdPlan p = td_plan(rows, n, m);
   QD_REQUIRE(p.groups <= 65535 && p.nsplit <= 65535, "too many direction vectors");
-  static bool attr = false;
-  if (!attr) {
-    QD_CHECK_CUDA(cudaFuncSetAttribute(tall_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTdSmem));
-    attr = true;
-  }
+  static bool attr[64] = {};
+  int rc0 = opt_in_smem(tall_dots_kernel, kTdSmem, attr);
+  if (rc0) return rc0;
   tall_dots_kernel<<<dim3(p.row_tiles, p.nsplit, p.groups), 256, kTdSmem, s>>>(A, rows, n, M, (int)m,
                                                                                p.cols_per_split, part);
   return check_launch("tall_dots_kernel");
@@ -747,11 +756,8 @@ static int lmma_block(const double* z, int64_t rows, int64_t n, const int32_t* r
     sum_splits_wide_kernel<<<grid_for((int64_t)m * rows, 256), 256, 0, s>>>(wb + w.ppart, nsp, (int64_t)m * rows,
                                                                             wb + w.p);
     if ((rc = check_launch("sum_splits_wide_kernel"))) return rc;
-    static bool attr = false;
-    if (!attr) {
-      QD_CHECK_CUDA(cudaFuncSetAttribute(lmma_coef_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
-    }
+    static bool attr[64] = {};
+    if ((rc = opt_in_smem(lmma_coef_kernel<true>, 200 * 1024, attr))) return rc;
     const unsigned cgrid = (unsigned)((rows + kCoefThreads - 1) / kCoefThreads);
     const size_t tsm = ((size_t)m * kCoefThreads + 2 * m + (size_t)m * m) * sizeof(double);
     if (m <= kCoefSmemMax)
@@ -765,12 +771,9 @@ static int lmma_block(const double* z, int64_t rows, int64_t n, const int32_t* r
   const dim3 grid((unsigned)((n + kLoCols - 1) / kLoCols), (unsigned)((rows + kLoRows - 1) / kLoRows));
   QD_REQUIRE(grid.y <= 65535, "too many sample rows");
   constexpr size_t zsm = (size_t)kLoRows * kLoLd * sizeof(double);
-  static bool out_attr = false;
-  if (!out_attr) {
-    QD_CHECK_CUDA(cudaFuncSetAttribute(lmma_out_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
-    QD_CHECK_CUDA(cudaFuncSetAttribute(lmma_out_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
-    out_attr = true;
-  }
+  static bool attr_even[64] = {}, attr_odd[64] = {};
+  if ((rc = opt_in_smem(lmma_out_kernel<true>, zsm, attr_even)) || (rc = opt_in_smem(lmma_out_kernel<false>, zsm, attr_odd)))
+    return rc;
   if (n % 2 == 0)
     lmma_out_kernel<true><<<grid, kLoThreads, zsm, s>>>(z, rows, n, row_ids, mean, status, M, m, Tt, qm, X);
   else

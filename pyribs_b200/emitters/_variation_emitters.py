@@ -63,7 +63,7 @@ class _VariationEmitter:
         # device side
         self._device = archive.device
         self._n = int(np.prod(self._noise_shape[1:]))
-        ss = np.random.SeedSequence(seed)
+        ss = seed if isinstance(seed, np.random.SeedSequence) else np.random.SeedSequence(seed)
         self._seed = int(ss.generate_state(1, dtype=np.uint64)[0])
         self._rng_offset = 0
         self._dt_code = _lib.QD_F64 if np.dtype(sdt) == np.float64 else _lib.QD_F32

@@ -86,6 +86,7 @@ def test_variation_emitters_interface():
     np.testing.assert_array_equal(e.ask(), np.clip(init, -1, 5))  # empty archive: the initial solutions, clipped
     assert e.x0 is None and e.batch_size == 8 and e.sigma == 0.1
     np.testing.assert_array_equal(e.lower_bounds, np.full(4, -1.0))
+    GaussianEmitter(a, sigma=0.1, x0=np.zeros(4), seed=np.random.SeedSequence(3).spawn(1)[0]).ask()  # as sphere.py seeds them
     e1 = IsoLineEmitter(a, x0=np.ones(4), batch_size=16, seed=11)
     e2 = IsoLineEmitter(a, x0=np.ones(4), batch_size=16, seed=11)
     x1, x2 = e1.ask(), e2.ask()
