@@ -317,6 +317,19 @@ int qd_emit_variation(const void* store_solution /*[dev] capacity x n*/, int dty
                       int sigma_is_vector, double line_sigma, const void* lower /*[dev] n*/,
                       const void* upper /*[dev] n*/, void* X_out /*[dev] B x n*/, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * k_means_centroids   ribs/archives/_cvt_archive.py:36-134 (sklearn.cluster.k_means, Lloyd)
+ * One update step: samples X (n x d) with their nearest centroid idx (from qd_cvt_index_of) -> new centroids
+ * (k x d, dtype of X), the per-centroid sums (k x d doubles; the host relocates empty clusters with them),
+ * member counts and the squared shift of every centroid. Order-independent exact accumulation: reproducible.
+ * bins: qd_kmeans_workspace_doubles(k, d) doubles; absmax: a bound on |X|.
+ * ---------------------------------------------------------------------------------- */
+size_t qd_kmeans_workspace_doubles(int64_t k, int64_t d);
+int qd_kmeans_update(const void* X /*[dev] n x d*/, int dtype, int64_t n, int64_t d, const int32_t* idx /*[dev] n*/,
+                     int64_t k, double absmax, double* bins /*[dev]*/, uint32_t* count /*[dev] k*/,
+                     const void* old_centroids /*[dev] k x d*/, void* new_centroids /*[dev] k x d*/,
+                     double* sums /*[dev] k x d*/, double* shift /*[dev] k*/, void* stream);
+
 /* CMA-ES pool: E strategies of identical (n, lambda) whose state is stacked in device memory; every
  * kernel is batched over the emitters (the many-emitter regime: ribs/schedulers/_scheduler.py:180-213,
  * 361-412 loops ask/tell over the emitters in Python). Arithmetic identical to the single-strategy entry

@@ -83,10 +83,11 @@ class CVTArchive(DeviceArchive):
         from pyribs_b200.archives._archive_base import parse_all_dtypes
 
         _, _, mdt = parse_all_dtypes(dtype, solution_dtype, objective_dtype, measures_dtype)
-        if isinstance(centroids, numbers.Integral):
-            raise NotImplementedError(
-                "Generating centroids with k-means is one-off set-up outside the accelerated path; generate "
-                "them first (e.g. sklearn.cluster.k_means) and pass the array.")
+        if isinstance(centroids, numbers.Integral):  # _cvt_archive.py:351-360: k-means over uniform samples
+            from pyribs_b200.archives._k_means import k_means_centroids
+
+            centroids, _ = k_means_centroids(centroids=centroids, ranges=ranges, samples=samples, dtype=mdt, seed=seed,
+                                             k_means_kwargs=k_means_kwargs, device=device)
         if isinstance(centroids, (str, Path)):
             cen = np.load(centroids).astype(mdt)
         else:

@@ -9,7 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 
 PUBLISHED = {  # docs/examples/sphere.md
-    "map_elites": (416_111.64, 2_681.37, 50.72, 0.40), "line_map_elites": (491_013.92, 1_118.74, 60.44, 0.17),
+    "map_elites": (416_111.64, 2_681.37, 50.72, 0.40), "cvt_map_elites": (416_350.11, 3_942.42, 50.67, 0.49),
+    "line_map_elites": (491_013.92, 1_118.74, 60.44, 0.17),
     "me_map_elites": (533_477.98, 15_041.68, 65.28, 2.05), "cma_me_imp": (456_678.01, 2_882.10, 55.84, 0.41),
     "cma_me_imp_mu": (498_464.35, 2_214.86, 61.11, 0.34), "cma_me_basic": (398_192.00, 10_174.36, 47.04, 1.30),
     "cma_me_rd": (458_403.60, 2_739.42, 56.21, 0.42), "cma_mae": (633_368.55, 1_504.43, 81.02, 0.27),
@@ -32,7 +33,7 @@ def sphere(sol):
 
 def build(algorithm, seed, dim=100):
     """examples/sphere.py CONFIG + create_scheduler (:1020-1150)."""
-    from pyribs_b200.archives import GridArchive
+    from pyribs_b200.archives import CVTArchive, GridArchive
     from pyribs_b200.emitters import EvolutionStrategyEmitter, GaussianEmitter, IsoLineEmitter
     from pyribs_b200.schedulers import BanditScheduler, Scheduler
 
@@ -41,6 +42,7 @@ def build(algorithm, seed, dim=100):
     es = lambda **kw: (EvolutionStrategyEmitter, dict(sigma0=0.5, batch_size=36, **kw), 15)  # noqa: E731
     cfg = {
         "map_elites": dict(emitters=[(GaussianEmitter, dict(sigma=0.5, batch_size=540), 1)]),
+        "cvt_map_elites": dict(cvt=True, emitters=[(GaussianEmitter, dict(sigma=0.5, batch_size=540), 1)]),
         "line_map_elites": dict(emitters=[(IsoLineEmitter, dict(iso_sigma=0.5, line_sigma=0.2, batch_size=540), 1)]),
         "me_map_elites": dict(emitters=[es(ranker="obj"), es(ranker="2rd"), es(ranker="2imp"),
                                         (IsoLineEmitter, dict(iso_sigma=0.01, line_sigma=0.1, batch_size=36), 15)],
@@ -53,7 +55,10 @@ def build(algorithm, seed, dim=100):
                         emitters=[es(ranker="imp", selection_rule="mu", restart_rule="basic")]),
     }[algorithm]
     result = GridArchive(solution_dim=dim, dims=(100, 100), ranges=bounds, seed=seed) if cfg.get("result") else None
-    archive = GridArchive(solution_dim=dim, dims=(100, 100), ranges=bounds, seed=seed, **cfg.get("archive", {}))
+    if cfg.get("cvt"):  # centroids=10000: k-means over 100 000 uniform samples, as the reference's constructor does
+        archive = CVTArchive(solution_dim=dim, centroids=10_000, ranges=bounds, seed=seed)
+    else:
+        archive = GridArchive(solution_dim=dim, dims=(100, 100), ranges=bounds, seed=seed, **cfg.get("archive", {}))
     ss = np.random.SeedSequence(seed)
     emitters = []
     for cls, kw, count in cfg["emitters"]:
