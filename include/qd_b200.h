@@ -291,6 +291,17 @@ int qd_sep_ask(const double* z, int64_t rows, int64_t n, const int32_t* row_ids,
 int qd_sep_ask_rng(int64_t rows, int64_t n, const int32_t* row_ids, const double* mean, const double* C,
                    const double* status, uint64_t seed, uint64_t offset, double* X, double* z_out /*or NULL*/,
                    void* stream);
+/* OpenAI-ES   (ribs/emitters/opt/_openai_es.py:127-208, AdamOpt ribs/emitters/opt/_adam_opt.py)
+ * mirrored ask: X[k] = mean + scale * (sigma z_k), X[k + half_rows] = mean + scale * (sigma * -z_k), z_out = z
+ * (half_rows x n), sigma = status[0]; same counter layout as qd_sep_ask_rng.
+ * tell: theta <- Adam step on g = -(grad_sum / denom) + l2 * theta, a = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+ * computed by the caller; status[4] receives |theta - theta_prev| / |theta|. workspace: qd_es_workspace_doubles(n). */
+int qd_mirror_ask_rng(int64_t half_rows, int64_t n, const double* mean, const double* scale /*[dev] n, sqrt'ed*/,
+                      const double* status, uint64_t seed, uint64_t offset, double* X /*[dev] 2 half_rows x n*/,
+                      double* z_out /*[dev] half_rows x n or NULL*/, void* stream);
+int qd_openai_tell(int64_t n, const double* grad_sum /*[dev] n*/, double denom, double* theta, double* m, double* v,
+                   double a, double beta1, double beta2, double eps, double l2, double* status, double* workspace,
+                   void* stream);
 int qd_sep_tell(int64_t n, const double* new_mean, const double* rank_mu /*[dev] n*/, double* mean, double* pc,
                 double* ps, double* C, double* status, const qd_cma_scalars* sc /*[host]*/,
                 double* workspace /*[dev] qd_es_workspace_doubles(n)*/, void* stream);

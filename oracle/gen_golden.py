@@ -290,7 +290,7 @@ class InjectedRNG:
         z, self.z = self.z, None
         return loc + scale * z
 
-    def standard_normal(self, size):
+    def standard_normal(self, size, dtype=None):
         assert self.z is not None and tuple(size) == self.z.shape
         z, self.z = self.z, None
         return z
@@ -417,6 +417,36 @@ def gen_emitters():
 
 
 # ---------------------------------------------------------------------------------------
+# 6b. OpenAI-ES traces with injected noise (mirror sampling on / off, Adam options)
+# ---------------------------------------------------------------------------------------
+def gen_openai_es():
+    rng = np.random.default_rng(91)
+    out = {}
+    for tag, n, lam, mirror, adam in (("mirror_n10", 10, 8, True, {}), ("mirror_n300", 300, 64, True, {"lr": 0.05}),
+                                      ("plain_n40", 40, 15, False, {"lr": 0.02, "l2_coeff": 0.01, "beta1": 0.8})):
+        es = _get_es("openai_es", sigma0=0.3, solution_dim=n, batch_size=lam, seed=1, dtype=np.float64,
+                     lower_bounds=-np.inf, upper_bounds=np.inf, mirror_sampling=mirror, **adam)
+        es._rng = InjectedRNG()
+        x0 = rng.standard_normal(n)
+        es.reset(x0)
+        case = {"cfg": {"n": n, "lam": lam, "sigma0": 0.3, "x0": x0, "mirror": int(mirror), "lr": adam.get("lr", 0.001),
+                        "l2": adam.get("l2_coeff", 0.0), "beta1": adam.get("beta1", 0.9)}}
+        for g in range(12):
+            zseed = int(rng.integers(0, 2**31))
+            z = np.random.default_rng(zseed).standard_normal((lam // 2 if mirror else lam, n))
+            es._rng.z = z
+            sol = np.array(es.ask())
+            fit = -np.sum((sol - 1.0) ** 2, axis=1)
+            ranking = np.flip(np.argsort(fit))
+            es.tell(ranking, fit, lam // 2)
+            case[f"g{g}"] = {"zseed": zseed, "ranking": ranking, "solutions": sol, "theta": np.array(es.adam_opt.theta),
+                             "m": np.array(es.adam_opt._m), "v": np.array(es.adam_opt._v),
+                             "ratio": float(es.last_update_ratio), "stop": int(es.check_stop(fit[ranking]))}
+        out[tag] = case
+    save("openai_es", out)
+
+
+# ---------------------------------------------------------------------------------------
 # 7. BanditScheduler (UCB1 emitter selection) driven by deterministic stub emitters
 # ---------------------------------------------------------------------------------------
 def gen_bandit():
@@ -443,4 +473,5 @@ if __name__ == "__main__":
     gen_es()
     gen_rankers()
     gen_emitters()
+    gen_openai_es()
     gen_bandit()

@@ -653,7 +653,76 @@ class OracleLMMAES:
         return bool(_flat_fitness(rv))
 
 
-ORACLE_ES = {"cma_es": OracleCMAES, "sep_cma_es": OracleSepCMAES, "lm_ma_es": OracleLMMAES}
+class OracleOpenAIES:
+    """ribs/emitters/opt/_openai_es.py:49-208 with AdamOpt (ribs/emitters/opt/_adam_opt.py:60-120) inlined; the
+    unit normals are injectable (`ask(z)`: the (batch/2, n) half under mirror sampling, else (batch, n))."""
+
+    def __init__(self, sigma0, solution_dim, batch_size=None, seed=None, dtype=np.float64, mirror_sampling=True,
+                 lr=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, l2_coeff=0.0):
+        self.n = solution_dim
+        self.batch_size = 4 + int(3 * np.log(solution_dim)) if batch_size is None else batch_size
+        if batch_size is None and self.batch_size % 2 != 0:  # :100-102
+            self.batch_size += 1
+        if self.batch_size <= 1:
+            raise ValueError("Batch size of 1 is not supported")
+        if mirror_sampling and self.batch_size % 2 != 0:
+            raise ValueError("If using mirror sampling, batch_size must be an even number.")
+        self.sigma0, self.dtype, self.mirror = sigma0, dtype, mirror_sampling
+        self.lr, self.beta1, self.beta2, self.eps, self.l2 = lr, beta1, beta2, epsilon, l2_coeff
+        self.rng = np.random.default_rng(seed)
+
+    def reset(self, x0):  # :120-123, AdamOpt.reset
+        self.theta = np.asarray(x0, dtype=np.float64).copy()
+        self.m = np.zeros_like(self.theta)
+        self.v = np.zeros_like(self.theta)
+        self.t = 0
+        self.last_update_ratio = np.inf
+        self.noise = None
+
+    @property
+    def mean(self):
+        return self.theta
+
+    def ask(self, z=None):  # :141-178 (unbounded)
+        lam = self.batch_size
+        if self.mirror:
+            half = self.rng.standard_normal((lam // 2, self.n)) if z is None else np.asarray(z, dtype=np.float64)
+            self.noise = np.concatenate((half, -half))
+        else:
+            self.noise = self.rng.standard_normal((lam, self.n)) if z is None else np.asarray(z, dtype=np.float64)
+        self.solutions = self.theta[None] + self.sigma0 * self.noise
+        return self.solutions
+
+    def tell(self, ranking_indices, num_parents=None):  # :180-208
+        lam = self.batch_size
+        ranks = np.empty(lam, dtype=np.int32)
+        ranks[np.asarray(ranking_indices)[::-1]] = np.arange(lam)
+        ranks = (ranks / (lam - 1)) - 0.5
+        if self.mirror:
+            half = lam // 2
+            gradient = np.sum(self.noise[:half] * (ranks[:half] - ranks[half:])[:, None], axis=0)
+            gradient /= half * self.sigma0
+        else:
+            gradient = np.sum(self.noise * ranks[:, None], axis=0)
+            gradient /= lam * self.sigma0
+        prev = self.theta.copy()
+        g = -gradient  # AdamOpt.step
+        g += self.l2 * self.theta
+        self.t += 1
+        a = self.lr * np.sqrt(1 - self.beta2**self.t) / (1 - self.beta1**self.t)
+        self.m = self.beta1 * self.m + (1 - self.beta1) * g
+        self.v = self.beta2 * self.v + (1 - self.beta2) * (g * g)
+        self.theta = self.theta + (-a * self.m / (np.sqrt(self.v) + self.eps))
+        self.last_update_ratio = np.linalg.norm(self.theta - prev) / np.linalg.norm(self.theta)
+
+    def check_stop(self, rv):  # :125-139
+        if self.last_update_ratio < 1e-9:
+            return True
+        return bool(_flat_fitness(rv))
+
+
+ORACLE_ES = {"cma_es": OracleCMAES, "sep_cma_es": OracleSepCMAES, "lm_ma_es": OracleLMMAES,
+             "openai_es": OracleOpenAIES}
 
 
 # ---------------------------------------------------------------------------------------

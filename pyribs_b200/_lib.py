@@ -125,6 +125,8 @@ PROTOTYPES = {
                            C.POINTER(CmaScalars), _vp, _vp]),
     "qd_lmma_ask": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "qd_lmma_ask_rng": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
+    "qd_mirror_ask_rng": (_int, [_i64, _i64, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
+    "qd_openai_tell": (_int, [_i64, _vp, _dbl, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "qd_kmeans_workspace_doubles": (C.c_size_t, [_i64, _i64]),
     "qd_kmeans_update": (_int, [_vp, _int, _i64, _i64, _vp, _i64, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qd_lmma_set_block_bytes": (_i64, [_i64]),

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) sep_ask_rng_kernel(int64_t rows, int64_t 
                                                           const double* __restrict__ mean, const double* __restrict__ C,
                                                           const double* __restrict__ sigma_p, uint64_t seed,
                                                           uint64_t offset, double* __restrict__ X,
-                                                          double* __restrict__ z_out) {
+                                                          double* __restrict__ z_out, int mirror) {
   __shared__ double2 swb[kZigLayers];
   zig_stage_tables(swb);
   const int64_t qpr = (n + 3) / 4;
@@ -248,7 +248,76 @@ __global__ void __launch_bounds__(256) sep_ask_rng_kernel(int64_t rows, int64_t 
           if (z_out) z_out[k * n + j0 + i] = z[i];
         }
     }
+    if (mirror) {  // mirrored sampling (_openai_es.py:163-172): sample k + rows is drawn from -z
+      double y[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = __dadd_rn(__dmul_rn(sd[i], __dmul_rn(sigma, -z[i])), mu[i]);
+      if (VEC) {
+        store4_cs(X + (k + rows) * n + j0, y);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (j0 + i < n) X[(k + rows) * n + j0 + i] = y[i];
+      }
+    }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// OpenAI-ES tell (ribs/emitters/opt/_openai_es.py:180-208 + AdamOpt.step, _adam_opt.py): the gradient estimate
+// is a weighted sum of the noise rows (qd_weighted_rows); this kernel scales it, runs the Adam step on theta and
+// leaves the block sums of |theta - theta_prev|^2 and |theta|^2 for the update ratio (check_stop).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) openai_tell_kernel(int64_t n, const double* __restrict__ grad_sum, double denom,
+                                                          double* __restrict__ theta, double* __restrict__ m,
+                                                          double* __restrict__ v, double a, double beta1, double beta2,
+                                                          double eps, double l2, double* __restrict__ blocksum) {
+  __shared__ double sh[2][8];
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double d2 = 0.0, t2 = 0.0;
+  if (j < n) {
+    const double th = theta[j];
+    double g = -__ddiv_rn(grad_sum[j], denom);          // gradient /= half * sigma0; inverted: we maximise
+    g = __dadd_rn(g, __dmul_rn(l2, th));                // L2 regularisation
+    const double mn = __dadd_rn(__dmul_rn(beta1, m[j]), __dmul_rn(1.0 - beta1, g));
+    const double vn = __dadd_rn(__dmul_rn(beta2, v[j]), __dmul_rn(1.0 - beta2, __dmul_rn(g, g)));
+    const double step = __ddiv_rn(__dmul_rn(-a, mn), __dadd_rn(sqrt(vn), eps));
+    const double tn = __dadd_rn(th, step);
+    m[j] = mn;
+    v[j] = vn;
+    theta[j] = tn;
+    const double df = tn - th;
+    d2 = df * df;
+    t2 = tn * tn;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    d2 += __shfl_down_sync(0xffffffffu, d2, o);
+    t2 += __shfl_down_sync(0xffffffffu, t2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = d2;
+    sh[1][threadIdx.x >> 5] = t2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a2 = 0.0, b2 = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      a2 += sh[0][w];
+      b2 += sh[1][w];
+    }
+    blocksum[2 * blockIdx.x] = a2;
+    blocksum[2 * blockIdx.x + 1] = b2;
+  }
+}
+
+// status[4] = |theta - theta_prev| / |theta| of the last step (fixed-order sum of the block sums)
+__global__ void openai_ratio_kernel(const double* __restrict__ blocksum, int nblocks, double* __restrict__ status) {
+  double a2 = 0.0, b2 = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    a2 += blocksum[2 * b];
+    b2 += blocksum[2 * b + 1];
+  }
+  status[4] = sqrt(a2) / sqrt(b2);
 }
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool pred) {  // !pred: zero fill
@@ -706,9 +775,39 @@ extern "C" int qd_fill_normal_zig(double* out, int64_t count, uint64_t seed, uin
   return check_launch("fill_normal_zig_kernel");
 }
 
+static int sep_ask_rng_impl(int64_t rows, int64_t n, const int32_t* row_ids, const double* mean, const double* C,
+                            const double* status, uint64_t seed, uint64_t offset, double* X, double* z_out,
+                            int mirror, void* stream);
+
 extern "C" int qd_sep_ask_rng(int64_t rows, int64_t n, const int32_t* row_ids, const double* mean, const double* C,
                               const double* status, uint64_t seed, uint64_t offset, double* X, double* z_out,
                               void* stream) {
+  return sep_ask_rng_impl(rows, n, row_ids, mean, C, status, seed, offset, X, z_out, 0, stream);
+}
+
+extern "C" int qd_mirror_ask_rng(int64_t half_rows, int64_t n, const double* mean, const double* scale,
+                                 const double* status, uint64_t seed, uint64_t offset, double* X, double* z_out,
+                                 void* stream) {
+  return sep_ask_rng_impl(half_rows, n, nullptr, mean, scale, status, seed, offset, X, z_out, 1, stream);
+}
+
+extern "C" int qd_openai_tell(int64_t n, const double* grad_sum, double denom, double* theta, double* m, double* v,
+                              double a, double beta1, double beta2, double eps, double l2, double* status,
+                              double* workspace, void* stream) {
+  using namespace qd;
+  QD_REQUIRE(n >= 1 && grad_sum && theta && m && v && status && workspace && denom != 0.0, "bad arguments");
+  const int nb = (int)((n + 255) / 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  openai_tell_kernel<<<nb, 256, 0, s>>>(n, grad_sum, denom, theta, m, v, a, beta1, beta2, eps, l2, workspace);
+  int rc = check_launch("openai_tell_kernel");
+  if (rc) return rc;
+  openai_ratio_kernel<<<1, 1, 0, s>>>(workspace, nb, status);
+  return check_launch("openai_ratio_kernel");
+}
+
+static int sep_ask_rng_impl(int64_t rows, int64_t n, const int32_t* row_ids, const double* mean, const double* C,
+                            const double* status, uint64_t seed, uint64_t offset, double* X, double* z_out,
+                            int mirror, void* stream) {
   using namespace qd;
   if (rows == 0) return QD_OK;
   QD_REQUIRE(mean && C && status && X && rows > 0 && n > 0, "bad arguments");
@@ -724,9 +823,9 @@ extern "C" int qd_sep_ask_rng(int64_t rows, int64_t n, const int32_t* row_ids, c
   const dim3 grid(gx, (unsigned)gy);
   cudaStream_t s = (cudaStream_t)stream;
   if (n % 4 == 0)
-    sep_ask_rng_kernel<true><<<grid, 256, 0, s>>>(rows, n, row_ids, mean, C, status, seed, offset, X, z_out);
+    sep_ask_rng_kernel<true><<<grid, 256, 0, s>>>(rows, n, row_ids, mean, C, status, seed, offset, X, z_out, mirror);
   else
-    sep_ask_rng_kernel<false><<<grid, 256, 0, s>>>(rows, n, row_ids, mean, C, status, seed, offset, X, z_out);
+    sep_ask_rng_kernel<false><<<grid, 256, 0, s>>>(rows, n, row_ids, mean, C, status, seed, offset, X, z_out, mirror);
   return check_launch("sep_ask_rng_kernel");
 }
 

@@ -2,15 +2,18 @@
 from pyribs_b200.emitters.opt._cma_es import CMAEvolutionStrategy
 from pyribs_b200.emitters.opt._es_base import DeviceES
 from pyribs_b200.emitters.opt._lm_ma_es import LMMAEvolutionStrategy
+from pyribs_b200.emitters.opt._openai_es import OpenAIEvolutionStrategy
 from pyribs_b200.emitters.opt._sep_cma_es import SeparableCMAEvolutionStrategy
 
 _NAME_TO_ES_MAP = {
     "CMAEvolutionStrategy": CMAEvolutionStrategy,
     "SeparableCMAEvolutionStrategy": SeparableCMAEvolutionStrategy,
     "LMMAEvolutionStrategy": LMMAEvolutionStrategy,
+    "OpenAIEvolutionStrategy": OpenAIEvolutionStrategy,
     "cma_es": CMAEvolutionStrategy,
     "sep_cma_es": SeparableCMAEvolutionStrategy,
     "lm_ma_es": LMMAEvolutionStrategy,
+    "openai_es": OpenAIEvolutionStrategy,
 }
 
 
@@ -30,4 +33,5 @@ def _get_es(klass, **es_kwargs):
     raise ValueError(f"`{klass}` is neither a callable nor a string")
 
 
-__all__ = ["CMAEvolutionStrategy", "DeviceES", "LMMAEvolutionStrategy", "SeparableCMAEvolutionStrategy", "_get_es"]
+__all__ = ["CMAEvolutionStrategy", "DeviceES", "LMMAEvolutionStrategy", "OpenAIEvolutionStrategy",
+           "SeparableCMAEvolutionStrategy", "_get_es"]

@@ -426,3 +426,77 @@ def test_lmma_bounds_with_fused_generator():
         if g == 0:
             np.testing.assert_array_equal(sol, 0.8 * es._z.cpu().numpy())
         es.tell(np.argsort(np.sum(sol ** 2, axis=1)), None, 12)
+
+
+# ---- OpenAI-ES ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(load_golden("openai_es").keys()))
+def test_openai_es_trace(name):
+    """ribs/emitters/opt/_openai_es.py + AdamOpt against the reference's traces (noise injected: the half batch
+    under mirror sampling). Solutions are bit-identical (theta + sigma0 * z); theta / m / v within 1e-6 relative
+    (observed ~1e-13: the gradient's row sum is blocked differently from NumPy's)."""
+    from pyribs_b200.emitters.opt import _get_es
+
+    case = load_golden("openai_es")[name]
+    cfg = case["cfg"]
+    n, lam, mirror = int(cfg["n"]), int(cfg["lam"]), bool(int(cfg["mirror"]))
+    es = _get_es("openai_es", sigma0=float(cfg["sigma0"]), solution_dim=n, batch_size=lam, seed=1, dtype=np.float64,
+                 lower_bounds=-np.inf, upper_bounds=np.inf, mirror_sampling=mirror, lr=float(cfg["lr"]),
+                 l2_coeff=float(cfg["l2"]), beta1=float(cfg["beta1"]))
+    es.reset(cfg["x0"])
+    for gi, g in enumerate(gens_of(case)):
+        z = np.random.default_rng(int(g["zseed"])).standard_normal((lam // 2 if mirror else lam, n))
+        sol = es.ask(z=z)
+        if gi == 0:
+            np.testing.assert_array_equal(sol, g["solutions"], err_msg=f"{name} g0 solutions")
+        assert_close(sol, g["solutions"], RTOL, f"{name} g{gi} solutions")
+        es.tell(g["ranking"], None, lam // 2)
+        assert_close(es.theta, g["theta"], RTOL, f"{name} g{gi} theta")
+        assert_close(es._to_host(es._m), g["m"], RTOL, f"{name} g{gi} m")
+        assert_close(es._to_host(es._v), g["v"], RTOL, f"{name} g{gi} v")
+        fit = -np.sum((np.asarray(g["solutions"]) - 1.0) ** 2, axis=1)
+        assert int(es.check_stop(fit[g["ranking"]])) == int(g["stop"])
+        assert_close(es.last_update_ratio, g["ratio"], 1e-6, f"{name} g{gi} ratio")
+
+
+def test_openai_es_default_ask_and_emitter():
+    """Own normal stream: the two halves of a mirrored batch are reflections of each other about theta; the
+    contract checks of the constructor (_openai_es.py:80-111); and an EvolutionStrategyEmitter(es="openai_es") makes
+    progress on the sphere function."""
+    from pyribs_b200.archives import GridArchive
+    from pyribs_b200.emitters import EvolutionStrategyEmitter
+    from pyribs_b200.emitters.opt import OpenAIEvolutionStrategy
+    from pyribs_b200.schedulers import Scheduler
+
+    n = 50
+    es = OpenAIEvolutionStrategy(0.2, n, 32, seed=5)
+    es.reset(np.full(n, 0.5))
+    x = es.ask()
+    assert x.shape == (32, n)
+    np.testing.assert_allclose(x[:16] - 0.5, -(x[16:] - 0.5), rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(es.noise[:16], -es.noise[16:])
+    np.testing.assert_array_equal(x, 0.5 + 0.2 * es.noise)  # theta + sigma0 * noise, bit for bit
+    zz = (x[:16] - 0.5) / 0.2
+    assert abs(zz.mean()) < 0.15 and abs(zz.var() - 1) < 0.2
+    es2 = OpenAIEvolutionStrategy(0.2, n, 32, seed=5)
+    es2.reset(np.full(n, 0.5))
+    np.testing.assert_array_equal(es2.ask(), x)
+    assert OpenAIEvolutionStrategy(0.1, 100).batch_size % 2 == 0
+    with pytest.raises(ValueError):
+        OpenAIEvolutionStrategy(0.1, n, 7)
+    with pytest.raises(ValueError):
+        OpenAIEvolutionStrategy(0.1, n, 8, lower_bounds=-1.0, upper_bounds=1.0)
+    b = OpenAIEvolutionStrategy(0.3, n, 9, mirror_sampling=False, lower_bounds=-1.0, upper_bounds=1.0, seed=2)
+    b.reset(np.zeros(n))
+    xb = b.ask()
+    assert xb.shape == (9, n) and np.all(np.abs(xb) <= 1.0)
+    a = GridArchive(solution_dim=n, dims=(30, 30), ranges=[(-25.6, 25.6)] * 2, seed=1)
+    ems = [EvolutionStrategyEmitter(a, x0=np.zeros(n), sigma0=0.3, es="openai_es", es_kwargs={"lr": 0.05},
+                                    ranker="2imp", batch_size=24, seed=s) for s in (1, 2)]
+    sched = Scheduler(a, ems)
+    best = []
+    for it in range(40):
+        sol = sched.ask()
+        obj = -np.sum((sol - 2.0) ** 2, axis=1)
+        sched.tell(obj, np.stack([sol[:, : n // 2].sum(1), sol[:, n // 2:].sum(1)], axis=1))
+        best.append(a.stats.obj_max)
+    assert best[-1] > best[0] and len(a) > 10

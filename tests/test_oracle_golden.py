@@ -104,6 +104,28 @@ def test_es_golden(name):
                 assert_close(getattr(es, attr), g[key], 1e-9, f"{name} g{gi} {key}")
 
 
+@pytest.mark.parametrize("name", sorted(load_golden("openai_es").keys()))
+def test_openai_es_golden(name):
+    """OpenAI-ES + Adam (ribs/emitters/opt/_openai_es.py, _adam_opt.py) with the reference's noise injected."""
+    case = load_golden("openai_es")[name]
+    cfg = case["cfg"]
+    n, lam, mirror = int(cfg["n"]), int(cfg["lam"]), bool(int(cfg["mirror"]))
+    es = O.OracleOpenAIES(float(cfg["sigma0"]), n, lam, seed=1, mirror_sampling=mirror, lr=float(cfg["lr"]),
+                          l2_coeff=float(cfg["l2"]), beta1=float(cfg["beta1"]))
+    es.reset(cfg["x0"])
+    for gi, g in enumerate(gens_of(case)):
+        z = np.random.default_rng(int(g["zseed"])).standard_normal((lam // 2 if mirror else lam, n))
+        sol = es.ask(z)
+        np.testing.assert_array_equal(sol, g["solutions"], err_msg=f"{name} g{gi} solutions")
+        es.tell(g["ranking"])
+        assert_close(es.theta, g["theta"], EXACT, f"{name} g{gi} theta")
+        assert_close(es.m, g["m"], EXACT, f"{name} g{gi} m")
+        assert_close(es.v, g["v"], EXACT, f"{name} g{gi} v")
+        assert_close(es.last_update_ratio, g["ratio"], 1e-10, f"{name} g{gi} ratio")
+        fit = -np.sum((sol - 1.0) ** 2, axis=1)
+        assert int(es.check_stop(fit[g["ranking"]])) == int(g["stop"])
+
+
 def test_rankers_golden():
     g = load_golden("rankers")
     for tag, c in g.items():
