@@ -541,12 +541,46 @@ __device__ void phase_update_list(const InsertArgs<T>& a, double (*sh_d)[kThread
   update_reduce<T>(a, acc, sh_d, sh_n, sh_k);
 }
 
+// Short rows (every field below the bulk-copy threshold, e.g. configs[1]: 80-byte solutions, 16-byte measures):
+// the thread that updates a cell also moves its winner's rows, so small archives skip the copy phase and one
+// grid barrier altogether (at 100k rows the insertion is a chain of barrier and L2 latencies, not bandwidth).
+constexpr int kInlineRowMax = 256;  // == kBulkMinRow: rows the bulk path would not take anyway
+
+__device__ __forceinline__ bool inline_copy_ok(const FieldCopy& fc) {
+  if (fc.peer_tab != nullptr || fc.n == 0) return false;
+  int64_t total = 0;
+  for (int f = 0; f < fc.n; ++f) {
+    if (fc.host_src[f] || fc.row_bytes[f] >= kInlineRowMax) return false;
+    total += fc.row_bytes[f];
+  }
+  return total <= 512;
+}
+
+__device__ __forceinline__ void copy_row_inline(const FieldCopy& fc, int row, int cell) {
+  for (int f = 0; f < fc.n; ++f) {
+    const int64_t rb = fc.row_bytes[f];
+    const char* __restrict__ sp = fc.src[f] + (int64_t)row * rb;
+    char* __restrict__ dp = fc.dst[f] + (int64_t)cell * rb;
+    const int vec = fc.vec[f];
+    if (vec == 16) {
+      for (int64_t o = 0; o < rb; o += 16) *reinterpret_cast<uint4*>(dp + o) = *reinterpret_cast<const uint4*>(sp + o);
+    } else if (vec == 8) {
+      for (int64_t o = 0; o < rb; o += 8) *reinterpret_cast<uint2*>(dp + o) = *reinterpret_cast<const uint2*>(sp + o);
+    } else if (vec == 4) {
+      for (int64_t o = 0; o < rb; o += 4) *reinterpret_cast<uint32_t*>(dp + o) = *reinterpret_cast<const uint32_t*>(sp + o);
+    } else {
+      for (int64_t o = 0; o < rb; ++o) dp[o] = sp[o];
+    }
+  }
+}
+
 // cell mode: one thread per CELL, everything coalesced. The winner's objective is decoded from the cell's
 // key, its row comes from `win`; the (row, cell) list it emits is sorted by cell within each CTA tile, so
 // the row copy writes the store in nearly ascending address order.
 template <typename T>
-__device__ void phase_update_cells(const InsertArgs<T>& a, double (*sh_d)[kThreads / 32], uint32_t* sh_n,
-                                   unsigned long long* sh_k, uint32_t* s_cnt, uint32_t* s_base) {
+__device__ void phase_update_cells(const InsertArgs<T>& a, const FieldCopy& fc, bool inline_copy,
+                                   double (*sh_d)[kThreads / 32], uint32_t* sh_n, unsigned long long* sh_k,
+                                   uint32_t* s_cnt, uint32_t* s_base) {
   const InsertState* g = a.s.g;
   const bool mae = a.mae;
   const double batch_absmax = __longlong_as_double((long long)g->absmax_bits);
@@ -562,6 +596,7 @@ __device__ void phase_update_cells(const InsertArgs<T>& a, double (*sh_d)[kThrea
     cell.best = 0ull;
     if (c < a.N) cell = a.s.cell[c];
     const bool has = cell.best != 0ull;
+    if (has && inline_copy) copy_row_inline(fc, cell.win, (int)c);  // _array_store.py:605-608
     if (has) update_cell<T>(a, (int32_t)c, (T)ord_unkey(cell.best), cell, mae, fx, bc, acc);
     const unsigned m = __ballot_sync(0xffffffffu, has);
     if (lane == 0) s_cnt[wi] = __popc(m);
@@ -990,16 +1025,18 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
     grid.sync();
   }
   if (phase_lo <= 3) stamp(4);
+  // one launch, cell mode, short rows: the update phase copies the winners' rows itself
+  const bool inline_copy = mode == 0 && phase_lo <= 4 && phase_hi >= 5 && cell_mode && inline_copy_ok(fc);
   if (phase_lo <= 4 && phase_hi >= 4 && committed) {
     if (cell_mode) {
-      phase_update_cells<T>(a, sh_d, sh_u + 32, sh_k, sh_u, &sh_base);
-      if (phase_hi >= 5 && mode == 0) grid.sync();  // the winner list is complete only now
+      phase_update_cells<T>(a, fc, inline_copy, sh_d, sh_u + 32, sh_k, sh_u, &sh_base);
+      if (phase_hi >= 5 && mode == 0 && !inline_copy) grid.sync();  // the winner list is complete only now
     } else {
       phase_update_list<T>(a, sh_d, sh_u + 32, sh_k);
     }
   }
   if (phase_lo <= 4) stamp(5);
-  if (mode == 0 && phase_lo <= 5 && phase_hi >= 5 && committed && fc.n > 0)
+  if (mode == 0 && phase_lo <= 5 && phase_hi >= 5 && committed && fc.n > 0 && !inline_copy)
     phase_copy(fc, a.s, g->n_winners, copy_slots, copy_bar, copy_parity);
   if (phase_hi < 6 && mode == 0) return;
   if (phase_lo <= 5 || mode == 1) grid.sync();
