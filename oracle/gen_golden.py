@@ -447,6 +447,41 @@ def gen_openai_es():
 
 
 # ---------------------------------------------------------------------------------------
+# 6c. CategoricalArchive trajectories (string categories, numeric solutions)
+# ---------------------------------------------------------------------------------------
+def gen_categorical():
+    from ribs.archives import CategoricalArchive
+
+    cats = [["A", "B", "C"], ["One", "Two", "Three", "Four"]]
+    out = {}
+    for tag, kw in (("me", {}), ("mae", {"learning_rate": 0.2, "threshold_min": -1.0})):
+        rng = np.random.default_rng(5)
+        a = CategoricalArchive(solution_dim=3, categories=cats, seed=9, **kw)
+        case = {}
+        for j in range(5):
+            B = 40
+            m = np.stack([rng.choice(cats[0], B), rng.choice(cats[1], B)], axis=1)
+            b = {"solution": rng.standard_normal((B, 3)), "objective": rng.uniform(-2, 4, B) + 0.5 * j}
+            info = a.add(b["solution"], b["objective"], m)
+            d = a.data()
+            order = np.argsort(d["index"])
+            st = a.stats
+            case[f"s{j}"] = {"solution": b["solution"], "objective": b["objective"], "measures": m.astype("U5"),
+                             "status": info["status"], "value": info["value"],
+                             "index": d["index"][order], "d_solution": d["solution"][order],
+                             "d_objective": d["objective"][order], "d_threshold": d["threshold"][order],
+                             "d_measures": d["measures"][order].astype("U5"),
+                             "qd_score": float(st.qd_score), "obj_max": float(st.obj_max), "n": len(a),
+                             "best_solution": a.best_elite["solution"], "best_measures": a.best_elite["measures"].astype("U5"),
+                             "index_of": a.index_of(m)}
+        single = a.add_single(np.ones(3), 100.0, ["B", "Four"])
+        case["single"] = {"status": np.asarray(single["status"]), "value": np.asarray(single["value"]),
+                          "best_measures": a.best_elite["measures"].astype("U5")}
+        out[tag] = case
+    save("categorical", out)
+
+
+# ---------------------------------------------------------------------------------------
 # 7. BanditScheduler (UCB1 emitter selection) driven by deterministic stub emitters
 # ---------------------------------------------------------------------------------------
 def gen_bandit():
@@ -474,4 +509,5 @@ if __name__ == "__main__":
     gen_rankers()
     gen_emitters()
     gen_openai_es()
+    gen_categorical()
     gen_bandit()
