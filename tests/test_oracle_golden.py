@@ -221,3 +221,47 @@ def test_live_reference_add_random():
             e1 = ref.sample_elites(5)
             e2 = ora.sample_elites(5)
             np.testing.assert_array_equal(e1["solution"], e2["solution"])
+
+
+def test_live_reference_openai_es_and_emitters():
+    """Fresh configurations (not the committed goldens): the oracle's OpenAI-ES + Adam and its variation emitters
+    against the reference imported here, driven by the same generators."""
+    _import_reference()
+    from ribs.archives import GridArchive
+    from ribs.emitters import GaussianEmitter, IsoLineEmitter
+    from ribs.emitters.opt import _get_es
+
+    rng = np.random.default_rng(12)
+    for mirror, lam, adam in ((True, 10, {"lr": 0.03, "beta2": 0.99}), (False, 7, {"l2_coeff": 0.05, "epsilon": 1e-6})):
+        n = 23
+        ref = _get_es("openai_es", sigma0=0.4, solution_dim=n, batch_size=lam, seed=3, dtype=np.float64,
+                      lower_bounds=-np.inf, upper_bounds=np.inf, mirror_sampling=mirror, **adam)
+        ora = O.OracleOpenAIES(0.4, n, lam, seed=3, mirror_sampling=mirror, **adam)
+        x0 = rng.standard_normal(n)
+        ref.reset(x0), ora.reset(x0)
+        for g in range(8):  # same seed, same generator calls: the oracle draws the very normals the reference draws
+            sr, so = np.array(ref.ask()), ora.ask()
+            np.testing.assert_array_equal(sr, so)
+            fit = -np.sum((sr + 0.3) ** 2, axis=1)
+            ranking = np.flip(np.argsort(fit))
+            ref.tell(ranking, fit, lam // 2), ora.tell(ranking)
+            np.testing.assert_array_equal(ref.adam_opt.theta, ora.theta)
+            assert ref.last_update_ratio == ora.last_update_ratio
+            assert ref.check_stop(fit[ranking]) == ora.check_stop(fit[ranking])
+    # variation emitters: same archive seed -> same parents, same emitter seed -> same noise
+    n, B = 5, 33
+    fill = dict(solution=rng.standard_normal((400, n)), objective=rng.standard_normal(400),
+                measures=rng.uniform(-1, 1, (400, 2)))
+    ra = GridArchive(solution_dim=n, dims=(9, 9), ranges=[(-1, 1)] * 2, seed=4)
+    oa = O.make_grid_oracle(solution_dim=n, dims=(9, 9), ranges=[(-1, 1)] * 2, seed=4)
+    lo, hi = np.full(n, -0.7), np.full(n, 1.1)
+    rg = GaussianEmitter(ra, sigma=0.2, x0=np.zeros(n), lower_bounds=lo, upper_bounds=hi, batch_size=B, seed=8)
+    og = O.OracleGaussianEmitter(oa, 0.2, np.zeros(n), B, lo, hi, seed=8)
+    ri = IsoLineEmitter(ra, iso_sigma=0.05, line_sigma=0.3, x0=np.zeros(n), lower_bounds=lo, upper_bounds=hi,
+                        batch_size=B, seed=9)
+    oi = O.OracleIsoLineEmitter(oa, 0.05, 0.3, np.zeros(n), B, lo, hi, seed=9)
+    for step in range(3):
+        if step == 1:
+            ra.add(**fill), oa.add(**fill)
+        np.testing.assert_array_equal(rg.ask(), og.ask())
+        np.testing.assert_array_equal(ri.ask(), oi.ask())
