@@ -79,6 +79,17 @@ class CVTArchive(DeviceArchive):
             raise NotImplementedError(
                 "nearest_neighbors='sklearn_nn' (arbitrary sklearn metrics) has no GPU implementation and this "
                 "package has no CPU fallback; use 'scipy_kd_tree' or 'brute_force' (Euclidean).")
+        # The search is exact Euclidean nearest neighbour. Options that would change the answer of the reference's
+        # KDTree.query (_cvt_archive.py:605-609) are refused rather than silently ignored; options that only tune
+        # the tree (leafsize, workers, ...) have no counterpart here and are accepted.
+        q = dict(kdtree_query_kwargs or {})
+        if q.get("p", 2) != 2 or q.get("eps", 0) != 0 or q.get("k", 1) != 1 \
+                or q.get("distance_upper_bound", np.inf) != np.inf:
+            raise NotImplementedError(
+                "kdtree_query_kwargs that change the result (p != 2, eps > 0, k != 1, distance_upper_bound) are not "
+                "supported by the GPU search, which returns the exact Euclidean nearest centroid.")
+        if kdtree_kwargs and kdtree_kwargs.get("boxsize") is not None:
+            raise NotImplementedError("periodic KD-trees (kdtree_kwargs['boxsize']) are not supported by the GPU search.")
         self._nearest_neighbors = nearest_neighbors
         from pyribs_b200.archives._archive_base import parse_all_dtypes
 
