@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 3
+#define QD_ABI_VERSION 4
 
 #define QD_OK 0
 #define QD_ERR_INVALID_ARG (-1)
@@ -83,7 +83,10 @@ int qd_grid_index_of(const void* measures /*[dev] B x d*/, int dtype, int64_t B,
  *   method: 0 = tensor-core filter (tcgen05) + fp64 rescoring, 1 = plain fp64 scan,
  *           2 = bucket grid (measure_dim <= 3; the GPU analogue of the reference's default
  *               KD-tree, _cvt_archive.py:605-609): `prepared` is then the structure built by
- *               qd_cvt_bucket_prepare. All three return identical indices.
+ *               qd_cvt_bucket_prepare.
+ *           3 = bounding-box tree (any measure_dim; the same analogue for measure_dim > 3,
+ *               one warp per query, exact fp64 leaves): `prepared` is the structure built by
+ *               qd_cvt_tree_prepare. All four return identical indices.
  * ---------------------------------------------------------------------------------- */
 size_t qd_cvt_prepared_bytes(int64_t C, int d);
 int qd_cvt_prepare(const void* centroids /*[dev] C x d*/, int dtype, int64_t C, int d,
@@ -93,6 +96,14 @@ int qd_cvt_prepare(const void* centroids /*[dev] C x d*/, int dtype, int64_t C, 
 size_t qd_cvt_bucket_bytes(int64_t C, int d);
 int qd_cvt_bucket_prepare(const void* centroids /*[dev] C x d*/, int dtype, int64_t C, int d,
                           void* buckets /*[dev] qd_cvt_bucket_bytes*/, void* stream);
+/* Bounding-box tree over a centroid shard (KD order, 32 points per leaf, 32 children per node), built on the
+ * host where the reference builds its KD-tree (_cvt_archive.py:410-429) and copied to `tree`. The _host variant
+ * takes and fills HOST memory (used by qd_cvt_tree_prepare and by the CPU tests of the structure). */
+size_t qd_cvt_tree_bytes(int64_t C, int d);
+int qd_cvt_tree_prepare(const void* centroids /*[dev] C x d*/, int dtype, int64_t C, int d,
+                        void* tree /*[dev] qd_cvt_tree_bytes*/, void* stream);
+int qd_cvt_tree_build_host(const void* centroids /*[host] C x d*/, int dtype, int64_t C, int d,
+                           void* tree /*[host] qd_cvt_tree_bytes*/);
 size_t qd_cvt_scratch_bytes(int64_t B, int64_t C, int d);
 int qd_cvt_index_of(const void* measures /*[dev] B x d*/, int dtype, int64_t B, int d,
                     const void* centroids /*[dev] C x d*/, int64_t C,

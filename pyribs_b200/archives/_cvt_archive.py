@@ -116,8 +116,8 @@ class CVTArchive(DeviceArchive):
         self._interval_size = self._upper_bounds - self._lower_bounds
         self._meas_code = _lib.QD_F64 if np.dtype(mdt) == np.float64 else _lib.QD_F32
         search_method = os.environ.get("QD_CVT_METHOD", search_method)
-        if search_method not in ("auto", "tensor", "scan", "bucket"):
-            raise ValueError("search_method must be 'auto', 'tensor', 'scan' or 'bucket'")
+        if search_method not in ("auto", "tensor", "scan", "bucket", "tree"):
+            raise ValueError("search_method must be 'auto', 'tensor', 'scan', 'bucket' or 'tree'")
         if search_method == "bucket" and self._measure_dim > 3:
             raise ValueError("search_method='bucket' supports measure_dim <= 3")
         self._search_method = search_method
@@ -138,7 +138,17 @@ class CVTArchive(DeviceArchive):
             self._centroids_dev = torch.from_numpy(shard).to(self._device) if len(shard) else None
             self._prepared = None
             self._buckets = None
-            if len(shard) and self._measure_dim <= 3 and search_method in ("auto", "bucket"):
+            self._tree = None
+            if len(shard) and (search_method == "tree" or (search_method == "auto" and 3 < self._measure_dim <= 16)):
+                # mid measure_dim: bounding-box tree in KD order (csrc/cvt_tree.cu), the analogue of the reference's
+                # KD-tree where a bucket grid no longer works; beyond ~16-D boxes stop pruning and the exhaustive
+                # tensor-core contraction below takes over
+                nbytes = int(_lib.lib().qd_cvt_tree_bytes(len(shard), self._measure_dim))
+                self._tree = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+                _lib.check(_lib.lib().qd_cvt_tree_prepare(self._centroids_dev.data_ptr(), self._meas_code, len(shard),
+                                                          self._measure_dim, self._tree.data_ptr(),
+                                                          current_stream_ptr()))
+            elif len(shard) and self._measure_dim <= 3 and search_method in ("auto", "bucket"):
                 # low measure_dim: bucket grid, the analogue of the KD-tree the reference builds here
                 nbytes = int(_lib.lib().qd_cvt_bucket_bytes(len(shard), self._measure_dim))
                 self._buckets = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
@@ -190,6 +200,8 @@ class CVTArchive(DeviceArchive):
             return 1
         if self._buckets is not None:
             return 2
+        if self._tree is not None:
+            return 3
         if self._search_method == "tensor":
             return 0
         return 0 if B * C >= (1 << 26) else 1
@@ -212,7 +224,7 @@ class CVTArchive(DeviceArchive):
         need = int(_lib.lib().qd_cvt_scratch_bytes(B, Cn, self._measure_dim)) if method == 0 else 256
         if self._cvt_scratch is None or self._cvt_scratch.numel() < need:
             self._cvt_scratch = torch.empty(max(need, 256), dtype=torch.uint8, device=self._device)
-        prepared = self._buckets if method == 2 else self._prepared
+        prepared = self._buckets if method == 2 else (self._tree if method == 3 else self._prepared)
         _lib.check(_lib.lib().qd_cvt_index_of(
             measures.data_ptr(), self._meas_code, B, self._measure_dim, self._centroids_dev.data_ptr(), Cn,
             prepared.data_ptr() if prepared is not None else None, self._shard_lo, method, idx.data_ptr(),

@@ -93,6 +93,9 @@ int cvt_tc_index_of(const void* measures, int dtype, int64_t B, int d, const voi
 int cvt_bucket_index_of(const void* measures, int dtype, int64_t B, int d, int64_t C, const void* buckets,
                         int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags,
                         cudaStream_t s);  // cvt_bucket.cu
+int cvt_tree_index_of(const void* measures, int dtype, int64_t B, int d, int64_t C, const void* tree,
+                      int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags,
+                      cudaStream_t s);  // cvt_tree.cu
 
 }  // namespace qd
 
@@ -117,7 +120,11 @@ extern "C" int qd_cvt_index_of(const void* measures, int dtype, int64_t B, int d
     QD_REQUIRE(prepared != nullptr, "method 2 needs the bucket grid built by qd_cvt_bucket_prepare");
     return cvt_bucket_index_of(measures, dtype, B, d, C, prepared, index_base, idx_out, dist_out, flags, s);
   }
-  QD_REQUIRE(method == 0, "method must be 0 (tensor-core), 1 (fp64 scan) or 2 (bucket grid)");
+  if (method == 3) {
+    QD_REQUIRE(prepared != nullptr, "method 3 needs the box tree built by qd_cvt_tree_prepare");
+    return cvt_tree_index_of(measures, dtype, B, d, C, prepared, index_base, idx_out, dist_out, flags, s);
+  }
+  QD_REQUIRE(method == 0, "method must be 0 (tensor-core), 1 (fp64 scan), 2 (bucket grid) or 3 (box tree)");
   QD_REQUIRE(prepared != nullptr, "method 0 needs the image built by qd_cvt_prepare");
   return cvt_tc_index_of(measures, dtype, B, d, centroids, C, prepared, index_base, idx_out, dist_out, flags, scratch,
                          scratch_bytes, s);

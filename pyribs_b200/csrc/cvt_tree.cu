@@ -1,0 +1,393 @@
+// A3, measure_dim > 3: exact nearest centroid through a bounding-box tree (method 3).
+//
+// Reference: ribs/archives/_cvt_archive.py:579-609. The reference's default search is
+// scipy.spatial.KDTree.query(k=1) over a tree it builds in __init__ (:410-429) -- a spatial
+// index that looks at ~10^3 of 10^6 centroids per query, not a B x C contraction. This file is
+// its GPU form for measure dimensions where the bucket grid of cvt_bucket.cu (<= 3-D) stops
+// working and an exhaustive contraction (cvt_tc.cu) does 10^2..10^3 times the necessary work.
+//
+// Structure (qd_cvt_tree_prepare, built once where the reference builds its KD-tree): the
+// centroids are put in KD order by recursive median splits along the widest axis; every 32
+// consecutive points form a LEAF (one point per lane), every 32 consecutive leaves a level-1
+// node, every 32 of those a level-2 node, ... (splits fall on multiples of the largest power of
+// 32 below the leaf count, so an aligned group of 32^k leaves is a subtree and node j of level l
+// is simply leaf >> 5l -- no pointers). A node stores the axis-aligned boxes of its 32 children
+// as fp32 rounded outwards, struct-of-arrays, so a warp reads them as coalesced 128-byte rows.
+//
+// Search: ONE WARP PER QUERY. At a node lane j computes a rigorous fp32 lower bound (directed
+// rounding) of the squared distance from the query to child j's box; children are visited best
+// first (one redux.min over keys = bound bits | lane) and the walk of a node stops at the first
+// child whose bound exceeds the best squared distance found so far. At a leaf lane j evaluates
+// the exact fp64 squared distance to point j in NumPy's summation order (cvt_common.cuh); the
+// (distance, centroid index) minimum is lexicographic, so the result is bit-identical to the
+// fp64 scan and to np.argmin over the unsorted centroid array (_cvt_archive.py:632) -- lowest
+// centroid index on exact ties. A subtree is skipped only if its bound is STRICTLY above the best
+// distance inflated by 2^-21, far more than the rounding of either side (see prune note below).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "cvt_common.cuh"
+
+namespace qd {
+
+constexpr int kLeaf = 32;         // points per leaf (= lanes)
+constexpr int kFan = 32;          // children per node (= lanes)
+constexpr int kTreeMaxLev = 7;    // 32^6 leaves x 32 points > 2^31
+constexpr size_t kTreeHeaderBytes = 256;
+constexpr int kTreeWarps = 8;     // warps (= queries in flight) per CTA
+
+struct TreeHeader {
+  int64_t C;
+  int32_t d, nleaves, nlev, pad;
+  int32_t n[kTreeMaxLev + 1];         // boxes per level; n[0] = leaves, n[nlev-1] = 1
+  uint64_t off_box[kTreeMaxLev + 1];  // byte offset of the level-l boxes, grouped by parent (l < nlev-1)
+  uint64_t off_pts, off_ids, total;
+};
+static_assert(sizeof(TreeHeader) <= kTreeHeaderBytes, "header too large");
+
+static TreeHeader tree_layout(int64_t C, int d) {
+  TreeHeader h;
+  memset(&h, 0, sizeof(h));
+  h.C = C;
+  h.d = d;
+  h.nleaves = (int32_t)((C + kLeaf - 1) / kLeaf);
+  int l = 0;
+  h.n[0] = h.nleaves;
+  while (h.n[l] > 1) {
+    h.n[l + 1] = (h.n[l] + kFan - 1) / kFan;
+    ++l;
+  }
+  h.nlev = l + 1;
+  uint64_t off = kTreeHeaderBytes;
+  h.off_pts = off;
+  off += (uint64_t)h.nleaves * d * kLeaf * sizeof(double);
+  h.off_ids = off;
+  off += (uint64_t)h.nleaves * kLeaf * sizeof(int32_t);
+  for (int k = 0; k + 1 < h.nlev; ++k) {
+    h.off_box[k] = off;
+    off += (uint64_t)h.n[k + 1] * 2 * d * kFan * sizeof(float);
+  }
+  h.total = (off + 255) / 256 * 256;
+  return h;
+}
+
+// ---- host build ------------------------------------------------------------------------------
+static float f32_down(double v) {
+  float f = (float)v;
+  if ((double)f > v) f = nextafterf(f, -INFINITY);
+  return f;
+}
+static float f32_up(double v) {
+  float f = (float)v;
+  if ((double)f < v) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+// KD order of `n` points (ids in idx[0..n)) that will fill `nleaves` leaves: split along the widest axis at
+// a multiple of the largest power of kFan below nleaves, recurse.
+static void kd_split(const double* pts, int d, int32_t* idx, int64_t n, int64_t nleaves, int depth) {
+  if (nleaves <= 1 || n <= 1) return;
+  int64_t u = 1;
+  while (u * kFan < nleaves) u *= kFan;
+  const int64_t nu = (nleaves + u - 1) / u;
+  const int64_t left_leaves = (nu / 2) * u;
+  const int64_t k = left_leaves * kLeaf;
+  if (k <= 0 || k >= n) return;
+  // widest axis of the node (large nodes: of an evenly spaced sample, the choice only shapes the boxes)
+  const int64_t step = n > 8192 ? n / 4096 : 1;
+  int dim = 0;
+  double widest = -1.0;
+  for (int a = 0; a < d; ++a) {
+    double lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = 0; i < n; i += step) {
+      const double v = pts[(int64_t)idx[i] * d + a];
+      lo = v < lo ? v : lo;
+      hi = v > hi ? v : hi;
+    }
+    if (hi - lo > widest) {
+      widest = hi - lo;
+      dim = a;
+    }
+  }
+  {  // select on a contiguous (coordinate, id) array: nth_element through the index would miss the cache on every compare
+    std::vector<std::pair<double, int32_t>> keyed((size_t)n);
+    for (int64_t i = 0; i < n; ++i) keyed[i] = {pts[(int64_t)idx[i] * d + dim], idx[i]};
+    std::nth_element(keyed.begin(), keyed.begin() + k, keyed.end());
+    for (int64_t i = 0; i < n; ++i) idx[i] = keyed[i].second;
+  }
+  if (depth < 4 && n > (1 << 16)) {
+    std::thread t(kd_split, pts, d, idx, k, left_leaves, depth + 1);
+    kd_split(pts, d, idx + k, n - k, nleaves - left_leaves, depth + 1);
+    t.join();
+  } else {
+    kd_split(pts, d, idx, k, left_leaves, depth + 1);
+    kd_split(pts, d, idx + k, n - k, nleaves - left_leaves, depth + 1);
+  }
+}
+
+template <typename T>
+static void tree_build_host(const T* cent, int64_t C, int d, unsigned char* blob) {
+  const TreeHeader h = tree_layout(C, d);
+  memcpy(blob, &h, sizeof(h));
+  std::vector<double> pts((size_t)C * d);
+  for (int64_t i = 0; i < C * d; ++i) pts[i] = (double)cent[i];
+  std::vector<int32_t> order((size_t)C);
+  for (int64_t i = 0; i < C; ++i) order[i] = (int32_t)i;
+  auto T0 = std::chrono::steady_clock::now();
+  kd_split(pts.data(), d, order.data(), C, h.nleaves, 0);
+  auto T1 = std::chrono::steady_clock::now();
+  if (getenv("QD_TREE_TIMING")) fprintf(stderr, "kd_split %.3f s\n", std::chrono::duration<double>(T1 - T0).count());
+  double* lp = reinterpret_cast<double*>(blob + h.off_pts);
+  int32_t* li = reinterpret_cast<int32_t*>(blob + h.off_ids);
+  // leaves + their boxes (level 0)
+  std::vector<float> lo((size_t)h.n[0] * d), hi((size_t)h.n[0] * d);
+  for (int64_t leaf = 0; leaf < h.nleaves; ++leaf) {
+    for (int a = 0; a < d; ++a) {
+      lo[leaf * d + a] = INFINITY;
+      hi[leaf * d + a] = -INFINITY;
+    }
+    for (int j = 0; j < kLeaf; ++j) {
+      const int64_t p = leaf * kLeaf + j;
+      if (p < C) {
+        const int32_t id = order[p];
+        li[leaf * kLeaf + j] = id;
+        for (int a = 0; a < d; ++a) {
+          const double v = pts[(int64_t)id * d + a];
+          lp[(leaf * d + a) * kLeaf + j] = v;
+          lo[leaf * d + a] = std::min(lo[leaf * d + a], f32_down(v));
+          hi[leaf * d + a] = std::max(hi[leaf * d + a], f32_up(v));
+        }
+      } else {  // padding of the last leaf: infinitely far away, never the minimum
+        li[leaf * kLeaf + j] = INT32_MAX;
+        for (int a = 0; a < d; ++a) lp[(leaf * d + a) * kLeaf + j] = INFINITY;
+      }
+    }
+  }
+  for (int l = 0; l + 1 < h.nlev; ++l) {
+    float* bx = reinterpret_cast<float*>(blob + h.off_box[l]);
+    const int64_t groups = h.n[l + 1];
+    std::vector<float> plo((size_t)groups * d, INFINITY), phi((size_t)groups * d, -INFINITY);
+    for (int64_t g = 0; g < groups; ++g) {
+      float* gb = bx + (size_t)g * 2 * d * kFan;
+      for (int s = 0; s < kFan; ++s) {
+        const int64_t c = g * kFan + s;
+        for (int a = 0; a < d; ++a) {
+          const float l0 = c < h.n[l] ? lo[c * d + a] : INFINITY;
+          const float h0 = c < h.n[l] ? hi[c * d + a] : -INFINITY;
+          gb[a * kFan + s] = l0;
+          gb[(d + a) * kFan + s] = h0;
+          plo[g * d + a] = std::min(plo[g * d + a], l0);
+          phi[g * d + a] = std::max(phi[g * d + a], h0);
+        }
+      }
+    }
+    lo.swap(plo);
+    hi.swap(phi);
+  }
+}
+
+// ---- search ------------------------------------------------------------------------------------
+struct TreeView {
+  const double* pts;
+  const int32_t* ids;
+  const float* box[kTreeMaxLev];
+  int32_t nlev, d;
+};
+
+// Prune note. lbk <= (fp32, every operation rounded down, query coordinates widened to an enclosing fp32
+// interval) <= the true squared distance from the query to anything inside the box. fl(dist^2) of cvt_common.cuh
+// is a sum of non-negative terms, each off by at most three roundings: fl(dist^2) >= true * (1 - 2^-48). bestf >=
+// best * (1 + 2^-22). Hence lbk > bestf implies fl(dist^2(p)) > best for every p in the box: p is neither the
+// minimum nor an exact tie.
+template <typename T, int D>
+__global__ void __launch_bounds__(kTreeWarps * 32) cvt_tree_kernel(const T* __restrict__ meas, int64_t B, TreeView tv,
+                                                                 int32_t base, int32_t* __restrict__ idx,
+                                                                 double* __restrict__ dist_out, uint32_t* flags) {
+  constexpr int XN = D > 0 ? D : QD_MAX_MEASURE_DIM;
+  const int d = D > 0 ? D : tv.d;
+  __shared__ uint32_t skey[kTreeWarps][kTreeMaxLev][32];  // per-lane slots: child keys of the nodes on the path
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ const float* sbox[kTreeMaxLev];  // (indexing the kernel parameter dynamically would spill it to local memory)
+  if (threadIdx.x < kTreeMaxLev) sbox[threadIdx.x] = tv.box[threadIdx.x];
+  __syncthreads();
+  uint32_t(*key)[32] = skey[warp];
+  bool bad = false;
+  for (int64_t q = (int64_t)blockIdx.x * kTreeWarps + warp; q < B; q += (int64_t)gridDim.x * kTreeWarps) {
+    double x[XN];
+    float xlo[XN], xhi[XN];
+    bool qbad = false;
+#pragma unroll
+    for (int k = 0; k < XN; ++k)
+      if (k < d) {
+        x[k] = (double)meas[q * d + k];
+        qbad |= !finite_d(x[k]);
+        xlo[k] = __double2float_rd(x[k]);
+        xhi[k] = __double2float_ru(x[k]);
+      }
+    bad |= qbad;
+    double best = INFINITY;
+    int32_t bi = INT32_MAX;
+    float bestf = INFINITY;
+
+    auto eval_leaf = [&](int leaf) {
+      const double* p = tv.pts + ((int64_t)leaf * d) * kLeaf + lane;
+      double c[XN];
+#pragma unroll
+      for (int k = 0; k < XN; ++k)
+        if (k < d) c[k] = __ldg(p + k * kLeaf);
+      const double dd = sqdist_np<D>(x, c, d);
+      const bool cand = dd <= best;
+      if (__any_sync(0xffffffffu, cand)) {
+        int32_t id = cand ? __ldg(tv.ids + (int64_t)leaf * kLeaf + lane) : INT32_MAX;
+        unsigned long long bits = cand ? (unsigned long long)__double_as_longlong(dd) : ~0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bits, o);
+          const int32_t oi = __shfl_xor_sync(0xffffffffu, id, o);
+          if (ob < bits || (ob == bits && oi < id)) {
+            bits = ob;
+            id = oi;
+          }
+        }
+        const double nd = __longlong_as_double((long long)bits);
+        if (nd < best || (nd == best && id < bi)) {
+          best = nd;
+          bi = id;
+          bestf = __fmul_ru(__double2float_ru(best), 1.0000005f);
+        }
+      }
+    };
+    // keys of the 32 children (boxes of level `lvl`, group `parent`): lower-bound bits | lane
+    auto node_key = [&](int lvl, int parent) -> uint32_t {
+      const float* p = sbox[lvl] + (int64_t)parent * (2 * d * kFan) + lane;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < XN; ++k)
+        if (k < d) {
+          const float lo = __ldg(p + k * kFan), hi = __ldg(p + (d + k) * kFan);
+          const float g = fmaxf(fmaxf(__fsub_rd(lo, xhi[k]), __fsub_rd(xlo[k], hi)), 0.f);
+          acc = __fmaf_rd(g, g, acc);
+        }
+      return (__float_as_uint(acc) & 0x7fffffe0u) | (uint32_t)lane;
+    };
+
+    if (!qbad) {
+      if (tv.nlev == 1) {
+        eval_leaf(0);
+      } else {
+        int level = tv.nlev - 1;  // level of the current node; its children are the boxes of level - 1
+        int cur = 0;              // index of the current node within its level
+        key[level][lane] = node_key(level - 1, 0);
+        while (true) {
+          const uint32_t k = __reduce_min_sync(0xffffffffu, key[level][lane]);
+          if (k >= 0x7f800000u || __uint_as_float(k & 0xffffffe0u) > bestf) {  // nothing left below this node
+            if (++level >= tv.nlev) break;
+            cur >>= 5;
+            continue;
+          }
+          const int child = (int)(k & 31u);
+          if (lane == child) key[level][lane] = 0xffffffffu;  // visited
+          const int cnode = cur * kFan + child;
+          if (level == 1) {
+            eval_leaf(cnode);
+          } else {
+            --level;
+            cur = cnode;
+            key[level][lane] = node_key(level - 1, cur);
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      idx[q] = qbad ? base : ((bi == INT32_MAX ? 0 : bi) + base);
+      if (dist_out) dist_out[q] = qbad ? INFINITY : best;
+    }
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, QD_FLAG_NONFINITE_MEASURES);
+}
+
+template <typename T>
+static int launch_tree(const T* meas, int64_t B, int d, const unsigned char* tree, const TreeHeader& h, int32_t base,
+                       int32_t* idx, double* dist, uint32_t* flags, cudaStream_t s) {
+  TreeView v;
+  v.pts = reinterpret_cast<const double*>(tree + h.off_pts);
+  v.ids = reinterpret_cast<const int32_t*>(tree + h.off_ids);
+  for (int l = 0; l < kTreeMaxLev; ++l)
+    v.box[l] = l + 1 < h.nlev ? reinterpret_cast<const float*>(tree + h.off_box[l]) : nullptr;
+  v.nlev = h.nlev;
+  v.d = d;
+  const int64_t blocks = (B + kTreeWarps - 1) / kTreeWarps;
+  const int grid = (int)std::min<int64_t>(blocks, (int64_t)kNumSMs * 8);
+#define QD_TREE(DD) cvt_tree_kernel<T, DD><<<grid, kTreeWarps * 32, 0, s>>>(meas, B, v, base, idx, dist, flags)
+  switch (d) {
+    case 2: QD_TREE(2); break;
+    case 3: QD_TREE(3); break;
+    case 4: QD_TREE(4); break;
+    case 5: QD_TREE(5); break;
+    case 6: QD_TREE(6); break;
+    case 7: QD_TREE(7); break;
+    case 8: QD_TREE(8); break;
+    case 10: QD_TREE(10); break;
+    case 12: QD_TREE(12); break;
+    case 16: QD_TREE(16); break;
+    default: QD_TREE(0);
+  }
+#undef QD_TREE
+  return check_launch("cvt_tree_kernel");
+}
+
+int cvt_tree_index_of(const void* measures, int dtype, int64_t B, int d, int64_t C, const void* tree,
+                      int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags, cudaStream_t s) {
+  const TreeHeader h = tree_layout(C, d);  // the layout is a pure function of (C, d): no device read needed
+  if (dtype == QD_F64)
+    return launch_tree<double>((const double*)measures, B, d, (const unsigned char*)tree, h, index_base, idx_out,
+                               dist_out, flags, s);
+  return launch_tree<float>((const float*)measures, B, d, (const unsigned char*)tree, h, index_base, idx_out, dist_out,
+                            flags, s);
+}
+
+}  // namespace qd
+
+extern "C" size_t qd_cvt_tree_bytes(int64_t C, int d) {
+  if (C < 1 || d < 1 || d > QD_MAX_MEASURE_DIM) return 0;
+  return (size_t)qd::tree_layout(C, d).total;
+}
+
+extern "C" int qd_cvt_tree_build_host(const void* centroids, int dtype, int64_t C, int d, void* tree) {
+  using namespace qd;
+  QD_REQUIRE(d >= 1 && d <= QD_MAX_MEASURE_DIM, "measure_dim out of range [1, 32]");
+  QD_REQUIRE(dtype == QD_F32 || dtype == QD_F64, "dtype must be QD_F32 or QD_F64");
+  QD_REQUIRE(C >= 1 && C < ((int64_t)1 << 31) - kLeaf, "centroid count out of range");
+  QD_REQUIRE(centroids && tree, "null pointer");
+  memset(tree, 0, (size_t)tree_layout(C, d).total);
+  if (dtype == QD_F64)
+    tree_build_host<double>((const double*)centroids, C, d, (unsigned char*)tree);
+  else
+    tree_build_host<float>((const float*)centroids, C, d, (unsigned char*)tree);
+  return QD_OK;
+}
+
+extern "C" int qd_cvt_tree_prepare(const void* centroids, int dtype, int64_t C, int d, void* tree, void* stream) {
+  using namespace qd;
+  QD_REQUIRE(d >= 1 && d <= QD_MAX_MEASURE_DIM, "measure_dim out of range [1, 32]");
+  QD_REQUIRE(dtype == QD_F32 || dtype == QD_F64, "dtype must be QD_F32 or QD_F64");
+  QD_REQUIRE(C >= 1 && C < ((int64_t)1 << 31) - kLeaf, "centroid count out of range");
+  QD_REQUIRE(centroids && tree, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t esz = dtype == QD_F64 ? 8 : 4;
+  std::vector<unsigned char> host_c((size_t)C * d * esz);
+  QD_CHECK_CUDA(cudaMemcpyAsync(host_c.data(), centroids, host_c.size(), cudaMemcpyDeviceToHost, s));
+  QD_CHECK_CUDA(cudaStreamSynchronize(s));
+  const size_t total = (size_t)tree_layout(C, d).total;
+  std::vector<unsigned char> blob(total);
+  int rc = qd_cvt_tree_build_host(host_c.data(), dtype, C, d, blob.data());
+  if (rc) return rc;
+  QD_CHECK_CUDA(cudaMemcpyAsync(tree, blob.data(), total, cudaMemcpyHostToDevice, s));
+  QD_CHECK_CUDA(cudaStreamSynchronize(s));  // `blob` is pageable and dies with this frame
+  return QD_OK;
+}

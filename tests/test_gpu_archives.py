@@ -60,7 +60,7 @@ def test_grid_index_golden():
         np.testing.assert_array_equal(a.index_of(c["measures"]), c["index"], err_msg=name)
 
 
-@pytest.mark.parametrize("method", ["scan", "tensor", "bucket"])
+@pytest.mark.parametrize("method", ["scan", "tensor", "bucket", "tree"])
 def test_cvt_index_golden(method):
     from pyribs_b200.archives import CVTArchive
 
@@ -145,6 +145,62 @@ def test_cvt_bucket_equals_scan(case, d):
         sub = rng.choice(B, 300, replace=False)
         dd = ((meas[sub, None, :] - cen[None, :, :]) ** 2).sum(-1)
         np.testing.assert_array_equal(out["bucket"][sub], dd.argmin(1))
+
+
+@pytest.mark.parametrize("case", ["uniform", "clustered", "degenerate_axis", "one_centroid", "few", "lattice_ties", "f32",
+                                  "all_equal"])
+@pytest.mark.parametrize("d", [2, 4, 8, 9, 20])
+def test_cvt_tree_equals_scan(case, d):
+    """The bounding-box tree search (csrc/cvt_tree.cu, the default for 3 < measure_dim <= 16) must return exactly
+    what the fp64 scan returns: clustered centroids, a zero-extent axis, a single leaf, queries far outside the
+    boxes (beyond fp32 range too), exact ties on a lattice and between duplicates (lowest index wins), float32
+    archives, compile-time (2, 4, 8) and run-time (9, 20) measure dimensions."""
+    from pyribs_b200.archives import CVTArchive
+
+    rng = np.random.default_rng(d * 100 + len(case))
+    C, B = 6000, 8000
+    dt = np.float32 if case == "f32" else np.float64
+    if case == "clustered":
+        cen = np.concatenate([rng.normal(m, 0.01, (C // 5, d)) for m in rng.uniform(-1, 1, (5, d))])
+    elif case == "one_centroid":
+        cen = rng.uniform(-1, 1, (1, d))
+    elif case == "few":
+        cen = rng.uniform(-1, 1, (33, d))
+    elif case == "all_equal":
+        cen = np.tile(rng.uniform(-1, 1, (1, d)), (700, 1))
+    elif case == "lattice_ties":
+        side = max(2, int(round(C ** (1.0 / d))))
+        cen = np.stack(np.meshgrid(*[np.arange(side) / 4.0] * d, indexing="ij"), -1).reshape(-1, d)[:20000]
+        cen = np.concatenate([cen, cen[::7]])  # duplicates: the first copy must win
+    else:
+        cen = rng.uniform(-1, 1, (C, d))
+    if case == "degenerate_axis":
+        cen[:, -1] = 0.25
+    span = np.abs(cen).max() + 0.1
+    meas = rng.uniform(-1.2, 1.2, (B, d)) * span
+    if case == "lattice_ties":
+        meas[: B // 2] = np.round(meas[: B // 2] * 8) / 8  # many exactly equidistant queries
+    meas[:20] *= 50.0
+    meas[20:25] *= 1e6
+    if dt == np.float64:
+        meas[25:28] *= 1e40  # finite in fp64, beyond fp32: the box bounds saturate and the walk degrades to a scan
+    meas[30:40] = cen[:10] if len(cen) >= 10 else cen[0]
+    cen, meas = cen.astype(dt), meas.astype(dt)
+    out = {}
+    for method in ("scan", "tree"):
+        a = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, search_method=method, dtype=dt)
+        out[method] = a.index_of(meas)
+    np.testing.assert_array_equal(out["tree"], out["scan"])
+    if dt == np.float64:
+        sub = rng.choice(B, 200, replace=False)
+        dd = ((meas[sub, None, :] - cen[None, :, :]) ** 2).sum(-1)
+        np.testing.assert_array_equal(out["tree"][sub], dd.argmin(1))
+    a = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, dtype=dt)
+    assert a._pick_method(B, len(cen)) == (2 if d <= 3 else 3 if d <= 16 else (0 if B * len(cen) >= 1 << 26 else 1))
+    bad = meas.copy()
+    bad[5, 0] = np.nan
+    with pytest.raises(ValueError, match="measures must be finite"):
+        CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, search_method="tree", dtype=dt).index_of(bad)
 
 
 def _random_batches(rng, steps, B, n, md, scale):
@@ -361,11 +417,12 @@ def test_cvt_tensor_equals_scan(shape):
     meas[50:60] *= 1e9
     meas[60:70] = cen[C // 2: C // 2 + 10]
     out = {}
-    for method in ("scan", "tensor") + (("bucket",) if d <= 3 else ()):
+    for method in ("scan", "tensor", "tree") + (("bucket",) if d <= 3 else ()):
         a = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, search_method=method)
         out[method] = a.index_of(meas)
         assert a._overflow_fallbacks == 0
     np.testing.assert_array_equal(out["tensor"], out["scan"])
+    np.testing.assert_array_equal(out["tree"], out["scan"])
     if "bucket" in out:
         np.testing.assert_array_equal(out["bucket"], out["scan"])
     assert np.all(out["scan"][60:70] == np.arange(10))

@@ -131,6 +131,19 @@ if __name__ == "__main__":
         es_case("C4 LM-MA n=10000 lam=4096 default vectors", "lm_ma_es", 10_000, 4096, 12)
         es_case("C1 CMA-ES n=100 lam=36", "cma_es", 100, 36, 30)
         es_case("CMA-ES n=1000 lam=36", "cma_es", 1000, 36, 12)
+    if "tree" in what:
+        cvt_case("C5 full (1M x 1M, 8-D) box tree", 1_000_000, 1_000_000, 8, "tree", 3)
+        cvt_case("C5 per-rank shard (1M x 125k, 8-D) box tree", 1_000_000, 125_000, 8, "tree", 3)
+        cvt_case("C5 batch shard (125k x 1M, 8-D) box tree", 125_000, 1_000_000, 8, "tree", 3)
+        cvt_case("1M x 1M, 4-D box tree", 1_000_000, 1_000_000, 4, "tree", 3)
+        cvt_case("200k x 1M, 12-D box tree", 200_000, 1_000_000, 12, "tree", 2)
+        cvt_case("100k x 200k, 16-D box tree", 100_000, 200_000, 16, "tree", 2)
+        cvt_case("100k x 200k, 16-D tensor", 100_000, 200_000, 16, "tensor", 2)
+        cvt_case("51200 x 1M, 8-D box tree", 51_200, 1_000_000, 8, "tree", 3)
+    if "tree5" in what:
+        cvt_case("C5 full (1M x 1M, 8-D) box tree", 1_000_000, 1_000_000, 8, "tree", 3)
+    if "cvt5" in what:
+        cvt_case("C5 per-rank shard (1M x 125k, 8-D)", 1_000_000, 125_000, 8, "tensor", 2)
     if "cvt" in what:
         cvt_case("C2 search", 100_000, 10_000, 2, "tensor", 10)
         cvt_case("C5 per-rank shard (1M x 125k, 8-D)", 1_000_000, 125_000, 8, "tensor", 2)
