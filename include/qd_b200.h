@@ -100,6 +100,10 @@ int qd_cvt_bucket_prepare(const void* centroids /*[dev] C x d*/, int dtype, int6
  * host where the reference builds its KD-tree (_cvt_archive.py:410-429) and copied to `tree`. The _host variant
  * takes and fills HOST memory (used by qd_cvt_tree_prepare and by the CPU tests of the structure). */
 size_t qd_cvt_tree_bytes(int64_t C, int d);
+/* Scratch of a method-3 search (`scratch` of qd_cvt_index_of): large batches are counting-sorted by their home
+ * leaf first so that neighbouring warps walk neighbouring parts of the tree. 0 = none needed; without it the
+ * search runs in input order (same results). */
+size_t qd_cvt_tree_scratch_bytes(int64_t B, int64_t C);
 int qd_cvt_tree_prepare(const void* centroids /*[dev] C x d*/, int dtype, int64_t C, int d,
                         void* tree /*[dev] qd_cvt_tree_bytes*/, void* stream);
 int qd_cvt_tree_build_host(const void* centroids /*[host] C x d*/, int dtype, int64_t C, int d,

@@ -85,6 +85,7 @@ PROTOTYPES = {
     "qd_cvt_bucket_bytes": (_sz, [_i64, _int]),
     "qd_cvt_bucket_prepare": (_int, [_vp, _int, _i64, _int, _vp, _vp]),
     "qd_cvt_tree_bytes": (_sz, [_i64, _int]),
+    "qd_cvt_tree_scratch_bytes": (_sz, [_i64, _i64]),
     "qd_cvt_tree_prepare": (_int, [_vp, _int, _i64, _int, _vp, _vp]),
     "qd_cvt_tree_build_host": (_int, [_vp, _int, _i64, _int, _vp]),
     "qd_cvt_scratch_bytes": (_sz, [_i64, _i64, _int]),

@@ -221,7 +221,12 @@ class CVTArchive(DeviceArchive):
         # the tensor-core filter can (rarely) overflow its candidate list, which is only visible in the
         # flags of the finished call: such insertions are waited for even when given CUDA tensors
         self._needs_flag_check = method == 0
-        need = int(_lib.lib().qd_cvt_scratch_bytes(B, Cn, self._measure_dim)) if method == 0 else 256
+        if method == 0:
+            need = int(_lib.lib().qd_cvt_scratch_bytes(B, Cn, self._measure_dim))
+        elif method == 3:
+            need = int(_lib.lib().qd_cvt_tree_scratch_bytes(B, Cn))
+        else:
+            need = 256
         if self._cvt_scratch is None or self._cvt_scratch.numel() < need:
             self._cvt_scratch = torch.empty(max(need, 256), dtype=torch.uint8, device=self._device)
         prepared = self._buckets if method == 2 else (self._tree if method == 3 else self._prepared)

@@ -94,8 +94,8 @@ int cvt_bucket_index_of(const void* measures, int dtype, int64_t B, int d, int64
                         int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags,
                         cudaStream_t s);  // cvt_bucket.cu
 int cvt_tree_index_of(const void* measures, int dtype, int64_t B, int d, int64_t C, const void* tree,
-                      int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags,
-                      cudaStream_t s);  // cvt_tree.cu
+                      int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags, void* scratch,
+                      size_t scratch_bytes, cudaStream_t s);  // cvt_tree.cu
 
 }  // namespace qd
 
@@ -122,7 +122,8 @@ extern "C" int qd_cvt_index_of(const void* measures, int dtype, int64_t B, int d
   }
   if (method == 3) {
     QD_REQUIRE(prepared != nullptr, "method 3 needs the box tree built by qd_cvt_tree_prepare");
-    return cvt_tree_index_of(measures, dtype, B, d, C, prepared, index_base, idx_out, dist_out, flags, s);
+    return cvt_tree_index_of(measures, dtype, B, d, C, prepared, index_base, idx_out, dist_out, flags, scratch,
+                             scratch_bytes, s);
   }
   QD_REQUIRE(method == 0, "method must be 0 (tensor-core), 1 (fp64 scan), 2 (bucket grid) or 3 (box tree)");
   QD_REQUIRE(prepared != nullptr, "method 0 needs the image built by qd_cvt_prepare");

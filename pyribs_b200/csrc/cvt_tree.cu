@@ -204,116 +204,230 @@ struct TreeView {
 // is a sum of non-negative terms, each off by at most three roundings: fl(dist^2) >= true * (1 - 2^-48). bestf >=
 // best * (1 + 2^-22). Hence lbk > bestf implies fl(dist^2(p)) > best for every p in the box: p is neither the
 // minimum nor an exact tie.
-template <typename T, int D>
-__global__ void __launch_bounds__(kTreeWarps * 32) cvt_tree_kernel(const T* __restrict__ meas, int64_t B, TreeView tv,
-                                                                 int32_t base, int32_t* __restrict__ idx,
-                                                                 double* __restrict__ dist_out, uint32_t* flags) {
+//
+// HOME = true is the ordering pre-pass: a greedy descent to the leaf with the smallest bound at every level; the
+// leaf number is the query's position along the KD order of the centroids. Large batches are counting-sorted by
+// it (tree_scan_kernel / tree_scatter_kernel) and every CTA then walks a contiguous run of the sorted queries with
+// all of its warps, so that the nodes and leaves the queries of one SM touch overlap and come out of L1 instead of
+// L2 (the walk is bound by L2 round trips: ~125 KB per query unsorted).
+template <typename T, int D, bool HOME, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <= 8) ? 4 : 2))
+    cvt_tree_kernel(const T* __restrict__ meas, int64_t B, TreeView tv, int32_t base, const int32_t* __restrict__ order,
+                    int64_t chunk, int32_t* __restrict__ idx, double* __restrict__ dist_out, uint32_t* flags,
+                    uint32_t* __restrict__ home_key, uint32_t* __restrict__ home_count) {
   constexpr int XN = D > 0 ? D : QD_MAX_MEASURE_DIM;
   const int d = D > 0 ? D : tv.d;
-  __shared__ uint32_t skey[kTreeWarps][kTreeMaxLev][32];  // per-lane slots: child keys of the nodes on the path
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  extern __shared__ uint32_t skey_raw[];  // [warps][kTreeMaxLev][32] per-lane slots: child keys of the nodes on the path
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __shared__ const float* sbox[kTreeMaxLev];  // (indexing the kernel parameter dynamically would spill it to local memory)
+  __shared__ int s_next;  // sorted mode: the CTA's warps draw the queries of its run one by one (their costs differ)
   if (threadIdx.x < kTreeMaxLev) sbox[threadIdx.x] = tv.box[threadIdx.x];
+  if (threadIdx.x == 0) s_next = nw;
   __syncthreads();
-  uint32_t(*key)[32] = skey[warp];
+  uint32_t(*key)[32] = reinterpret_cast<uint32_t(*)[32]>(skey_raw + (size_t)warp * kTreeMaxLev * 32);
   bool bad = false;
-  for (int64_t q = (int64_t)blockIdx.x * kTreeWarps + warp; q < B; q += (int64_t)gridDim.x * kTreeWarps) {
-    double x[XN];
-    float xlo[XN], xhi[XN];
-    bool qbad = false;
-#pragma unroll
-    for (int k = 0; k < XN; ++k)
-      if (k < d) {
-        x[k] = (double)meas[q * d + k];
-        qbad |= !finite_d(x[k]);
-        xlo[k] = __double2float_rd(x[k]);
-        xhi[k] = __double2float_ru(x[k]);
+  const bool dynamic = order != nullptr;  // then gridDim.x * chunk >= B: one run per CTA
+  for (int64_t c0 = (int64_t)blockIdx.x * chunk; c0 < B; c0 += (int64_t)gridDim.x * chunk) {
+    const int64_t c1 = min(B, c0 + chunk);
+    for (int64_t pos = c0 + warp; pos < c1;) {
+      const int64_t q = order ? (int64_t)__ldg(order + pos) : pos;
+      // next query of this warp: drawn now so that the shared-memory atomic is off the critical path
+      int64_t next_pos = pos + nw;
+      if (dynamic) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&s_next, 1);
+        next_pos = c0 + __shfl_sync(0xffffffffu, t, 0);
       }
-    bad |= qbad;
-    double best = INFINITY;
-    int32_t bi = INT32_MAX;
-    float bestf = INFINITY;
-
-    auto eval_leaf = [&](int leaf) {
-      const double* p = tv.pts + ((int64_t)leaf * d) * kLeaf + lane;
-      double c[XN];
-#pragma unroll
-      for (int k = 0; k < XN; ++k)
-        if (k < d) c[k] = __ldg(p + k * kLeaf);
-      const double dd = sqdist_np<D>(x, c, d);
-      const bool cand = dd <= best;
-      if (__any_sync(0xffffffffu, cand)) {
-        int32_t id = cand ? __ldg(tv.ids + (int64_t)leaf * kLeaf + lane) : INT32_MAX;
-        unsigned long long bits = cand ? (unsigned long long)__double_as_longlong(dd) : ~0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bits, o);
-          const int32_t oi = __shfl_xor_sync(0xffffffffu, id, o);
-          if (ob < bits || (ob == bits && oi < id)) {
-            bits = ob;
-            id = oi;
-          }
-        }
-        const double nd = __longlong_as_double((long long)bits);
-        if (nd < best || (nd == best && id < bi)) {
-          best = nd;
-          bi = id;
-          bestf = __fmul_ru(__double2float_ru(best), 1.0000005f);
-        }
-      }
-    };
-    // keys of the 32 children (boxes of level `lvl`, group `parent`): lower-bound bits | lane
-    auto node_key = [&](int lvl, int parent) -> uint32_t {
-      const float* p = sbox[lvl] + (int64_t)parent * (2 * d * kFan) + lane;
-      float acc = 0.f;
+      pos = next_pos;
+      double x[XN];
+      float xlo[XN], xhi[XN];
+      bool qbad = false;
 #pragma unroll
       for (int k = 0; k < XN; ++k)
         if (k < d) {
-          const float lo = __ldg(p + k * kFan), hi = __ldg(p + (d + k) * kFan);
-          const float g = fmaxf(fmaxf(__fsub_rd(lo, xhi[k]), __fsub_rd(xlo[k], hi)), 0.f);
-          acc = __fmaf_rd(g, g, acc);
+          x[k] = (double)meas[q * d + k];
+          qbad |= !finite_d(x[k]);
+          xlo[k] = __double2float_rd(x[k]);
+          xhi[k] = __double2float_ru(x[k]);
         }
-      return (__float_as_uint(acc) & 0x7fffffe0u) | (uint32_t)lane;
-    };
+      bad |= qbad;
+      double best = INFINITY;
+      int32_t bi = INT32_MAX;
+      float bestf = INFINITY;
 
-    if (!qbad) {
-      if (tv.nlev == 1) {
-        eval_leaf(0);
-      } else {
-        int level = tv.nlev - 1;  // level of the current node; its children are the boxes of level - 1
-        int cur = 0;              // index of the current node within its level
-        key[level][lane] = node_key(level - 1, 0);
-        while (true) {
-          const uint32_t k = __reduce_min_sync(0xffffffffu, key[level][lane]);
-          if (k >= 0x7f800000u || __uint_as_float(k & 0xffffffe0u) > bestf) {  // nothing left below this node
-            if (++level >= tv.nlev) break;
-            cur >>= 5;
-            continue;
+      auto eval_leaf = [&](int leaf) {
+        const double* p = tv.pts + ((int64_t)leaf * d) * kLeaf + lane;
+        double c[XN];
+#pragma unroll
+        for (int k = 0; k < XN; ++k)
+          if (k < d) c[k] = __ldg(p + k * kLeaf);
+        const double dd = sqdist_np<D>(x, c, d);
+        const bool cand = dd <= best;
+        if (__any_sync(0xffffffffu, cand)) {
+          int32_t id = cand ? __ldg(tv.ids + (int64_t)leaf * kLeaf + lane) : INT32_MAX;
+          unsigned long long bits = cand ? (unsigned long long)__double_as_longlong(dd) : ~0ull;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bits, o);
+            const int32_t oi = __shfl_xor_sync(0xffffffffu, id, o);
+            if (ob < bits || (ob == bits && oi < id)) {
+              bits = ob;
+              id = oi;
+            }
           }
-          const int child = (int)(k & 31u);
-          if (lane == child) key[level][lane] = 0xffffffffu;  // visited
-          const int cnode = cur * kFan + child;
-          if (level == 1) {
-            eval_leaf(cnode);
-          } else {
-            --level;
-            cur = cnode;
-            key[level][lane] = node_key(level - 1, cur);
+          const double nd = __longlong_as_double((long long)bits);
+          if (nd < best || (nd == best && id < bi)) {
+            best = nd;
+            bi = id;
+            bestf = __fmul_ru(__double2float_ru(best), 1.0000005f);
+          }
+        }
+      };
+      // keys of the 32 children (boxes of level `lvl`, group `parent`): lower-bound bits | lane
+      auto node_key = [&](int lvl, int parent) -> uint32_t {
+        const float* p = sbox[lvl] + (int64_t)parent * (2 * d * kFan) + lane;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < XN; ++k)
+          if (k < d) {
+            const float lo = __ldg(p + k * kFan), hi = __ldg(p + (d + k) * kFan);
+            const float g = fmaxf(fmaxf(__fsub_rd(lo, xhi[k]), __fsub_rd(xlo[k], hi)), 0.f);
+            acc = __fmaf_rd(g, g, acc);
+          }
+        return (__float_as_uint(acc) & 0x7fffffe0u) | (uint32_t)lane;
+      };
+
+      if constexpr (HOME) {
+        int cur = 0;
+        if (!qbad)
+          for (int level = tv.nlev - 1; level >= 1; --level)
+            cur = cur * kFan + (int)(__reduce_min_sync(0xffffffffu, node_key(level - 1, cur)) & 31u);
+        if (lane == 0) {
+          home_key[q] = (uint32_t)cur;
+          atomicAdd(&home_count[cur + 1], 1u);
+        }
+        continue;
+      }
+      if (!qbad) {
+        if (tv.nlev == 1) {
+          eval_leaf(0);
+        } else {
+          int level = tv.nlev - 1;  // level of the current node; its children are the boxes of level - 1
+          int cur = 0;              // index of the current node within its level
+          key[level][lane] = node_key(level - 1, 0);
+          while (true) {
+            const uint32_t k = __reduce_min_sync(0xffffffffu, key[level][lane]);
+            if (k >= 0x7f800000u || __uint_as_float(k & 0xffffffe0u) > bestf) {  // nothing left below this node
+              if (++level >= tv.nlev) break;
+              cur >>= 5;
+              continue;
+            }
+            const int child = (int)(k & 31u);
+            if (lane == child) key[level][lane] = 0xffffffffu;  // visited
+            const int cnode = cur * kFan + child;
+            if (level == 1) {
+              eval_leaf(cnode);
+            } else {
+              --level;
+              cur = cnode;
+              key[level][lane] = node_key(level - 1, cur);
+            }
           }
         }
       }
-    }
-    if (lane == 0) {
-      idx[q] = qbad ? base : ((bi == INT32_MAX ? 0 : bi) + base);
-      if (dist_out) dist_out[q] = qbad ? INFINITY : best;
+      if (lane == 0) {
+        idx[q] = qbad ? base : ((bi == INT32_MAX ? 0 : bi) + base);
+        if (dist_out) dist_out[q] = qbad ? INFINITY : best;
+      }
     }
   }
-  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, QD_FLAG_NONFINITE_MEASURES);
+  if (!HOME && __syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, QD_FLAG_NONFINITE_MEASURES);
+}
+
+// exclusive scan of the per-leaf query counts (count[0] = 0, count[l + 1] = queries of leaf l), single block
+__global__ void __launch_bounds__(1024) tree_scan_kernel(uint32_t* __restrict__ count, int64_t n) {
+  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t b0 = 1; b0 <= n; b0 += 1024) {
+    const int64_t i = b0 + threadIdx.x;
+    sh[threadIdx.x] = i <= n ? count[i] : 0u;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i <= n) count[i] = sh[threadIdx.x] + carry;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+}
+
+__global__ void tree_scatter_kernel(const uint32_t* __restrict__ home_key, uint32_t* __restrict__ cursor, int64_t B,
+                                    int32_t* __restrict__ order) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < B; q += (int64_t)gridDim.x * blockDim.x)
+    order[atomicAdd(&cursor[home_key[q]], 1u)] = (int32_t)q;  // cursor[l] starts at the scanned offset of leaf l
+}
+
+constexpr int64_t kTreeSortMin = 16384;  // smaller batches are walked in input order
+
+static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
+static size_t tree_scratch_bytes(int64_t B, int64_t C) {
+  if (B < kTreeSortMin) return 0;
+  const int64_t nleaves = (C + kLeaf - 1) / kLeaf;
+  return 2 * a256((size_t)B * 4) + a256((size_t)(nleaves + 2) * 4);
+}
+
+template <typename T, int D>
+static int launch_tree_d(const T* meas, int64_t B, const TreeView& v, const TreeHeader& h, int32_t base, int32_t* idx,
+                         double* dist, uint32_t* flags, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+  const bool sorted = B >= kTreeSortMin && h.nlev > 1 && scratch && scratch_bytes >= tree_scratch_bytes(B, h.C);
+  int rc;
+  if (!sorted) {
+    // input order: 8 warps per CTA, one query per warp and pass
+    const int64_t blocks = (B + kTreeWarps - 1) / kTreeWarps;
+    const int grid = (int)std::min<int64_t>(blocks, (int64_t)kNumSMs * 8);
+    cvt_tree_kernel<T, D, false, kTreeWarps><<<grid, kTreeWarps * 32, kTreeWarps * kTreeMaxLev * 32 * 4, s>>>(
+        meas, B, v, base, nullptr, kTreeWarps, idx, dist, flags, nullptr, nullptr);
+    return check_launch("cvt_tree_kernel");
+  }
+  char* p = (char*)scratch;
+  uint32_t* home_key = (uint32_t*)p;
+  p += a256((size_t)B * 4);
+  int32_t* order = (int32_t*)p;
+  p += a256((size_t)B * 4);
+  uint32_t* count = (uint32_t*)p;
+  QD_CHECK_CUDA(cudaMemsetAsync(count, 0, (size_t)(h.nleaves + 2) * 4, s));
+  {
+    const int64_t blocks = (B + kTreeWarps - 1) / kTreeWarps;
+    const int grid = (int)std::min<int64_t>(blocks, (int64_t)kNumSMs * 8);
+    cvt_tree_kernel<T, D, true, kTreeWarps><<<grid, kTreeWarps * 32, kTreeWarps * kTreeMaxLev * 32 * 4, s>>>(
+        meas, B, v, base, nullptr, kTreeWarps, idx, dist, flags, home_key, count);
+    if ((rc = check_launch("cvt_tree_kernel(home)"))) return rc;
+  }
+  tree_scan_kernel<<<1, 1024, 0, s>>>(count, h.nleaves);
+  if ((rc = check_launch("tree_scan_kernel"))) return rc;
+  tree_scatter_kernel<<<grid_for(B, 256), 256, 0, s>>>(home_key, count, B, order);
+  if ((rc = check_launch("tree_scatter_kernel"))) return rc;
+  // every CTA walks a contiguous run of the sorted queries with all of its warps: one CTA of 32 warps per SM
+  // where the per-thread state fits 64 registers (measure_dim <= 8), two of 8 warps otherwise
+  constexpr int kBig = (D >= 1 && D <= 8) ? 32 : kTreeWarps;
+  int64_t chunk = (B + (int64_t)kNumSMs * 16 - 1) / ((int64_t)kNumSMs * 16);
+  chunk = (chunk + kBig - 1) / kBig * kBig;
+  const int grid = (int)((B + chunk - 1) / chunk);
+  cvt_tree_kernel<T, D, false, kBig><<<grid, kBig * 32, kBig * kTreeMaxLev * 32 * 4, s>>>(
+      meas, B, v, base, order, chunk, idx, dist, flags, nullptr, nullptr);
+  return check_launch("cvt_tree_kernel(sorted)");
 }
 
 template <typename T>
 static int launch_tree(const T* meas, int64_t B, int d, const unsigned char* tree, const TreeHeader& h, int32_t base,
-                       int32_t* idx, double* dist, uint32_t* flags, cudaStream_t s) {
+                       int32_t* idx, double* dist, uint32_t* flags, void* scratch, size_t scratch_bytes,
+                       cudaStream_t s) {
   TreeView v;
   v.pts = reinterpret_cast<const double*>(tree + h.off_pts);
   v.ids = reinterpret_cast<const int32_t*>(tree + h.off_ids);
@@ -321,37 +435,37 @@ static int launch_tree(const T* meas, int64_t B, int d, const unsigned char* tre
     v.box[l] = l + 1 < h.nlev ? reinterpret_cast<const float*>(tree + h.off_box[l]) : nullptr;
   v.nlev = h.nlev;
   v.d = d;
-  const int64_t blocks = (B + kTreeWarps - 1) / kTreeWarps;
-  const int grid = (int)std::min<int64_t>(blocks, (int64_t)kNumSMs * 8);
-#define QD_TREE(DD) cvt_tree_kernel<T, DD><<<grid, kTreeWarps * 32, 0, s>>>(meas, B, v, base, idx, dist, flags)
+#define QD_TREE(DD) return launch_tree_d<T, DD>(meas, B, v, h, base, idx, dist, flags, scratch, scratch_bytes, s)
   switch (d) {
-    case 2: QD_TREE(2); break;
-    case 3: QD_TREE(3); break;
-    case 4: QD_TREE(4); break;
-    case 5: QD_TREE(5); break;
-    case 6: QD_TREE(6); break;
-    case 7: QD_TREE(7); break;
-    case 8: QD_TREE(8); break;
-    case 10: QD_TREE(10); break;
-    case 12: QD_TREE(12); break;
-    case 16: QD_TREE(16); break;
+    case 2: QD_TREE(2);
+    case 3: QD_TREE(3);
+    case 4: QD_TREE(4);
+    case 5: QD_TREE(5);
+    case 6: QD_TREE(6);
+    case 7: QD_TREE(7);
+    case 8: QD_TREE(8);
+    case 10: QD_TREE(10);
+    case 12: QD_TREE(12);
+    case 16: QD_TREE(16);
     default: QD_TREE(0);
   }
 #undef QD_TREE
-  return check_launch("cvt_tree_kernel");
 }
 
 int cvt_tree_index_of(const void* measures, int dtype, int64_t B, int d, int64_t C, const void* tree,
-                      int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags, cudaStream_t s) {
+                      int32_t index_base, int32_t* idx_out, double* dist_out, uint32_t* flags, void* scratch,
+                      size_t scratch_bytes, cudaStream_t s) {
   const TreeHeader h = tree_layout(C, d);  // the layout is a pure function of (C, d): no device read needed
   if (dtype == QD_F64)
     return launch_tree<double>((const double*)measures, B, d, (const unsigned char*)tree, h, index_base, idx_out,
-                               dist_out, flags, s);
+                               dist_out, flags, scratch, scratch_bytes, s);
   return launch_tree<float>((const float*)measures, B, d, (const unsigned char*)tree, h, index_base, idx_out, dist_out,
-                            flags, s);
+                            flags, scratch, scratch_bytes, s);
 }
 
 }  // namespace qd
+
+extern "C" size_t qd_cvt_tree_scratch_bytes(int64_t B, int64_t C) { return qd::tree_scratch_bytes(B, C); }
 
 extern "C" size_t qd_cvt_tree_bytes(int64_t C, int d) {
   if (C < 1 || d < 1 || d > QD_MAX_MEASURE_DIM) return 0;
