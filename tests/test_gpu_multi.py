@@ -157,3 +157,64 @@ def test_two_gpu_sharded_emitters():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def _shard_tie_worker(rank, world, port, q):
+    """Centroid-sharded search at 8-D with exact ties ACROSS the shard boundary: duplicated centroids whose copies
+    live on different ranks and lattice points equidistant from centroids of both shards. The two all-reduces
+    (distance, then index among the ranks holding the minimum) must return the lowest GLOBAL index, like
+    np.argmin over the unsharded array (_cvt_archive.py:626-632)."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from pyribs_b200.archives import CVTArchive
+
+    rng = np.random.default_rng(11)
+    C, B, d = 40_000, 30_000, 8
+    cen = rng.uniform(-1, 1, (C, d))
+    cen[C // 2: C // 2 + 60] = cen[:60]                       # copies on the other rank
+    cen[C // 2 + 100: C // 2 + 164] = np.round(cen[100:164] * 4) / 4
+    cen[200:264] = cen[C // 2 + 100: C // 2 + 164]            # lattice points present in both shards
+    meas = rng.uniform(-1.1, 1.1, (B, d))
+    meas[:60] = cen[:60]
+    meas[60:124] = cen[200:264]
+    meas[124:188] = cen[200:264] + 0.125                       # exactly representable offsets: ties in fp64
+    ok = True
+    want = None
+    for method in ("auto", "tensor", "scan"):
+        sh = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, shard_centroids=True, search_method=method)
+        got = sh.index_of(meas)
+        if want is None:
+            one = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, search_method="scan")
+            want = one.index_of(meas)
+            sub = np.r_[0:188, rng.choice(B, 300, replace=False)]
+            dd = ((meas[sub, None, :] - cen[None, :, :]) ** 2).sum(-1)
+            ok &= bool(np.array_equal(want[sub], dd.argmin(1)))
+            ok &= bool(np.array_equal(want[:60], np.arange(60)))
+            ok &= bool(np.array_equal(want[60:124], np.arange(200, 264)))
+        ok &= bool(np.array_equal(got, want))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_search_cross_shard_ties():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_tie_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
