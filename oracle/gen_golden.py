@@ -500,14 +500,53 @@ def gen_bandit():
     save("bandit", out)
 
 
+# ---------------------------------------------------------------------------------------
+# 10. BASELINE.json configs[4] shape: 1M centroids, 8-D -- cell indices of 20k seeded queries
+#     (inputs are regenerated from the seeds by the test; only the indices are stored)
+# ---------------------------------------------------------------------------------------
+C5_SEEDS = {"centroids": 0, "queries": 1, "C": 1_000_000, "d": 8, "Q": 20_000}
+
+
+def gen_c5_index():
+    cen = np.random.default_rng(C5_SEEDS["centroids"]).uniform(-1, 1, (C5_SEEDS["C"], C5_SEEDS["d"]))
+    q = np.random.default_rng(C5_SEEDS["queries"]).uniform(-1, 1, (C5_SEEDS["Q"], C5_SEEDS["d"]))
+    a = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * C5_SEEDS["d"],
+                   kdtree_query_kwargs={"workers": -1})
+    idx = a.index_of(q)
+    save("c5_index", {"index": idx.astype(np.int32), "checksum_centroids": np.float64(cen.sum()),
+                      "checksum_queries": np.float64(q.sum()), **{k: np.int64(v) for k, v in C5_SEEDS.items()}})
+
+
+# ---------------------------------------------------------------------------------------
+# 11. GridArchive.retessellate (_grid_archive.py:926-976): add -> retessellate -> reads
+# ---------------------------------------------------------------------------------------
+def gen_retessellate():
+    rng = np.random.default_rng(77)
+    out = {}
+    for name, n_adds in (("one_add", 1), ("three_adds", 3)):
+        a = GridArchive(solution_dim=3, dims=[10, 20], ranges=[(-1, 1), (-2, 2)])
+        ins = []
+        for j in range(n_adds):
+            b = {"solution": rng.standard_normal((400, 3)), "objective": rng.uniform(0, 10, 400) - 2.0 * j,
+                 "measures": rng.uniform(-1.1, 1.1, (400, 2)) * np.array([1.0, 2.0])}
+            a.add(**b)
+            ins.append(b)
+        before = dump_archive(a)
+        a.retessellate([5, 8])
+        out[name] = {"in": {f"b{j}": b for j, b in enumerate(ins)}, "before": before, "after": dump_archive(a),
+                     "data_index": a.data("index"), "data_objective": a.data("objective")}
+        b = {"solution": rng.standard_normal((100, 3)), "objective": rng.uniform(0, 12, 100),
+             "measures": rng.uniform(-1, 1, (100, 2))}
+        info = a.add(**b)
+        out[name]["again"] = {"in": b, "status": info["status"], "value": info["value"], "after": dump_archive(a)}
+    save("retessellate", out)
+
+
+ALL = {"grid_index": gen_grid_index, "cvt_index": gen_cvt_index, "add": gen_add, "es": gen_es, "rankers": gen_rankers,
+       "emitters": gen_emitters, "openai_es": gen_openai_es, "categorical": gen_categorical, "bandit": gen_bandit,
+       "c5_index": gen_c5_index, "retessellate": gen_retessellate}
+
 if __name__ == "__main__":
     print("reference", ribs.__version__, "from", os.path.dirname(ribs.__file__))
-    gen_grid_index()
-    gen_cvt_index()
-    gen_add()
-    gen_es()
-    gen_rankers()
-    gen_emitters()
-    gen_openai_es()
-    gen_categorical()
-    gen_bandit()
+    for name in (sys.argv[1:] or list(ALL)):  # `python oracle/gen_golden.py c5_index retessellate` regenerates two files
+        ALL[name]()

@@ -172,7 +172,65 @@ class DeviceArchive:
         self._pipe = None          # (side stream, rows-done event, [copy-done event of list buffer 0, 1])
         self._pipe_calls = 0
         self._pipe_pending = None  # copy-done event nobody has waited for yet
-        self._store._copy_join = self._join_copy
+        self._attach_store(self._store)
+
+    def _attach_store(self, store):
+        """Adopts `store` (construction, retessellate, unpickling): the store's hooks point back at this archive
+        and every piece of host state that described the previous store starts over."""
+        self._store = store
+        store._copy_join = self._join_copy
+        store._owner_sync = self._sync
+        self._st = (0, 0.0, None, 0)
+        self._best_serial = 0
+        self._best_elite = None
+        self._last_idx = None
+        self._shared_idx = None
+        self._pipe_pending = None
+        self._inflight = None
+
+    # state that cannot (streams, events, ctypes arrays, page-locked pools, process groups) or need not (device
+    # search structures, scratch) travel through pickle; rebuilt by __setstate__ / on first use
+    _TRANSIENT = {"_pinned": dict, "_outbuf": dict, "_copy_stream": None, "_copy_event": None, "_inflight": None,
+                  "_dp_symm": None, "_zc": None, "_shared_idx": None, "_last_idx": None, "_pin_cache": dict,
+                  "_pipe": None, "_pipe_pending": None, "_dp_group": None}
+
+    def __getstate__(self):
+        """Checkpoint (the reference's archives pickle as plain NumPy holders; SURVEY.md lists checkpoint / resume):
+        device tensors travel as NumPy through DeviceStore.__getstate__, the running stats and the best elite as the
+        host values `stats` / `best_elite` report."""
+        self._sync()
+        self._join_copy()
+        if self._stats_dirty:
+            self._build_stats()
+        d = {k: v for k, v in self.__dict__.items() if k not in self._TRANSIENT and k not in self._transient_extra()}
+        d["_best_elite"] = self.best_elite
+        return d
+
+    def _transient_extra(self):
+        return ()
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        for k, v in self._TRANSIENT.items():
+            setattr(self, k, v() if callable(v) else v)
+        self._device = self._store.device
+        best, st = self._best_elite, self._st
+        self._attach_store(self._store)
+        self._rebuild_device_side()
+        # re-seed the device-side running state with the archive's own values (the best objective of a CMA-MAE
+        # archive can exceed every stored row's) and adopt what the device reports back
+        store = self._store
+        n = len(store)
+        absmax = float(store._fields["objective"][store._occupied.bool()].abs().max().item()) if n else 0.0
+        store._owner_sync = None
+        store._push_state(st[1], st[2], absmax)
+        store._owner_sync = self._sync
+        self._apply_state(store._last)
+        self._best_elite = best
+        self._best_serial = self._st[3]
+
+    def _rebuild_device_side(self):
+        """Subclasses: ABI constants / search structures dropped by __getstate__."""
 
     # ---- properties ---------------------------------------------------------------------
     @property
@@ -294,9 +352,10 @@ class DeviceArchive:
         them on the host lands here. A batch dropped by the device-side finite check surfaces as
         the reference's ValueError at this point."""
         store = self._store
+        store.join_row_copy()
         if not store._pending:
             return
-        flags = store.sync()
+        flags = store._read_back()
         self._apply_state(store._last)
         self._raise_for_flags(flags)
 
@@ -551,6 +610,8 @@ class DeviceArchive:
     # ---- add (A5) -----------------------------------------------------------------------------
     def add(self, solution, objective, measures, **fields):
         dev_in = is_device_tensor(solution)
+        # a hand-over from an archive of the same geometry is good for this call only, also when the call raises
+        preset, self._shared_idx = self._shared_idx, None
         data = validate_batch(self, {"solution": solution, "objective": objective, "measures": measures, **fields})
         if self._extra_names != set(fields):
             raise ValueError(
@@ -561,7 +622,6 @@ class DeviceArchive:
         B = int(data["solution"].shape[0])
         odt = self.dtypes["objective"]
         self._last_idx = None
-        preset, self._shared_idx = self._shared_idx, None
         if preset is not None and preset[1] != B:
             preset = None
         if B == 0:
@@ -839,6 +899,7 @@ class DeviceArchive:
         return occupied[0], {f: a[0] for f, a in data.items()}
 
     def data(self, fields=None, return_type="dict"):
+        self._sync()  # adopts the state of insertions still in flight (and raises for a batch the device dropped)
         return self._store.data(fields, return_type)
 
     def sample_elite_cells(self, n, replace=True):

@@ -133,16 +133,29 @@ class CVTArchive(DeviceArchive):
             self._world = dist.get_world_size(process_group)
             self._rank = dist.get_rank(process_group)
         self._shard_lo, self._shard_hi = shard_bounds(len(cen), self._world, self._rank)
+        self._geom_cache = {}
+        self._force_scan = False
+        self._rebuild_device_side()
+
+    def _transient_extra(self):
+        return ("_centroids_dev", "_prepared", "_buckets", "_tree", "_cvt_scratch", "_geom_cache", "_pg")
+
+    def _rebuild_device_side(self):
+        """Centroid shard + search structure on the device (construction and unpickling)."""
+        self.__dict__.setdefault("_pg", None)
+        self._geom_cache = {}
+        cen, search_method = self._centroids, self._search_method
         shard = np.ascontiguousarray(cen[self._shard_lo:self._shard_hi])
         with torch.cuda.device(self._device):
             self._centroids_dev = torch.from_numpy(shard).to(self._device) if len(shard) else None
             self._prepared = None
             self._buckets = None
             self._tree = None
-            if len(shard) and (search_method == "tree" or (search_method == "auto" and 3 < self._measure_dim <= 16)):
+            if len(shard) and (search_method == "tree" or (search_method == "auto" and 3 < self._measure_dim <= 10)):
                 # mid measure_dim: bounding-box tree in KD order (csrc/cvt_tree.cu), the analogue of the reference's
-                # KD-tree where a bucket grid no longer works; beyond ~16-D boxes stop pruning and the exhaustive
-                # tensor-core contraction below takes over
+                # KD-tree where a bucket grid no longer works. Measured on uniform data (tools/bench_extras.py):
+                # 8-D 1M x 1M 9.7 ms against 89 ms exhaustive; from ~12-D on boxes stop pruning (16-D: 14x slower
+                # than the contraction) and the exhaustive tensor-core search below takes over
                 nbytes = int(_lib.lib().qd_cvt_tree_bytes(len(shard), self._measure_dim))
                 self._tree = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
                 _lib.check(_lib.lib().qd_cvt_tree_prepare(self._centroids_dev.data_ptr(), self._meas_code, len(shard),
@@ -162,8 +175,6 @@ class CVTArchive(DeviceArchive):
                                                      self._measure_dim, self._prepared.data_ptr(),
                                                      current_stream_ptr()))
         self._cvt_scratch = None
-        self._geom_cache = {}
-        self._force_scan = False
 
     @property
     def centroids(self):
@@ -182,15 +193,19 @@ class CVTArchive(DeviceArchive):
         return self._interval_size
 
     def same_geometry(self, other):
-        key = id(other)
-        hit = self._geom_cache.get(key)
-        if hit is None:
-            hit = self._geom_cache[key] = bool(
+        import weakref
+
+        hit = self._geom_cache.get(id(other))
+        if hit is None or hit[0]() is not other:  # (an id can be reused by a new object after garbage collection)
+            same = bool(
                 type(other) is type(self) and self._device == other._device
                 and self._centroids.shape == other._centroids.shape and self._centroids.dtype == other._centroids.dtype
                 and getattr(other, "_world", 1) == 1 and self._world == 1
                 and np.array_equal(self._centroids, other._centroids))
-        return hit
+            if len(self._geom_cache) > 16:
+                self._geom_cache.clear()
+            hit = self._geom_cache[id(other)] = (weakref.ref(other), same)
+        return hit[1]
 
     def _host_measures_ok(self):
         return self._buckets is not None and not self._force_scan and self._search_method != "scan"

@@ -157,10 +157,24 @@ class DeviceStore:
 
     def sync(self):
         """Reads the device-side store state back if insertions are still in flight. Returns the
-        unreported validation flags (see consume)."""
+        unreported validation flags (see consume). A store that belongs to an archive hands the read-back to
+        the archive (`_owner_sync` = DeviceArchive._sync), which also adopts the running stats and raises the
+        reference's ValueError for a batch the device-side finite check dropped -- whichever of `len(store)`,
+        `store.data()`, iteration ... notices the pending insertion first."""
         self.join_row_copy()
         if not self._pending:
             return 0
+        owner = self.__dict__.get("_owner_sync")
+        if owner is not None and not self.__dict__.get("_in_owner_sync", False):
+            self._in_owner_sync = True
+            try:
+                owner()
+            finally:
+                self._in_owner_sync = False
+            return 0
+        return self._read_back()
+
+    def _read_back(self):
         with torch.cuda.device(self._device):
             self._result_host.copy_(self._result_dev, non_blocking=True)
             _lib.check(_lib.lib().qd_stream_synchronize(current_stream_ptr()))
@@ -396,8 +410,8 @@ class DeviceStore:
         self._occupied_list.copy_(torch.from_numpy(st["occupied_list"]))
         for n, a in st["fields"].items():
             self._fields[n].copy_(torch.from_numpy(a))
-        # objective sum / best objective are re-seeded by the owning archive (DeviceArchive.__setstate__);
-        # a bare store restores the element count and re-marks unoccupied thresholds
+        # objective sum / best objective: a bare store re-derives them from its rows; an owning archive re-seeds
+        # them with its own running values afterwards (DeviceArchive.__setstate__)
         occ = st["occupied"].astype(bool)
         obj = st["fields"]["objective"][occ] if "objective" in st["fields"] else np.zeros(0)
         self._push_state(float(obj.sum()) if obj.size else 0.0, float(obj.max()) if obj.size else None,

@@ -134,8 +134,15 @@ class GridArchive(DeviceArchive):
         del cur["threshold"]
         self._dims = np.array(new_dims, dtype=np.int32)
         self._boundaries = self._compute_boundaries(self._dims, self._lower_bounds, self._upper_bounds)
-        self._store = DeviceStore(self._store.field_desc, capacity=int(np.prod(self._dims)), device=self._device)
+        self._attach_store(DeviceStore(self._store.field_desc, capacity=int(np.prod(self._dims)), device=self._device))
         self._refresh_abi_consts()
         self._idx_buf = None
         self._stats_reset()
         self.add(**cur)
+
+    def _transient_extra(self):
+        return ("_c_dims", "_c_lower", "_c_interval", "_idx_buf")
+
+    def _rebuild_device_side(self):
+        self._refresh_abi_consts()
+        self._idx_buf = None

@@ -76,6 +76,8 @@ class DeviceES:
         self._stream = None
         self._ask_event = None
         self._host_buf = None
+        self._host_bufs = [None, None]  # two page-locked buffers alternate: the array ask() returned stays intact
+        self._host_turn = 0             # until the ask after the next one
         self._pending = None
         self._host_ready = False
         self._rng_mark = 0
@@ -125,8 +127,11 @@ class DeviceES:
     def _enqueue_host_copy(self):
         lam, n = self._solutions.shape
         with torch.cuda.device(self._device), torch.cuda.stream(self._es_stream()):
-            if self._host_buf is None or tuple(self._host_buf.shape) != (lam, n):
-                self._host_buf = torch.empty((lam, n), dtype=torch.float64).pin_memory()
+            self._host_turn ^= 1
+            buf = self._host_bufs[self._host_turn]
+            if buf is None or tuple(buf.shape) != (lam, n):
+                buf = self._host_bufs[self._host_turn] = torch.empty((lam, n), dtype=torch.float64).pin_memory()
+            self._host_buf = buf
             self._host_buf.copy_(self._solutions, non_blocking=True)
             self._ask_event.record(self._stream)
         self._host_ready = True
@@ -203,13 +208,45 @@ class DeviceES:
         if not self._host_ready:
             self._enqueue_host_copy()
         self._ask_event.synchronize()
-        out = self._host_buf.numpy().copy()
+        # Like the reference (`arr_readonly(self._solutions)`, _cma_es.py:237) the result is a read-only view of a
+        # buffer the strategy owns, valid until it is sampled into again (here: the second ask from now) -- copying
+        # 328 MB out of the page-locked buffer cost 4x the device->host transfer at configs[3].
+        out = self._host_buf.numpy()
         if np.dtype(self.dtype) != np.float64:
             out = out.astype(self.dtype)
-        return arr_readonly(out)
+        return arr_readonly(out, view=True)
 
     def _prepare_ask(self, lam):
         pass
+
+    # ---- checkpoint / resume -------------------------------------------------------------------------
+    _ES_TRANSIENT = ("_L", "_stream", "_ask_event", "_host_buf", "_host_bufs", "_partial", "_w_cache", "_pending",
+                     "_host_ready")
+
+    def __getstate__(self):
+        if self._pool is not None:
+            raise TypeError("a strategy adopted by a pooled Scheduler cannot be pickled on its own; pickle the scheduler")
+        self._cancel_prefetch()
+        if self._stream is not None:
+            self._stream.synchronize()
+        d = {}
+        for k, v in self.__dict__.items():
+            if k in self._ES_TRANSIENT:
+                continue
+            d[k] = ("__cuda__", v.cpu().numpy()) if isinstance(v, torch.Tensor) and v.is_cuda else v
+        return d
+
+    def __setstate__(self, d):
+        self._L = _lib.lib()
+        dev = d["_device"]
+        for k, v in d.items():
+            if isinstance(v, tuple) and len(v) == 2 and isinstance(v[0], str) and v[0] == "__cuda__":
+                v = torch.from_numpy(v[1]).to(dev)
+            self.__dict__[k] = v
+        self._stream = self._ask_event = self._host_buf = self._partial = self._pending = None
+        self._host_bufs = [None, None]
+        self._host_turn = 0
+        self._host_ready = False
 
     def _weighted(self, X, rank_d, w_d, mu, old_mean, out_mean, out_sq):
         n = self.solution_dim

@@ -196,7 +196,7 @@ def test_cvt_tree_equals_scan(case, d):
         dd = ((meas[sub, None, :] - cen[None, :, :]) ** 2).sum(-1)
         np.testing.assert_array_equal(out["tree"][sub], dd.argmin(1))
     a = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, dtype=dt)
-    assert a._pick_method(B, len(cen)) == (2 if d <= 3 else 3 if d <= 16 else (0 if B * len(cen) >= 1 << 26 else 1))
+    assert a._pick_method(B, len(cen)) == (2 if d <= 3 else 3 if d <= 10 else (0 if B * len(cen) >= 1 << 26 else 1))
     bad = meas.copy()
     bad[5, 0] = np.nan
     with pytest.raises(ValueError, match="measures must be finite"):

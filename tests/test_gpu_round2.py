@@ -1,0 +1,275 @@
+"""GPU parity tests at the BASELINE.json shapes themselves (configs[2], [3], [4]) and regressions for the state
+hand-over between the device-resident store and the host mirror (async adds, retessellate, checkpoint / resume).
+
+Tolerances: indices, statuses, winners, occupied_list order bit-exact; values / thresholds / ES state 1e-6
+relative (north_star), observed ~1e-12."""
+import os
+import pickle
+import sys
+
+import numpy as np
+import pytest
+
+from golden_util import assert_close, check_archive_dump, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import qd_oracle as O  # noqa: E402
+
+from test_gpu_archives import gpu_dump  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+# ---- configs[4]: CVTArchive 1M centroids, 8-D ------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["auto", "tensor"])
+def test_c5_shape_index_golden(method):
+    """Cell indices of 20k seeded queries against the seeded 1M x 8 centroid set: the reference's KD-tree
+    (tests/golden/c5_index.npz, oracle/gen_golden.py gen_c5_index) vs the box-tree and the tcgen05 search."""
+    from pyribs_b200.archives import CVTArchive
+
+    g = load_golden("c5_index")
+    C, d, Q = int(g["C"]), int(g["d"]), int(g["Q"])
+    cen = np.random.default_rng(int(g["centroids"])).uniform(-1, 1, (C, d))
+    q = np.random.default_rng(int(g["queries"])).uniform(-1, 1, (Q, d))
+    assert cen.sum() == float(g["checksum_centroids"]) and q.sum() == float(g["checksum_queries"]), \
+        "NumPy regenerated different inputs than the golden was made from"
+    a = CVTArchive(solution_dim=1, centroids=cen, ranges=[(-1, 1)] * d, search_method=method)
+    assert a._pick_method(Q, C) == (3 if method == "auto" else 0)
+    np.testing.assert_array_equal(a.index_of(q), g["index"])
+    assert a._overflow_fallbacks == 0
+    if method == "auto":  # a large batch takes the home-leaf-sorted walk; same answer in any order
+        big = np.tile(q, (2, 1))[:30_000]
+        np.testing.assert_array_equal(a.index_of(big), np.tile(g["index"], 2)[:30_000])
+
+
+def test_c5_shape_add_vs_oracle():
+    """Two 200k-row adds into the 1M-centroid archive against the oracle (SciPy KD-tree + the reference's add
+    algebra): statuses bit-exact, values 1e-6, same cells occupied in the same order."""
+    from pyribs_b200.archives import CVTArchive
+
+    C, d, n, B = 1_000_000, 8, 10, 200_000
+    cen = np.random.default_rng(0).uniform(-1, 1, (C, d))
+    rng = np.random.default_rng(5)
+    gpu = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * d)
+    ora = O.make_cvt_oracle(solution_dim=n, centroids=cen, workers=-1)
+    for step in range(2):
+        b = dict(solution=rng.uniform(-1, 1, (B, n)), objective=rng.standard_normal(B) + 0.1 * step,
+                 measures=rng.uniform(-1, 1, (B, d)))
+        if step == 1:
+            b["measures"][:50_000] = prev[:50_000] + rng.normal(0, 1e-3, (50_000, d))  # revisit occupied cells
+        prev = b["measures"]
+        g, o = gpu.add(**b), ora.add(**b)
+        np.testing.assert_array_equal(g["status"], o["status"])
+        assert_close(g["value"], o["value"], RTOL, f"step {step} value")
+    assert len(gpu) == len(ora)
+    np.testing.assert_array_equal(gpu._store.occupied_list, ora.store.occupied_list[: len(ora)])
+    assert_close(gpu.stats.qd_score, ora.objective_sum, RTOL, "qd_score")
+
+
+# ---- configs[2]: CMA-MAE GridArchive 500x500, 100 emitters x 512 ---------------------------------------------------
+def test_c3_shape_add_vs_oracle():
+    from pyribs_b200.archives import GridArchive
+
+    rng = np.random.default_rng(33)
+    E, lam, n = 100, 512, 100
+    kw = dict(solution_dim=n, dims=(500, 500), ranges=[(-1, 1)] * 2, learning_rate=0.01, threshold_min=0.0)
+    gpu, ora = GridArchive(**kw), O.make_grid_oracle(**kw)
+    uniq = []
+    for step in range(3):
+        mu = rng.normal(0, 0.05, (E, 1, 2))
+        meas = np.clip(mu + rng.normal(0, 0.02, (E, lam, 2)), -1, 1).reshape(E * lam, 2)
+        b = dict(solution=rng.standard_normal((E * lam, n)), objective=rng.uniform(0, 100, E * lam) + 10.0 * step,
+                 measures=meas)
+        g, o = gpu.add(**b), ora.add(**b)
+        np.testing.assert_array_equal(g["status"], o["status"], err_msg=f"step {step}")
+        assert_close(g["value"], o["value"], RTOL, f"step {step} value")
+        uniq.append(len(np.unique(ora.index_fn(meas))))
+        assert len(gpu) == len(ora)
+        np.testing.assert_array_equal(gpu._store.occupied_list, ora.store.occupied_list[: len(ora)])
+        occ = ora.store.occupied
+        assert_close(gpu._store._fields["threshold"].cpu().numpy()[occ], ora.store.fields["threshold"][occ], RTOL,
+                     f"step {step} thresholds")
+        np.testing.assert_array_equal(gpu._store._fields["objective"].cpu().numpy()[occ],
+                                      ora.store.fields["objective"][occ])
+        np.testing.assert_array_equal(gpu._store._fields["solution"].cpu().numpy()[occ],
+                                      ora.store.fields["solution"][occ])
+    assert all(2000 < u < 12000 for u in uniq), uniq  # ~10x same-cell collisions per batch, as configs[2] describes
+
+
+# ---- configs[3]: sep-CMA-ES / LM-MA-ES, n = 10 000, batch 4096 -------------------------------------------------------
+@pytest.mark.parametrize("es_name,kw", [("sep_cma_es", {}), ("lm_ma_es", {}), ("lm_ma_es", {"n_vectors": 20})])
+def test_c4_shape_es_vs_oracle(es_name, kw):
+    from pyribs_b200.emitters.opt import _get_es
+
+    n, lam, mu = 10_000, 4096, 2048
+    gpu = _get_es(es_name, sigma0=0.5, solution_dim=n, batch_size=lam, seed=1, dtype=np.float64,
+                  lower_bounds=np.full(n, -np.inf), upper_bounds=np.full(n, np.inf), **kw)
+    ora = O.ORACLE_ES[es_name](0.5, n, lam, seed=1, **kw)
+    x0 = np.random.default_rng(0).standard_normal(n) * 0.1
+    gpu.reset(x0), ora.reset(x0)
+    for g in range(2):  # the second LM-MA ask applies the first direction vector
+        z = np.random.default_rng(100 + g).standard_normal((lam, n))
+        so = ora.ask(z)
+        sg = gpu.ask(z=z)
+        assert_close(sg, so, RTOL, f"{es_name} g{g} solutions")
+        rank = np.argsort(np.sum((so - 1.0) ** 2, axis=1))
+        ora.tell(rank, mu), gpu.tell(rank, None, mu)
+        assert_close(gpu.mean, ora.mean, RTOL, f"{es_name} g{g} mean")
+        assert_close(gpu.sigma, ora.sigma, RTOL, f"{es_name} g{g} sigma")
+        assert_close(gpu.ps, ora.ps, RTOL, f"{es_name} g{g} ps")
+        if es_name == "sep_cma_es":
+            assert_close(gpu.pc, ora.pc, RTOL, f"g{g} pc")
+            assert_close(gpu.cov, ora.C, RTOL, f"g{g} C")
+    x = gpu.ask()  # the library's own stream at this size; the returned array is a read-only view
+    assert x.shape == (lam, n) and not x.flags.writeable and np.all(np.isfinite(x))
+
+
+# ---- device-resident state vs host mirror (async adds) ---------------------------------------------------------------
+def test_async_add_then_data_then_stats():
+    """add(CUDA tensors) only enqueues; whichever read comes first (data() here, not len()) must adopt the
+    device-side state -- stats / best_elite afterwards are those of the batch."""
+    import torch
+
+    from pyribs_b200.archives import GridArchive
+
+    rng = np.random.default_rng(4)
+    kw = dict(solution_dim=3, dims=(20, 20), ranges=[(-1, 1)] * 2)
+    gpu, ora = GridArchive(**kw), O.make_grid_oracle(**kw)
+    b = dict(solution=rng.standard_normal((500, 3)), objective=rng.uniform(0, 5, 500), measures=rng.uniform(-1, 1, (500, 2)))
+    gpu.add(**{k: torch.from_numpy(v).cuda() for k, v in b.items()})
+    ora.add(**b)
+    d = gpu.data()
+    assert len(d["index"]) == len(ora)
+    assert gpu.stats.num_elites == len(ora)
+    assert_close(gpu.stats.qd_score, ora.objective_sum, 1e-12, "qd_score")
+    assert gpu.best_elite is not None and gpu.best_elite["objective"] == b["objective"].max()
+    # a batch the device drops (NaN objective) surfaces as the reference's ValueError at the first read
+    bad = {k: torch.from_numpy(v).cuda() for k, v in b.items()}
+    bad["objective"][7] = float("nan")
+    gpu.add(**bad)
+    with pytest.raises(ValueError, match="objective must be finite"):
+        gpu.data()
+    assert gpu.stats.num_elites == len(ora)  # nothing of the dropped batch was committed
+
+
+@pytest.mark.parametrize("name", ["one_add", "three_adds"])
+def test_retessellate_golden(name):
+    """add -> retessellate -> best_elite / stats / data, then another add: the reference's trajectory
+    (_grid_archive.py:926-976; tests/golden/retessellate.npz)."""
+    from pyribs_b200.archives import GridArchive
+
+    c = load_golden("retessellate")[name]
+    a = GridArchive(solution_dim=3, dims=[10, 20], ranges=[(-1, 1), (-2, 2)])
+    a.pipeline_commit = name == "three_adds"  # the replaced store must keep joining the side-stream row copy
+    for k in sorted(c["in"]):
+        a.add(**c["in"][k])
+    check_archive_dump(gpu_dump(a), c["before"], RTOL, f"{name} before")
+    a.retessellate([5, 8])
+    assert a.best_elite is not None
+    check_archive_dump(gpu_dump(a), c["after"], RTOL, f"{name} after")
+    np.testing.assert_array_equal(a.data("index"), c["data_index"])
+    np.testing.assert_array_equal(a.data("objective"), c["data_objective"])
+    info = a.add(**c["again"]["in"])
+    np.testing.assert_array_equal(info["status"], c["again"]["status"])
+    assert_close(info["value"], c["again"]["value"], RTOL, "value after retessellate")
+    check_archive_dump(gpu_dump(a), c["again"]["after"], RTOL, f"{name} again")
+
+
+# ---- checkpoint / resume -------------------------------------------------------------------------------------
+def _archive(kind):
+    from pyribs_b200.archives import CVTArchive, GridArchive
+
+    if kind == "grid_mae":
+        return GridArchive(solution_dim=4, dims=(30, 30), ranges=[(-1, 1)] * 2, learning_rate=0.1, threshold_min=0.0,
+                           extra_fields={"meta": ((2,), np.int32)}, seed=3)
+    if kind == "grid_me":
+        return GridArchive(solution_dim=4, dims=(30, 30), ranges=[(-1, 1)] * 2, seed=3)
+    d = 2 if kind == "cvt2" else 6
+    return CVTArchive(solution_dim=4, centroids=np.random.default_rng(1).uniform(-1, 1, (3000, d)),
+                      ranges=[(-1, 1)] * d, seed=3)
+
+
+@pytest.mark.parametrize("kind", ["grid_mae", "grid_me", "cvt2", "cvt6"])
+def test_archive_pickle_round_trip(kind):
+    rng = np.random.default_rng(8)
+    a = _archive(kind)
+    d = a.measure_dim
+
+    def batch(j):
+        b = dict(solution=rng.standard_normal((2000, 4)), objective=rng.uniform(0, 10, 2000) + (3 - j),
+                 measures=rng.uniform(-1, 1, (2000, d)))
+        if kind == "grid_mae":
+            b["meta"] = rng.integers(0, 100, (2000, 2)).astype(np.int32)
+        return b
+
+    empty = pickle.loads(pickle.dumps(a))
+    assert len(empty) == 0 and empty.best_elite is None and empty.stats.num_elites == 0
+    bs = [batch(j) for j in range(4)]
+    for b in bs[:2]:
+        a.add(**b), empty.add(**b)
+    twin = pickle.loads(pickle.dumps(a))
+    for x in (twin, empty):
+        assert len(x) == len(a)
+        for f in ("num_elites", "coverage", "qd_score", "norm_qd_score", "obj_max", "obj_mean"):
+            assert getattr(x.stats, f) == getattr(a.stats, f), f
+        for k, v in a.best_elite.items():
+            np.testing.assert_array_equal(x.best_elite[k], v)
+    for b in bs[2:]:  # continue adding: the restored archive behaves like the one that never left the device
+        ra, rt = a.add(**b), twin.add(**b)
+        np.testing.assert_array_equal(ra["status"], rt["status"])
+        np.testing.assert_array_equal(ra["value"], rt["value"])
+    da, dt = a.data(), twin.data()
+    for k in da:
+        np.testing.assert_array_equal(da[k], dt[k], err_msg=k)
+    assert a.stats.qd_score == twin.stats.qd_score and a.best_elite["objective"] == twin.best_elite["objective"]
+    np.testing.assert_array_equal(a.sample_elites(5)["index"], twin.sample_elites(5)["index"])  # same generator state
+
+
+@pytest.mark.parametrize("es_name", ["sep_cma_es", "lm_ma_es", "cma_es", "openai_es"])
+def test_es_pickle_round_trip(es_name):
+    from pyribs_b200.emitters.opt import _get_es
+
+    n, lam = 40, 16
+    es = _get_es(es_name, sigma0=0.5, solution_dim=n, batch_size=lam, seed=5, dtype=np.float64,
+                 lower_bounds=np.full(n, -np.inf), upper_bounds=np.full(n, np.inf))
+    es.reset(np.zeros(n))
+
+    def generation(e):
+        x = np.array(e.ask())
+        fit = -np.sum((x - 1.0) ** 2, axis=1)
+        order = np.argsort(-fit)
+        e.tell(order, fit[order], lam // 2)
+        return x
+
+    for _ in range(3):
+        generation(es)
+    twin = pickle.loads(pickle.dumps(es))
+    for _ in range(3):  # same state, same Philox counter -> the same samples from here on
+        np.testing.assert_array_equal(generation(es), generation(twin))
+
+
+def test_emitter_and_scheduler_pickle():
+    from pyribs_b200.archives import GridArchive
+    from pyribs_b200.emitters import EvolutionStrategyEmitter
+    from pyribs_b200.schedulers import Scheduler
+
+    def make():
+        a = GridArchive(solution_dim=6, dims=(20, 20), ranges=[(-3, 3)] * 2, seed=1)
+        ems = [EvolutionStrategyEmitter(a, x0=np.zeros(6), sigma0=0.5, batch_size=8, seed=s, es="sep_cma_es")
+               for s in (1, 2)]
+        return Scheduler(a, ems)
+
+    def it(s):
+        x = s.ask()
+        s.tell(-np.sum(x**2, axis=1), x[:, :2])
+        return np.array(x)
+
+    s = make()
+    for _ in range(3):
+        it(s)
+    twin = pickle.loads(pickle.dumps(s))
+    for _ in range(3):
+        np.testing.assert_array_equal(it(s), it(twin))
+    assert s.archive.stats.qd_score == twin.archive.stats.qd_score
