@@ -315,22 +315,35 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
           int level = tv.nlev - 1;  // level of the current node; its children are the boxes of level - 1
           int cur = 0;              // index of the current node within its level
           key[level][lane] = node_key(level - 1, 0);
+          uint32_t k = __reduce_min_sync(0xffffffffu, key[level][lane]);
           while (true) {
-            const uint32_t k = __reduce_min_sync(0xffffffffu, key[level][lane]);
             if (k >= 0x7f800000u || __uint_as_float(k & 0xffffffe0u) > bestf) {  // nothing left below this node
               if (++level >= tv.nlev) break;
               cur >>= 5;
+              k = __reduce_min_sync(0xffffffffu, key[level][lane]);
               continue;
             }
             const int child = (int)(k & 31u);
             if (lane == child) key[level][lane] = 0xffffffffu;  // visited
             const int cnode = cur * kFan + child;
             if (level == 1) {
+              // The walk is a chain of dependent L2 round trips (one per leaf). The leaf that comes next is known
+              // before this one is evaluated -- unless this one tightens the bound below it, which is rare after the
+              // first few leaves -- so its rows are requested now (CCTL.PF1, no registers) and are in L1 by then.
+              const uint32_t kn = __reduce_min_sync(0xffffffffu, key[1][lane]);
+              if (kn < 0x7f800000u && !(__uint_as_float(kn & 0xffffffe0u) > bestf)) {
+                const double* pn = tv.pts + ((int64_t)(cur * kFan + (int)(kn & 31u)) * d) * kLeaf + lane;
+#pragma unroll
+                for (int c = 0; c < XN; ++c)
+                  if (c < d) asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + c * kLeaf));
+              }
               eval_leaf(cnode);
+              k = kn;
             } else {
               --level;
               cur = cnode;
               key[level][lane] = node_key(level - 1, cur);
+              k = __reduce_min_sync(0xffffffffu, key[level][lane]);
             }
           }
         }
@@ -344,26 +357,38 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
   if (!HOME && __syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, QD_FLAG_NONFINITE_MEASURES);
 }
 
-// exclusive scan of the per-leaf query counts (count[0] = 0, count[l + 1] = queries of leaf l), single block
+// inclusive scan of the per-leaf query counts in place (count[0] = 0, count[l + 1] = queries of leaf l): one block,
+// every thread owns a contiguous segment, one block-wide scan of the 1024 segment sums
 __global__ void __launch_bounds__(1024) tree_scan_kernel(uint32_t* __restrict__ count, int64_t n) {
-  __shared__ uint32_t sh[1024];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
+  __shared__ uint32_t warp_sum[32];
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t i0 = 1 + (int64_t)threadIdx.x * per, i1 = min(n + 1, i0 + per);
+  uint32_t tot = 0;
+  for (int64_t i = i0; i < i1; ++i) tot += count[i];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  uint32_t incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sum[wi] = incl;
   __syncthreads();
-  for (int64_t b0 = 1; b0 <= n; b0 += 1024) {
-    const int64_t i = b0 + threadIdx.x;
-    sh[threadIdx.x] = i <= n ? count[i] : 0u;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
+  if (wi == 0) {
+    const uint32_t v = warp_sum[lane];
+    uint32_t iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
+      if (lane >= o) iv += t;
     }
-    if (i <= n) count[i] = sh[threadIdx.x] + carry;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += sh[1023];
-    __syncthreads();
+    warp_sum[lane] = iv - v;
+  }
+  __syncthreads();
+  uint32_t run = warp_sum[wi] + incl - tot;
+  for (int64_t i = i0; i < i1; ++i) {
+    run += count[i];
+    count[i] = run;
   }
 }
 
@@ -416,7 +441,11 @@ static int launch_tree_d(const T* meas, int64_t B, const TreeView& v, const Tree
   // every CTA walks a contiguous run of the sorted queries with all of its warps: one CTA of 32 warps per SM
   // where the per-thread state fits 64 registers (measure_dim <= 8), two of 8 warps otherwise
   constexpr int kBig = (D >= 1 && D <= 8) ? 32 : kTreeWarps;
-  int64_t chunk = (B + (int64_t)kNumSMs * 16 - 1) / ((int64_t)kNumSMs * 16);
+  // Runs of >= ~16 queries per warp (a CTA ends when its slowest warp does: short runs are mostly tail -- 125k
+  // queries in runs of 64 ran at half the per-query rate of 1M), at most 16 runs per SM.
+  int64_t runs_per_sm = B / ((int64_t)kNumSMs * kBig * 16);
+  runs_per_sm = runs_per_sm < 1 ? 1 : (runs_per_sm > 16 ? 16 : runs_per_sm);
+  int64_t chunk = (B + (int64_t)kNumSMs * runs_per_sm - 1) / ((int64_t)kNumSMs * runs_per_sm);
   chunk = (chunk + kBig - 1) / kBig * kBig;
   const int grid = (int)((B + chunk - 1) / chunk);
   cvt_tree_kernel<T, D, false, kBig><<<grid, kBig * 32, kBig * kTreeMaxLev * 32 * 4, s>>>(

@@ -11,24 +11,30 @@
 // Sort-free and deterministic. Per-cell scratch: one 32-byte record (one L2 sector), clean
 // between calls:
 //   best  u64  order key of the highest insertable objective            (atomicMax)
+//   pick  u64  (key with its low `rb` bits replaced by the inverted batch row) (atomicMax): the first
+//              row among those with the highest TRUNCATED key. It is the cell's winner -- first in batch
+//              among the rows holding the maximum, _grid_archive.py:693-696 -- whenever its own key equals
+//              `best`; otherwise two rows of the cell differ only below bit rb (relative 2^-(52-rb)) and the
+//              cell is settled by the resolve pass (mark) below
 //   w0,w1 i64  two-level fixed-point sum of the insertable objectives   (atomicAdd, CMA-MAE);
 //              the low bits of w1 carry the row count
-//   win   i32  lowest batch row holding `best`                          (atomicMin, ties only)
 // The threshold array doubles as the occupancy test of the row passes: unoccupied cells hold NaN
 // (the reference never reads the threshold of an unoccupied cell, _grid_archive.py:628-630), so
-// a row costs ONE scattered load + its atomics. Scattered accesses (~1.3 clk/lane/SM), not HBM
-// bytes, bound the row passes; everything else streams.
+// a row costs ONE scattered load + its atomics. Scattered accesses (~1.3-2 clk/lane/SM), not HBM
+// bytes, bound the row pass; everything else streams. Round 1 found the winner with a second row
+// pass (gather `best`, atomicMin(row): 20 us of 171 at 2M rows); `pick` costs one more RED in the
+// first pass and makes that pass an exception path.
 //
 // Phases (B rows, W winners, N cells):
 //   0 absmax    CMA-MAE only: max |objective| fixes the fixed-point scale of the sums
-//   1 classify  (grid: fused with index_of) status / value vs the PRE-batch store; best; sums
-//   2 mark      rows holding their cell's maximum: atomicMin(row) = first in batch wins
-//               (_grid_archive.py:693-696)
+//   1 classify  (grid: fused with index_of) status / value vs the PRE-batch store; best; pick; sums
+//   2 mark      list mode, and cell mode only for cells update found ambiguous: rows holding their
+//               cell's maximum compete with their row number, lowest wins
 //   3 select    list mode only (cells >> rows): winners -> compact (row, cell) list
-//   4 update    cell mode: one thread per cell, coalesced, emits the winner list sorted by cell;
+//   4 update    cell mode: one thread per cell, coalesced, emits the winner list in runs sorted by cell;
 //               list mode: one thread per winner. Threshold, objective, occupancy, sum delta
-//   5 copy      TMA bulk copies of the winners' row fields into the store (HBM stream)
 //   6 best/cnt  lowest winning cell holding the new best objective; new-cell bitmap counts
+//   5 copy      TMA bulk copies of the winners' row fields into the store (HBM stream)
 //   7 publish   occupied_list append in ascending cell order (_array_store.py:586-600), stats,
 //               best-elite snapshot, qd_add_result; re-arms the per-call globals
 // A non-finite objective or measure turns phases 3.. into a scratch clean-up, so the store is
@@ -46,11 +52,25 @@ constexpr int kMaxCtas = kNumSMs * 4;  // upper bound on the persistent grid
 
 struct __align__(32) Cell {
   unsigned long long best;
+  unsigned long long pick;
   long long w0;
   long long w1;
-  int32_t win;
-  uint32_t cnt;  // only when the count does not fit the low bits of w1 (B >= 2^24)
 };
+
+// `pick` arithmetic. rb = bits of a batch row number; keys of finite objectives never reach the all-ones
+// truncation (that is a NaN pattern), which therefore marks a cell whose winner the mark pass decides.
+struct PickConst {
+  unsigned long long rowmask;  // 2^rb - 1
+  unsigned long long amb;      // ~rowmask: base of the mark-pass entries
+};
+__host__ __device__ inline PickConst make_pick(int64_t B) {
+  int rb = 1;
+  while (((int64_t)1 << rb) < B) ++rb;
+  PickConst p;
+  p.rowmask = (1ull << rb) - 1ull;
+  p.amb = ~p.rowmask;
+  return p;
+}
 
 struct InsertState {
   // ---- per call (re-armed by the publish phase) ----
@@ -62,6 +82,8 @@ struct InsertState {
   uint32_t flags;
   uint32_t pad0;
   uint32_t n_winners;
+  uint32_t n_ambiguous;  // cells whose pick was not their maximum (per call, re-armed by publish)
+  uint32_t pad1;
   double dsum[3];
   // ---- persistent ----
   double store_absmax;            // max |objective| ever offered to the store
@@ -82,6 +104,7 @@ struct InsertState {
 
 struct Scratch {
   Cell* cell;
+  uint32_t* cnt;  // per-cell row count, only when it does not fit the low bits of w1 (B >= 2^24)
   uint32_t* newmask;
   uint32_t* ctacnt;  // kMaxCtas
   int2* wlist;       // (batch row, cell) of this call's winners, at most one per cell
@@ -95,6 +118,8 @@ static Scratch carve(void* base, int64_t N) {
   char* p = (char*)base;
   s.cell = (Cell*)p;
   p += align_up((size_t)N * sizeof(Cell), 256);
+  s.cnt = (uint32_t*)p;
+  p += align_up((size_t)N * 4, 256);
   const int64_t words = (N + 31) / 32;
   s.newmask = (uint32_t*)p;
   p += align_up((size_t)words * 4, 256);
@@ -108,7 +133,7 @@ static Scratch carve(void* base, int64_t N) {
 
 static size_t scratch_bytes(int64_t N) {
   const int64_t words = (N + 31) / 32;
-  return align_up((size_t)N * sizeof(Cell), 256) + align_up((size_t)words * 4, 256) +
+  return align_up((size_t)N * sizeof(Cell), 256) + align_up((size_t)N * 4, 256) + align_up((size_t)words * 4, 256) +
          align_up((size_t)kMaxCtas * 4, 256) + 2 * align_up((size_t)N * 8, 256) + align_up(sizeof(InsertState), 256);
 }
 
@@ -117,11 +142,10 @@ __global__ void scratch_init_kernel(Scratch s, int64_t N) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t c = i; c < N; c += stride) {
     Cell z;
-    z.best = 0ull;
+    z.best = z.pick = 0ull;
     z.w0 = z.w1 = 0ll;
-    z.win = INT32_MAX;
-    z.cnt = 0u;
     s.cell[c] = z;
+    s.cnt[c] = 0u;
   }
   for (int64_t w = i; w < (N + 31) / 32; w += stride) s.newmask[w] = 0u;
   if (i == 0) {
@@ -164,7 +188,7 @@ __host__ __device__ inline FxConst make_fx(double absmax, int64_t B) {
   return k;
 }
 
-__device__ __forceinline__ void fx_add(Cell* c, double x, const FxConst& k) {
+__device__ __forceinline__ void fx_add(Cell* c, uint32_t* cnt, double x, const FxConst& k) {
   const double xs = __dmul_rn(x, k.scale0);
   const long long q0 = __double2ll_rn(xs);
   const double r = __dsub_rn(xs, (double)q0);  // exact
@@ -174,17 +198,18 @@ __device__ __forceinline__ void fx_add(Cell* c, double x, const FxConst& k) {
     atomicAdd((unsigned long long*)&c->w1, ((unsigned long long)q1 << k.b) + 1ull);
   } else {
     if (q1) atomicAdd((unsigned long long*)&c->w1, (unsigned long long)q1);
-    atomicAdd(&c->cnt, 1u);
+    atomicAdd(cnt, 1u);
   }
 }
 
-__device__ __forceinline__ void fx_read(const Cell& c, const FxConst& k, double& sum, uint32_t& count) {
+__device__ __forceinline__ void fx_read(const Cell& c, const uint32_t* cnt, const FxConst& k, double& sum,
+                                        uint32_t& count) {
   long long s1 = c.w1;
   if (k.b) {
     count = (uint32_t)((unsigned long long)s1 & ((1ull << k.b) - 1ull));
     s1 = (s1 - (long long)count) >> k.b;
   } else {
-    count = c.cnt;
+    count = *cnt;
   }
   sum = __dadd_rn(__dmul_rn((double)c.w0, k.inv0), __dmul_rn((double)s1, k.inv1));
 }
@@ -287,8 +312,10 @@ __device__ void phase_absmax(const InsertArgs<T>& a, double* sh_d) {
 
 // ---- phase 1 ----------------------------------------------------------------------------------
 template <typename T, typename MT, int D, bool FUSED>
-__device__ void phase_classify(const InsertArgs<T>& a, const GridParams& gp, double* sh_d, uint32_t* sh_u) {
+__device__ void phase_classify(const InsertArgs<T>& a, const GridParams& gp, bool cell_mode, double* sh_d,
+                               uint32_t* sh_u) {
   const bool mae = a.mae;
+  const PickConst pc = make_pick(a.B);
   const bool cma_me = !mae;
   FxConst fx;
   if (mae) fx = make_fx(__longlong_as_double((long long)a.s.g->absmax_bits), a.B);
@@ -329,8 +356,10 @@ __device__ void phase_classify(const InsertArgs<T>& a, const GridParams& gp, dou
       a.value[i] = o[u] - tval;                                     // :649
       if (can) {
         Cell* cell = &a.s.cell[c[u]];
-        atomicMax(&cell->best, ord_key((double)o[u]));  // result unused: a fire-and-forget RED
-        if (mae) fx_add(cell, (double)o[u], fx);
+        const unsigned long long key = ord_key((double)o[u]);
+        atomicMax(&cell->best, key);  // results unused: fire-and-forget REDs
+        if (cell_mode) atomicMax(&cell->pick, (key & pc.amb) | (pc.rowmask - (unsigned long long)i));
+        if (mae) fx_add(cell, &a.s.cnt[c[u]], (double)o[u], fx);
         ++ncan;
       }
       if (!mae && fin) amax = fmax(amax, fabs((double)o[u]));
@@ -355,17 +384,20 @@ __device__ void phase_classify(const InsertArgs<T>& a, const GridParams& gp, dou
 }
 
 // ---- phase 2 ----------------------------------------------------------------------------------
-// Every row whose objective equals its cell's maximum competes for the cell: the lowest row wins
-// (first in batch wins ties, _grid_archive.py:693-696). A row holding the maximum of its cell is
+// Every row whose objective equals its cell's maximum competes for the cell with its row number: the lowest
+// row wins (first in batch wins ties, _grid_archive.py:693-696). A row holding the maximum of its cell is
 // insertable by construction (insertability depends on (objective, cell) only), and cells without
 // insertable rows keep best == 0, which is no finite objective's key -- so `status` is not read.
+// List mode runs it for every cell; cell mode (only_flagged) only for the cells whose `pick` the update
+// phase found not to hold the maximum and re-armed to pc.amb.
 template <typename T>
-__device__ void phase_mark_winner(const InsertArgs<T>& a) {
+__device__ void phase_mark_winner(const InsertArgs<T>& a, bool only_flagged) {
+  const PickConst pc = make_pick(a.B);
   const int64_t S = (int64_t)gridDim.x * blockDim.x;
   for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < a.B; base += kRows * S) {
     int32_t c[kRows];
     T o[kRows];
-    unsigned long long best[kRows];
+    ulonglong2 rec[kRows];
 #pragma unroll
     for (int u = 0; u < kRows; ++u) {
       const int64_t i = base + u * S;
@@ -377,10 +409,11 @@ __device__ void phase_mark_winner(const InsertArgs<T>& a) {
     }
 #pragma unroll
     for (int u = 0; u < kRows; ++u)
-      if (c[u] >= 0) best[u] = a.s.cell[c[u]].best;
+      if (c[u] >= 0) rec[u] = *reinterpret_cast<const ulonglong2*>(&a.s.cell[c[u]]);  // (best, pick)
 #pragma unroll
     for (int u = 0; u < kRows; ++u)
-      if (c[u] >= 0 && ord_key((double)o[u]) == best[u]) atomicMin(&a.s.cell[c[u]].win, (int32_t)(base + u * S));
+      if (c[u] >= 0 && ord_key((double)o[u]) == rec[u].x && (!only_flagged || rec[u].y >= pc.amb))
+        atomicMax(&a.s.cell[c[u]].pick, pc.amb | (pc.rowmask - (unsigned long long)(base + u * S)));
   }
 }
 
@@ -390,10 +423,9 @@ __device__ void phase_cleanup(const InsertArgs<T>& a) {  // validation failed: l
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x) {
     if (a.status[i] == 0) continue;
     Cell* cell = &a.s.cell[a.idx[i]];
-    cell->best = 0ull;
+    cell->best = cell->pick = 0ull;
     cell->w0 = cell->w1 = 0ll;
-    cell->cnt = 0u;
-    cell->win = INT32_MAX;
+    a.s.cnt[a.idx[i]] = 0u;
   }
 }
 
@@ -401,15 +433,16 @@ __device__ void phase_cleanup(const InsertArgs<T>& a) {  // validation failed: l
 // kThreads rows
 template <typename T>
 __device__ void phase_select(const InsertArgs<T>& a, uint32_t* s_cnt, uint32_t* s_base) {
+  const PickConst pc = make_pick(a.B);
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   constexpr int NW = kThreads / 32;
   for (int64_t b0 = (int64_t)blockIdx.x * kThreads; b0 < a.B; b0 += (int64_t)gridDim.x * kThreads) {
     const int64_t i = b0 + threadIdx.x;
     int32_t c = 0;
     bool iswin = false;
-    if (i < a.B) {  // `win` stays INT32_MAX for cells without an insertable row: no need to read status
+    if (i < a.B) {  // `pick` stays 0 for cells without an insertable row: no need to read status
       c = a.idx[i];
-      iswin = a.s.cell[c].win == (int32_t)i;
+      iswin = a.s.cell[c].pick == (pc.amb | (pc.rowmask - (unsigned long long)i));
     }
     const unsigned m = __ballot_sync(0xffffffffu, iswin);
     if (lane == 0) s_cnt[wi] = __popc(m);
@@ -440,8 +473,10 @@ struct UpdateAcc {
   unsigned long long kbest = 0ull;
 };
 
-template <typename T>
-__device__ __forceinline__ void update_cell(const InsertArgs<T>& a, int32_t c, T o, const Cell& cell, bool mae,
+// Returns true when the cell was unoccupied (ATOMIC_MASK = false: the caller owns the cell's bitmap word and
+// sets the bit itself).
+template <typename T, bool ATOMIC_MASK>
+__device__ __forceinline__ bool update_cell(const InsertArgs<T>& a, int32_t c, T o, const Cell& cell, bool mae,
                                             const FxConst& fx, const BinConst& bc, UpdateAcc<T>& acc) {
   const T tc = a.store_thr[c];
   const bool occ = (tc == tc);
@@ -452,7 +487,7 @@ __device__ __forceinline__ void update_cell(const InsertArgs<T>& a, int32_t c, T
   } else {       // _compute_thresholds, :473-516 (fp64 arithmetic after NumPy promotion)
     double S;
     uint32_t kc;
-    fx_read(cell, fx, S, kc);
+    fx_read(cell, &a.s.cnt[c], fx, S, kc);
     S = (double)(T)S;
     const double k = (double)kc;
     const double tcell = (double)(occ ? tc : a.tmin);
@@ -463,7 +498,7 @@ __device__ __forceinline__ void update_cell(const InsertArgs<T>& a, int32_t c, T
   a.store_obj[c] = o;
   if (!occ) {
     a.occupied[c] = 1;
-    atomicOr(&a.s.newmask[c >> 5], 1u << (c & 31));
+    if (ATOMIC_MASK) atomicOr(&a.s.newmask[c >> 5], 1u << (c & 31));
     ++acc.nnew;
   }
   double h0, h1, h2;
@@ -474,11 +509,11 @@ __device__ __forceinline__ void update_cell(const InsertArgs<T>& a, int32_t c, T
   const unsigned long long k2 = ord_key((double)o);
   acc.kbest = k2 > acc.kbest ? k2 : acc.kbest;
   Cell z;  // scratch back to its clean state
-  z.best = 0ull;
+  z.best = z.pick = 0ull;
   z.w0 = z.w1 = 0ll;
-  z.win = INT32_MAX;
-  z.cnt = 0u;
   a.s.cell[c] = z;
+  if (mae && !fx.b) a.s.cnt[c] = 0u;
+  return !occ;
 }
 
 // warp -> block -> global accumulation (bins add exactly, so the grouping does not matter)
@@ -536,7 +571,7 @@ __device__ void phase_update_list(const InsertArgs<T>& a, double (*sh_d)[kThread
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < W; t += (int64_t)gridDim.x * blockDim.x) {
     const int2 rc = a.s.wlist[t];
     const Cell cell = a.s.cell[rc.y];
-    update_cell<T>(a, rc.y, a.obj[rc.x], cell, mae, fx, bc, acc);
+    update_cell<T, true>(a, rc.y, a.obj[rc.x], cell, mae, fx, bc, acc);
   }
   update_reduce<T>(a, acc, sh_d, sh_n, sh_k);
 }
@@ -575,46 +610,59 @@ __device__ __forceinline__ void copy_row_inline(const FieldCopy& fc, int row, in
 }
 
 // cell mode: one thread per CELL, everything coalesced. The winner's objective is decoded from the cell's
-// key, its row comes from `win`; the (row, cell) list it emits is sorted by cell within each CTA tile, so
-// the row copy writes the store in nearly ascending address order.
+// key, its row comes from `pick`; a warp appends its (row, cell) pairs to the list with one atomic, in cell
+// order, so the row copy writes the store in runs of ascending addresses.
+// second_pass = false: every cell the batch touched. A cell whose pick does not hold the maximum (two rows of the
+// cell with keys equal above bit rb, see Cell) is left for the mark pass: pick := pc.amb, counted in n_ambiguous.
+// second_pass = true: exactly those cells, after the mark pass.
 template <typename T>
-__device__ void phase_update_cells(const InsertArgs<T>& a, const FieldCopy& fc, bool inline_copy,
-                                   double (*sh_d)[kThreads / 32], uint32_t* sh_n, unsigned long long* sh_k,
-                                   uint32_t* s_cnt, uint32_t* s_base) {
+__device__ void phase_update_cells(const InsertArgs<T>& a, const FieldCopy& fc, bool inline_copy, bool second_pass,
+                                   double (*sh_d)[kThreads / 32], uint32_t* sh_n, unsigned long long* sh_k) {
   const InsertState* g = a.s.g;
   const bool mae = a.mae;
   const double batch_absmax = __longlong_as_double((long long)g->absmax_bits);
   const BinConst bc = make_bins(batch_absmax + g->store_absmax, a.B);
+  const PickConst pc = make_pick(a.B);
+  // keys of float objectives have 29 zero bits at the bottom: the truncation drops nothing
+  const bool exact_pick = sizeof(T) == 4 && pc.rowmask < (1ull << 29);
   FxConst fx;
   if (mae) fx = make_fx(batch_absmax, a.B);
   UpdateAcc<T> acc;
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  constexpr int NW = kThreads / 32;
+  uint32_t namb = 0;
+  const int lane = threadIdx.x & 31;
   for (int64_t c0 = (int64_t)blockIdx.x * kThreads; c0 < a.N; c0 += (int64_t)gridDim.x * kThreads) {
-    const int64_t c = c0 + threadIdx.x;
+    const int64_t c = c0 + threadIdx.x;  // a warp covers 32 aligned cells = one word of the new-cell bitmap
     Cell cell;
-    cell.best = 0ull;
+    cell.best = cell.pick = 0ull;
     if (c < a.N) cell = a.s.cell[c];
-    const bool has = cell.best != 0ull;
-    if (has && inline_copy) copy_row_inline(fc, cell.win, (int)c);  // _array_store.py:605-608
-    if (has) update_cell<T>(a, (int32_t)c, (T)ord_unkey(cell.best), cell, mae, fx, bc, acc);
-    const unsigned m = __ballot_sync(0xffffffffu, has);
-    if (lane == 0) s_cnt[wi] = __popc(m);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t tot = 0;
-#pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        const uint32_t n = s_cnt[k];
-        s_cnt[k] = tot;
-        tot += n;
-      }
-      *s_base = tot ? atomicAdd(&a.s.g->n_winners, tot) : 0u;
+    bool has = cell.best != 0ull;
+    if (second_pass) has = has && cell.pick >= pc.amb;
+    const int32_t row = (int32_t)(pc.rowmask - (cell.pick & pc.rowmask));
+    if (has && !second_pass && !exact_pick && ord_key((double)a.obj[row]) != cell.best) {
+      a.s.cell[c].pick = pc.amb;  // nobody else writes the record in this phase
+      ++namb;
+      has = false;
     }
-    __syncthreads();
-    if (has) a.s.wlist[*s_base + s_cnt[wi] + __popc(m & ((1u << lane) - 1u))] = make_int2(cell.win, (int32_t)c);
-    __syncthreads();
+    if (has && inline_copy) copy_row_inline(fc, row, (int)c);  // _array_store.py:605-608
+    bool fresh = false;
+    if (has) fresh = update_cell<T, false>(a, (int32_t)c, (T)ord_unkey(cell.best), cell, mae, fx, bc, acc);
+    const unsigned mnew = __ballot_sync(0xffffffffu, fresh);
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    if (m) {
+      uint32_t base = 0;
+      if (lane == 0) {
+        base = atomicAdd(&a.s.g->n_winners, (uint32_t)__popc(m));
+        if (mnew) {
+          if (second_pass) atomicOr(&a.s.newmask[c >> 5], mnew);  // (the first pass may have set other bits)
+          else a.s.newmask[c >> 5] = mnew;
+        }
+      }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (has) a.s.wlist[base + __popc(m & ((1u << lane) - 1u))] = make_int2(row, (int32_t)c);
+    }
   }
+  namb = __reduce_add_sync(0xffffffffu, namb);
+  if (lane == 0 && namb) atomicAdd(&a.s.g->n_ambiguous, namb);
   update_reduce<T>(a, acc, sh_d, sh_n, sh_k);
 }
 
@@ -947,7 +995,7 @@ __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool 
     g.absmax_bits = 0ull;
     g.best_cell = INT32_MAX;
     g.best_pack = ~0ull;
-    g.n_insertable = g.n_new = g.flags = g.n_winners = 0u;
+    g.n_insertable = g.n_new = g.flags = g.n_winners = g.n_ambiguous = 0u;
     g.dsum[0] = g.dsum[1] = g.dsum[2] = 0.0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g.t_phase[8]));
     *gp = g;
@@ -957,7 +1005,10 @@ __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool 
 // ---- the kernel ------------------------------------------------------------------------------------
 // Phases [phase_lo, phase_hi] run inside one launch; a launch boundary stands in for the barrier
 // when add() is split in two (host batches: the row copy waits for the H2D of the solutions).
-template <typename T, typename MT, int D, bool FUSED>
+// SINGLE: the whole add() in ONE CTA, launched plainly -- small batches (the reference's own benchmark protocol
+// adds 100 rows at a time, benchmarks/cvt_add.py:79-86) are a chain of barrier latencies, and a block barrier
+// plus fence costs a tenth of a cooperative grid barrier (and the launch itself is cheaper).
+template <typename T, typename MT, int D, bool FUSED, bool SINGLE>
 __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_constant__ InsertArgs<T> a,
                                                            const __grid_constant__ GridParams gp,
                                                            const __grid_constant__ FieldCopy fc, int phase_lo,
@@ -966,7 +1017,15 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
   // 0-4, then best / count and publish with the best elite taken from the batch; the winner list stays in list
   // buffer `buf` (a.s.wlist points at it). mode 2 (QD_INSERT_COPY): only the row copy of that list, a plain
   // launch on another stream that overlaps the row phases of the next add().
-  cg::grid_group grid = cg::this_grid();
+  auto gsync = [&]() {
+    if constexpr (SINGLE) {
+      __threadfence();  // (MEMBAR + L1 invalidate: REDs of the other threads land in L2)
+      __syncthreads();
+      __threadfence();
+    } else {
+      cg::this_grid().sync();
+    }
+  };
   extern __shared__ __align__(128) unsigned char copy_slots[];
   __shared__ uint64_t copy_bar[kCopyWarps];
   uint32_t copy_parity = 0;
@@ -997,24 +1056,24 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
   if (phase_lo <= 0) stamp(0);
   if (phase_lo <= 0 && mae) {
     phase_absmax<T>(a, &sh_d[0][0]);
-    grid.sync();
+    gsync();
   }
   if (phase_lo <= 0) stamp(1);
+  // cell mode: the update runs over the cells (coalesced) and emits a cell-sorted winner list; list mode
+  // (archives much larger than the batch) never touches cells the batch did not
+  const bool cell_mode = a.N <= 16 * a.B;
   if (phase_lo <= 1 && phase_hi >= 1) {
-    phase_classify<T, MT, D, FUSED>(a, gp, &sh_d[0][0], sh_u);
-    grid.sync();
+    phase_classify<T, MT, D, FUSED>(a, gp, cell_mode, &sh_d[0][0], sh_u);
+    gsync();
   }
   if (phase_lo <= 1) stamp(2);
   // the globals below were last written before a barrier / launch boundary: uniform over the grid
   const bool failed = g->flags != 0u;
   const bool any = g->n_insertable != 0u;
   const bool committed = any && !failed;
-  // cell mode: the update runs over the cells (coalesced) and emits a cell-sorted winner list; list mode
-  // (archives much larger than the batch) never touches cells the batch did not
-  const bool cell_mode = a.N <= 16 * a.B;
-  if (phase_lo <= 2 && phase_hi >= 2 && committed) {
-    phase_mark_winner<T>(a);
-    grid.sync();
+  if (phase_lo <= 2 && phase_hi >= 2 && committed && !cell_mode) {
+    phase_mark_winner<T>(a, false);
+    gsync();
   }
   if (phase_lo <= 2) stamp(3);
   if (phase_lo <= 3 && phase_hi >= 3 && any && (failed || !cell_mode)) {
@@ -1022,32 +1081,38 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
       phase_cleanup<T>(a);
     else
       phase_select<T>(a, sh_u, &sh_base);
-    grid.sync();
+    gsync();
   }
   if (phase_lo <= 3) stamp(4);
   // one launch, cell mode, short rows: the update phase copies the winners' rows itself
   const bool inline_copy = mode == 0 && phase_lo <= 4 && phase_hi >= 5 && cell_mode && inline_copy_ok(fc);
   if (phase_lo <= 4 && phase_hi >= 4 && committed) {
     if (cell_mode) {
-      phase_update_cells<T>(a, fc, inline_copy, sh_d, sh_u + 32, sh_k, sh_u, &sh_base);
-      if (phase_hi >= 5 && mode == 0 && !inline_copy) grid.sync();  // the winner list is complete only now
+      phase_update_cells<T>(a, fc, inline_copy, false, sh_d, sh_u + 32, sh_k);
+      gsync();
+      if (g->n_ambiguous != 0u) {  // near-ties below bit rb inside a cell: the exact row pass, for those cells only
+        phase_mark_winner<T>(a, true);
+        gsync();
+        phase_update_cells<T>(a, fc, inline_copy, true, sh_d, sh_u + 32, sh_k);
+        gsync();
+      }
     } else {
       phase_update_list<T>(a, sh_d, sh_u + 32, sh_k);
+      gsync();
     }
   }
   if (phase_lo <= 4) stamp(5);
-  if (mode == 0 && phase_lo <= 5 && phase_hi >= 5 && committed && fc.n > 0 && !inline_copy)
-    phase_copy(fc, a.s, g->n_winners, copy_slots, copy_bar, copy_parity);
-  if (phase_hi < 6 && mode == 0) return;
-  if (phase_lo <= 5 || mode == 1) grid.sync();
-  stamp(6);
+  if (phase_hi < 5 && mode == 0) return;
+  // winner list, best key and new-cell bitmap are complete (barrier above / launch boundary)
   const unsigned long long gk = g->gbest_key, pk = g->obj_max_key;
   const bool new_record = committed && gk != 0ull && (pk == 0ull || gk > pk);
   const bool any_new = committed && g->n_new != 0u;
-  if (new_record || any_new) {
-    phase_best_and_count<T>(a, new_record, any_new, sh_u);
-    grid.sync();
-  }
+  if (new_record || any_new) phase_best_and_count<T>(a, new_record, any_new, sh_u);
+  if (mode == 0 && committed && fc.n > 0 && !inline_copy)
+    phase_copy(fc, a.s, g->n_winners, copy_slots, copy_bar, copy_parity);
+  stamp(6);
+  if (phase_hi < 6 && mode == 0) return;
+  gsync();
   stamp(7);
   phase_publish<T>(a, fc, committed, new_record, any_new, n_before, sh_u, &sh_base, mode == 1, mode == 1 ? buf : -1);
 }
@@ -1066,16 +1131,21 @@ struct GridSpec {  // non-null measures => fused grid index
   GridParams gp;
 };
 
+constexpr int64_t kSingleMaxRows = 2048;      // one CTA handles the whole batch up to here ...
+constexpr int64_t kSingleMaxCells = 1 << 18;  // ... in archives whose cell passes one CTA walks in a few microseconds
+
 template <typename T, typename MT, int D, bool FUSED>
 static int launch_insert(InsertArgs<T> a, const GridParams& gp, const FieldCopy& fc, int64_t work, int part,
                          cudaStream_t stream) {
   static int max_ctas = 0, sm_count = kNumSMs;  // per instantiation
   if (max_ctas == 0) {
     int per_sm = 0, dev = 0, sms = kNumSMs;
-    QD_CHECK_CUDA(cudaFuncSetAttribute(insert_kernel<T, MT, D, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kCopySmem));
-    QD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel<T, MT, D, FUSED>, kThreads,
-                                                                kCopySmem));
+    QD_CHECK_CUDA(cudaFuncSetAttribute(insert_kernel<T, MT, D, FUSED, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kCopySmem));
+    QD_CHECK_CUDA(cudaFuncSetAttribute(insert_kernel<T, MT, D, FUSED, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kCopySmem));
+    QD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel<T, MT, D, FUSED, false>,
+                                                                kThreads, kCopySmem));
     QD_CHECK_CUDA(cudaGetDevice(&dev));
     QD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (per_sm < 1) {
@@ -1098,12 +1168,16 @@ static int launch_insert(InsertArgs<T> a, const GridParams& gp, const FieldCopy&
   int mode = kind == QD_INSERT_ROWS ? 1 : kind == QD_INSERT_COPY ? 2 : 0;
   int bufi = buf;
   if (mode == 2) {  // no grid barrier inside: a plain launch, free to run next to the following add()'s row phases
-    insert_kernel<T, MT, D, FUSED><<<grid, kThreads, kCopySmem, stream>>>(a, gp, fc, 5, 5, mode, bufi);
+    insert_kernel<T, MT, D, FUSED, false><<<grid, kThreads, kCopySmem, stream>>>(a, gp, fc, 5, 5, mode, bufi);
     return check_launch("insert_kernel(copy)");
   }
+  if (mode == 0 && a.B <= kSingleMaxRows && a.N <= kSingleMaxCells && fc.peer_tab == nullptr) {
+    insert_kernel<T, MT, D, FUSED, true><<<1, kThreads, kCopySmem, stream>>>(a, gp, fc, lo, hi, mode, bufi);
+    return check_launch("insert_kernel(single)");
+  }
   void* params[] = {(void*)&a, (void*)&gp, (void*)&fc, (void*)&lo, (void*)&hi, (void*)&mode, (void*)&bufi};
-  QD_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)insert_kernel<T, MT, D, FUSED>, dim3(grid), dim3(kThreads),
-                                            params, mode == 1 ? 0 : kCopySmem, stream));
+  QD_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)insert_kernel<T, MT, D, FUSED, false>, dim3(grid),
+                                            dim3(kThreads), params, mode == 1 ? 0 : kCopySmem, stream));
   return check_launch("insert_kernel");
 }
 

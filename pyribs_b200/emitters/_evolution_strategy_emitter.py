@@ -1,5 +1,13 @@
 """EvolutionStrategyEmitter (reference ribs/emitters/_evolution_strategy_emitter.py:20-265,
-bounds handling ribs/emitters/_emitter_base.py:47-123)."""
+bounds handling ribs/emitters/_emitter_base.py:47-123).
+
+STAND-IN, not a built component. The restart / ranking policy of this emitter is host logic with exactly one
+legal behaviour, so this file is necessarily a restatement of the reference's; nothing here is on the GPU. It
+exists so that examples, tests and benchmarks run on boxes where `ribs` is not installed. Where `ribs` IS
+installed, the reference's own emitter drives the device strategies of this repo directly -- pass
+`es=pyribs_b200.emitters.opt.<class>` (a callable, ribs/emitters/opt/__init__.py:149-155) to
+`ribs.emitters.EvolutionStrategyEmitter`; tests/test_gpu_ref_scheduler.py::test_reference_emitter_over_device_es
+does exactly that. The product of this package is the strategies (emitters/opt, csrc/es*.cu) and the archives."""
 from __future__ import annotations
 
 import numbers

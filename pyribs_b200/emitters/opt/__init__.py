@@ -33,5 +33,16 @@ def _get_es(klass, **es_kwargs):
     raise ValueError(f"`{klass}` is neither a callable nor a string")
 
 
+def register_with_reference():
+    """Declares the device strategies virtual subclasses of the reference's abstract `EvolutionStrategyBase`
+    (ribs/emitters/opt/_evolution_strategy_base.py:25), so that `ribs.emitters.EvolutionStrategyEmitter(...,
+    es=pyribs_b200.emitters.opt.SeparableCMAEvolutionStrategy)` passes the isinstance check of the reference's
+    registry (ribs/emitters/opt/__init__.py:149-155). This is the binding a maintainer adds; it
+    needs `ribs` importable and is never called by this package itself."""
+    from ribs.emitters.opt import EvolutionStrategyBase
+
+    EvolutionStrategyBase.register(DeviceES)
+
+
 __all__ = ["CMAEvolutionStrategy", "DeviceES", "LMMAEvolutionStrategy", "OpenAIEvolutionStrategy",
-           "SeparableCMAEvolutionStrategy", "_get_es"]
+           "SeparableCMAEvolutionStrategy", "_get_es", "register_with_reference"]

@@ -4,6 +4,11 @@ Call contract and selection rule of ribs/schedulers/_bandit_scheduler.py:82-427 
 selection in `ask` :233-318, credit assignment in `tell` :415-427). The policy is host arithmetic over a handful
 of emitters; the batches themselves go through the same device insertion as `Scheduler` (one index_of shared with
 `result_archive` when the geometries match).
+
+STAND-IN, not a built component: the reference's `ribs.schedulers.BanditScheduler` works unchanged on top of
+these archives and emitters (tests/test_gpu_ref_scheduler.py::test_reference_bandit_scheduler_drives_these_classes
+runs it and compares trajectories with this file's). This restatement of its host policy exists only for boxes
+where `ribs` is not installed.
 """
 from __future__ import annotations
 

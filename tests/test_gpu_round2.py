@@ -273,3 +273,41 @@ def test_emitter_and_scheduler_pickle():
     for _ in range(3):
         np.testing.assert_array_equal(it(s), it(twin))
     assert s.archive.stats.qd_score == twin.archive.stats.qd_score
+
+
+# ---- near-ties: the winner of a cell is the first row holding the EXACT maximum -----------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("B", [64, 3000, 300_000])
+def test_near_tie_objectives_resolve_exactly(B, dtype):
+    """The insert kernel picks a cell's winner through a key truncated to make room for the row number
+    (csrc/insert.cu `pick`); rows of one cell whose objectives differ only in the bits below the truncation, and
+    exact ties, must still resolve like the reference (highest objective, first in batch: _grid_archive.py:689-696).
+    B = 64 is list mode (cells >> rows), the others cell mode with 6 / 12 / 19 row bits."""
+    from pyribs_b200.archives import GridArchive
+
+    rng = np.random.default_rng(B)
+    kw = dict(solution_dim=2, dims=(30, 30), ranges=[(-1, 1)] * 2, dtype=dtype)
+    for mae in (False, True):
+        kw2 = dict(kw, learning_rate=0.1, threshold_min=-1.0) if mae else kw
+        gpu, ora = GridArchive(**kw2), O.make_grid_oracle(**kw2)
+        meas = rng.uniform(-1, 1, (B, 2))
+        base = rng.choice([1.0, 2.5, -3.0, 1e-3, 7e5], B)
+        ulps = rng.integers(0, 4, B)  # 0..3 ulps above the base value: ties and near-ties galore
+        obj = base.astype(dtype)
+        for _ in range(3):
+            obj = np.where(ulps > 0, np.nextafter(obj, dtype(np.inf)), obj)
+            ulps = ulps - 1
+        b = dict(solution=rng.standard_normal((B, 2)).astype(dtype), objective=obj.astype(dtype),
+                 measures=meas.astype(dtype))
+        for step in range(2):
+            g, o = gpu.add(**b), ora.add(**b)
+            np.testing.assert_array_equal(g["status"], o["status"])
+            assert_close(g["value"], o["value"], RTOL, "value")
+            occ = ora.store.occupied
+            np.testing.assert_array_equal(gpu._store._fields["objective"].cpu().numpy()[occ],
+                                          ora.store.fields["objective"][occ])
+            # the solution row identifies WHICH of the tied rows won
+            np.testing.assert_array_equal(gpu._store._fields["solution"].cpu().numpy()[occ],
+                                          ora.store.fields["solution"][occ])
+            np.testing.assert_array_equal(gpu._store.occupied_list, ora.store.occupied_list[: len(ora)])
+            b = dict(b, objective=np.nextafter(b["objective"], dtype(np.inf)))  # everything improves by one ulp

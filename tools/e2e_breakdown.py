@@ -7,7 +7,7 @@ from pyribs_b200 import _lib
 from pyribs_b200.archives import CVTArchive, GridArchive
 from pyribs_b200.archives._device_store import current_stream_ptr
 
-PH = ["absmax", "classify", "resolve", "select", "update", "copy", "best/count", "publish"]
+PH = ["absmax", "classify", "mark(list mode)", "select(list mode)", "update(+resolve)", "best/count+copy", "barrier", "publish"]
 
 def phase_times(a):
     out = (C.c_uint64 * 10)()
