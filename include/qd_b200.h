@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 4
+#define QD_ABI_VERSION 5
 
 #define QD_OK 0
 #define QD_ERR_INVALID_ARG (-1)
@@ -173,6 +173,10 @@ typedef struct qd_store {
 
 size_t qd_insert_scratch_bytes(int64_t capacity);
 int qd_insert_scratch_init(void* scratch /*[dev]*/, int64_t capacity, void* stream);
+/* Every insertion on this store also writes its qd_add_result to `host_mirror` (page-locked host memory, or NULL
+ * to stop): the host reads it after its stream synchronize without a device->host copy call. The reference
+ * returns add_info synchronously (_grid_archive.py:606-714); this is the cheapest way to learn what it needs. */
+int qd_insert_set_result_mirror(void* scratch /*[dev]*/, int64_t capacity, qd_add_result* host_mirror, void* stream);
 /* Device address of the validation flag word inside `scratch`. Pass it as `flags` to the
  * index kernels of the same add() so that a non-finite measure aborts the commit on the
  * device (the store stays untouched, the host raises ValueError after reading

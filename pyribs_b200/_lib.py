@@ -94,6 +94,7 @@ PROTOTYPES = {
     "qd_cvt_mask_losers": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "qd_insert_scratch_bytes": (_sz, [_i64]),
     "qd_insert_scratch_init": (_int, [_vp, _i64, _vp]),
+    "qd_insert_set_result_mirror": (_int, [_vp, _i64, _vp, _vp]),
     "qd_insert_flags_ptr": (_vp, [_vp, _i64]),
     "qd_flags_or": (_int, [_vp, _int, _vp, _vp]),
     "qd_insert_phase_times": (_int, [_vp, _i64, C.POINTER(_u64), _vp]),

@@ -88,6 +88,12 @@ _PROBE = [np.empty(1)]
 _IDLE_REFS = sys.getrefcount(_PROBE[0])
 
 
+# host batches up to these sizes are staged in one page-locked block that the kernels read in place (_add_small);
+# below csrc/insert.cu's kSingleMaxRows / kSingleMaxWork one CTA then inserts the whole batch
+_SMALL_ROWS = 16384
+_SMALL_BYTES = 4 << 20
+
+
 def _pool_entry_free(entry):
     """True when nothing but the pool refers to the master arrays entry[2], entry[3]. Every view handed to
     a caller (and every view of such a view) has the master as its `.base`, so a larger count means a result
@@ -157,6 +163,8 @@ class DeviceArchive:
         self._needs_flag_check = False
         self._dp_symm = None  # {batch signature: symmetric-memory exchange state}; False = unavailable
         self._zero_copy_rows = True   # read winners' rows straight from page-locked host arrays when that saves PCIe traffic
+        self._small_adds = True       # host batches of <= _SMALL_ROWS rows take the two-launch path (_add_small)
+        self._small = {}              # its per-batch-size plans
         self._last_zero_copy = False
         self._zero_copy_bytes = 0
         self._zc = None
@@ -191,7 +199,7 @@ class DeviceArchive:
     # state that cannot (streams, events, ctypes arrays, page-locked pools, process groups) or need not (device
     # search structures, scratch) travel through pickle; rebuilt by __setstate__ / on first use
     _TRANSIENT = {"_pinned": dict, "_outbuf": dict, "_copy_stream": None, "_copy_event": None, "_inflight": None,
-                  "_dp_symm": None, "_zc": None, "_shared_idx": None, "_last_idx": None, "_pin_cache": dict,
+                  "_dp_symm": None, "_zc": None, "_shared_idx": None, "_last_idx": None, "_pin_cache": dict, "_small": dict,
                   "_pipe": None, "_pipe_pending": None, "_dp_group": None}
 
     def __getstate__(self):
@@ -425,7 +433,7 @@ class DeviceArchive:
         stage.copy_(src)
         return stage.to(self._device, non_blocking=True)
 
-    def _index_of_device(self, measures: torch.Tensor, flags_ptr: int) -> torch.Tensor:
+    def _index_of_device(self, measures: torch.Tensor, flags_ptr: int, out=None) -> torch.Tensor:
         raise NotImplementedError
 
     def same_geometry(self, other):
@@ -630,6 +638,10 @@ class DeviceArchive:
                         "value": torch.empty(0, dtype=torch_dtype(odt), device=self._device)}
             return {"status": np.empty(0, dtype=np.int32), "value": np.empty(0, dtype=odt)}
         store = self._store
+        if (not dev_in and B <= _SMALL_ROWS and B * self._row_bytes_total <= _SMALL_BYTES and self._dp_world == 1
+                and self._small_adds and self._small_index_ok(B)
+                and torch.cuda.current_device() == self._device.index):
+            return self._add_small(data, B, preset)
         if (not dev_in and self._dp_world == 1 and self.cells * 2 <= B and self._zero_copy_rows
                 and (preset is not None or self._host_measures_ok())
                 and torch.cuda.current_device() == self._device.index):
@@ -774,6 +786,87 @@ class DeviceArchive:
         if pooled is not None:  # views of a pooled page-locked buffer (see _out_buffers)
             return {"status": pooled[2][lo:hi], "value": pooled[3][lo:hi]}
         return {"status": status_h.numpy()[lo:hi].copy(), "value": value_h.numpy()[lo:hi].copy()}
+
+    # ---- add() of small host batches ---------------------------------------------------------------------
+    def _small_index_ok(self, B):
+        """True when the index kernel of a B-row add may read the measures straight from page-locked host memory."""
+        return True
+
+    def _small_plan(self, B):
+        """Everything a B-row host add() needs, built once per batch size: a page-locked block the NumPy inputs
+        are copied into and the kernels read (and write status / value) directly, and the ABI argument arrays."""
+        plan = self._small.get(B)
+        if plan is not None:
+            return plan
+        if len(self._small) > 16:
+            self._small.clear()
+        store = self._store
+        names = ["measures", "objective"] + [n for n in store.row_fields if n != "measures"]
+        odt = np.dtype(self.dtypes["objective"])
+        spec = [(n, store._np_dtypes[n], tuple(store._fields[n].shape[1:])) for n in names]
+        spec += [("status", np.dtype(np.int32), ()), ("value", odt, ())]
+        offs, total = [], 0
+        for _, dt, shp in spec:
+            offs.append(total)
+            total += (int(np.prod((B, *shp))) * dt.itemsize + 255) // 256 * 256
+        block = torch.zeros(total, dtype=torch.uint8).pin_memory()
+        host = block.numpy()
+        views, ptrs = {}, {}
+        for (n, dt, shp), off in zip(spec, offs):
+            views[n] = host[off:off + int(np.prod((B, *shp))) * dt.itemsize].view(dt).reshape((B, *shp))
+            ptrs[n] = block.data_ptr() + off
+        rows = store.row_fields
+        plan = self._small[B] = {
+            "block": block, "views": views, "ptrs": ptrs, "inputs": names,
+            "src": (C.c_void_p * max(len(rows), 1))(*[ptrs[n] for n in rows]),
+            "meas": self._HostRows(ptrs["measures"], (B, self.measure_dim)),
+            "obj": self._HostRows(ptrs["objective"], (B,)),
+            "status": self._HostRows(ptrs["status"], (B,)), "value": self._HostRows(ptrs["value"], (B,)),
+            "idx": torch.empty(B, dtype=torch.int32, device=self._device),
+        }
+        return plan
+
+    def _add_small(self, data, B, preset=None):
+        """Host batches of up to a few thousand rows (the reference's own benchmark adds 100 rows at a time,
+        benchmarks/cvt_add.py:79-86): the cost of such an add() is launch and copy-call latency, not work. The
+        inputs are copied into one page-locked block (host memcpy), the index kernel and the single-CTA insert
+        kernel read them there and write status / value / qd_add_result back into page-locked memory themselves:
+        two launches and one stream synchronize, no copy calls."""
+        store = self._store
+        plan = self._small_plan(B)
+        views = plan["views"]
+        for n in plan["inputs"]:
+            np.copyto(views[n], data[n], casting="unsafe")
+        self._join_copy()
+        self._last_zero_copy = False
+        L = _lib.lib()
+        sp = current_stream_ptr()
+        fused = self._fused_index_insert and preset is None
+        if fused:
+            self._grid_insert({"measures": plan["meas"], "objective": plan["obj"]}, B, plan["src"], plan["status"],
+                              plan["value"], _lib.INSERT_WHOLE)
+            idx = None
+        else:
+            idx = preset[0] if preset is not None else self._index_of_device(plan["meas"], store._flags_ptr,
+                                                                            out=plan["idx"])
+            _lib.check(L.qd_insert(C.byref(store.abi_store()), B, idx.data_ptr(), plan["ptrs"]["objective"], plan["src"],
+                                   self._lr_f, self._tmin_f, plan["ptrs"]["status"], plan["ptrs"]["value"],
+                                   store._result_dev.data_ptr(), _lib.INSERT_WHOLE, sp))
+        store._pending = True
+        _lib.check(L.qd_stream_synchronize(sp))
+        res = store._result_live
+        flags = store.consume(res) | res.flags
+        if flags & _lib.FLAG_CVT_OVERFLOW and not flags & (_lib.FLAG_NONFINITE_OBJECTIVE | _lib.FLAG_NONFINITE_MEASURES):
+            self._overflow_fallbacks += 1
+            self._force_scan = True
+            try:
+                return self._add_small(data, B, preset)
+            finally:
+                self._force_scan = False
+        self._raise_for_flags(flags)
+        self._apply_state(res)
+        self._last_idx = (idx if idx is not None else self._idx_buf[:B], B)
+        return {"status": views["status"].copy(), "value": views["value"].copy()}
 
     # ---- add() of page-locked host batches: zero-copy plan ----------------------------------------------
     class _HostRows:

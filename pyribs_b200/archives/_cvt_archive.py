@@ -222,10 +222,14 @@ class CVTArchive(DeviceArchive):
         return 0 if B * C >= (1 << 26) else 1
 
     # ---- A3 ---------------------------------------------------------------------------------
-    def _local_search(self, measures, flags_ptr, want_dist):
+    def _small_index_ok(self, B):
+        # (the tensor-core search stages the queries with TMA: device memory only)
+        return self._world == 1 and self._pick_method(B, self._shard_hi - self._shard_lo) != 0
+
+    def _local_search(self, measures, flags_ptr, want_dist, out=None):
         B = int(measures.shape[0])
         Cn = self._shard_hi - self._shard_lo
-        idx = torch.empty(B, dtype=torch.int32, device=self._device)
+        idx = out if out is not None else torch.empty(B, dtype=torch.int32, device=self._device)
         dist = torch.empty(B, dtype=torch.float64, device=self._device) if want_dist else None
         if Cn == 0:
             idx.fill_(2**31 - 1)
@@ -252,9 +256,9 @@ class CVTArchive(DeviceArchive):
             self._cvt_scratch.numel(), current_stream_ptr()))
         return idx, dist
 
-    def _index_of_device(self, measures: torch.Tensor, flags_ptr: int) -> torch.Tensor:
+    def _index_of_device(self, measures: torch.Tensor, flags_ptr: int, out=None) -> torch.Tensor:
         if self._world == 1:
-            return self._local_search(measures, flags_ptr, False)[0]
+            return self._local_search(measures, flags_ptr, False, out)[0]
         idx, d_local = self._local_search(measures, flags_ptr, True)
 
         def mask(d_loc, d_min, ix):

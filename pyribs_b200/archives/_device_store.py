@@ -91,6 +91,11 @@ class DeviceStore:
             self._flags_ptr = _lib.lib().qd_insert_flags_ptr(self._scratch.data_ptr(), capacity)
             self._result_dev = torch.zeros(C.sizeof(_lib.AddResult), dtype=torch.uint8, device=self._device)
             self._result_host = torch.zeros(C.sizeof(_lib.AddResult), dtype=torch.uint8).pin_memory()
+            # every insertion also writes its result block into this page-locked buffer (read after a stream
+            # synchronize, no device->host copy call); `_result_live` is a live view of it
+            _lib.check(_lib.lib().qd_insert_set_result_mirror(self._scratch.data_ptr(), capacity,
+                                                              self._result_host.data_ptr(), current_stream_ptr()))
+            self._result_live = _lib.AddResult.from_address(self._result_host.data_ptr())
             self._abi = None
             self._snapshot = None
             nsnap = int(_lib.lib().qd_best_snapshot_bytes(C.byref(self.abi_store())))

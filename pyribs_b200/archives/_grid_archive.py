@@ -86,9 +86,9 @@ class GridArchive(DeviceArchive):
         return self._epsilon
 
     # ---- A2 ---------------------------------------------------------------------------------
-    def _index_of_device(self, measures: torch.Tensor, flags_ptr: int) -> torch.Tensor:
+    def _index_of_device(self, measures: torch.Tensor, flags_ptr: int, out=None) -> torch.Tensor:
         B = int(measures.shape[0])
-        idx = torch.empty(B, dtype=torch.int32, device=self._device)
+        idx = out if out is not None else torch.empty(B, dtype=torch.int32, device=self._device)
         _lib.check(_lib.lib().qd_grid_index_of(
             measures.data_ptr(), self._meas_code, B, len(self._dims), self._c_dims, self._c_lower, self._c_interval,
             float(self._epsilon), idx.data_ptr(), flags_ptr, current_stream_ptr()))
@@ -132,12 +132,25 @@ class GridArchive(DeviceArchive):
         cur = self.data()
         del cur["index"]
         del cur["threshold"]
+        best, (_, osum, omax, _) = self.best_elite, self._st
         self._dims = np.array(new_dims, dtype=np.int32)
         self._boundaries = self._compute_boundaries(self._dims, self._lower_bounds, self._upper_bounds)
-        self._attach_store(DeviceStore(self._store.field_desc, capacity=int(np.prod(self._dims)), device=self._device))
+        store = DeviceStore(self._store.field_desc, capacity=int(np.prod(self._dims)), device=self._device)
+        self._attach_store(store)
         self._refresh_abi_consts()
         self._idx_buf = None
-        self._stats_reset()
+        # Like the reference, which swaps the store and re-adds WITHOUT resetting its statistics
+        # (_grid_archive.py:970-976): the running objective sum and the best objective carry over into the new
+        # store's device-side state, so qd_score counts the survivors on top of the old sum and best_elite stays
+        # the old record (old cell index included) until a strictly better solution arrives.
+        absmax = float(np.abs(cur["objective"]).max()) if len(cur["objective"]) else 0.0
+        store._owner_sync = None
+        store._push_state(osum, omax, absmax)
+        store._owner_sync = self._sync
+        self._apply_state(store._last)
+        self._best_elite, self._best_serial = best, self._st[3]
+        if self._stats_dirty:
+            self._build_stats()
         self.add(**cur)
 
     def _transient_extra(self):

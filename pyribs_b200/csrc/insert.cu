@@ -96,10 +96,14 @@ struct InsertState {
   uint32_t last_failed_flags;     // flags of the most recent such call
   uint32_t pad;
   unsigned long long t_phase[10]; // %globaltimer at the phase boundaries of the last call (diagnostics)
+  qd_add_result* result_mirror;   // page-locked host copy of every call's qd_add_result (qd_insert_set_result_mirror) or NULL
   // ---- per call, re-armed by publish ----
   unsigned long long best_pack;   // (cell << 32 | batch row) of the lowest winning cell holding the new maximum
   // ---- pipelined commit (QD_INSERT_ROWS / QD_INSERT_COPY): winners of the row phases, one count per list buffer
   uint32_t copy_w[2];
+  // ---- row copy: next undistributed piece of every bulk field, per list buffer (re-armed by the publish phase of
+  // the launch that fills that buffer)
+  unsigned long long copy_next[2][QD_MAX_FIELDS];
 };
 
 struct Scratch {
@@ -477,10 +481,10 @@ struct UpdateAcc {
 // sets the bit itself).
 template <typename T, bool ATOMIC_MASK>
 __device__ __forceinline__ bool update_cell(const InsertArgs<T>& a, int32_t c, T o, const Cell& cell, bool mae,
-                                            const FxConst& fx, const BinConst& bc, UpdateAcc<T>& acc) {
-  const T tc = a.store_thr[c];
+                                            const FxConst& fx, const BinConst& bc, UpdateAcc<T>& acc, T tc,
+                                            T stored_obj) {
   const bool occ = (tc == tc);
-  const T old_obj = occ ? a.store_obj[c] : (T)0;
+  const T old_obj = occ ? stored_obj : (T)0;
   T newthr;
   if (!mae) {
     newthr = o;  // :663-665
@@ -571,7 +575,7 @@ __device__ void phase_update_list(const InsertArgs<T>& a, double (*sh_d)[kThread
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < W; t += (int64_t)gridDim.x * blockDim.x) {
     const int2 rc = a.s.wlist[t];
     const Cell cell = a.s.cell[rc.y];
-    update_cell<T, true>(a, rc.y, a.obj[rc.x], cell, mae, fx, bc, acc);
+    update_cell<T, true>(a, rc.y, a.obj[rc.x], cell, mae, fx, bc, acc, a.store_thr[rc.y], a.store_obj[rc.y]);
   }
   update_reduce<T>(a, acc, sh_d, sh_n, sh_k);
 }
@@ -630,35 +634,65 @@ __device__ void phase_update_cells(const InsertArgs<T>& a, const FieldCopy& fc, 
   UpdateAcc<T> acc;
   uint32_t namb = 0;
   const int lane = threadIdx.x & 31;
-  for (int64_t c0 = (int64_t)blockIdx.x * kThreads; c0 < a.N; c0 += (int64_t)gridDim.x * kThreads) {
-    const int64_t c = c0 + threadIdx.x;  // a warp covers 32 aligned cells = one word of the new-cell bitmap
-    Cell cell;
-    cell.best = cell.pick = 0ull;
-    if (c < a.N) cell = a.s.cell[c];
-    bool has = cell.best != 0ull;
-    if (second_pass) has = has && cell.pick >= pc.amb;
-    const int32_t row = (int32_t)(pc.rowmask - (cell.pick & pc.rowmask));
-    if (has && !second_pass && !exact_pick && ord_key((double)a.obj[row]) != cell.best) {
-      a.s.cell[c].pick = pc.amb;  // nobody else writes the record in this phase
-      ++namb;
-      has = false;
-    }
-    if (has && inline_copy) copy_row_inline(fc, row, (int)c);  // _array_store.py:605-608
-    bool fresh = false;
-    if (has) fresh = update_cell<T, false>(a, (int32_t)c, (T)ord_unkey(cell.best), cell, mae, fx, bc, acc);
-    const unsigned mnew = __ballot_sync(0xffffffffu, fresh);
-    const unsigned m = __ballot_sync(0xffffffffu, has);
-    if (m) {
-      uint32_t base = 0;
-      if (lane == 0) {
-        base = atomicAdd(&a.s.g->n_winners, (uint32_t)__popc(m));
-        if (mnew) {
-          if (second_pass) atomicOr(&a.s.newmask[c >> 5], mnew);  // (the first pass may have set other bits)
-          else a.s.newmask[c >> 5] = mnew;
-        }
+  // two tiles per trip, every load of both issued before the first use: the phase is 1-2 trips per thread, i.e. a
+  // chain of L2 round trips (record -> pick's objective -> list slot), not bandwidth
+  constexpr int U = 2;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t c0 = (int64_t)blockIdx.x * kThreads; c0 < a.N; c0 += U * stride) {
+    Cell cell[U];
+    T tc[U], so[U], po[U];
+    int32_t row[U];
+    bool has[U], fresh[U];
+    unsigned m[U], mnew[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {  // a warp covers 32 aligned cells = one word of the new-cell bitmap
+      const int64_t c = c0 + u * stride + threadIdx.x;
+      cell[u].best = cell[u].pick = 0ull;
+      tc[u] = so[u] = (T)0;
+      if (c < a.N) {
+        cell[u] = a.s.cell[c];
+        tc[u] = a.store_thr[c];
+        so[u] = a.store_obj[c];
       }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      has[u] = cell[u].best != 0ull;
+      if (second_pass) has[u] = has[u] && cell[u].pick >= pc.amb;
+      row[u] = (int32_t)(pc.rowmask - (cell[u].pick & pc.rowmask));
+      po[u] = (has[u] && !second_pass && !exact_pick) ? a.obj[row[u]] : (T)0;
+    }
+    uint32_t nwin = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t c = c0 + u * stride + threadIdx.x;
+      if (has[u] && !second_pass && !exact_pick && ord_key((double)po[u]) != cell[u].best) {
+        a.s.cell[c].pick = pc.amb;  // nobody else writes the record in this phase
+        ++namb;
+        has[u] = false;
+      }
+      if (has[u] && inline_copy) copy_row_inline(fc, row[u], (int)c);  // _array_store.py:605-608
+      fresh[u] = false;
+      if (has[u])
+        fresh[u] = update_cell<T, false>(a, (int32_t)c, (T)ord_unkey(cell[u].best), cell[u], mae, fx, bc, acc, tc[u], so[u]);
+      mnew[u] = __ballot_sync(0xffffffffu, fresh[u]);
+      m[u] = __ballot_sync(0xffffffffu, has[u]);
+      nwin += __popc(m[u]);
+    }
+    if (nwin) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&a.s.g->n_winners, nwin);  // one list reservation per warp and trip
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (has) a.s.wlist[base + __popc(m & ((1u << lane) - 1u))] = make_int2(row, (int32_t)c);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t c = c0 + u * stride + threadIdx.x;
+        if (lane == 0 && mnew[u]) {
+          if (second_pass) atomicOr(&a.s.newmask[c >> 5], mnew[u]);  // (the first pass may have set other bits)
+          else a.s.newmask[c >> 5] = mnew[u];
+        }
+        if (has[u]) a.s.wlist[base + __popc(m[u] & ((1u << lane) - 1u))] = make_int2(row[u], (int32_t)c);
+        base += __popc(m[u]);
+      }
     }
   }
   namb = __reduce_add_sync(0xffffffffu, namb);
@@ -770,8 +804,8 @@ __device__ void copy_rows_small(const FieldCopy& fc, int f, const Scratch& s, in
   }
 }
 
-__device__ void phase_copy(const FieldCopy& fc, const Scratch& s, int64_t W, unsigned char* slots, uint64_t* mbar,
-                           uint32_t& parity) {
+__device__ void phase_copy(const FieldCopy& fc, const Scratch& s, int64_t W, int buf, unsigned char* slots,
+                           uint64_t* mbar, uint32_t& parity) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bool any_bulk = false;
   for (int f = 0; f < fc.n; ++f) any_bulk |= is_bulk_field(fc, f);
@@ -794,8 +828,13 @@ __device__ void phase_copy(const FieldCopy& fc, const Scratch& s, int64_t W, uns
     const int64_t total = W * ppr;
     unsigned char* slot = slots + warp * kSlotBytes + lane * piece;
     uint64_t* bar = &mbar[warp];
-    const int64_t gw = (int64_t)blockIdx.x * kCopyWarps + warp, ngw = (int64_t)gridDim.x * kCopyWarps;
-    for (int64_t it0 = gw * L; it0 < total; it0 += ngw * L) {
+    // Rounds are drawn from a counter, not dealt out: SMs do not copy at the same speed (the phase used to end
+    // 13 us after its first CTA was done), and the draw for the next round travels while this round's loads land.
+    unsigned long long* next = &s.g->copy_next[buf][f];
+    unsigned long long drawn = 0;
+    if (lane == 0) drawn = atomicAdd(next, (unsigned long long)L);
+    int64_t it0 = (int64_t)__shfl_sync(0xffffffffu, drawn, 0);
+    while (it0 < total) {
       const int64_t item = it0 + lane;
       const bool active = lane < L && item < total;
       uint32_t len = 0;
@@ -813,12 +852,13 @@ __device__ void phase_copy(const FieldCopy& fc, const Scratch& s, int64_t W, uns
       if (lane == 0) mbar_expect_tx(bar, round_bytes);
       __syncwarp();
       if (active) bulk_g2s(slot, sp, len, bar);
+      if (lane == 0) drawn = atomicAdd(next, (unsigned long long)L);
       mbar_wait(bar, parity);
       parity ^= 1u;
       if (active) bulk_s2g(dp, slot, len);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the slot may be refilled
-      __syncwarp();
+      it0 = (int64_t)__shfl_sync(0xffffffffu, drawn, 0);
     }
   }
   // bulk stores are complete (not just read) and ordered before the generic-proxy accesses that follow
@@ -878,7 +918,7 @@ __device__ void phase_best_and_count(const InsertArgs<T>& a, bool new_record, bo
 template <typename T>
 __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool committed, bool new_record,
                               bool any_new, int64_t n_before, uint32_t* sh, uint32_t* sh_base, bool from_source,
-                              int save_w) {
+                              int save_w, int rearm_buf) {
   InsertState* gp = a.s.g;
   const int lane = threadIdx.x & 31;
   if (any_new) {
@@ -990,12 +1030,14 @@ __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool 
     r.n_failed = g.n_failed;
     r.n_winners = committed ? g.n_winners : 0;
     *a.result = r;
+    if (g.result_mirror) *g.result_mirror = r;  // the host reads it after its stream synchronize: no D2H call
     if (save_w >= 0) g.copy_w[save_w] = committed ? g.n_winners : 0u;
     g.gbest_key = 0ull;
     g.absmax_bits = 0ull;
     g.best_cell = INT32_MAX;
     g.best_pack = ~0ull;
     g.n_insertable = g.n_new = g.flags = g.n_winners = g.n_ambiguous = 0u;
+    for (int f = 0; f < QD_MAX_FIELDS; ++f) g.copy_next[rearm_buf][f] = 0ull;
     g.dsum[0] = g.dsum[1] = g.dsum[2] = 0.0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g.t_phase[8]));
     *gp = g;
@@ -1005,11 +1047,15 @@ __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool 
 // ---- the kernel ------------------------------------------------------------------------------------
 // Phases [phase_lo, phase_hi] run inside one launch; a launch boundary stands in for the barrier
 // when add() is split in two (host batches: the row copy waits for the H2D of the solutions).
+constexpr int64_t kSingleMaxRows = 2048;      // one CTA handles the whole batch up to here ...
+constexpr int64_t kSingleMaxCells = 1 << 18;  // ... in archives whose cell passes one CTA walks in a few microseconds
+constexpr int64_t kSingleMaxWork = 1 << 15;   // ... and at most 512 KB of winner rows to move (16-byte units)
+
 // SINGLE: the whole add() in ONE CTA, launched plainly -- small batches (the reference's own benchmark protocol
 // adds 100 rows at a time, benchmarks/cvt_add.py:79-86) are a chain of barrier latencies, and a block barrier
 // plus fence costs a tenth of a cooperative grid barrier (and the launch itself is cheaper).
 template <typename T, typename MT, int D, bool FUSED, bool SINGLE>
-__global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_constant__ InsertArgs<T> a,
+__global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_constant__ InsertArgs<T> a_in,
                                                            const __grid_constant__ GridParams gp,
                                                            const __grid_constant__ FieldCopy fc, int phase_lo,
                                                            int phase_hi, int mode, int buf) {
@@ -1038,10 +1084,23 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
   __shared__ uint32_t sh_base;
   __shared__ double sh_d[3][kThreads / 32];
   __shared__ unsigned long long sh_k[kThreads / 32];
+  InsertArgs<T> a_staged;
+  const InsertArgs<T>* ap = &a_in;
+  if constexpr (SINGLE) {
+    // the objectives are read by up to four phases; a small batch handed over in page-locked host memory would pay
+    // a PCIe round trip in each: one coalesced read into shared memory instead
+    __shared__ T obj_stage[kSingleMaxRows];
+    for (int64_t i = threadIdx.x; i < a_in.B; i += kThreads) obj_stage[i] = a_in.obj[i];
+    a_staged = a_in;
+    a_staged.obj = obj_stage;
+    ap = &a_staged;
+    __syncthreads();
+  }
+  const InsertArgs<T>& a = *ap;
   const InsertState* g = a.s.g;
   if (mode == 2) {
     const int64_t W = g->copy_w[buf];
-    if (W > 0 && fc.n > 0) phase_copy(fc, a.s, W, copy_slots, copy_bar, copy_parity);
+    if (W > 0 && fc.n > 0) phase_copy(fc, a.s, W, buf, copy_slots, copy_bar, copy_parity);
     return;
   }
   const bool mae = a.mae;
@@ -1109,12 +1168,13 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
   const bool any_new = committed && g->n_new != 0u;
   if (new_record || any_new) phase_best_and_count<T>(a, new_record, any_new, sh_u);
   if (mode == 0 && committed && fc.n > 0 && !inline_copy)
-    phase_copy(fc, a.s, g->n_winners, copy_slots, copy_bar, copy_parity);
+    phase_copy(fc, a.s, g->n_winners, buf, copy_slots, copy_bar, copy_parity);
   stamp(6);
   if (phase_hi < 6 && mode == 0) return;
   gsync();
   stamp(7);
-  phase_publish<T>(a, fc, committed, new_record, any_new, n_before, sh_u, &sh_base, mode == 1, mode == 1 ? buf : -1);
+  phase_publish<T>(a, fc, committed, new_record, any_new, n_before, sh_u, &sh_base, mode == 1, mode == 1 ? buf : -1,
+                   buf);
 }
 
 static int pick_vec(const void* a, const void* b, int64_t row_bytes) {
@@ -1130,9 +1190,6 @@ struct GridSpec {  // non-null measures => fused grid index
   int meas_dtype = QD_F64;
   GridParams gp;
 };
-
-constexpr int64_t kSingleMaxRows = 2048;      // one CTA handles the whole batch up to here ...
-constexpr int64_t kSingleMaxCells = 1 << 18;  // ... in archives whose cell passes one CTA walks in a few microseconds
 
 template <typename T, typename MT, int D, bool FUSED>
 static int launch_insert(InsertArgs<T> a, const GridParams& gp, const FieldCopy& fc, int64_t work, int part,
@@ -1171,7 +1228,7 @@ static int launch_insert(InsertArgs<T> a, const GridParams& gp, const FieldCopy&
     insert_kernel<T, MT, D, FUSED, false><<<grid, kThreads, kCopySmem, stream>>>(a, gp, fc, 5, 5, mode, bufi);
     return check_launch("insert_kernel(copy)");
   }
-  if (mode == 0 && a.B <= kSingleMaxRows && a.N <= kSingleMaxCells && fc.peer_tab == nullptr) {
+  if (mode == 0 && a.B <= kSingleMaxRows && a.N <= kSingleMaxCells && work <= kSingleMaxWork && fc.peer_tab == nullptr) {
     insert_kernel<T, MT, D, FUSED, true><<<1, kThreads, kCopySmem, stream>>>(a, gp, fc, lo, hi, mode, bufi);
     return check_launch("insert_kernel(single)");
   }
@@ -1320,6 +1377,22 @@ extern "C" int qd_insert_phase_times(const void* scratch, int64_t capacity, uint
   QD_CHECK_CUDA(cudaMemcpyAsync(out_ns, s.g->t_phase, 10 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                                 (cudaStream_t)stream));
   QD_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return QD_OK;
+}
+
+extern "C" int qd_insert_set_result_mirror(void* scratch, int64_t capacity, qd_add_result* host_mirror, void* stream) {
+  using namespace qd;
+  QD_REQUIRE(scratch && capacity >= 1, "bad scratch arguments");
+  Scratch s = carve(scratch, capacity);
+  if (host_mirror) {
+    cudaPointerAttributes pa;
+    QD_CHECK_CUDA(cudaPointerGetAttributes(&pa, host_mirror));
+    QD_REQUIRE(pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr, "mirror must be page-locked host memory");
+    host_mirror = (qd_add_result*)pa.devicePointer;
+  }
+  QD_CHECK_CUDA(cudaMemcpyAsync(&s.g->result_mirror, &host_mirror, sizeof(host_mirror), cudaMemcpyHostToDevice,
+                                (cudaStream_t)stream));
+  QD_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // `host_mirror` is a stack variable
   return QD_OK;
 }
 

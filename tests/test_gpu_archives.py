@@ -480,8 +480,9 @@ def test_zero_copy_rows_from_pinned_host_arrays():
     for make in (lambda: CVTArchive(solution_dim=7, centroids=cen, ranges=[(-1, 1)] * 2, extra_fields={"tag": ((), np.int32)}),
                  lambda: GridArchive(solution_dim=7, dims=[12, 12], ranges=[(-1, 1)] * 2, learning_rate=0.2,
                                      threshold_min=-2.0, extra_fields={"tag": ((), np.int32)})):
-        a, b = make(), make()
+        a, b, c = make(), make(), make()
         b._zero_copy_rows = False
+        a._small_adds = b._small_adds = False  # (c: batches of this size are staged in one page-locked block, _add_small)
         for j in range(4):
             B = 5000
             pin = dict(solution=torch.from_numpy(rng.standard_normal((B, 7))).pin_memory(),
@@ -489,13 +490,16 @@ def test_zero_copy_rows_from_pinned_host_arrays():
                        measures=torch.from_numpy(rng.uniform(-1, 1, (B, 2))).pin_memory(),
                        tag=torch.from_numpy(rng.integers(0, 1000, B).astype(np.int32)).pin_memory())
             host = {k: v.numpy() for k, v in pin.items()}
-            ra, rb = a.add(**host), b.add(**host)
-            assert a._last_zero_copy and not b._last_zero_copy
+            ra, rb, rc = a.add(**host), b.add(**host), c.add(**host)
+            assert a._last_zero_copy and not b._last_zero_copy and not c._last_zero_copy
             np.testing.assert_array_equal(ra["status"], rb["status"])
             np.testing.assert_array_equal(ra["value"], rb["value"])
-        da, db = a.data(), b.data()
+            np.testing.assert_array_equal(rc["status"], rb["status"])
+            np.testing.assert_array_equal(rc["value"], rb["value"])
+        da, db, dc = a.data(), b.data(), c.data()
         for k in da:
             np.testing.assert_array_equal(da[k], db[k], err_msg=k)
+            np.testing.assert_array_equal(dc[k], db[k], err_msg=k)
         assert a._zero_copy_bytes > 0
         for k in a.best_elite:
             np.testing.assert_array_equal(a.best_elite[k], b.best_elite[k])

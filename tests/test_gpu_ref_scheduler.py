@@ -42,7 +42,7 @@ def _make(kind, es="cma_es"):
     from pyribs_b200.archives import CVTArchive, GridArchive
     from pyribs_b200.emitters import EvolutionStrategyEmitter, GaussianEmitter
 
-    n = 12
+    n = 16
     if kind == "grid":
         a = GridArchive(solution_dim=n, dims=(20, 20), ranges=[(-1, 1)] * 2, seed=1)
         r = None
@@ -78,7 +78,7 @@ def test_reference_scheduler_drives_these_classes(kind, es):
     for it in range(12):
         x1, x2 = ref.ask(), own.ask()
         np.testing.assert_array_equal(np.asarray(x1), np.asarray(x2), err_msg=f"ask {it}")
-        assert np.asarray(x1).shape == (3 * 16 + 8, 12)
+        assert np.asarray(x1).shape == (3 * 16 + 8, 16)
         o, m = _sphere(x1)
         ref.tell(o, m)
         own.tell(o, m)
@@ -162,7 +162,7 @@ def test_reference_emitter_over_device_es(es_name):
 
     opt.register_with_reference()
     klass = opt._NAME_TO_ES_MAP[es_name]
-    n = 10
+    n = 12
 
     def make(emitter_cls, es):
         a = GridArchive(solution_dim=n, dims=(20, 20), ranges=[(-1, 1)] * 2, seed=5)

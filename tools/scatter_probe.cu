@@ -11,12 +11,14 @@
 struct __align__(32) Rec { unsigned long long a, b, c, d; };
 
 enum { G_CA, G_CG, G_NC, G_CV, G_REC32, G_U32, R_MAX, R_ADD1, R_ADD2, R_ADD3, R_MAXADD2, A_ADD, S_8, S_16, S_32,
-       C_CLASSIFY, C_CLASSIFY_CG, B_RED16, B_RED32, R_MAX32, R_ADD32, NKIND };
+       C_CLASSIFY, C_CLASSIFY_CG, B_RED16, B_RED32, R_MAX32, R_ADD32, C_FOUR, B_BATCH16, C_MIX, C_MIX_NOSUM, NKIND };
 const char* kNames[NKIND] = {"gather8 ld.ca", "gather8 ld.cg", "gather8 ld.nc", "gather8 ld.volatile", "gather 32B record (2x LDG.128 cg)",
                              "gather4 ld.cg", "red.max.u64", "red.add.u64 x1", "red.add.u64 x2 same sector", "red.add.u64 x3 same sector",
                              "red.max + 2 red.add same sector", "atom.add.u64 returning", "store 8B", "store 16B", "store 32B (2x16)",
                              "classify-like: gather8.ca + max + 2 add", "classify-like: gather8.cg + max + 2 add",
-                             "cp.reduce.async.bulk add.u64 16B", "cp.reduce.async.bulk add.u64 32B", "red.max.u32", "red.add.u32"};
+                             "cp.reduce.async.bulk add.u64 16B", "cp.reduce.async.bulk add.u64 32B", "red.max.u32", "red.add.u32",
+                             "gather8 + 2 red.max + 2 red.add (one sector)", "bulk add.u64 16B, 4 ops per commit",
+                             "gather8 + 2 red.max (LSU) + bulk add 16B (TMA)", "gather8 + 2 red.max"};
 
 __device__ __forceinline__ unsigned long long ld_cg(const unsigned long long* p) {
   unsigned long long v;
@@ -100,6 +102,43 @@ __global__ void __launch_bounds__(512, 2) probe(const int32_t* __restrict__ idx,
         *(uint4*)r = make_uint4(base, u, 3, 4);
         *((uint4*)r + 1) = make_uint4(base, u, 5, 6);
       }
+    }
+    if constexpr (KIND == C_FOUR || KIND == C_MIX || KIND == C_MIX_NOSUM || KIND == B_BATCH16) {
+      unsigned long long t[R];
+      unsigned long long* st = stage + threadIdx.x * 4;  // (two u64 per row would do; 4 rows x 2 = 8 words needs a second slot)
+      __shared__ __align__(16) unsigned long long stage2[512 * 4];
+      unsigned long long* st2 = stage2 + threadIdx.x * 4;
+#pragma unroll
+      for (int u = 0; u < R; ++u)
+        if (c[u] >= 0 && KIND != B_BATCH16) t[u] = ld_ca(tab + c[u]);
+      if constexpr (KIND == C_MIX || KIND == B_BATCH16) {
+        st[0] = 3; st[1] = 5; st[2] = 7; st[3] = 9;
+        st2[0] = 3; st2[1] = 5; st2[2] = 7; st2[3] = 9;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+#pragma unroll
+      for (int u = 0; u < R; ++u)
+        if (c[u] >= 0 && (KIND == B_BATCH16 || t[u] != 12345ull)) {
+          if constexpr (KIND != B_BATCH16) {
+            atomicMax(&rec[c[u]].a, (unsigned long long)(base + u));
+            atomicMax(&rec[c[u]].b, (unsigned long long)(base + 2 * u));
+          }
+          if constexpr (KIND == C_FOUR) {
+            atomicAdd(&rec[c[u]].c, 3ull);
+            atomicAdd(&rec[c[u]].d, 5ull);
+          }
+          if constexpr (KIND == C_MIX || KIND == B_BATCH16) {
+            const unsigned long long* src = (u < 2 ? st : st2) + 2 * (u & 1);
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;" ::"l"(&rec[c[u]].c),
+                         "r"(su32(src))
+                         : "memory");
+          }
+        }
+      if constexpr (KIND == C_MIX || KIND == B_BATCH16) {
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      continue;
     }
     if constexpr (KIND == B_RED16 || KIND == B_RED32) {
       constexpr int NB = KIND == B_RED16 ? 16 : 32;
