@@ -47,6 +47,8 @@ struct TreeHeader {
   int32_t n[kTreeMaxLev + 1];         // boxes per level; n[0] = leaves, n[nlev-1] = 1
   uint64_t off_box[kTreeMaxLev + 1];  // byte offset of the level-l boxes, grouped by parent (l < nlev-1)
   uint64_t off_pts, off_ids, total;
+  uint64_t off_pf;   // the leaf points again, rounded to fp32 (same layout as off_pts): the leaf pre-filter
+  uint64_t off_rad;  // d floats: max |p_k - fp32(p_k)| over all points, rounded up
 };
 static_assert(sizeof(TreeHeader) <= kTreeHeaderBytes, "header too large");
 
@@ -72,6 +74,12 @@ static TreeHeader tree_layout(int64_t C, int d) {
     h.off_box[k] = off;
     off += (uint64_t)h.n[k + 1] * 2 * d * kFan * sizeof(float);
   }
+  off = (off + 255) / 256 * 256;
+  h.off_pf = off;
+  off += (uint64_t)h.nleaves * d * kLeaf * sizeof(float);
+  off = (off + 255) / 256 * 256;
+  h.off_rad = off;
+  off += (uint64_t)QD_MAX_MEASURE_DIM * sizeof(float);
   h.total = (off + 255) / 256 * 256;
   return h;
 }
@@ -144,6 +152,9 @@ static void tree_build_host(const T* cent, int64_t C, int d, unsigned char* blob
   if (getenv("QD_TREE_TIMING")) fprintf(stderr, "kd_split %.3f s\n", std::chrono::duration<double>(T1 - T0).count());
   double* lp = reinterpret_cast<double*>(blob + h.off_pts);
   int32_t* li = reinterpret_cast<int32_t*>(blob + h.off_ids);
+  float* lf = reinterpret_cast<float*>(blob + h.off_pf);
+  float* rad = reinterpret_cast<float*>(blob + h.off_rad);
+  std::vector<double> radd((size_t)d, 0.0);
   // leaves + their boxes (level 0)
   std::vector<float> lo((size_t)h.n[0] * d), hi((size_t)h.n[0] * d);
   for (int64_t leaf = 0; leaf < h.nleaves; ++leaf) {
@@ -159,15 +170,22 @@ static void tree_build_host(const T* cent, int64_t C, int d, unsigned char* blob
         for (int a = 0; a < d; ++a) {
           const double v = pts[(int64_t)id * d + a];
           lp[(leaf * d + a) * kLeaf + j] = v;
+          const float vf = (float)v;
+          lf[(leaf * d + a) * kLeaf + j] = vf;
+          if (std::isfinite(v) && std::isfinite(vf)) radd[a] = std::max(radd[a], std::fabs(v - (double)vf));
           lo[leaf * d + a] = std::min(lo[leaf * d + a], f32_down(v));
           hi[leaf * d + a] = std::max(hi[leaf * d + a], f32_up(v));
         }
       } else {  // padding of the last leaf: infinitely far away, never the minimum
         li[leaf * kLeaf + j] = INT32_MAX;
-        for (int a = 0; a < d; ++a) lp[(leaf * d + a) * kLeaf + j] = INFINITY;
+        for (int a = 0; a < d; ++a) {
+          lp[(leaf * d + a) * kLeaf + j] = INFINITY;
+          lf[(leaf * d + a) * kLeaf + j] = INFINITY;
+        }
       }
     }
   }
+  for (int a = 0; a < d; ++a) rad[a] = f32_up(radd[a]);
   for (int l = 0; l + 1 < h.nlev; ++l) {
     float* bx = reinterpret_cast<float*>(blob + h.off_box[l]);
     const int64_t groups = h.n[l + 1];
@@ -194,6 +212,8 @@ static void tree_build_host(const T* cent, int64_t C, int d, unsigned char* blob
 // ---- search ------------------------------------------------------------------------------------
 struct TreeView {
   const double* pts;
+  const float* pf;
+  const float* rad;
   const int32_t* ids;
   const float* box[kTreeMaxLev];
   int32_t nlev, d;
@@ -225,6 +245,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
   if (threadIdx.x == 0) s_next = nw;
   __syncthreads();
   uint32_t(*key)[32] = reinterpret_cast<uint32_t(*)[32]>(skey_raw + (size_t)warp * kTreeMaxLev * 32);
+  // the query's fp64 coordinates live in shared memory (behind the key slots): only the exact evaluation of a leaf
+  // reads them (broadcast), the walk itself runs on the fp32 interval below
+  double* sx = reinterpret_cast<double*>(skey_raw + (size_t)nw * kTreeMaxLev * 32) + (size_t)warp * XN;
   bool bad = false;
   const bool dynamic = order != nullptr;  // then gridDim.x * chunk >= B: one run per CTA
   for (int64_t c0 = (int64_t)blockIdx.x * chunk; c0 < B; c0 += (int64_t)gridDim.x * chunk) {
@@ -239,17 +262,22 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
         next_pos = c0 + __shfl_sync(0xffffffffu, t, 0);
       }
       pos = next_pos;
-      double x[XN];
+      // fp32 interval around the query, widened by the rounding radius of the fp32 copies of the leaf points: the
+      // boxes AND the fp32 points are then compared against an interval that certainly contains (x - p + pf)
       float xlo[XN], xhi[XN];
       bool qbad = false;
+      __syncwarp();
 #pragma unroll
       for (int k = 0; k < XN; ++k)
         if (k < d) {
-          x[k] = (double)meas[q * d + k];
-          qbad |= !finite_d(x[k]);
-          xlo[k] = __double2float_rd(x[k]);
-          xhi[k] = __double2float_ru(x[k]);
+          const double xk = (double)meas[q * d + k];
+          if (lane == 0) sx[k] = xk;
+          qbad |= !finite_d(xk);
+          const float r = __ldg(tv.rad + k);
+          xlo[k] = __fsub_rd(__double2float_rd(xk), r);
+          xhi[k] = __fadd_ru(__double2float_ru(xk), r);
         }
+      __syncwarp();
       bad |= qbad;
       double best = INFINITY;
       int32_t bi = INT32_MAX;
@@ -257,10 +285,13 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
 
       auto eval_leaf = [&](int leaf) {
         const double* p = tv.pts + ((int64_t)leaf * d) * kLeaf + lane;
-        double c[XN];
+        double c[XN], x[XN];
 #pragma unroll
         for (int k = 0; k < XN; ++k)
           if (k < d) c[k] = __ldg(p + k * kLeaf);
+#pragma unroll
+        for (int k = 0; k < XN; ++k)
+          if (k < d) x[k] = sx[k];
         const double dd = sqdist_np<D>(x, c, d);
         const bool cand = dd <= best;
         if (__any_sync(0xffffffffu, cand)) {
@@ -282,6 +313,22 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
             bestf = __fmul_ru(__double2float_ru(best), 1.0000005f);
           }
         }
+      };
+      // Leaf pre-filter. Lane j holds a rigorous fp32 lower bound of the squared distance to point j (the point's
+      // fp32 copy against the widened interval, every operation rounded down -- the argument of the prune note with
+      // a degenerate box); the 2 KB of exact fp64 coordinates are read only if some point of the leaf can still be
+      // the minimum or tie it. After the first few leaves of a walk that is rare: the walk reads half the bytes,
+      // and two leaves per step halve its chain of dependent round trips.
+      auto leaf_bound = [&](const float* __restrict__ pp) -> float {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < XN; ++k)
+          if (k < d) {
+            const float c = __ldg(pp + k * kLeaf);
+            const float g = fmaxf(fmaxf(__fsub_rd(c, xhi[k]), __fsub_rd(xlo[k], c)), 0.f);
+            acc = __fmaf_rd(g, g, acc);
+          }
+        return acc;
       };
       // keys of the 32 children (boxes of level `lvl`, group `parent`): lower-bound bits | lane
       auto node_key = [&](int lvl, int parent) -> uint32_t {
@@ -327,18 +374,17 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
             if (lane == child) key[level][lane] = 0xffffffffu;  // visited
             const int cnode = cur * kFan + child;
             if (level == 1) {
-              // The walk is a chain of dependent L2 round trips (one per leaf). The leaf that comes next is known
-              // before this one is evaluated -- unless this one tightens the bound below it, which is rare after the
-              // first few leaves -- so its rows are requested now (CCTL.PF1, no registers) and are in L1 by then.
-              const uint32_t kn = __reduce_min_sync(0xffffffffu, key[1][lane]);
-              if (kn < 0x7f800000u && !(__uint_as_float(kn & 0xffffffe0u) > bestf)) {
-                const double* pn = tv.pts + ((int64_t)(cur * kFan + (int)(kn & 31u)) * d) * kLeaf + lane;
-#pragma unroll
-                for (int c = 0; c < XN; ++c)
-                  if (c < d) asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + c * kLeaf));
-              }
-              eval_leaf(cnode);
-              k = kn;
+              // second leaf of this step: the next child in bound order, if it passes now
+              const uint32_t k2 = __reduce_min_sync(0xffffffffu, key[1][lane]);
+              const bool two = k2 < 0x7f800000u && !(__uint_as_float(k2 & 0xffffffe0u) > bestf);
+              const int cnode2 = cur * kFan + (int)(k2 & 31u);
+              if (two && lane == (int)(k2 & 31u)) key[1][lane] = 0xffffffffu;
+              const float b1 = leaf_bound(tv.pf + ((int64_t)cnode * d) * kLeaf + lane);
+              float b2 = INFINITY;
+              if (two) b2 = leaf_bound(tv.pf + ((int64_t)cnode2 * d) * kLeaf + lane);
+              if (__any_sync(0xffffffffu, !(b1 > bestf))) eval_leaf(cnode);
+              if (two && __any_sync(0xffffffffu, !(b2 > bestf))) eval_leaf(cnode2);
+              k = __reduce_min_sync(0xffffffffu, key[1][lane]);
             } else {
               --level;
               cur = cnode;
@@ -407,6 +453,10 @@ static size_t tree_scratch_bytes(int64_t B, int64_t C) {
   return 2 * a256((size_t)B * 4) + a256((size_t)(nleaves + 2) * 4);
 }
 
+static size_t tree_smem(int warps, int D) {  // per warp: key slots of the path + the query's fp64 coordinates
+  return (size_t)warps * kTreeMaxLev * 32 * 4 + (size_t)warps * (D > 0 ? D : QD_MAX_MEASURE_DIM) * 8;
+}
+
 template <typename T, int D>
 static int launch_tree_d(const T* meas, int64_t B, const TreeView& v, const TreeHeader& h, int32_t base, int32_t* idx,
                          double* dist, uint32_t* flags, void* scratch, size_t scratch_bytes, cudaStream_t s) {
@@ -416,7 +466,7 @@ static int launch_tree_d(const T* meas, int64_t B, const TreeView& v, const Tree
     // input order: 8 warps per CTA, one query per warp and pass
     const int64_t blocks = (B + kTreeWarps - 1) / kTreeWarps;
     const int grid = (int)std::min<int64_t>(blocks, (int64_t)kNumSMs * 8);
-    cvt_tree_kernel<T, D, false, kTreeWarps><<<grid, kTreeWarps * 32, kTreeWarps * kTreeMaxLev * 32 * 4, s>>>(
+    cvt_tree_kernel<T, D, false, kTreeWarps><<<grid, kTreeWarps * 32, tree_smem(kTreeWarps, D), s>>>(
         meas, B, v, base, nullptr, kTreeWarps, idx, dist, flags, nullptr, nullptr);
     return check_launch("cvt_tree_kernel");
   }
@@ -430,7 +480,7 @@ static int launch_tree_d(const T* meas, int64_t B, const TreeView& v, const Tree
   {
     const int64_t blocks = (B + kTreeWarps - 1) / kTreeWarps;
     const int grid = (int)std::min<int64_t>(blocks, (int64_t)kNumSMs * 8);
-    cvt_tree_kernel<T, D, true, kTreeWarps><<<grid, kTreeWarps * 32, kTreeWarps * kTreeMaxLev * 32 * 4, s>>>(
+    cvt_tree_kernel<T, D, true, kTreeWarps><<<grid, kTreeWarps * 32, tree_smem(kTreeWarps, D), s>>>(
         meas, B, v, base, nullptr, kTreeWarps, idx, dist, flags, home_key, count);
     if ((rc = check_launch("cvt_tree_kernel(home)"))) return rc;
   }
@@ -448,7 +498,7 @@ static int launch_tree_d(const T* meas, int64_t B, const TreeView& v, const Tree
   int64_t chunk = (B + (int64_t)kNumSMs * runs_per_sm - 1) / ((int64_t)kNumSMs * runs_per_sm);
   chunk = (chunk + kBig - 1) / kBig * kBig;
   const int grid = (int)((B + chunk - 1) / chunk);
-  cvt_tree_kernel<T, D, false, kBig><<<grid, kBig * 32, kBig * kTreeMaxLev * 32 * 4, s>>>(
+  cvt_tree_kernel<T, D, false, kBig><<<grid, kBig * 32, tree_smem(kBig, D), s>>>(
       meas, B, v, base, order, chunk, idx, dist, flags, nullptr, nullptr);
   return check_launch("cvt_tree_kernel(sorted)");
 }
@@ -459,6 +509,8 @@ static int launch_tree(const T* meas, int64_t B, int d, const unsigned char* tre
                        cudaStream_t s) {
   TreeView v;
   v.pts = reinterpret_cast<const double*>(tree + h.off_pts);
+  v.pf = reinterpret_cast<const float*>(tree + h.off_pf);
+  v.rad = reinterpret_cast<const float*>(tree + h.off_rad);
   v.ids = reinterpret_cast<const int32_t*>(tree + h.off_ids);
   for (int l = 0; l < kTreeMaxLev; ++l)
     v.box[l] = l + 1 < h.nlev ? reinterpret_cast<const float*>(tree + h.off_box[l]) : nullptr;

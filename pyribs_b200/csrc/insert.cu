@@ -101,9 +101,7 @@ struct InsertState {
   unsigned long long best_pack;   // (cell << 32 | batch row) of the lowest winning cell holding the new maximum
   // ---- pipelined commit (QD_INSERT_ROWS / QD_INSERT_COPY): winners of the row phases, one count per list buffer
   uint32_t copy_w[2];
-  // ---- row copy: next undistributed piece of every bulk field, per list buffer (re-armed by the publish phase of
-  // the launch that fills that buffer)
-  unsigned long long copy_next[2][QD_MAX_FIELDS];
+
 };
 
 struct Scratch {
@@ -112,6 +110,9 @@ struct Scratch {
   uint32_t* newmask;
   uint32_t* ctacnt;  // kMaxCtas
   int2* wlist;       // (batch row, cell) of this call's winners, at most one per cell
+  // row copy: next undistributed piece of every bulk field, per list buffer [2][QD_MAX_FIELDS] (re-armed by the
+  // publish phase of the launch that fills that buffer)
+  unsigned long long* copy_next;
   InsertState* g;
 };
 
@@ -131,6 +132,8 @@ static Scratch carve(void* base, int64_t N) {
   p += align_up((size_t)kMaxCtas * 4, 256);
   s.wlist = (int2*)p;  // two buffers of N entries (a pipelined row copy reads one while the next call fills the other)
   p += 2 * align_up((size_t)N * 8, 256);
+  s.copy_next = (unsigned long long*)p;
+  p += align_up((size_t)2 * QD_MAX_FIELDS * 8, 256);
   s.g = (InsertState*)p;
   return s;
 }
@@ -138,7 +141,9 @@ static Scratch carve(void* base, int64_t N) {
 static size_t scratch_bytes(int64_t N) {
   const int64_t words = (N + 31) / 32;
   return align_up((size_t)N * sizeof(Cell), 256) + align_up((size_t)N * 4, 256) + align_up((size_t)words * 4, 256) +
-         align_up((size_t)kMaxCtas * 4, 256) + 2 * align_up((size_t)N * 8, 256) + align_up(sizeof(InsertState), 256);
+         align_up((size_t)kMaxCtas * 4, 256) + 2 * align_up((size_t)N * 8, 256) +
+         align_up((size_t)2 * QD_MAX_FIELDS * 8, 256) +
+         align_up(sizeof(InsertState), 256);
 }
 
 __global__ void scratch_init_kernel(Scratch s, int64_t N) {
@@ -158,6 +163,7 @@ __global__ void scratch_init_kernel(Scratch s, int64_t N) {
     g.best_cell = INT32_MAX;
     g.best_pack = ~0ull;
     *s.g = g;
+    for (int k = 0; k < 2 * QD_MAX_FIELDS; ++k) s.copy_next[k] = 0ull;
   }
 }
 
@@ -313,6 +319,8 @@ __device__ void phase_absmax(const InsertArgs<T>& a, double* sh_d) {
   if (threadIdx.x == 0 && amax > 0.0)
     atomicMax(&a.s.g->absmax_bits, (unsigned long long)__double_as_longlong(amax));
 }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- phase 1 ----------------------------------------------------------------------------------
 template <typename T, typename MT, int D, bool FUSED>
@@ -614,14 +622,15 @@ __device__ __forceinline__ void copy_row_inline(const FieldCopy& fc, int row, in
 }
 
 // cell mode: one thread per CELL, everything coalesced. The winner's objective is decoded from the cell's
-// key, its row comes from `pick`; a warp appends its (row, cell) pairs to the list with one atomic, in cell
-// order, so the row copy writes the store in runs of ascending addresses.
+// key, its row comes from `pick`; the (row, cell) pairs go to the list in cell order within a CTA trip (one
+// reservation per trip), so the row copy writes the store in runs of ascending addresses.
 // second_pass = false: every cell the batch touched. A cell whose pick does not hold the maximum (two rows of the
 // cell with keys equal above bit rb, see Cell) is left for the mark pass: pick := pc.amb, counted in n_ambiguous.
 // second_pass = true: exactly those cells, after the mark pass.
 template <typename T>
 __device__ void phase_update_cells(const InsertArgs<T>& a, const FieldCopy& fc, bool inline_copy, bool second_pass,
-                                   double (*sh_d)[kThreads / 32], uint32_t* sh_n, unsigned long long* sh_k) {
+                                   double (*sh_d)[kThreads / 32], uint32_t* sh_n, unsigned long long* sh_k,
+                                   uint32_t* s_cnt, uint32_t* s_base) {
   const InsertState* g = a.s.g;
   const bool mae = a.mae;
   const double batch_absmax = __longlong_as_double((long long)g->absmax_bits);
@@ -634,9 +643,9 @@ __device__ void phase_update_cells(const InsertArgs<T>& a, const FieldCopy& fc, 
   UpdateAcc<T> acc;
   uint32_t namb = 0;
   const int lane = threadIdx.x & 31;
-  // two tiles per trip, every load of both issued before the first use: the phase is 1-2 trips per thread, i.e. a
-  // chain of L2 round trips (record -> pick's objective -> list slot), not bandwidth
-  constexpr int U = 2;
+  // U tiles per trip, every load issued before the first use: the phase is 1-2 trips per thread, i.e. a chain of
+  // L2 round trips (record -> pick's objective -> list slot), not bandwidth. (U = 2 spilled and measured slower.)
+  constexpr int U = 1;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   for (int64_t c0 = (int64_t)blockIdx.x * kThreads; c0 < a.N; c0 += U * stride) {
     Cell cell[U];
@@ -679,21 +688,33 @@ __device__ void phase_update_cells(const InsertArgs<T>& a, const FieldCopy& fc, 
       m[u] = __ballot_sync(0xffffffffu, has[u]);
       nwin += __popc(m[u]);
     }
-    if (nwin) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&a.s.g->n_winners, nwin);  // one list reservation per warp and trip
-      base = __shfl_sync(0xffffffffu, base, 0);
+    // one list reservation per CTA and trip (a reservation per warp is 8 000 atomics on one address per add, which
+    // the L2 serialises: measured +8 us)
+    if (lane == 0) s_cnt[threadIdx.x >> 5] = nwin;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t c = c0 + u * stride + threadIdx.x;
-        if (lane == 0 && mnew[u]) {
-          if (second_pass) atomicOr(&a.s.newmask[c >> 5], mnew[u]);  // (the first pass may have set other bits)
-          else a.s.newmask[c >> 5] = mnew[u];
-        }
-        if (has[u]) a.s.wlist[base + __popc(m[u] & ((1u << lane) - 1u))] = make_int2(row[u], (int32_t)c);
-        base += __popc(m[u]);
+      for (int k = 0; k < kThreads / 32; ++k) {
+        const uint32_t n = s_cnt[k];
+        s_cnt[k] = tot;
+        tot += n;
       }
+      *s_base = tot ? atomicAdd(&a.s.g->n_winners, tot) : 0u;
     }
+    __syncthreads();
+    uint32_t base = *s_base + s_cnt[threadIdx.x >> 5];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t c = c0 + u * stride + threadIdx.x;
+      if (lane == 0 && mnew[u]) {
+        if (second_pass) atomicOr(&a.s.newmask[c >> 5], mnew[u]);  // (the first pass may have set other bits)
+        else a.s.newmask[c >> 5] = mnew[u];
+      }
+      if (has[u]) a.s.wlist[base + __popc(m[u] & ((1u << lane) - 1u))] = make_int2(row[u], (int32_t)c);
+      base += __popc(m[u]);
+    }
+    __syncthreads();
   }
   namb = __reduce_add_sync(0xffffffffu, namb);
   if (lane == 0 && namb) atomicAdd(&a.s.g->n_ambiguous, namb);
@@ -711,7 +732,6 @@ constexpr int kSlotBytes = 24 * 1024;
 constexpr int kPieceMax = 2048;
 constexpr int kCopySmem = kCopyWarps * kSlotBytes;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -804,17 +824,27 @@ __device__ void copy_rows_small(const FieldCopy& fc, int f, const Scratch& s, in
   }
 }
 
+// Shape of the bulk path: kBulkWarps x kBulkStages = kCopyWarps slots of 24 KB per CTA. Measured at 2M rows / 249k
+// winners of 800 B (tools/grid_insert_probe.py): 4 warps x 1 stage on both CTAs of an SM 76 us, 2 warps x 2 stages
+// 76 us, 2 warps x 2 stages on ONE elected CTA per SM 97 us -- although a contiguous 2 x 200 MB copy is fastest in
+// that last shape (tools/overlap_probe.cu: 5.9 vs 5.5 TB/s): scattered 800-byte rows want more requests in flight.
+constexpr int kBulkWarps = 4;
+constexpr int kBulkStages = 1;
+static_assert(kBulkWarps * kBulkStages == kCopyWarps, "one mbarrier and one 24 KB slot per (warp, stage)");
+
 __device__ void phase_copy(const FieldCopy& fc, const Scratch& s, int64_t W, int buf, unsigned char* slots,
                            uint64_t* mbar, uint32_t& parity) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bool any_bulk = false;
   for (int f = 0; f < fc.n; ++f) any_bulk |= is_bulk_field(fc, f);
-  if (!any_bulk || warp >= kCopyWarps) {
-    // the register path: every warp when no field is bulk, otherwise the warps the bulk copy leaves idle
-    const int team = any_bulk ? kThreads - 32 * kCopyWarps : kThreads;
-    const int64_t tid = (int64_t)blockIdx.x * team + (threadIdx.x - (any_bulk ? 32 * kCopyWarps : 0));
-    for (int f = 0; f < fc.n; ++f)
-      if (!is_bulk_field(fc, f)) copy_rows_small(fc, f, s, W, tid, (int64_t)gridDim.x * team);
+  if (!any_bulk || warp >= kBulkWarps) {
+    // the register path: the warps the bulk copy leaves idle
+    const int lean = any_bulk ? kThreads - 32 * kBulkWarps : kThreads;
+    const int local = threadIdx.x - (kThreads - lean);
+    if (local >= 0)
+      for (int f = 0; f < fc.n; ++f)
+        if (!is_bulk_field(fc, f))
+          copy_rows_small(fc, f, s, W, (int64_t)blockIdx.x * lean + local, (int64_t)gridDim.x * lean);
     return;
   }
   for (int f = 0; f < fc.n; ++f) {
@@ -826,45 +856,52 @@ __device__ void phase_copy(const FieldCopy& fc, const Scratch& s, int64_t W, int
     const int64_t ppr = (rb + piece - 1) / piece;  // pieces per row
     const int L = kSlotBytes / piece < 32 ? kSlotBytes / piece : 32;
     const int64_t total = W * ppr;
-    unsigned char* slot = slots + warp * kSlotBytes + lane * piece;
-    uint64_t* bar = &mbar[warp];
-    // Rounds are drawn from a counter, not dealt out: SMs do not copy at the same speed (the phase used to end
-    // 13 us after its first CTA was done), and the draw for the next round travels while this round's loads land.
-    unsigned long long* next = &s.g->copy_next[buf][f];
-    unsigned long long drawn = 0;
-    if (lane == 0) drawn = atomicAdd(next, (unsigned long long)L);
-    int64_t it0 = (int64_t)__shfl_sync(0xffffffffu, drawn, 0);
-    while (it0 < total) {
-      const int64_t item = it0 + lane;
-      const bool active = lane < L && item < total;
-      uint32_t len = 0;
+    // Rounds are drawn from a counter, not dealt out: SMs do not copy at the same speed (with a static split the
+    // phase ended 13 us after its first CTA was done).
+    unsigned long long* next = &s.copy_next[buf * QD_MAX_FIELDS + f];
+    int64_t it[kBulkStages];
+    char* dp[kBulkStages];
+    uint32_t len[kBulkStages];
+    auto issue = [&](int st) {
+      unsigned long long drawn = 0;
+      if (lane == 0) drawn = atomicAdd(next, (unsigned long long)L);
+      it[st] = (int64_t)__shfl_sync(0xffffffffu, drawn, 0);
+      len[st] = 0;
+      dp[st] = nullptr;
+      if (it[st] >= total) return;
+      const int64_t item = it[st] + lane;
       const char* sp = nullptr;
-      char* dp = nullptr;
-      if (active) {
+      if (lane < L && item < total) {
         const int64_t w = ppr == 1 ? item : item / ppr;
         const int64_t off = (item - w * ppr) * piece;
-        len = (uint32_t)(rb - off < piece ? rb - off : piece);
+        len[st] = (uint32_t)(rb - off < piece ? rb - off : piece);
         const int2 rc = s.wlist[w];
         sp = src + (int64_t)rc.x * rb + off;
-        dp = dst + (int64_t)rc.y * rb + off;
+        dp[st] = dst + (int64_t)rc.y * rb + off;
       }
-      const uint32_t round_bytes = __reduce_add_sync(0xffffffffu, len);
+      uint64_t* bar = &mbar[warp * kBulkStages + st];
+      const uint32_t round_bytes = __reduce_add_sync(0xffffffffu, len[st]);
       if (lane == 0) mbar_expect_tx(bar, round_bytes);
       __syncwarp();
-      if (active) bulk_g2s(slot, sp, len, bar);
-      if (lane == 0) drawn = atomicAdd(next, (unsigned long long)L);
-      mbar_wait(bar, parity);
-      parity ^= 1u;
-      if (active) bulk_s2g(dp, slot, len);
+      if (len[st]) bulk_g2s(slots + (warp * kBulkStages + st) * kSlotBytes + lane * piece, sp, len[st], bar);
+    };
+#pragma unroll
+    for (int st = 0; st < kBulkStages; ++st) issue(st);
+    for (int st = 0; it[st] < total; st = (st + 1) % kBulkStages) {
+      mbar_wait(&mbar[warp * kBulkStages + st], (parity >> st) & 1u);
+      parity ^= 1u << st;
+      if (len[st]) bulk_s2g(dp[st], slots + (warp * kBulkStages + st) * kSlotBytes + lane * piece, len[st]);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the slot may be refilled
-      it0 = (int64_t)__shfl_sync(0xffffffffu, drawn, 0);
+      __syncwarp();
+      issue(st);
     }
   }
   // bulk stores are complete (not just read) and ordered before the generic-proxy accesses that follow
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   asm volatile("fence.proxy.async;" ::: "memory");
 }
+
 
 // ---- phase 6 ----------------------------------------------------------------------------------
 // Words of the new-cell bitmap owned by one CTA: a contiguous chunk, so that the concatenation of
@@ -987,6 +1024,7 @@ __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool 
     }
   }
   __syncthreads();  // every warp has read best_pack before thread 0 re-arms it
+  if (threadIdx.x < QD_MAX_FIELDS) a.s.copy_next[rearm_buf * QD_MAX_FIELDS + threadIdx.x] = 0ull;
   if (threadIdx.x == 0) {
     InsertState g = *gp;
     const double delta = (double)(T)__dadd_rn(__dadd_rn(g.dsum[0], g.dsum[1]), g.dsum[2]);
@@ -1037,7 +1075,7 @@ __device__ void phase_publish(const InsertArgs<T>& a, const FieldCopy& fc, bool 
     g.best_cell = INT32_MAX;
     g.best_pack = ~0ull;
     g.n_insertable = g.n_new = g.flags = g.n_winners = g.n_ambiguous = 0u;
-    for (int f = 0; f < QD_MAX_FIELDS; ++f) g.copy_next[rearm_buf][f] = 0ull;
+
     g.dsum[0] = g.dsum[1] = g.dsum[2] = 0.0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g.t_phase[8]));
     *gp = g;
@@ -1147,12 +1185,13 @@ __global__ void __launch_bounds__(kThreads, 2) insert_kernel(const __grid_consta
   const bool inline_copy = mode == 0 && phase_lo <= 4 && phase_hi >= 5 && cell_mode && inline_copy_ok(fc);
   if (phase_lo <= 4 && phase_hi >= 4 && committed) {
     if (cell_mode) {
-      phase_update_cells<T>(a, fc, inline_copy, false, sh_d, sh_u + 32, sh_k);
+      phase_update_cells<T>(a, fc, inline_copy, false, sh_d, sh_u + 32, sh_k, sh_u, &sh_base);
+      stamp(9);  // (diagnostics: CTA 0 is through its cells; the rest of the phase is the barrier)
       gsync();
       if (g->n_ambiguous != 0u) {  // near-ties below bit rb inside a cell: the exact row pass, for those cells only
         phase_mark_winner<T>(a, true);
         gsync();
-        phase_update_cells<T>(a, fc, inline_copy, true, sh_d, sh_u + 32, sh_k);
+        phase_update_cells<T>(a, fc, inline_copy, true, sh_d, sh_u + 32, sh_k, sh_u, &sh_base);
         gsync();
       }
     } else {
@@ -1196,6 +1235,7 @@ static int launch_insert(InsertArgs<T> a, const GridParams& gp, const FieldCopy&
                          cudaStream_t stream) {
   static int max_ctas = 0, sm_count = kNumSMs;  // per instantiation
   if (max_ctas == 0) {
+
     int per_sm = 0, dev = 0, sms = kNumSMs;
     QD_CHECK_CUDA(cudaFuncSetAttribute(insert_kernel<T, MT, D, FUSED, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kCopySmem));

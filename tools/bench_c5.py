@@ -90,7 +90,6 @@ def main():
         ref = ora.add(**sb)
         cpu_s = time.perf_counter() - t0
         # parity spot check on the sample: same indices as the KD-tree
-        chk = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * d, search_method="tensor") if world == 1 else None
         line = {
             "config": f"CVTArchive {C} centroids, {d}-D, batch add of {B}, centroids sharded over {world} GPU(s)",
             "n_gpus": world, "ms_per_add": ms, "insertions_per_s": B / ms * 1e3,

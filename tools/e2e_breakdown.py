@@ -13,7 +13,10 @@ def phase_times(a):
     out = (C.c_uint64 * 10)()
     _lib.check(_lib.lib().qd_insert_phase_times(a._store._scratch.data_ptr(), a._store.capacity, out, current_stream_ptr()))
     t = list(out)
-    return {PH[i]: (t[i + 1] - t[i]) / 1e3 for i in range(8)}, (t[8] - t[0]) / 1e3
+    ph = {PH[i]: (t[i + 1] - t[i]) / 1e3 for i in range(8)}
+    if t[9] > t[4]:
+        ph["update: CTA 0 done after"] = (t[9] - t[4]) / 1e3
+    return ph, (t[8] - t[0]) / 1e3
 
 def h2d_bw():
     res = {}
