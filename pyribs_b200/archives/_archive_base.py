@@ -163,6 +163,8 @@ class DeviceArchive:
         self._needs_flag_check = False
         self._dp_symm = None  # {batch signature: symmetric-memory exchange state}; False = unavailable
         self._zero_copy_rows = True   # read winners' rows straight from page-locked host arrays when that saves PCIe traffic
+        self._dev_fast = True         # CUDA-tensor batches in the store's dtypes take the lean path (_add_device)
+        self._dev_idx = None          # its reusable cell-index buffer
         self._small_adds = True       # host batches of <= _SMALL_ROWS rows take the two-launch path (_add_small)
         self._small = {}              # its per-batch-size plans
         self._last_zero_copy = False
@@ -186,6 +188,7 @@ class DeviceArchive:
         """Adopts `store` (construction, retessellate, unpickling): the store's hooks point back at this archive
         and every piece of host state that described the previous store starts over."""
         self._store = store
+        self._tdt = {n: store._fields[n].dtype for n in ("solution", "objective", "measures")}
         store._copy_join = self._join_copy
         store._owner_sync = self._sync
         self._st = (0, 0.0, None, 0)
@@ -199,7 +202,7 @@ class DeviceArchive:
     # state that cannot (streams, events, ctypes arrays, page-locked pools, process groups) or need not (device
     # search structures, scratch) travel through pickle; rebuilt by __setstate__ / on first use
     _TRANSIENT = {"_pinned": dict, "_outbuf": dict, "_copy_stream": None, "_copy_event": None, "_inflight": None,
-                  "_dp_symm": None, "_zc": None, "_shared_idx": None, "_last_idx": None, "_pin_cache": dict, "_small": dict,
+                  "_dp_symm": None, "_zc": None, "_shared_idx": None, "_last_idx": None, "_pin_cache": dict, "_small": dict, "_dev_idx": None,
                   "_pipe": None, "_pipe_pending": None, "_dp_group": None}
 
     def __getstate__(self):
@@ -620,6 +623,10 @@ class DeviceArchive:
         dev_in = is_device_tensor(solution)
         # a hand-over from an archive of the same geometry is good for this call only, also when the call raises
         preset, self._shared_idx = self._shared_idx, None
+        if dev_in and self._dev_fast:
+            out = self._add_device(solution, objective, measures, fields, preset)
+            if out is not None:
+                return out
         data = validate_batch(self, {"solution": solution, "objective": objective, "measures": measures, **fields})
         if self._extra_names != set(fields):
             raise ValueError(
@@ -786,6 +793,62 @@ class DeviceArchive:
         if pooled is not None:  # views of a pooled page-locked buffer (see _out_buffers)
             return {"status": pooled[2][lo:hi], "value": pooled[3][lo:hi]}
         return {"status": status_h.numpy()[lo:hi].copy(), "value": value_h.numpy()[lo:hi].copy()}
+
+    # ---- add() of CUDA tensors that need nothing done to them --------------------------------------------
+    def _add_device(self, solution, objective, measures, fields, preset):
+        """The asynchronous route with the host work cut to what it has to be: the batch is already on this
+        archive's device in the store's dtypes, so it is checked (same errors as validate_batch would raise: any
+        mismatch falls back to the general path, which raises them) and handed to the two launches. configs[1]'s
+        device-resident step is bound by this function, not by its kernels (36 us)."""
+        if (self._dp_world != 1 or self._pipeline_commit or self._sync_device_adds
+                or self._extra_names != fields.keys() or torch.cuda.current_device() != self._device.index):
+            return None
+        store = self._store
+        tdt = self._tdt
+        B = solution.shape[0] if (solution.dim() == 2 and isinstance(self._solution_dim, int)) else -1
+        if (B <= 0 or solution.shape[1] != self._solution_dim or solution.dtype != tdt["solution"]
+                or not solution.is_contiguous() or solution.device != self._device
+                or not is_device_tensor(objective) or objective.dim() != 1 or objective.shape[0] != B
+                or objective.dtype != tdt["objective"] or not objective.is_contiguous()
+                or not is_device_tensor(measures) or measures.dim() != 2 or measures.shape[0] != B
+                or measures.shape[1] != self._measure_dim or measures.dtype != tdt["measures"]
+                or not measures.is_contiguous()):
+            return None
+        for n, t in fields.items():
+            want = store._fields[n]
+            if (not is_device_tensor(t) or t.shape[0] != B or tuple(t.shape[1:]) != tuple(want.shape[1:])
+                    or t.dtype != want.dtype or not t.is_contiguous()):
+                return None
+        if preset is not None and preset[1] != B:
+            preset = None
+        if not self._small_index_ok(B):  # (tensor-core search: its overflow flag needs the general path's re-run)
+            return None
+        self._join_copy()
+        self._last_zero_copy = False
+        out = torch.empty(B * 12 if tdt["objective"] == torch.float64 else B * 8, dtype=torch.uint8, device=self._device)
+        vbytes = out.numel() - 4 * B
+        value, status = out[:vbytes].view(tdt["objective"]), out[vbytes:].view(torch.int32)
+        dev = {"solution": solution, "objective": objective, "measures": measures, **fields}
+        src = (C.c_void_p * max(len(store.row_fields), 1))(*[dev[n].data_ptr() for n in store.row_fields])
+        fused = self._fused_index_insert and preset is None
+        if fused:
+            self._grid_insert(dev, B, src, status, value, _lib.INSERT_WHOLE)
+            idx = None
+        else:
+            if preset is not None:
+                idx = preset[0]
+            else:
+                buf = self._dev_idx
+                if buf is None or buf.numel() < B:
+                    buf = self._dev_idx = torch.empty(B, dtype=torch.int32, device=self._device)
+                idx = self._index_of_device(measures, store._flags_ptr, out=buf[:B] if buf.numel() != B else buf)
+            _lib.check(_lib.lib().qd_insert(C.byref(store.abi_store()), B, idx.data_ptr(), objective.data_ptr(), src,
+                                            self._lr_f, self._tmin_f, status.data_ptr(), value.data_ptr(),
+                                            store._result_dev.data_ptr(), _lib.INSERT_WHOLE, current_stream_ptr()))
+        store._pending = True
+        self._inflight = dev  # keeps the batch alive until the stream has consumed it
+        self._last_idx = (idx if idx is not None else self._idx_buf[:B], B)
+        return {"status": status, "value": value}
 
     # ---- add() of small host batches ---------------------------------------------------------------------
     def _small_index_ok(self, B):

@@ -311,3 +311,42 @@ def test_near_tie_objectives_resolve_exactly(B, dtype):
                                           ora.store.fields["solution"][occ])
             np.testing.assert_array_equal(gpu._store.occupied_list, ora.store.occupied_list[: len(ora)])
             b = dict(b, objective=np.nextafter(b["objective"], dtype(np.inf)))  # everything improves by one ulp
+
+
+# ---- lean host routes equal the general one -------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["grid_mae", "grid_me", "cvt2", "cvt6"])
+@pytest.mark.parametrize("B", [1, 100, 3000, 20_000])
+def test_lean_add_routes_equal_the_general_route(kind, B):
+    """CUDA tensors through `_add_device`, NumPy batches through `_add_small`, and both through the general route
+    (`_dev_fast = _small_adds = False`): same status / value bits, same store."""
+    import torch
+
+    rng = np.random.default_rng(B)
+    archives = [_archive(kind) for _ in range(4)]
+    archives[2]._dev_fast = False
+    archives[3]._small_adds = False
+    d = archives[0].measure_dim
+    for step in range(3):
+        b = dict(solution=rng.standard_normal((B, 4)), objective=rng.uniform(0, 10, B) + step,
+                 measures=rng.uniform(-1, 1, (B, d)))
+        if kind == "grid_mae":
+            b["meta"] = rng.integers(0, 100, (B, 2)).astype(np.int32)
+        dev = {k: torch.from_numpy(v).cuda() for k, v in b.items()}
+        outs = [archives[0].add(**dev), archives[1].add(**b), archives[2].add(**dev), archives[3].add(**b)]
+        outs = [{k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in o.items()} for o in outs]
+        for o in outs[1:]:
+            np.testing.assert_array_equal(o["status"], outs[0]["status"])
+            np.testing.assert_array_equal(o["value"], outs[0]["value"])
+    ref = archives[0].data()
+    for a in archives[1:]:
+        da = a.data()
+        for k in ref:
+            np.testing.assert_array_equal(da[k], ref[k], err_msg=k)
+        assert a.stats.qd_score == archives[0].stats.qd_score
+    # what falls back: wrong dtype / non-contiguous tensors still work (general route), wrong shapes still raise
+    a = archives[0]
+    b32 = {k: (v.float() if v.dtype == torch.float64 else v) for k, v in dev.items()}
+    a.add(**b32)
+    with pytest.raises(ValueError):
+        a.add(**dict(dev, objective=dev["objective"][:-1]))
+    assert len(a) > 0
