@@ -231,7 +231,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "insertions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": make_config(args.gpus),
         "cpu_baseline": {"value": val, "unit": "insertions/s", "cores": cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": val, "unit": "insertions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -245,7 +245,7 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------------------------------------
 C_SIZEOF_RESULT = 120  # sizeof(qd_add_result)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-NCU_TRAFFIC = {"insert_kernel_grid_2M": 311_130_624 + 205_896_704}
+NCU_TRAFFIC = {"insert_kernel_grid_2M": 315_400_704 + 206_669_312}  # dram read + write, profiles/r02j_grid_insert_2M_ncu_full.txt
 
 
 def grid_insert_roofline(torch, dev, peak_hbm):
@@ -614,10 +614,12 @@ def main():
         "launches_per_search": k_launches / args.steps, "queries_per_s": Bl / s_k,
         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
         "note": "algorithmic bytes of SURVEY 8(d) for index_of, (B + C) d s + 4 B, over the measured kernel time. The "
-                "search is neither HBM- nor tensor-bound: a query walks ~16 nodes and ~44 leaves of an L2-resident "
-                "72 MB tree (~125 KB of L2 reads and ~3 300 warp instructions per query, see DESIGN.md 4.3b), so the "
-                "frac against HBM is small by construction; the exhaustive tcgen05 contraction this replaces on this "
-                "shape ran at 164 TFLOP/s = 10 % of the bf16 peak and took 6.6x longer (profiles/r02_*).",
+                "search is neither HBM- nor tensor-bound, so the frac against HBM is small by construction: a query walks "
+                "~16 nodes and ~44 leaves of an L2-resident 104 MB tree in ~5 300 warp instructions; the sorted-walk "
+                "kernel issues on 76 % of its cycles at 50 % occupancy (ncu: profiles/r02j_cvt_tree_c5_ncu_full.txt, "
+                "DESIGN.md 4.3b) -- it is instruction-issue-bound. The exhaustive tcgen05 contraction it replaces on "
+                "this shape ran at 164 TFLOP/s = 10 % of the bf16 peak and took 13x longer (profiles/r02_cvt_tc_*). The "
+                "bandwidth-regime roofline of this line is the GridArchive insertion under `secondary`.",
         "exhaustive_equivalent_TFLOPs": 2.0 * Bl * C * d / s_k / 1e12, "bf16_peak_TFLOPs": peak_tf,
     }
 
@@ -702,7 +704,7 @@ def main():
         "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak",
+        "scaling": "strong",  # the global batch (1M rows) is fixed; --gpus N splits it
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
