@@ -650,6 +650,37 @@ def main():
         except Exception as e:  # noqa: BLE001
             alt = {"error": f"{type(e).__name__}: {e}"}
 
+    if world > 1:
+        # ---- owner-computes store beside the replicated one: cells sharded by contiguous range, every rank commits
+        # only the rows of its own cells (DeviceArchive._add_owned) -----------------------------
+        try:
+            own = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * d, search_method=args.search,
+                             data_parallel=True, shard_store=True)
+
+            def step_own(j):
+                b = dev_batches[j % N_RESIDENT]
+                own.add(b["solution"], b["objective"] + OBJ_DRIFT * j, b["measures"])
+
+            ms_own, _ = timed(step_own, args.steps, args.warmup)
+            n_own = len(own)
+            own.clear()
+
+            def step_own_e2e(j):
+                b = host_batches[j % N_RESIDENT]
+                own.add(b["solution"], b["objective"], b["measures"])
+
+            ms_own_e2e, _ = timed(step_own_e2e, e2e_steps, 3)
+            alt["owner_computes_store"] = {
+                "parallelism": f"as the headline, but the STORE is sharded by cell range over the {world} ranks: every "
+                               "rank classifies / commits only the rows of its own cells and pulls only its own "
+                               "winners' rows; status / value return by a reverse push over NVLink",
+                "insertions_per_s": B * args.steps / (ms_own * 1e-3), "ms_per_add": ms_own / args.steps,
+                "e2e_insertions_per_s": B * e2e_steps / (ms_own_e2e * 1e-3), "e2e_ms_per_add": ms_own_e2e / e2e_steps,
+                "elites_after_timed_adds": n_own}
+            del own
+        except Exception as e:  # noqa: BLE001
+            alt["owner_computes_store"] = {"error": f"{type(e).__name__}: {e}"}
+
     secondary = []
     cpu = None
     if world == 1 and rank == 0:

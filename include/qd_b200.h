@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 5
+#define QD_ABI_VERSION 6
 
 #define QD_OK 0
 #define QD_ERR_INVALID_ARG (-1)
@@ -249,6 +249,19 @@ int qd_insert_sharded_rows(const qd_store* store, int64_t B, const int32_t* idx,
                            const void* const* field_src, const void* const* peer_field_src /*[dev]*/,
                            int64_t rows_per_rank, double learning_rate, double threshold_min,
                            int32_t* status_out, void* value_out, qd_add_result* result, int part, void* stream);
+/* Owner-computes insertion (scatter target ribs/archives/_array_store.py:535-608): `store`
+ * holds only the cells [cell_lo, cell_hi) of an archive whose cells are sharded over the ranks by contiguous range.
+ * Every rank passes the GLOBAL batch -- idx / objective of all B rows (exchanged beforehand, 12 B per row), the
+ * row fields through the peer table as in qd_insert_sharded_rows -- and this rank classifies, resolves and commits
+ * only the rows whose cell it owns: per-rank work is B / n_ranks rows and its own winners' row copies. `idx` is
+ * rewritten in place to local cell numbers (-1: not this rank's). Status / value of row i go to the rank its batch
+ * slice came from: out_tab [dev] = { status_0, value_0, status_1, value_1, ... }, rank r's arrays of rows_per_rank
+ * entries in peer memory; a cross-rank barrier after this call completes them. Validation verdicts are global: every
+ * rank checks every objective. */
+int qd_insert_owned_cells(const qd_store* store, int64_t B, int32_t* idx /*[dev] B, rewritten*/,
+                          const void* objective /*[dev] B*/, const void* const* peer_field_src /*[dev]*/,
+                          int64_t rows_per_rank, int32_t cell_lo, int32_t cell_hi, void* const* out_tab /*[dev]*/,
+                          double learning_rate, double threshold_min, qd_add_result* result, void* stream);
 /* GridArchive.add with A2 fused into the first pass (measures are read once, idx_out is
  * written for the later passes and for the caller). Arguments as qd_grid_index_of + qd_insert. */
 int qd_grid_insert(const qd_store* store, int64_t B, const void* measures /*[dev] B x d*/, int meas_dtype,

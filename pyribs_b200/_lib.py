@@ -106,6 +106,7 @@ PROTOTYPES = {
     "qd_insert": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _dbl, _dbl, _vp, _vp, _vp, _int, _vp]),
     "qd_insert_sharded_rows": (_int, [C.POINTER(Store), _i64, _vp, _vp, C.POINTER(_vp), _vp, _i64, _dbl, _dbl, _vp, _vp,
                                       _vp, _int, _vp]),
+    "qd_insert_owned_cells": (_int, [C.POINTER(Store), _i64, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _dbl, _dbl, _vp, _vp]),
     "qd_grid_insert": (_int, [C.POINTER(Store), _i64, _vp, _int, _int, C.POINTER(_i32), C.POINTER(_dbl),
                               C.POINTER(_dbl), _dbl, _vp, C.POINTER(_vp), _dbl, _dbl, _vp, _vp, _vp, _vp, _int,
                               _vp]),

@@ -104,7 +104,7 @@ def _pool_entry_free(entry):
 class DeviceArchive:
     def __init__(self, *, solution_dim, measure_dim, cells, learning_rate, threshold_min, qd_score_offset, seed,
                  solution_dtype, objective_dtype, measures_dtype, dtype, extra_fields, device=None,
-                 data_parallel=False, process_group=None):
+                 data_parallel=False, process_group=None, shard_store=False):
         self._rng = np.random.default_rng(seed)
         # data-parallel insertion: every rank passes its own slice of the global batch to add();
         # indices are computed locally, then (index, objective, row fields) are all-gathered over
@@ -118,6 +118,23 @@ class DeviceArchive:
                 raise RuntimeError("data_parallel=True needs an initialised torch.distributed process group")
             self._dp_world = dist.get_world_size(process_group)
             self._dp_rank = dist.get_rank(process_group)
+        # owner-computes store: the cells are sharded over the ranks by contiguous range, every
+        # rank classifies / commits only the rows of its own cells and holds only their elites (see _add_owned,
+        # csrc/insert.cu qd_insert_owned_cells). Reads of the whole archive are collectives.
+        if shard_store and not data_parallel:
+            raise ValueError("shard_store=True needs data_parallel=True (the cells are sharded over the ranks)")
+        self._shard_store = bool(shard_store) and self._dp_world > 1
+        self._cells_global = int(cells)
+        self._cell_lo, self._cell_hi = 0, int(cells)
+        if self._shard_store:
+            per = -(-int(cells) // self._dp_world)
+            self._cell_lo = min(self._dp_rank * per, int(cells))
+            self._cell_hi = min(self._cell_lo + per, int(cells))
+            if self._cell_hi <= self._cell_lo:
+                raise ValueError("shard_store=True needs at least one cell per rank")
+            cells = self._cell_hi - self._cell_lo
+        self._global_cache = None  # (adds seen, gathered per-rank state) of the last collective stats read
+        self._adds_enqueued = 0
         self._solution_dim = as_dim_tuple(solution_dim) if not np.isscalar(solution_dim) else int(solution_dim)
         self._objective_dim = ()
         self._measure_dim = int(measure_dim)
@@ -266,6 +283,15 @@ class DeviceArchive:
 
     @property
     def stats(self):
+        if self._shard_store:  # collective: the shards' running sums in rank (= cell) order
+            rows = self._global_state()
+            odt = self.dtypes["objective"]
+            osum = np.asarray(0.0, dtype=odt)
+            for v in rows[:, 1]:
+                osum = np.asarray(osum + np.asarray(v, dtype=odt), dtype=odt)
+            has = rows[:, 3] > 0
+            self._build_stats((int(rows[:, 0].sum()), float(osum), float(rows[has, 2].max()) if has.any() else None, 0))
+            return self._stats
         self._sync()
         if self._stats_dirty:
             self._build_stats()
@@ -277,6 +303,26 @@ class DeviceArchive:
 
     @property
     def best_elite(self):
+        if self._shard_store:
+            # collective: the shard holding the highest objective hands out its record (lowest rank = lowest cells on
+            # equal maxima; a tie between maxima reached in different add() calls on different ranks is not ordered
+            # by time as the reference would)
+            import torch.distributed as dist
+
+            rows = self._global_state()
+            has = rows[:, 3] > 0
+            if not has.any():
+                return None
+            owner = int(np.argmax(np.where(has, rows[:, 2], -np.inf)))
+            box = [None]
+            if self._dp_rank == owner:
+                if self._st[3] != self._best_serial:
+                    self._best_serial = self._st[3]
+                    self._best_elite = self._store.read_snapshot()
+                box[0] = dict(self._best_elite, index=np.int32(self._best_elite["index"] + self._cell_lo))
+            group = self._dp_group
+            dist.broadcast_object_list(box, src=owner if group is None else dist.get_global_rank(group, owner), group=group)
+            return box[0]
         self._sync()
         if self._st[3] != self._best_serial:  # the device replaced its best-elite snapshot since the last read
             self._best_serial = self._st[3]
@@ -285,7 +331,7 @@ class DeviceArchive:
 
     @property
     def cells(self):
-        return self._store.capacity
+        return self._cells_global if self._shard_store else self._store.capacity
 
     @property
     def learning_rate(self):
@@ -304,10 +350,15 @@ class DeviceArchive:
         return self._device
 
     def __len__(self):
+        if self._shard_store:
+            return int(self._global_state()[:, 0].sum())
         self._sync()
         return len(self._store)
 
     def __iter__(self):
+        if self._shard_store:  # collective snapshot, then a plain host iteration
+            d = self.data()
+            return iter([{k: v[i] for k, v in d.items()} for i in range(len(d["index"]))])
         self._sync()
         return iter(self._store)
 
@@ -376,10 +427,10 @@ class DeviceArchive:
                     int(res.best_serial))
         self._stats_dirty = True
 
-    def _build_stats(self):
+    def _build_stats(self, st=None):
         """_stats_update (_grid_archive.py:325-360) from the device-side running state."""
         self._stats_dirty = False
-        n, osum, omax, _ = self._st
+        n, osum, omax, _ = self._st if st is None else st
         if n == 0 or omax is None:
             return
         odt = self.dtypes["objective"]
@@ -496,14 +547,23 @@ class DeviceArchive:
                 for nb in local:
                     loffs.append(total)
                     total += (nb + 255) // 256 * 256
+                # owner-computes insertion: status / value of this rank's rows, written by the ranks that own their cells
+                ooffs = []
+                for nb in (4 * B_local, osz * B_local):
+                    ooffs.append(total)
+                    total += (nb + 255) // 256 * 256
                 bufs, handles = [], []
                 for _ in range(2):
                     t = symm.empty(total, dtype=torch.uint8, device=self._device)
                     handles.append(symm.rendezvous(t, group))
                     bufs.append(t)
-                peers, own, tabs, views = [], [], [], []
+                peers, own, tabs, views, outs = [], [], [], [], []
                 for G, h in zip(bufs, handles):
                     ptrs = [int(p) for p in h.buffer_ptrs]
+                    otab = np.array([[ptrs[r] + ooffs[0], ptrs[r] + ooffs[1]] for r in range(R)], dtype=np.int64)
+                    outs.append((torch.from_numpy(otab).to(self._device),
+                                 G[ooffs[0]:ooffs[0] + 4 * B_local].view(torch.int32),
+                                 G[ooffs[1]:ooffs[1] + osz * B_local].view(dev["objective"].dtype)))
                     peers.append((C.c_void_p * R)(*ptrs))
                     own.append((C.c_void_p * 1)(ptrs[self._dp_rank]))
                     tab = np.array([[ptrs[r] + lo for lo in loffs] for r in range(R)], dtype=np.int64)
@@ -511,7 +571,7 @@ class DeviceArchive:
                     views.append((G[offs[1]:offs[1] + R * small[1]].view(torch.int32),
                                   G[offs[2]:offs[2] + R * small[2]].view(dev["objective"].dtype),
                                   G[offs[0]:offs[0] + 4 * R].data_ptr()))
-                st = dict(handles=handles, peers=peers, own=own, tabs=tabs, views=views, bufs=bufs, turn=0,
+                st = dict(handles=handles, peers=peers, own=own, tabs=tabs, views=views, bufs=bufs, turn=0, outs=outs,
                           c_small=(C.c_int64 * 3)(*small), c_offs=(C.c_int64 * 3)(*offs),
                           c_local=(C.c_int64 * max(len(local), 1))(*local),
                           c_loffs=(C.c_int64 * max(len(loffs), 1))(*loffs))
@@ -533,6 +593,7 @@ class DeviceArchive:
         st["handles"][turn].barrier()
         g_idx, g_obj, flags_ptr = st["views"][turn]
         _lib.check(L.qd_flags_or(flags_ptr, R, store._flags_ptr, sp))
+        self._symm_last = (st["handles"][turn], st["outs"][turn])  # (_add_owned: the reverse route of status / value)
         return g_idx, g_obj, st["tabs"][turn].data_ptr(), R * B_local
 
     def _gather_global_batch(self, idx, dev, B_local, skip=()):
@@ -645,6 +706,8 @@ class DeviceArchive:
                         "value": torch.empty(0, dtype=torch_dtype(odt), device=self._device)}
             return {"status": np.empty(0, dtype=np.int32), "value": np.empty(0, dtype=odt)}
         store = self._store
+        if self._shard_store:
+            return self._add_owned(data, B, dev_in)
         if (not dev_in and B <= _SMALL_ROWS and B * self._row_bytes_total <= _SMALL_BYTES and self._dp_world == 1
                 and self._small_adds and self._small_index_ok(B)
                 and torch.cuda.current_device() == self._device.index):
@@ -793,6 +856,61 @@ class DeviceArchive:
         if pooled is not None:  # views of a pooled page-locked buffer (see _out_buffers)
             return {"status": pooled[2][lo:hi], "value": pooled[3][lo:hi]}
         return {"status": status_h.numpy()[lo:hi].copy(), "value": value_h.numpy()[lo:hi].copy()}
+
+    # ---- add() into a store sharded by cell range (owner computes) ------------------------------------------
+    def _add_owned(self, data, B_local, dev_in):
+        """SURVEY.md 8(e) row 2. Every rank passes its slice of the global batch; the slices' (cell, objective) are
+        exchanged over NVLink peer memory exactly as for the replicated store (12 B per row), but every rank then
+        classifies, resolves and commits only the rows whose cell it OWNS (qd_insert_owned_cells), pulls only its own
+        winners' rows from their owners, and writes status / value of a row back into the symmetric buffer of the
+        rank the row came from; a second cross-rank barrier completes that reverse route. Per-rank insert work and
+        row traffic are 1 / n_ranks of the replicated store's."""
+        store = self._store
+        with (_NULL_CTX if torch.cuda.current_device() == self._device.index else torch.cuda.device(self._device)):
+            self._join_copy()
+            dev = {name: self._to_device(data[name], store.dtypes[name], name).contiguous() for name in data}
+            idx = self._index_of_device(dev["measures"], store._flags_ptr)
+            got = self._symm_exchange(idx, dev, B_local)
+            if got is None:
+                raise RuntimeError("shard_store=True needs NVLink peer memory (torch symmetric memory) between the ranks")
+            g_idx, g_obj, peer_tab, B = got
+            handle, (out_tab, status_v, value_v) = self._symm_last
+            _lib.check(_lib.lib().qd_insert_owned_cells(
+                C.byref(store.abi_store()), B, g_idx.data_ptr(), g_obj.data_ptr(), peer_tab, B_local, self._cell_lo,
+                self._cell_hi, out_tab.data_ptr(), self._lr_f, self._tmin_f, store._result_dev.data_ptr(),
+                current_stream_ptr()))
+            handle.barrier()  # every owner's status / value of my rows has landed
+            status, value = status_v.clone(), value_v.clone()  # (the buffer set is written again two adds from now)
+            store._pending = True
+            self._adds_enqueued += 1
+            self._inflight = dev
+            if dev_in and not self._sync_device_adds:
+                return {"status": status, "value": value}
+            out = {"status": status.cpu().numpy(), "value": value.cpu().numpy()}
+        self._sync()  # validation verdict (global: every rank saw every objective and the OR of the index flags)
+        return out
+
+    def _global_state(self):
+        """COLLECTIVE (every rank, after the same add() calls): per-rank (elites, objective sum, best objective,
+        has-best) of a sharded store, gathered once per add."""
+        import torch.distributed as dist
+
+        self._sync()
+        if self._global_cache is not None and self._global_cache[0] == self._adds_enqueued:
+            return self._global_cache[1]
+        n, osum, omax, _ = self._st
+        mine = torch.tensor([float(n), float(osum), float(omax) if omax is not None else float("-inf"),
+                             0.0 if omax is None else 1.0], dtype=torch.float64, device=self._device)
+        allr = torch.empty(4 * self._dp_world, dtype=torch.float64, device=self._device)
+        dist.all_gather_into_tensor(allr, mine, group=self._dp_group)
+        rows = allr.view(self._dp_world, 4).cpu().numpy()
+        self._global_cache = (self._adds_enqueued, rows)
+        return rows
+
+    def _no_sharded_read(self, what):
+        raise NotImplementedError(
+            f"{what} is not available on a shard_store=True archive (every rank holds only the elites of its own "
+            "cells); use data() -- a collective -- or a replicated data_parallel archive")
 
     # ---- add() of CUDA tensors that need nothing done to them --------------------------------------------
     def _add_device(self, solution, objective, measures, fields, preset):
@@ -1037,15 +1155,50 @@ class DeviceArchive:
         self._sync()
         self._store.clear()
         self._stats_reset()
+        self._global_cache = None
+        self._adds_enqueued += 1
 
     # ---- read side (A10, _grid_archive.py:850-924) ---------------------------------------------
     def retrieve(self, measures):
         measures = np.asarray(measures, dtype=self.dtypes["measures"])
         check_batch_shape(measures, "measures", self.measure_dim, "measure_dim")
         idx = self.index_of(measures)
+        if self._shard_store:
+            return self._retrieve_cells_sharded(np.asarray(idx))
         occupied, data = self._store.retrieve(idx)
         fill_sentinel_values(occupied, data)
         return occupied, data
+
+    def _retrieve_cells_sharded(self, cells):
+        """COLLECTIVE retrieve by archive-wide cell number: every rank looks up the cells it owns, the answers are
+        exchanged (host objects: this is a read API for a handful of rows, not a data path) and stitched."""
+        import torch.distributed as dist
+
+        self._sync()
+        cells = np.asarray(cells, dtype=np.int64)
+        mine = (cells >= self._cell_lo) & (cells < self._cell_hi)
+        occ, data = self._store.retrieve(np.where(mine, cells - self._cell_lo, 0).astype(np.int32))
+        parts = [None] * self._dp_world
+        dist.all_gather_object(parts, (mine, np.asarray(occ) & mine, data), group=self._dp_group)
+        occupied = np.zeros(len(cells), dtype=bool)
+        out = {k: np.array(v, copy=True) for k, v in parts[0][2].items()}
+        for m, o, dd in parts:
+            occupied[m] = o[m]
+            for k in out:
+                out[k][m] = dd[k][m]
+        out["index"] = cells.astype(np.int32)
+        fill_sentinel_values(occupied, out)
+        return occupied, out
+
+    def _sharded_occupied_list(self):
+        """COLLECTIVE: the archive-wide occupied list, shard after shard."""
+        import torch.distributed as dist
+
+        self._sync()
+        local = (self._store._sync_occupied_list()[: len(self._store)].astype(np.int64) + self._cell_lo).astype(np.int32)
+        parts = [None] * self._dp_world
+        dist.all_gather_object(parts, local, group=self._dp_group)
+        return np.concatenate(parts)
 
     def retrieve_single(self, measures):
         measures = np.asarray(measures, dtype=self.dtypes["measures"])
@@ -1056,6 +1209,21 @@ class DeviceArchive:
 
     def data(self, fields=None, return_type="dict"):
         self._sync()  # adopts the state of insertions still in flight (and raises for a batch the device dropped)
+        if self._shard_store:
+            # collective: the shards' elites, rank after rank (= ascending cell ranges, insertion order within a
+            # shard), with archive-wide cell indices
+            import torch.distributed as dist
+
+            if return_type != "dict":
+                self._no_sharded_read(f"data(return_type={return_type!r})")
+            single = isinstance(fields, str)
+            want = None if fields is None else ([fields] if single else list(fields))
+            local = self._store.data(None if want is None else sorted(set(want) | {"index"}), "dict")
+            local["index"] = (local["index"] + self._cell_lo).astype(np.int32)
+            parts = [None] * self._dp_world
+            dist.all_gather_object(parts, local, group=self._dp_group)
+            out = {k: np.concatenate([p[k] for p in parts], axis=0) for k in (want or local)}
+            return out[fields] if single else out
         return self._store.data(fields, return_type)
 
     def sample_elite_cells(self, n, replace=True):
@@ -1063,6 +1231,12 @@ class DeviceArchive:
         _grid_archive.py:912-924), without fetching the rows: device-side consumers gather them in place."""
         if self.empty:
             raise IndexError("No elements in archive.")
+        if self._shard_store:  # collective; the ranks' generators were seeded alike and draw alike
+            glist = self._sharded_occupied_list()
+            if not replace and n > len(glist):
+                raise ValueError(
+                    "Cannot take a larger sample than the number of elites in the archive when 'replace=False'")
+            return np.ascontiguousarray(glist[self._rng.choice(len(glist), size=n, replace=replace)])
         if not replace and n > len(self._store):
             raise ValueError(
                 "Cannot take a larger sample than the number of elites in the archive when 'replace=False'")
@@ -1070,6 +1244,8 @@ class DeviceArchive:
         return np.ascontiguousarray(self._store._sync_occupied_list()[random_indices])
 
     def sample_elites(self, n, replace=True):
+        if self._shard_store:
+            return self._retrieve_cells_sharded(self.sample_elite_cells(n, replace))[1]
         if self.empty:
             raise IndexError("No elements in archive.")
         self._sync()

@@ -67,7 +67,7 @@ class CVTArchive(DeviceArchive):
                  nearest_neighbors="scipy_kd_tree", kdtree_kwargs=None, kdtree_query_kwargs=None, chunk_size=None,
                  sklearn_nn_kwargs=None, cells=None, custom_centroids=None, centroid_method=None, use_kd_tree=None,
                  ckdtree_kwargs=None, device=None, search_method="auto", shard_centroids=False, data_parallel=False,
-                 process_group=None):
+                 process_group=None, shard_store=False):
         for name, val in (("cells", cells), ("custom_centroids", custom_centroids),
                           ("centroid_method", centroid_method), ("use_kd_tree", use_kd_tree),
                           ("ckdtree_kwargs", ckdtree_kwargs)):
@@ -109,7 +109,7 @@ class CVTArchive(DeviceArchive):
             self, solution_dim=solution_dim, measure_dim=len(ranges), cells=len(cen), learning_rate=learning_rate,
             threshold_min=threshold_min, qd_score_offset=qd_score_offset, seed=seed, solution_dtype=solution_dtype,
             objective_dtype=objective_dtype, measures_dtype=measures_dtype, dtype=dtype, extra_fields=extra_fields,
-            device=device, data_parallel=data_parallel, process_group=process_group)
+            device=device, data_parallel=data_parallel, process_group=process_group, shard_store=shard_store)
         lo, hi = zip(*ranges)
         self._lower_bounds = np.array(lo, dtype=mdt)
         self._upper_bounds = np.array(hi, dtype=mdt)

@@ -24,7 +24,8 @@ class GridArchive(DeviceArchive):
 
     def __init__(self, *, solution_dim, dims, ranges, learning_rate=None, threshold_min=-np.inf, epsilon=1e-6,
                  qd_score_offset=0.0, seed=None, solution_dtype=None, objective_dtype=None, measures_dtype=None,
-                 dtype=None, extra_fields=None, device=None, data_parallel=False, process_group=None):
+                 dtype=None, extra_fields=None, device=None, data_parallel=False, process_group=None,
+                 shard_store=False):
         self._dims = np.array(dims, dtype=np.int32)
         if len(self._dims) != len(ranges):
             raise ValueError(
@@ -35,7 +36,7 @@ class GridArchive(DeviceArchive):
             self, solution_dim=solution_dim, measure_dim=len(self._dims), cells=int(np.prod(self._dims)),
             learning_rate=learning_rate, threshold_min=threshold_min, qd_score_offset=qd_score_offset, seed=seed,
             solution_dtype=solution_dtype, objective_dtype=objective_dtype, measures_dtype=measures_dtype,
-            dtype=dtype, extra_fields=extra_fields, device=device, data_parallel=data_parallel,
+            dtype=dtype, extra_fields=extra_fields, device=device, data_parallel=data_parallel, shard_store=shard_store,
             process_group=process_group)
         mdt = self.dtypes["measures"]
         lo, hi = zip(*ranges)

@@ -262,7 +262,26 @@ struct InsertArgs {
   char* snapshot;  // best-elite snapshot buffer or NULL
   qd_add_result* result;
   Scratch s;
+  // owner-computes insertion (qd_insert_owned_cells): this store holds the cells [cell_lo, cell_hi) of a sharded
+  // archive. Rows of other cells are skipped, cell numbers are local from then on, and status / value of a row go to
+  // the rank its batch slice came from (out_tab[2 * r] = status, [2 * r + 1] = value of rank r, peer memory).
+  int32_t cell_lo, cell_hi;  // cell_hi == 0: the whole archive (idx is local already)
+  void* const* out_tab;      // [dev] or NULL: status / value stay in the arrays above
+  int64_t out_rows_per_rank;
 };
+
+template <typename T>
+__device__ __forceinline__ void store_out(const InsertArgs<T>& a, int64_t i, int32_t st, T v) {
+  if (a.out_tab == nullptr) {
+    a.status[i] = st;
+    a.value[i] = v;
+  } else {
+    const uint32_t r = (uint32_t)i / (uint32_t)a.out_rows_per_rank;
+    const uint32_t l = (uint32_t)i - r * (uint32_t)a.out_rows_per_rank;
+    reinterpret_cast<int32_t*>(a.out_tab[2 * r])[l] = st;
+    reinterpret_cast<T*>(a.out_tab[2 * r + 1])[l] = v;
+  }
+}
 
 // (1 - lr)^k for integral k >= 1 by binary powering (deterministic; k = 1 returns the base exactly)
 __device__ __forceinline__ double powi(double b, uint32_t k) {
@@ -348,6 +367,13 @@ __device__ void phase_classify(const InsertArgs<T>& a, const GridParams& gp, boo
         else
           c[u] = a.idx[i];
         o[u] = a.obj[i];
+        if (a.cell_hi > 0) {
+          // every rank looks at every objective (one verdict about the batch on all ranks), but only at the rows of
+          // its own cells from here on; the later passes see the local cell number or -1
+          bad |= !is_finite_t(o[u]);
+          c[u] = (c[u] >= a.cell_lo && c[u] < a.cell_hi) ? c[u] - a.cell_lo : -1;
+          a.idx[i] = c[u];
+        }
       }
     }
 #pragma unroll
@@ -363,9 +389,8 @@ __device__ void phase_classify(const InsertArgs<T>& a, const GridParams& gp, boo
       const bool occ = (tc[u] == tc[u]);   // unoccupied cells hold NaN
       const T t = occ ? tc[u] : a.tmin;    // _grid_archive.py:628-630
       const bool can = fin && (o[u] > t);  // :636
-      a.status[i] = can ? (occ ? 1 : 2) : 0;
       const T tval = (can && !occ) ? (cma_me ? (T)0 : a.tmin) : t;  // :646-648
-      a.value[i] = o[u] - tval;                                     // :649
+      store_out<T>(a, i, can ? (occ ? 1 : 2) : 0, o[u] - tval);     // :649
       if (can) {
         Cell* cell = &a.s.cell[c[u]];
         const unsigned long long key = ord_key((double)o[u]);
@@ -433,11 +458,13 @@ __device__ void phase_mark_winner(const InsertArgs<T>& a, bool only_flagged) {
 template <typename T>
 __device__ void phase_cleanup(const InsertArgs<T>& a) {  // validation failed: leave the store alone
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x) {
-    if (a.status[i] == 0) continue;
-    Cell* cell = &a.s.cell[a.idx[i]];
+    const int32_t c = a.idx[i];
+    if (c < 0) continue;  // (a row of another rank's cells)
+    Cell* cell = &a.s.cell[c];
+    if (cell->best == 0ull) continue;  // untouched (no insertable row), or reset by another row of the cell already
     cell->best = cell->pick = 0ull;
     cell->w0 = cell->w1 = 0ll;
-    a.s.cnt[a.idx[i]] = 0u;
+    a.s.cnt[c] = 0u;
   }
 }
 
@@ -454,7 +481,7 @@ __device__ void phase_select(const InsertArgs<T>& a, uint32_t* s_cnt, uint32_t* 
     bool iswin = false;
     if (i < a.B) {  // `pick` stays 0 for cells without an insertable row: no need to read status
       c = a.idx[i];
-      iswin = a.s.cell[c].pick == (pc.amb | (pc.rowmask - (unsigned long long)i));
+      iswin = c >= 0 && a.s.cell[c].pick == (pc.amb | (pc.rowmask - (unsigned long long)i));
     }
     const unsigned m = __ballot_sync(0xffffffffu, iswin);
     if (lane == 0) s_cnt[wi] = __popc(m);
@@ -1282,7 +1309,7 @@ template <typename T>
 int insert_impl(const qd_store* st, int64_t B, int32_t* idx, const GridSpec& gs, const void* objective,
                 const void* const* field_src, double lr, double tmin, int32_t* status, void* value,
                 qd_add_result* result, int part, cudaStream_t stream, const void* const* peer_tab = nullptr,
-                int64_t rows_per_rank = 0) {
+                int64_t rows_per_rank = 0, int32_t cell_lo = 0, int32_t cell_hi = 0, void* const* out_tab = nullptr) {
   const int64_t N = st->capacity;
   InsertArgs<T> a;
   a.B = B;
@@ -1301,6 +1328,10 @@ int insert_impl(const qd_store* st, int64_t B, int32_t* idx, const GridSpec& gs,
   a.value = (T*)value;
   a.snapshot = (char*)st->best_snapshot;
   a.result = result;
+  a.cell_lo = cell_lo;
+  a.cell_hi = cell_hi;
+  a.out_tab = out_tab;
+  a.out_rows_per_rank = rows_per_rank;
   a.s = carve(st->scratch, N);
   FieldCopy fc;
   fc.n = st->n_fields;
@@ -1518,6 +1549,29 @@ extern "C" int qd_insert_sharded_rows(const qd_store* store, int64_t B, const in
                                threshold_min, status_out, value_out, result, part, s, peer_field_src, rows_per_rank);
   return insert_impl<float>(store, B, const_cast<int32_t*>(idx), gs, objective, field_src, learning_rate,
                             threshold_min, status_out, value_out, result, part, s, peer_field_src, rows_per_rank);
+}
+
+extern "C" int qd_insert_owned_cells(const qd_store* store, int64_t B, int32_t* idx, const void* objective,
+                                     const void* const* peer_field_src, int64_t rows_per_rank, int32_t cell_lo,
+                                     int32_t cell_hi, void* const* out_tab, double learning_rate,
+                                     double threshold_min, qd_add_result* result, void* stream) {
+  using namespace qd;
+  QD_REQUIRE(store && result, "null store/result");
+  QD_REQUIRE(idx && objective && peer_field_src && out_tab, "null pointer");
+  QD_REQUIRE(rows_per_rank >= 1 && B >= 1 && B < ((int64_t)1 << 31), "bad batch shape");
+  QD_REQUIRE(cell_lo >= 0 && cell_hi > cell_lo && (int64_t)cell_hi - cell_lo == store->capacity,
+             "the store must hold exactly the cells [cell_lo, cell_hi)");
+  // (status / value go through out_tab: check_insert_args only needs non-null placeholders)
+  int rc = check_insert_args(store, B, objective, reinterpret_cast<const int32_t*>(out_tab), out_tab, result);
+  if (rc) return rc;
+  GridSpec gs;
+  gs.gp.d = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (store->obj_dtype == QD_F64)
+    return insert_impl<double>(store, B, idx, gs, objective, nullptr, learning_rate, threshold_min, nullptr, nullptr,
+                               result, QD_INSERT_WHOLE, s, peer_field_src, rows_per_rank, cell_lo, cell_hi, out_tab);
+  return insert_impl<float>(store, B, idx, gs, objective, nullptr, learning_rate, threshold_min, nullptr, nullptr,
+                            result, QD_INSERT_WHOLE, s, peer_field_src, rows_per_rank, cell_lo, cell_hi, out_tab);
 }
 
 extern "C" int qd_grid_insert(const qd_store* store, int64_t B, const void* measures, int meas_dtype, int d,

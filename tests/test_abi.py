@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/qd_b200.h but not exported"
     assert set(_lib.PROTOTYPES) == set(names), set(_lib.PROTOTYPES) ^ set(names)
-    assert _lib.lib().qd_abi_version() == 5
+    assert _lib.lib().qd_abi_version() == 6
 
 
 def test_struct_layouts_match_header(tmp_path):

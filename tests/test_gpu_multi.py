@@ -218,3 +218,105 @@ def test_two_gpu_sharded_search_cross_shard_ties():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def _owned_worker(rank, world, port, q):
+    """Owner-computes store: cells sharded over the ranks by contiguous range, every rank
+    commits only the rows of its own cells. Against a single-process archive fed the global batches: status / value
+    of the rank's rows bit-equal, the same elites (as a set -- the sharded list is shard after shard), the same
+    statistics and best elite, collective retrieve / sample_elites, and a batch with a NaN objective dropped by
+    every rank."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from pyribs_b200.archives import CVTArchive, GridArchive
+
+    ok, why = True, []
+
+    def check(cond, msg):
+        nonlocal ok
+        if not cond:
+            ok = False
+            why.append(msg)
+
+    rng = np.random.default_rng(11)
+    cen = rng.uniform(-1, 1, (3001, 6))
+    makers = {
+        "grid_mae": lambda **kw: GridArchive(solution_dim=5, dims=(37, 41), ranges=[(-1, 1)] * 2, learning_rate=0.1,
+                                             threshold_min=-1.0, extra_fields={"tag": ((), np.int32)}, seed=7, **kw),
+        "cvt6": lambda **kw: CVTArchive(solution_dim=5, centroids=cen, ranges=[(-1, 1)] * 6, seed=7, **kw),
+    }
+    for name, make in makers.items():
+        sharded, whole = make(data_parallel=True, shard_store=True), make()
+        d = whole.measure_dim
+        Bl = 4000
+        for step in range(4):
+            full = dict(solution=rng.standard_normal((world * Bl, 5)), objective=rng.uniform(0, 10, world * Bl) + step,
+                        measures=rng.uniform(-1, 1, (world * Bl, d)))
+            if step == 2:  # exact ties inside one cell, rows on different ranks: first in the GLOBAL batch wins
+                full["measures"][Bl - 5:Bl + 5] = full["measures"][0]
+                full["objective"][Bl - 5:Bl + 5] = 99.0
+            if name == "grid_mae":
+                full["tag"] = rng.integers(0, 1000, world * Bl).astype(np.int32)
+            mine = {k: v[rank * Bl:(rank + 1) * Bl] for k, v in full.items()}
+            if step % 2:  # CUDA tensors in (asynchronous) and NumPy in
+                got = sharded.add(**{k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in mine.items()})
+                got = {k: v.cpu().numpy() for k, v in got.items()}
+            else:
+                got = sharded.add(**mine)
+            ref = whole.add(**full)
+            check(np.array_equal(got["status"], ref["status"][rank * Bl:(rank + 1) * Bl]), f"{name} s{step} status")
+            check(np.array_equal(got["value"], ref["value"][rank * Bl:(rank + 1) * Bl]), f"{name} s{step} value")
+        check(len(sharded) == len(whole) and sharded.cells == whole.cells, f"{name} len / cells")
+        ds, dw = sharded.data(), whole.data()
+        o1, o2 = np.argsort(ds["index"]), np.argsort(dw["index"])
+        for k in dw:
+            check(np.array_equal(ds[k][o1], dw[k][o2]), f"{name} data[{k}]")
+        lo, hi = sharded._cell_lo, sharded._cell_hi
+        check(len(sharded._store) == int(np.count_nonzero((dw["index"] >= lo) & (dw["index"] < hi))), f"{name} shard size")
+        s1, s2 = sharded.stats, whole.stats
+        check(s1.num_elites == s2.num_elites and s1.obj_max == s2.obj_max and s1.coverage == s2.coverage, f"{name} stats")
+        check(abs(float(s1.qd_score) - float(s2.qd_score)) <= 1e-9 * abs(float(s2.qd_score)), f"{name} qd_score")
+        b1, b2 = sharded.best_elite, whole.best_elite
+        check(all(np.array_equal(b1[k], b2[k]) for k in b2), f"{name} best_elite")
+        probe = rng.uniform(-1, 1, (64, d))
+        occ1, r1 = sharded.retrieve(probe)
+        occ2, r2 = whole.retrieve(probe)
+        check(np.array_equal(occ1, occ2) and all(np.array_equal(r1[k], r2[k], equal_nan=True) for k in r2),
+              f"{name} retrieve")
+        e = sharded.sample_elites(8)
+        check(set(e["index"].tolist()) <= set(dw["index"].tolist()) and e["solution"].shape == (8, 5), f"{name} sample")
+        bad = {k: v.copy() for k, v in mine.items()}
+        bad["objective"][3] = np.nan if rank == 1 else 1.0  # only rank 1's slice is bad: every rank must drop the batch
+        n_before = len(sharded)
+        try:
+            sharded.add(**bad)
+            check(False, f"{name} NaN batch accepted")
+        except ValueError:
+            pass
+        check(len(sharded) == n_before, f"{name} store touched by a dropped batch")
+    q.put((rank, ok, why))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_owner_computes_store():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_owned_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
