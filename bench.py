@@ -248,14 +248,13 @@ C_SIZEOF_RESULT = 120  # sizeof(qd_add_result)
 NCU_TRAFFIC = {"insert_kernel_grid_2M": 315_400_704 + 206_669_312}  # dram read + write, profiles/r02j_grid_insert_2M_ncu_full.txt
 
 
-def grid_insert_roofline(torch, dev, peak_hbm):
+def grid_insert_roofline(torch, dev, peak_hbm, Bg=2_000_000, n=100, iters=12):
     """GridArchive insertion against the HBM roofline (north_star: >= 60 % of HBM peak at 1 GPU): CMA-MAE
     lr=0.01, 500x500 cells (the grid of configs[2]), n=100, 2M-row batches of uniform measures -- the size at
     which the insertion is throughput- rather than latency-bound. Algorithmic bytes per SURVEY 8(d):
     45 B/row + 1 648 B per winner."""
     from pyribs_b200.archives import GridArchive
 
-    Bg, n = 2_000_000, 100
     a = GridArchive(solution_dim=n, dims=(500, 500), ranges=[(-1, 1)] * 2, learning_rate=0.01, threshold_min=0.0)
     g = torch.Generator(device=dev).manual_seed(1)
     bs = [dict(solution=torch.randn(Bg, n, dtype=torch.float64, device=dev, generator=g),
@@ -265,10 +264,9 @@ def grid_insert_roofline(torch, dev, peak_hbm):
         a.add(**bs[j])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 12
     e0.record()
     for j in range(iters):
-        a.add(**bs[j % 3])  # 3 x 1.65 GB of inputs: nothing survives in the 126 MB L2 between calls
+        a.add(**bs[j % 3])  # 3 x 1.65 GB of inputs (n = 100): nothing survives in the 126 MB L2 between calls
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
@@ -276,10 +274,10 @@ def grid_insert_roofline(torch, dev, peak_hbm):
     W = int(torch.unique(a.index_of(bs[0]["measures"])[st != 0]).numel())
     alg = Bg * 45 + W * (2 * n * 8 + 2 * 2 * 8 + 2 * 8)
     return {"kernel": "insert_kernel<double, double, 2, fused grid index> (GridArchive.add, one launch per add)",
-            "workload": "GridArchive 500x500, CMA-MAE lr=0.01, n=100, 2M-row batches, uniform measures",
+            "workload": f"GridArchive 500x500, CMA-MAE lr=0.01, n={n}, {Bg // 1000}k-row batches, uniform measures",
             "bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak_hbm, "unit": "GB/s", "frac": alg / ms / 1e6 / peak_hbm,
             "ms_per_add": ms, "insertions_per_s": Bg / ms * 1e3, "winners_per_add": W, "algorithmic_bytes": alg,
-            "traffic": NCU_TRAFFIC.get("insert_kernel_grid_2M")}
+            "traffic": NCU_TRAFFIC.get("insert_kernel_grid_2M") if (Bg, n) == (2_000_000, 100) else None}
 
 
 def es_lines(torch, dev, peak_hbm, cpu=True):
@@ -657,11 +655,23 @@ def main():
             own = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * d, search_method=args.search,
                              data_parallel=True, shard_store=True)
 
+            first_own = []
+
             def step_own(j):
                 b = dev_batches[j % N_RESIDENT]
-                own.add(b["solution"], b["objective"] + OBJ_DRIFT * j, b["measures"])
+                out = own.add(b["solution"], b["objective"] + OBJ_DRIFT * j, b["measures"])
+                if j < 2:
+                    first_own.append({k: v.cpu().numpy() for k, v in out.items()})
 
-            ms_own, _ = timed(step_own, args.steps, args.warmup)
+            ms_own, launches_own = timed(step_own, args.steps, args.warmup)
+            # the two stores must tell every row the same thing (first two adds into the empty archives)
+            mism = sum(int(np.count_nonzero(x["status"] != y["status"])) + int(np.count_nonzero(x["value"] != y["value"]))
+                       for x, y in zip(first, first_own))
+            t = torch.tensor([mism], device=dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            if int(t.item()):
+                raise SystemExit(f"parity check failed: owner-computes and replicated store disagree on {int(t.item())} "
+                                 "status / value entries")
             n_own = len(own)
             own.clear()
 
@@ -676,7 +686,8 @@ def main():
                                "winners' rows; status / value return by a reverse push over NVLink",
                 "insertions_per_s": B * args.steps / (ms_own * 1e-3), "ms_per_add": ms_own / args.steps,
                 "e2e_insertions_per_s": B * e2e_steps / (ms_own_e2e * 1e-3), "e2e_ms_per_add": ms_own_e2e / e2e_steps,
-                "elites_after_timed_adds": n_own}
+                "elites_after_timed_adds": n_own, "gpu_launches": int(launches_own),
+                "parity": "status / value of the first two adds bit-equal to the replicated store's on every rank"}
             del own
         except Exception as e:  # noqa: BLE001
             alt["owner_computes_store"] = {"error": f"{type(e).__name__}: {e}"}
@@ -714,7 +725,10 @@ def main():
 
             for name, fn in (("configs[1]", lambda: c2_line(torch, dev, 200, factory)),
                              ("published protocol", lambda: published_protocol(torch, dev)),
-                             ("grid insert", lambda: grid_insert_roofline(torch, dev, peak_hbm))):
+                             ("grid insert", lambda: grid_insert_roofline(torch, dev, peak_hbm)),
+                             # the same archive with 10x longer solution rows: the row copy (HBM-bound) is 97 % of the
+                             # bytes instead of 81 %, i.e. how the kernel does where the roofline is the bound
+                             ("grid insert, n=1000", lambda: grid_insert_roofline(torch, dev, peak_hbm, 1_000_000, 1000, 8))):
                 try:
                     secondary.append(fn())
                     torch.cuda.empty_cache()
@@ -755,6 +769,27 @@ def main():
         "roofline": roofline,
     }
     if alt is not None:
+        own = alt.get("owner_computes_store") or {}
+        if "insertions_per_s" in own:
+            # N > 1: the owner-computes store is the configuration of record (per-rank insert work and row traffic 1/N);
+            # the replicated store measured in the same run moves to `alt`
+            alt["replicated_store"] = {
+                "parallelism": line["config"]["parallelism"], "insertions_per_s": line["value"],
+                "ms_per_add": line["ms_per_step"], "e2e_insertions_per_s": line["e2e"]["value"],
+                "e2e_ms_per_add": line["e2e"]["ms_per_step"], "e2e_pageable": line["e2e"]["pageable"],
+                "gpu_launches": line["gpu_launches"]}
+            line["value"], line["ms_per_step"] = own["insertions_per_s"], own["ms_per_add"]
+            line["gpu_launches"] = own["gpu_launches"]
+            line["e2e"] = {"value": own["e2e_insertions_per_s"], "unit": "insertions/s",
+                           "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": d2h * world,
+                           "ms_per_step": own["e2e_ms_per_add"], "inputs": "page-locked NumPy arrays"}
+            line["config"]["parallelism"] = (
+                f"strong scaling over {world} GPUs: batch rows sharded (B/{world} per rank), search index replicated, "
+                "(cell, objective) exchanged over NVLink peer memory (12 B per row), STORE sharded by cell range -- "
+                "every rank classifies / commits only the rows of its own cells, pulls only its own winners' rows "
+                "from their owners and pushes status / value back to the rows' ranks (owner computes)")
+            line["parity"] += "; owner-computes store bit-equal to the replicated store on the first two adds"
+            del alt["owner_computes_store"]
         line["alt"] = alt
     if cpu is not None:
         line["cpu_baseline"] = cpu

@@ -220,6 +220,7 @@ class DeviceArchive:
     # search structures, scratch) travel through pickle; rebuilt by __setstate__ / on first use
     _TRANSIENT = {"_pinned": dict, "_outbuf": dict, "_copy_stream": None, "_copy_event": None, "_inflight": None,
                   "_dp_symm": None, "_zc": None, "_shared_idx": None, "_last_idx": None, "_pin_cache": dict, "_small": dict, "_dev_idx": None,
+                  "_symm_last": None, "_global_cache": None,
                   "_pipe": None, "_pipe_pending": None, "_dp_group": None}
 
     def __getstate__(self):
@@ -868,8 +869,24 @@ class DeviceArchive:
         store = self._store
         with (_NULL_CTX if torch.cuda.current_device() == self._device.index else torch.cuda.device(self._device)):
             self._join_copy()
-            dev = {name: self._to_device(data[name], store.dtypes[name], name).contiguous() for name in data}
+            # measures + objective first: the search needs nothing else, so the (much larger) solution / extra-field
+            # rows of a host batch travel on a side stream while it runs
+            dev = {name: self._to_device(data[name], store.dtypes[name], name).contiguous()
+                   for name in ("measures", "objective")}
             idx = self._index_of_device(dev["measures"], store._flags_ptr)
+            rest = [n for n in data if n not in dev]
+            if dev_in or all(isinstance(data[n], torch.Tensor) for n in rest):
+                for n in rest:
+                    dev[n] = self._to_device(data[n], store.dtypes[n], n).contiguous()
+            else:
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self._device)
+                    self._copy_event = torch.cuda.Event()
+                with torch.cuda.stream(self._copy_stream):
+                    for n in rest:
+                        dev[n] = self._to_device(data[n], store.dtypes[n], n).contiguous()
+                    self._copy_event.record(self._copy_stream)
+                torch.cuda.current_stream().wait_event(self._copy_event)
             got = self._symm_exchange(idx, dev, B_local)
             if got is None:
                 raise RuntimeError("shard_store=True needs NVLink peer memory (torch symmetric memory) between the ranks")
