@@ -92,6 +92,7 @@ _IDLE_REFS = sys.getrefcount(_PROBE[0])
 # below csrc/insert.cu's kSingleMaxRows / kSingleMaxWork one CTA then inserts the whole batch
 _SMALL_ROWS = 16384
 _SMALL_BYTES = 4 << 20
+_CHUNK_MIN_ROWS = 1 << 18  # host batches from here on overlap the transfer of their measures with the search
 
 
 def _pool_entry_free(entry):
@@ -220,7 +221,7 @@ class DeviceArchive:
     # search structures, scratch) travel through pickle; rebuilt by __setstate__ / on first use
     _TRANSIENT = {"_pinned": dict, "_outbuf": dict, "_copy_stream": None, "_copy_event": None, "_inflight": None,
                   "_dp_symm": None, "_zc": None, "_shared_idx": None, "_last_idx": None, "_pin_cache": dict, "_small": dict, "_dev_idx": None,
-                  "_symm_last": None, "_global_cache": None,
+                  "_symm_last": None, "_global_cache": None, "_chunk_events": None,
                   "_pipe": None, "_pipe_pending": None, "_dp_group": None}
 
     def __getstate__(self):
@@ -491,6 +492,48 @@ class DeviceArchive:
     def _index_of_device(self, measures: torch.Tensor, flags_ptr: int, out=None) -> torch.Tensor:
         raise NotImplementedError
 
+    def _search_chunked(self, measures, B, pieces=4):
+        """index_of over a large host array, overlapped with its own host->device transfer: piece k is copied on the
+        side stream (through a page-locked staging piece when the array is pageable) and searched on the caller's
+        stream as soon as it has landed. Returns (device measures, device idx)."""
+        mdt = self.dtypes["measures"]
+        arr = np.ascontiguousarray(measures, dtype=mdt)
+        src = torch.from_numpy(arr)
+        pinned = src.is_pinned()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self._device)
+            self._copy_event = torch.cuda.Event()
+        meas = torch.empty(arr.shape, dtype=torch_dtype(mdt), device=self._device)
+        idx = torch.empty(B, dtype=torch.int32, device=self._device)
+        step = -(-B // pieces)
+        cur = torch.cuda.current_stream()
+        events = self.__dict__.get("_chunk_events")
+        if not events or len(events) < pieces:
+            events = self._chunk_events = [torch.cuda.Event() for _ in range(pieces)]
+        stage = None
+        if not pinned:
+            key = ("measures", np.dtype(mdt))
+            stage = self._pinned.get(key)
+            if stage is None or stage.numel() < arr.size:
+                stage = self._pinned[key] = torch.empty(max(arr.size, 1), dtype=torch_dtype(mdt)).pin_memory()
+            stage = stage[: arr.size].view(arr.shape)
+            self._copy_stream.wait_stream(cur)  # (the staging buffer's previous use was consumed on `cur`'s order)
+        for k in range(pieces):
+            lo, hi = k * step, min(B, (k + 1) * step)
+            if lo >= hi:
+                break
+            piece = src[lo:hi]
+            if stage is not None:
+                stage[lo:hi].copy_(piece)  # host memcpy of this piece while the previous pieces travel / are searched
+                piece = stage[lo:hi]
+            with torch.cuda.stream(self._copy_stream):
+                meas[lo:hi].copy_(piece, non_blocking=True)
+                events[k].record(self._copy_stream)
+            cur.wait_event(events[k])
+            self._index_of_device(meas[lo:hi], self._store._flags_ptr, out=idx[lo:hi])
+        meas.record_stream(self._copy_stream)
+        return meas, idx
+
     def same_geometry(self, other):
         """True when `other` maps every measure vector to the same cell index as this archive (then a batch
         indexed for one of them needs no second index_of: Scheduler's result_archive, _scheduler.py:260-264)."""
@@ -729,13 +772,21 @@ class DeviceArchive:
             self._last_zero_copy = False
             # measures + objective first: the index kernels only need those, so the (much larger)
             # solution / extra-field rows travel host->device on a side stream while the search runs
-            dev = {name: self._to_device(data[name], store.dtypes[name], name) for name in ("measures", "objective")}
+            idx = None
+            if (not dev_in and not fused and preset is None and self._dp_world == 1 and B >= _CHUNK_MIN_ROWS
+                    and isinstance(data["measures"], np.ndarray)):
+                # large host batch: the measures travel in pieces and the search of piece k runs while piece k+1 is
+                # still on the PCIe bus (and, for pageable arrays, still being staged by the host)
+                dev = {"objective": self._to_device(data["objective"], store.dtypes["objective"], "objective")}
+                dev["measures"], idx = self._search_chunked(data["measures"], B)
+            else:
+                dev = {name: self._to_device(data[name], store.dtypes[name], name) for name in ("measures", "objective")}
             if global_search:
                 # every rank searches ALL queries against its centroid shard: gather the measures first
                 dev["measures"] = self._all_gather_many([dev["measures"]])[0]
             if preset is not None:  # an archive of the same geometry has just indexed this very batch
                 idx = preset[0]
-            else:
+            elif idx is None:
                 idx = None if fused else self._index_of_device(dev["measures"], store._flags_ptr)
             rest = [n for n in data if n not in dev]
             if dev_in or all(isinstance(data[n], torch.Tensor) for n in rest):

@@ -350,3 +350,32 @@ def test_lean_add_routes_equal_the_general_route(kind, B):
     with pytest.raises(ValueError):
         a.add(**dict(dev, objective=dev["objective"][:-1]))
     assert len(a) > 0
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_chunked_host_search_equals_device_batch(pinned):
+    """Host batches of >= 2^18 rows overlap the transfer of their measures with the search, piece by piece
+    (DeviceArchive._search_chunked): same cells, statuses and values as the same batch handed over as CUDA tensors."""
+    import torch
+
+    from pyribs_b200.archives import CVTArchive
+
+    rng = np.random.default_rng(21)
+    cen = rng.uniform(-1, 1, (20_000, 6))
+    a, b = (CVTArchive(solution_dim=3, centroids=cen, ranges=[(-1, 1)] * 6) for _ in range(2))
+    B = 300_001
+    for step in range(2):
+        batch = dict(solution=rng.standard_normal((B, 3)), objective=rng.standard_normal(B) + step,
+                     measures=rng.uniform(-1.1, 1.1, (B, 6)))
+        host = {k: (torch.from_numpy(v).pin_memory().numpy() if pinned else v) for k, v in batch.items()}
+        ra = a.add(**host)
+        rb = b.add(**{k: torch.from_numpy(v).cuda() for k, v in batch.items()})
+        np.testing.assert_array_equal(ra["status"], rb["status"].cpu().numpy())
+        np.testing.assert_array_equal(ra["value"], rb["value"].cpu().numpy())
+    da, db = a.data(), b.data()
+    for k in da:
+        np.testing.assert_array_equal(da[k], db[k], err_msg=k)
+    bad = dict(host, measures=host["measures"].copy())
+    bad["measures"][B - 7, 2] = np.inf  # in the last piece
+    with pytest.raises(ValueError, match="measures must be finite"):
+        a.add(**bad)
