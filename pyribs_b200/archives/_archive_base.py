@@ -27,6 +27,7 @@ from pyribs_b200._utils import (
     validate_batch,
     validate_single,
 )
+from pyribs_b200.archives import _shard_util
 from pyribs_b200.archives._archive_stats import ArchiveStats
 from pyribs_b200.archives._device_store import DeviceStore, current_stream_ptr
 
@@ -128,9 +129,7 @@ class DeviceArchive:
         self._cells_global = int(cells)
         self._cell_lo, self._cell_hi = 0, int(cells)
         if self._shard_store:
-            per = -(-int(cells) // self._dp_world)
-            self._cell_lo = min(self._dp_rank * per, int(cells))
-            self._cell_hi = min(self._cell_lo + per, int(cells))
+            self._cell_lo, self._cell_hi = _shard_util.shard_cell_range(cells, self._dp_world, self._dp_rank)
             if self._cell_hi <= self._cell_lo:
                 raise ValueError("shard_store=True needs at least one cell per rank")
             cells = self._cell_hi - self._cell_lo
@@ -286,13 +285,8 @@ class DeviceArchive:
     @property
     def stats(self):
         if self._shard_store:  # collective: the shards' running sums in rank (= cell) order
-            rows = self._global_state()
-            odt = self.dtypes["objective"]
-            osum = np.asarray(0.0, dtype=odt)
-            for v in rows[:, 1]:
-                osum = np.asarray(osum + np.asarray(v, dtype=odt), dtype=odt)
-            has = rows[:, 3] > 0
-            self._build_stats((int(rows[:, 0].sum()), float(osum), float(rows[has, 2].max()) if has.any() else None, 0))
+            n, osum, omax, _ = _shard_util.merge_shard_stats(self._global_state(), self.dtypes["objective"])
+            self._build_stats((n, osum, omax, 0))
             return self._stats
         self._sync()
         if self._stats_dirty:
@@ -311,11 +305,9 @@ class DeviceArchive:
             # by time as the reference would)
             import torch.distributed as dist
 
-            rows = self._global_state()
-            has = rows[:, 3] > 0
-            if not has.any():
+            owner = _shard_util.merge_shard_stats(self._global_state(), self.dtypes["objective"])[3]
+            if owner < 0:
                 return None
-            owner = int(np.argmax(np.where(has, rows[:, 2], -np.inf)))
             box = [None]
             if self._dp_rank == owner:
                 if self._st[3] != self._best_serial:
@@ -967,11 +959,9 @@ class DeviceArchive:
         if self._global_cache is not None and self._global_cache[0] == self._adds_enqueued:
             return self._global_cache[1]
         n, osum, omax, _ = self._st
-        mine = torch.tensor([float(n), float(osum), float(omax) if omax is not None else float("-inf"),
-                             0.0 if omax is None else 1.0], dtype=torch.float64, device=self._device)
-        allr = torch.empty(4 * self._dp_world, dtype=torch.float64, device=self._device)
-        dist.all_gather_into_tensor(allr, mine, group=self._dp_group)
-        rows = allr.view(self._dp_world, 4).cpu().numpy()
+        rows = _shard_util.all_gather_rows(
+            (n, osum, omax if omax is not None else float("-inf"), 0.0 if omax is None else 1.0), self._dp_world,
+            self._dp_group, self._device)
         self._global_cache = (self._adds_enqueued, rows)
         return rows
 
@@ -1024,9 +1014,13 @@ class DeviceArchive:
             if preset is not None:
                 idx = preset[0]
             else:
-                buf = self._dev_idx
+                # one reusable index buffer per stream: the insert kernel of the previous add() still reads it, and
+                # only work queued on the same stream is ordered behind that
+                sp_now = current_stream_ptr()
+                buf = self._dev_idx if self.__dict__.get("_dev_idx_stream") == sp_now else None
                 if buf is None or buf.numel() < B:
                     buf = self._dev_idx = torch.empty(B, dtype=torch.int32, device=self._device)
+                    self._dev_idx_stream = sp_now
                 idx = self._index_of_device(measures, store._flags_ptr, out=buf[:B] if buf.numel() != B else buf)
             _lib.check(_lib.lib().qd_insert(C.byref(store.abi_store()), B, idx.data_ptr(), objective.data_ptr(), src,
                                             self._lr_f, self._tmin_f, status.data_ptr(), value.data_ptr(),
@@ -1248,13 +1242,7 @@ class DeviceArchive:
         occ, data = self._store.retrieve(np.where(mine, cells - self._cell_lo, 0).astype(np.int32))
         parts = [None] * self._dp_world
         dist.all_gather_object(parts, (mine, np.asarray(occ) & mine, data), group=self._dp_group)
-        occupied = np.zeros(len(cells), dtype=bool)
-        out = {k: np.array(v, copy=True) for k, v in parts[0][2].items()}
-        for m, o, dd in parts:
-            occupied[m] = o[m]
-            for k in out:
-                out[k][m] = dd[k][m]
-        out["index"] = cells.astype(np.int32)
+        occupied, out = _shard_util.stitch_shard_retrieve(cells, parts)
         fill_sentinel_values(occupied, out)
         return occupied, out
 
@@ -1290,7 +1278,7 @@ class DeviceArchive:
             local["index"] = (local["index"] + self._cell_lo).astype(np.int32)
             parts = [None] * self._dp_world
             dist.all_gather_object(parts, local, group=self._dp_group)
-            out = {k: np.concatenate([p[k] for p in parts], axis=0) for k in (want or local)}
+            out = _shard_util.stitch_shard_data(parts, want)
             return out[fields] if single else out
         return self._store.data(fields, return_type)
 
