@@ -186,7 +186,8 @@ uint32_t* qd_insert_flags_ptr(void* scratch /*[dev]*/, int64_t capacity);
 int qd_flags_or(const uint32_t* in /*[dev] n*/, int n, uint32_t* out /*[dev] 1*/, void* stream);
 
 /* Diagnostics: %globaltimer (ns) at the phase boundaries of the last insertion on this store
- * (absmax, classify, resolve, select, update, copy, best/count, publish start, publish end).
+ * (absmax, classify, mark [list mode], select [list mode], update, best/count + copy, its barrier, publish start,
+ * publish end; slot 9: CTA 0 through its cells in the update phase).
  * Blocks until the stream is idle. */
 int qd_insert_phase_times(const void* scratch /*[dev]*/, int64_t capacity, uint64_t* out_ns /*[host] 10*/,
                           void* stream);

@@ -484,10 +484,12 @@ class DeviceArchive:
     def _index_of_device(self, measures: torch.Tensor, flags_ptr: int, out=None) -> torch.Tensor:
         raise NotImplementedError
 
-    def _search_chunked(self, measures, B, pieces=4):
+    def _search_chunked(self, measures, B):
         """index_of over a large host array, overlapped with its own host->device transfer: piece k is copied on the
         side stream (through a page-locked staging piece when the array is pageable) and searched on the caller's
-        stream as soon as it has landed. Returns (device measures, device idx)."""
+        stream as soon as it has landed. Page-locked arrays travel as a small first piece (the search can start
+        after an eighth of the transfer) and the rest; pageable ones as four equal pieces, so that the host's
+        staging memcpy of piece k+1 runs next to the search of piece k. Returns (device measures, device idx)."""
         mdt = self.dtypes["measures"]
         arr = np.ascontiguousarray(measures, dtype=mdt)
         src = torch.from_numpy(arr)
@@ -497,7 +499,8 @@ class DeviceArchive:
             self._copy_event = torch.cuda.Event()
         meas = torch.empty(arr.shape, dtype=torch_dtype(mdt), device=self._device)
         idx = torch.empty(B, dtype=torch.int32, device=self._device)
-        step = -(-B // pieces)
+        bounds = [0, B // 8, B] if pinned else [min(B, k * -(-B // 4)) for k in range(5)]
+        pieces = len(bounds) - 1
         cur = torch.cuda.current_stream()
         events = self.__dict__.get("_chunk_events")
         if not events or len(events) < pieces:
@@ -511,9 +514,9 @@ class DeviceArchive:
             stage = stage[: arr.size].view(arr.shape)
             self._copy_stream.wait_stream(cur)  # (the staging buffer's previous use was consumed on `cur`'s order)
         for k in range(pieces):
-            lo, hi = k * step, min(B, (k + 1) * step)
+            lo, hi = bounds[k], bounds[k + 1]
             if lo >= hi:
-                break
+                continue
             piece = src[lo:hi]
             if stage is not None:
                 stage[lo:hi].copy_(piece)  # host memcpy of this piece while the previous pieces travel / are searched
