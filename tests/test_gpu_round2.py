@@ -379,3 +379,28 @@ def test_chunked_host_search_equals_device_batch(pinned):
     bad["measures"][B - 7, 2] = np.inf  # in the last piece
     with pytest.raises(ValueError, match="measures must be finite"):
         a.add(**bad)
+
+
+def test_batch_of_2_pow_24_rows_uses_the_separate_row_counter():
+    """From 2^24 rows on the per-cell row count no longer fits the low bits of the fixed-point sum word and lives
+    in its own array (csrc/insert.cu FxConst::b == 0, Scratch::cnt); the row number in `pick` takes 25 bits. Same
+    statuses, values, thresholds and elites as the oracle."""
+    from pyribs_b200.archives import GridArchive
+
+    B = (1 << 24) + 3
+    rng = np.random.default_rng(24)
+    kw = dict(solution_dim=1, dims=(16, 16), ranges=[(-1, 1)] * 2, learning_rate=0.5, threshold_min=-1.0)
+    gpu, ora = GridArchive(**kw), O.make_grid_oracle(**kw)
+    for step in range(2):
+        b = dict(solution=rng.standard_normal((B, 1)), objective=rng.uniform(0, 1, B) + 0.25 * step,
+                 measures=rng.uniform(-1, 1, (B, 2)))
+        b["objective"][B - 1] = b["objective"][5] = 7.0  # a tie between the first rows and the very last one
+        b["measures"][B - 1] = b["measures"][5]
+        g, o = gpu.add(**b), ora.add(**b)
+        np.testing.assert_array_equal(g["status"], o["status"])
+        assert_close(g["value"], o["value"], RTOL, f"step {step} value")
+        occ = ora.store.occupied
+        assert_close(gpu._store._fields["threshold"].cpu().numpy()[occ], ora.store.fields["threshold"][occ], RTOL,
+                     f"step {step} thresholds")
+        np.testing.assert_array_equal(gpu._store._fields["solution"].cpu().numpy()[occ], ora.store.fields["solution"][occ])
+    assert len(gpu) == len(ora) == 256

@@ -87,13 +87,47 @@ def run_cpu(iters, n=100, E=15, lam=36, c3=False):
     dt = time.perf_counter() - t0
     return dict(it_per_s=iters / dt, solutions_per_s=iters * E * lam / dt, elites=len(a))
 
+def run_reference(iters, n=100, E=15, lam=36, c3=False):
+    """The same loop on the unmodified reference (ribs from baseline/_ref or /root/reference, through oracle/shim)."""
+    for ref in (os.environ.get("QD_REFERENCE", "/root/reference"), os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(ref, "ribs")):
+            break
+    else:
+        return {"unavailable": "no reference package on this box"}
+    for p in (os.path.join(ROOT, "oracle", "shim"), ref):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from ribs.archives import GridArchive
+    from ribs.emitters import EvolutionStrategyEmitter
+    from ribs.schedulers import Scheduler
+    mb = n / 2 * 5.12
+    if c3:
+        a = GridArchive(solution_dim=n, dims=(500, 500), ranges=[(-mb, mb)] * 2, learning_rate=0.01, threshold_min=0.0, seed=1)
+    else:
+        a = GridArchive(solution_dim=n, dims=(100, 100), ranges=[(-mb, mb)] * 2, seed=1)
+    kw = dict(ranker="imp", selection_rule="mu", restart_rule="basic") if c3 else dict(
+        ranker="2imp", selection_rule="filter", restart_rule="no_improvement")
+    ems = [EvolutionStrategyEmitter(a, x0=np.zeros(n), sigma0=0.5, batch_size=lam, seed=i, **kw) for i in range(E)]
+    s = Scheduler(a, ems)
+    for _ in range(3):
+        sol = s.ask(); s.tell(*sphere(sol))
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        sol = s.ask(); s.tell(*sphere(sol))
+    dt = time.perf_counter() - t0
+    return dict(it_per_s=iters / dt, solutions_per_s=iters * E * lam / dt, elites=len(a),
+                what="ribs.schedulers.Scheduler + ribs GridArchive + ribs EvolutionStrategyEmitter (cma_es), unmodified")
+
+
 if __name__ == "__main__":
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     if len(sys.argv) > 2 and sys.argv[2] == "c3":
         print(json.dumps({"case": "C3 sphere CMA-MAE 100x512 n=100, grid 500x500", "gpu": run_gpu(iters, E=100, lam=512, c3=True),
                           "gpu_device_eval": run_gpu(iters, E=100, lam=512, c3=True, device_eval=True),
                           "gpu_unpooled": run_gpu(max(3, iters // 5), E=100, lam=512, c3=True, pooled=False),
-                          "cpu_oracle_port": run_cpu(max(3, iters // 5), E=100, lam=512, c3=True), "cores": os.cpu_count()}))
+                          "cpu_oracle_port": run_cpu(max(3, iters // 5), E=100, lam=512, c3=True),
+                          "reference": run_reference(max(3, iters // 10), E=100, lam=512, c3=True), "cores": os.cpu_count()}))
     else:
         print(json.dumps({"case": "C1 sphere CMA-ME 15x36 n=100", "gpu": run_gpu(iters), "gpu_device_eval": run_gpu(iters, device_eval=True),
-                          "gpu_unpooled": run_gpu(iters, pooled=False), "cpu_oracle_port": run_cpu(iters), "cores": os.cpu_count()}))
+                          "gpu_unpooled": run_gpu(iters, pooled=False), "cpu_oracle_port": run_cpu(iters),
+                          "reference": run_reference(iters), "cores": os.cpu_count()}))
