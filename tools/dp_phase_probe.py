@@ -16,7 +16,8 @@ from tools.e2e_breakdown import phase_times
 B, C, d, n = 1_000_000, 1_000_000, 8, 10
 Bl = B // world
 cen = np.random.default_rng(0).uniform(-1, 1, (C, d))
-a = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * d, data_parallel=True)
+OWNED = len(sys.argv) > 1 and sys.argv[1] == "owned"  # owner-computes store instead of the replicated one
+a = CVTArchive(solution_dim=n, centroids=cen, ranges=[(-1, 1)] * d, data_parallel=True, shard_store=OWNED)
 rng = np.random.default_rng(1)
 bs = []
 for j in range(3):
@@ -39,8 +40,9 @@ class Wrap:  # the archive calls _lib.lib().qd_insert_sharded_rows(...): hand it
     def __init__(self, L):
         self._L = L
         self._ins = timed("insert", L.qd_insert_sharded_rows)
+        self._own = timed("insert", L.qd_insert_owned_cells)
     def __getattr__(self, k):
-        return self._ins if k == "qd_insert_sharded_rows" else getattr(self._L, k)
+        return self._ins if k == "qd_insert_sharded_rows" else self._own if k == "qd_insert_owned_cells" else getattr(self._L, k)
 _lib._lib = Wrap(L)
 for j in range(6):
     a.add(bs[j % 3]["solution"], bs[j % 3]["objective"] + 0.05 * j, bs[j % 3]["measures"])
@@ -52,12 +54,12 @@ t0.record()
 for j in range(6, 6 + K):
     a.add(bs[j % 3]["solution"], bs[j % 3]["objective"] + 0.05 * j, bs[j % 3]["measures"])
 t1.record(); torch.cuda.synchronize()
-out = {"rank": rank, "world": world, "ms_per_add": t0.elapsed_time(t1) / K}
+out = {"rank": rank, "world": world, "store": "owner computes" if OWNED else "replicated", "ms_per_add": t0.elapsed_time(t1) / K}
 for k, v in ev.items():
     out[k + " ms"] = round(float(np.mean([e0.elapsed_time(e1) for e0, e1 in v])), 4)
 ph, tot = phase_times(a)
 out["insert_phases_us"] = {k: round(v, 1) for k, v in ph.items()}
 out["insert_kernel_us"] = round(tot, 1)
-a._sync(); out["winners_last_add"] = int(a._store._last.n_winners)
+a._sync(); out["winners_last_add_on_this_rank"] = int(a._store._last.n_winners)
 print(json.dumps(out), flush=True)
 dist.destroy_process_group()
