@@ -438,49 +438,6 @@ __global__ void __launch_bounds__(1024) tree_scan_kernel(uint32_t* __restrict__ 
   }
 }
 
-// the same scan with the counts staged in shared memory (coalesced in, coalesced out; padded against bank conflicts):
-// the global version's strided walks were 26 us for 31k leaves, 3 % of one rank's search at N = 8
-constexpr int64_t kScanSmemMax = 48 * 1024;  // entries (203 KB with the padding)
-__host__ __device__ __forceinline__ int64_t scan_pad(int64_t i) { return i + (i >> 5); }
-
-__global__ void __launch_bounds__(1024) tree_scan_smem_kernel(uint32_t* __restrict__ count, int64_t n) {
-  extern __shared__ uint32_t sc[];
-  __shared__ uint32_t warp_sum[32];
-  for (int64_t i = threadIdx.x; i < n; i += 1024) sc[scan_pad(i)] = count[i + 1];
-  __syncthreads();
-  const int64_t per = (n + 1023) / 1024;
-  const int64_t i0 = (int64_t)threadIdx.x * per, i1 = min(n, i0 + per);
-  uint32_t tot = 0;
-  for (int64_t i = i0; i < i1; ++i) tot += sc[scan_pad(i)];
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  uint32_t incl = tot;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) warp_sum[wi] = incl;
-  __syncthreads();
-  if (wi == 0) {
-    const uint32_t v = warp_sum[lane];
-    uint32_t iv = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
-      if (lane >= o) iv += t;
-    }
-    warp_sum[lane] = iv - v;
-  }
-  __syncthreads();
-  uint32_t run = warp_sum[wi] + incl - tot;
-  for (int64_t i = i0; i < i1; ++i) {
-    run += sc[scan_pad(i)];
-    sc[scan_pad(i)] = run;
-  }
-  __syncthreads();
-  for (int64_t i = threadIdx.x; i < n; i += 1024) count[i + 1] = sc[scan_pad(i)];
-}
-
 __global__ void tree_scatter_kernel(const uint32_t* __restrict__ home_key, uint32_t* __restrict__ cursor, int64_t B,
                                     int32_t* __restrict__ order) {
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < B; q += (int64_t)gridDim.x * blockDim.x)
@@ -527,18 +484,9 @@ static int launch_tree_d(const T* meas, int64_t B, const TreeView& v, const Tree
         meas, B, v, base, nullptr, kTreeWarps, idx, dist, flags, home_key, count);
     if ((rc = check_launch("cvt_tree_kernel(home)"))) return rc;
   }
-  if (h.nleaves <= kScanSmemMax) {
-    static bool attr_set = false;
-    const size_t smem = (size_t)(scan_pad(h.nleaves) + 1) * 4;
-    if (!attr_set) {
-      QD_CHECK_CUDA(cudaFuncSetAttribute(tree_scan_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((scan_pad(kScanSmemMax) + 1) * 4)));
-      attr_set = true;
-    }
-    tree_scan_smem_kernel<<<1, 1024, smem, s>>>(count, h.nleaves);
-  } else {
-    tree_scan_kernel<<<1, 1024, 0, s>>>(count, h.nleaves);
-  }
+  // (a variant with the counts staged in 200 KB of shared memory measured slower: 45 vs 26 us under ncu -- the
+  // carve-out switch between its neighbours costs more than the strided walks it saves)
+  tree_scan_kernel<<<1, 1024, 0, s>>>(count, h.nleaves);
   if ((rc = check_launch("tree_scan_kernel"))) return rc;
   tree_scatter_kernel<<<grid_for(B, 256), 256, 0, s>>>(home_key, count, B, order);
   if ((rc = check_launch("tree_scatter_kernel"))) return rc;
