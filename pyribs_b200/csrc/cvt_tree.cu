@@ -70,13 +70,14 @@ static TreeHeader tree_layout(int64_t C, int d) {
   off += (uint64_t)h.nleaves * d * kLeaf * sizeof(double);
   h.off_ids = off;
   off += (uint64_t)h.nleaves * kLeaf * sizeof(int32_t);
+  const int dp = (d + 1) / 2;  // fp32 data is stored as PAIRS of coordinates (packed f32x2 arithmetic in the walk)
   for (int k = 0; k + 1 < h.nlev; ++k) {
     h.off_box[k] = off;
-    off += (uint64_t)h.n[k + 1] * 2 * d * kFan * sizeof(float);
+    off += (uint64_t)h.n[k + 1] * 2 * dp * kFan * sizeof(float2);
   }
   off = (off + 255) / 256 * 256;
   h.off_pf = off;
-  off += (uint64_t)h.nleaves * d * kLeaf * sizeof(float);
+  off += (uint64_t)h.nleaves * dp * kLeaf * sizeof(float2);
   off = (off + 255) / 256 * 256;
   h.off_rad = off;
   off += (uint64_t)QD_MAX_MEASURE_DIM * sizeof(float);
@@ -152,7 +153,11 @@ static void tree_build_host(const T* cent, int64_t C, int d, unsigned char* blob
   if (getenv("QD_TREE_TIMING")) fprintf(stderr, "kd_split %.3f s\n", std::chrono::duration<double>(T1 - T0).count());
   double* lp = reinterpret_cast<double*>(blob + h.off_pts);
   int32_t* li = reinterpret_cast<int32_t*>(blob + h.off_ids);
+  const int dp = (d + 1) / 2;
+  // fp32 copy of the points: pair j of leaf L and slot s at ((L * dp + j) * kLeaf + s), components (2j, 2j + 1);
+  // the missing partner of an odd last coordinate is 0 (the query's interval for it is [0, 0]: no contribution)
   float* lf = reinterpret_cast<float*>(blob + h.off_pf);
+  auto pf_at = [&](int64_t leaf, int a, int j) -> float& { return lf[(((leaf * dp + (a >> 1)) * kLeaf + j) << 1) + (a & 1)]; };
   float* rad = reinterpret_cast<float*>(blob + h.off_rad);
   std::vector<double> radd((size_t)d, 0.0);
   // leaves + their boxes (level 0)
@@ -171,7 +176,7 @@ static void tree_build_host(const T* cent, int64_t C, int d, unsigned char* blob
           const double v = pts[(int64_t)id * d + a];
           lp[(leaf * d + a) * kLeaf + j] = v;
           const float vf = (float)v;
-          lf[(leaf * d + a) * kLeaf + j] = vf;
+          pf_at(leaf, a, j) = vf;
           if (std::isfinite(v) && std::isfinite(vf)) radd[a] = std::max(radd[a], std::fabs(v - (double)vf));
           lo[leaf * d + a] = std::min(lo[leaf * d + a], f32_down(v));
           hi[leaf * d + a] = std::max(hi[leaf * d + a], f32_up(v));
@@ -180,8 +185,9 @@ static void tree_build_host(const T* cent, int64_t C, int d, unsigned char* blob
         li[leaf * kLeaf + j] = INT32_MAX;
         for (int a = 0; a < d; ++a) {
           lp[(leaf * d + a) * kLeaf + j] = INFINITY;
-          lf[(leaf * d + a) * kLeaf + j] = INFINITY;
+          pf_at(leaf, a, j) = INFINITY;
         }
+        if (d & 1) pf_at(leaf, d, j) = INFINITY;
       }
     }
   }
@@ -191,16 +197,21 @@ static void tree_build_host(const T* cent, int64_t C, int d, unsigned char* blob
     const int64_t groups = h.n[l + 1];
     std::vector<float> plo((size_t)groups * d, INFINITY), phi((size_t)groups * d, -INFINITY);
     for (int64_t g = 0; g < groups; ++g) {
-      float* gb = bx + (size_t)g * 2 * d * kFan;
+      // group g: lo pairs [dp][kFan] then hi pairs [dp][kFan], each entry a float2 of coordinates (2j, 2j + 1)
+      float* gb = bx + (size_t)g * 2 * dp * kFan * 2;
       for (int s = 0; s < kFan; ++s) {
         const int64_t c = g * kFan + s;
-        for (int a = 0; a < d; ++a) {
-          const float l0 = c < h.n[l] ? lo[c * d + a] : INFINITY;
-          const float h0 = c < h.n[l] ? hi[c * d + a] : -INFINITY;
-          gb[a * kFan + s] = l0;
-          gb[(d + a) * kFan + s] = h0;
-          plo[g * d + a] = std::min(plo[g * d + a], l0);
-          phi[g * d + a] = std::max(phi[g * d + a], h0);
+        const bool real = c < h.n[l];
+        for (int a = 0; a < 2 * dp; ++a) {
+          float l0 = real ? 0.f : INFINITY, h0 = real ? 0.f : -INFINITY;  // (odd d: the pad coordinate)
+          if (a < d) {
+            l0 = real ? lo[c * d + a] : INFINITY;
+            h0 = real ? hi[c * d + a] : -INFINITY;
+            plo[g * d + a] = std::min(plo[g * d + a], l0);
+            phi[g * d + a] = std::max(phi[g * d + a], h0);
+          }
+          gb[(((a >> 1) * kFan + s) << 1) + (a & 1)] = l0;
+          gb[((((dp + (a >> 1)) * kFan) + s) << 1) + (a & 1)] = h0;
         }
       }
     }
@@ -210,12 +221,48 @@ static void tree_build_host(const T* cent, int64_t C, int d, unsigned char* blob
 }
 
 // ---- search ------------------------------------------------------------------------------------
+// Packed fp32 pairs (Blackwell FADD2 / FFMA2 with directed rounding): the walk issues on 76 % of its cycles, and the
+// box / point bounds are two subtractions and one fused multiply-add per coordinate -- two coordinates per instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2_rd(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2_rd(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// acc += max(a - xhi, xlo - b, 0)^2, both halves, everything rounded down (a = b = the point for a leaf slot,
+// a = box lo / b = box hi for a child box)
+__device__ __forceinline__ f32x2 gap2_acc(f32x2 a, f32x2 b, f32x2 xlo, f32x2 xhi, f32x2 acc) {
+  float t0, t1, u0, u1;
+  unpack2(sub2_rd(a, xhi), t0, t1);
+  unpack2(sub2_rd(xlo, b), u0, u1);
+  const f32x2 g = pack2(fmaxf(fmaxf(t0, u0), 0.f), fmaxf(fmaxf(t1, u1), 0.f));
+  return fma2_rd(g, g, acc);
+}
+__device__ __forceinline__ float sum2_rd(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return __fadd_rd(lo, hi);
+}
+
 struct TreeView {
   const double* pts;
-  const float* pf;
+  const f32x2* pf;  // [leaf][pair][slot]
   const float* rad;
   const int32_t* ids;
-  const float* box[kTreeMaxLev];
+  const f32x2* box[kTreeMaxLev];  // [group][lo | hi][pair][child]
   int32_t nlev, d;
 };
 
@@ -239,7 +286,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
   const int d = D > 0 ? D : tv.d;
   extern __shared__ uint32_t skey_raw[];  // [warps][kTreeMaxLev][32] per-lane slots: child keys of the nodes on the path
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  __shared__ const float* sbox[kTreeMaxLev];  // (indexing the kernel parameter dynamically would spill it to local memory)
+  __shared__ const f32x2* sbox[kTreeMaxLev];  // (indexing the kernel parameter dynamically would spill it to local memory)
   __shared__ int s_next;  // sorted mode: the CTA's warps draw the queries of its run one by one (their costs differ)
   if (threadIdx.x < kTreeMaxLev) sbox[threadIdx.x] = tv.box[threadIdx.x];
   if (threadIdx.x == 0) s_next = nw;
@@ -264,18 +311,29 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
       pos = next_pos;
       // fp32 interval around the query, widened by the rounding radius of the fp32 copies of the leaf points: the
       // boxes AND the fp32 points are then compared against an interval that certainly contains (x - p + pf)
-      float xlo[XN], xhi[XN];
+      constexpr int XP = (XN + 1) / 2;
+      const int dp = (d + 1) >> 1;
+      f32x2 xlo[XP], xhi[XP];  // pairs of coordinates; the partner of an odd last one is the interval [0, 0]
       bool qbad = false;
       __syncwarp();
 #pragma unroll
-      for (int k = 0; k < XN; ++k)
-        if (k < d) {
-          const double xk = (double)meas[q * d + k];
-          if (lane == 0) sx[k] = xk;
-          qbad |= !finite_d(xk);
-          const float r = __ldg(tv.rad + k);
-          xlo[k] = __fsub_rd(__double2float_rd(xk), r);
-          xhi[k] = __fadd_ru(__double2float_ru(xk), r);
+      for (int j = 0; j < XP; ++j)
+        if (j < dp) {
+          float lo2[2] = {0.f, 0.f}, hi2[2] = {0.f, 0.f};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = 2 * j + h;
+            if (k < d) {
+              const double xk = (double)meas[q * d + k];
+              if (lane == 0) sx[k] = xk;
+              qbad |= !finite_d(xk);
+              const float r = __ldg(tv.rad + k);
+              lo2[h] = __fsub_rd(__double2float_rd(xk), r);
+              hi2[h] = __fadd_ru(__double2float_ru(xk), r);
+            }
+          }
+          xlo[j] = pack2(lo2[0], lo2[1]);
+          xhi[j] = pack2(hi2[0], hi2[1]);
         }
       __syncwarp();
       bad |= qbad;
@@ -319,29 +377,24 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
       // a degenerate box); the 2 KB of exact fp64 coordinates are read only if some point of the leaf can still be
       // the minimum or tie it. After the first few leaves of a walk that is rare: the walk reads half the bytes,
       // and two leaves per step halve its chain of dependent round trips.
-      auto leaf_bound = [&](const float* __restrict__ pp) -> float {
-        float acc = 0.f;
+      auto leaf_bound = [&](const f32x2* __restrict__ pp) -> float {
+        f32x2 acc = 0ull;
 #pragma unroll
-        for (int k = 0; k < XN; ++k)
-          if (k < d) {
-            const float c = __ldg(pp + k * kLeaf);
-            const float g = fmaxf(fmaxf(__fsub_rd(c, xhi[k]), __fsub_rd(xlo[k], c)), 0.f);
-            acc = __fmaf_rd(g, g, acc);
+        for (int j = 0; j < XP; ++j)
+          if (j < dp) {
+            const f32x2 c = __ldg(pp + j * kLeaf);
+            acc = gap2_acc(c, c, xlo[j], xhi[j], acc);
           }
-        return acc;
+        return sum2_rd(acc);
       };
       // keys of the 32 children (boxes of level `lvl`, group `parent`): lower-bound bits | lane
       auto node_key = [&](int lvl, int parent) -> uint32_t {
-        const float* p = sbox[lvl] + (int64_t)parent * (2 * d * kFan) + lane;
-        float acc = 0.f;
+        const f32x2* p = sbox[lvl] + (int64_t)parent * (2 * dp * kFan) + lane;
+        f32x2 acc = 0ull;
 #pragma unroll
-        for (int k = 0; k < XN; ++k)
-          if (k < d) {
-            const float lo = __ldg(p + k * kFan), hi = __ldg(p + (d + k) * kFan);
-            const float g = fmaxf(fmaxf(__fsub_rd(lo, xhi[k]), __fsub_rd(xlo[k], hi)), 0.f);
-            acc = __fmaf_rd(g, g, acc);
-          }
-        return (__float_as_uint(acc) & 0x7fffffe0u) | (uint32_t)lane;
+        for (int j = 0; j < XP; ++j)
+          if (j < dp) acc = gap2_acc(__ldg(p + j * kFan), __ldg(p + (dp + j) * kFan), xlo[j], xhi[j], acc);
+        return (__float_as_uint(sum2_rd(acc)) & 0x7fffffe0u) | (uint32_t)lane;
       };
 
       if constexpr (HOME) {
@@ -379,9 +432,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : ((D >= 1 && D <=
               const bool two = k2 < 0x7f800000u && !(__uint_as_float(k2 & 0xffffffe0u) > bestf);
               const int cnode2 = cur * kFan + (int)(k2 & 31u);
               if (two && lane == (int)(k2 & 31u)) key[1][lane] = 0xffffffffu;
-              const float b1 = leaf_bound(tv.pf + ((int64_t)cnode * d) * kLeaf + lane);
+              const float b1 = leaf_bound(tv.pf + ((int64_t)cnode * dp) * kLeaf + lane);
               float b2 = INFINITY;
-              if (two) b2 = leaf_bound(tv.pf + ((int64_t)cnode2 * d) * kLeaf + lane);
+              if (two) b2 = leaf_bound(tv.pf + ((int64_t)cnode2 * dp) * kLeaf + lane);
               if (__any_sync(0xffffffffu, !(b1 > bestf))) eval_leaf(cnode);
               if (two && __any_sync(0xffffffffu, !(b2 > bestf))) eval_leaf(cnode2);
               k = __reduce_min_sync(0xffffffffu, key[1][lane]);
@@ -511,11 +564,11 @@ static int launch_tree(const T* meas, int64_t B, int d, const unsigned char* tre
                        cudaStream_t s) {
   TreeView v;
   v.pts = reinterpret_cast<const double*>(tree + h.off_pts);
-  v.pf = reinterpret_cast<const float*>(tree + h.off_pf);
+  v.pf = reinterpret_cast<const f32x2*>(tree + h.off_pf);
   v.rad = reinterpret_cast<const float*>(tree + h.off_rad);
   v.ids = reinterpret_cast<const int32_t*>(tree + h.off_ids);
   for (int l = 0; l < kTreeMaxLev; ++l)
-    v.box[l] = l + 1 < h.nlev ? reinterpret_cast<const float*>(tree + h.off_box[l]) : nullptr;
+    v.box[l] = l + 1 < h.nlev ? reinterpret_cast<const f32x2*>(tree + h.off_box[l]) : nullptr;
   v.nlev = h.nlev;
   v.d = d;
 #define QD_TREE(DD) return launch_tree_d<T, DD>(meas, B, v, h, base, idx, dist, flags, scratch, scratch_bytes, s)

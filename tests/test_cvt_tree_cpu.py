@@ -39,11 +39,18 @@ def parse(blob, n, d):
     pts = blob[off_pts:off_pts + nleaves * d * LEAF * 8].view(np.float64).reshape(nleaves, d, LEAF)
     ids = blob[off_ids:off_ids + nleaves * LEAF * 4].view(np.int32).reshape(nleaves, LEAF)
     boxes = []
+    dp = (d + 1) // 2  # fp32 data is stored as pairs of coordinates: [group][lo | hi][pair][child][2]
     for l in range(nlev - 1):
         g = int(nl[l + 1])
         o = int(off_box[l])
-        b = blob[o:o + g * 2 * d * FAN * 4].view(np.float32).reshape(g, 2, d, FAN)
-        boxes.append(b)
+        b = blob[o:o + g * 2 * dp * FAN * 8].view(np.float32).reshape(g, 2, dp, FAN, 2)
+        b = np.ascontiguousarray(b.transpose(0, 1, 2, 4, 3)).reshape(g, 2, 2 * dp, FAN)
+        if d & 1:  # the partner of an odd last coordinate: [0, 0] for real children, empty like the rest otherwise
+            pad = b[:, :, d, :]
+            real = np.isfinite(b[:, 0, 0, :])
+            assert np.all(pad[:, 0][real] == 0) and np.all(pad[:, 1][real] == 0)
+            assert np.all(np.isposinf(pad[:, 0][~real])) and np.all(np.isneginf(pad[:, 1][~real]))
+        boxes.append(np.ascontiguousarray(b[:, :, :d, :]))
     return dict(pts=pts, ids=ids, boxes=boxes, nlev=nlev, n=[int(v) for v in nl[:nlev]])
 
 
