@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("QD_B200_LIB") or os.path.join(_HERE, "_C", "libqd_b200.so")  # (override: A/B runs of kernel variants)
+LIB_PATH = os.path.join(_HERE, "_C", "libqd_b200.so")
 
 QD_F32, QD_F64 = 0, 1
 QD_MAX_FIELDS = 16
