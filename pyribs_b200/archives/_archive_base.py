@@ -206,6 +206,7 @@ class DeviceArchive:
         and every piece of host state that described the previous store starts over."""
         self._store = store
         self._tdt = {n: store._fields[n].dtype for n in ("solution", "objective", "measures")}
+        self._np_dt = tuple(store._np_dtypes[n] for n in ("solution", "objective", "measures"))
         store._copy_join = self._join_copy
         store._owner_sync = self._sync
         self._st = (0, 0.0, None, 0)
@@ -727,6 +728,15 @@ class DeviceArchive:
             out = self._add_device(solution, objective, measures, fields, preset)
             if out is not None:
                 return out
+        if (not fields and type(solution) is np.ndarray and type(objective) is np.ndarray
+                and type(measures) is np.ndarray and self._small_adds and self._plain_batch_ok(solution, objective, measures)):
+            # a small, well-formed NumPy batch (the common case of the reference's own loop and benchmark): the checks
+            # validate_batch would make have all passed, straight to the staged path
+            B = solution.shape[0]
+            self._last_idx = None
+            if preset is not None and preset[1] != B:
+                preset = None
+            return self._add_small({"solution": solution, "objective": objective, "measures": measures}, B, preset)
         data = validate_batch(self, {"solution": solution, "objective": objective, "measures": measures, **fields})
         if self._extra_names != set(fields):
             raise ValueError(
@@ -1034,6 +1044,17 @@ class DeviceArchive:
         return {"status": status, "value": value}
 
     # ---- add() of small host batches ---------------------------------------------------------------------
+    def _plain_batch_ok(self, solution, objective, measures):
+        """True for a NumPy batch that needs no conversion or further validation and is small enough for _add_small."""
+        nd = self._np_dt
+        B = solution.shape[0] if solution.ndim == 2 else 0
+        return (0 < B <= _SMALL_ROWS and not self._extra_names and self._dp_world == 1
+                and isinstance(self._solution_dim, int) and solution.shape[1] == self._solution_dim
+                and solution.dtype == nd[0] and objective.ndim == 1 and objective.shape[0] == B and objective.dtype == nd[1]
+                and measures.ndim == 2 and measures.shape[0] == B and measures.shape[1] == self._measure_dim
+                and measures.dtype == nd[2] and B * self._row_bytes_total <= _SMALL_BYTES and self._small_index_ok(B)
+                and torch.cuda.current_device() == self._device.index)
+
     def _small_index_ok(self, B):
         """True when the index kernel of a B-row add may read the measures straight from page-locked host memory."""
         return True
