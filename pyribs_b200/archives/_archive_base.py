@@ -513,7 +513,9 @@ class DeviceArchive:
             if stage is None or stage.numel() < arr.size:
                 stage = self._pinned[key] = torch.empty(max(arr.size, 1), dtype=torch_dtype(mdt)).pin_memory()
             stage = stage[: arr.size].view(arr.shape)
-            self._copy_stream.wait_stream(cur)  # (the staging buffer's previous use was consumed on `cur`'s order)
+        # `meas` may be a block the allocator just took back from work still queued on `cur`, and the staging buffer's
+        # previous use was consumed in `cur`'s order: the side stream starts behind both
+        self._copy_stream.wait_stream(cur)
         for k in range(pieces):
             lo, hi = bounds[k], bounds[k + 1]
             if lo >= hi:
