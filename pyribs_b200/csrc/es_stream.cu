@@ -26,12 +26,14 @@ namespace qd {
 // ---------------------------------------------------------------------------------------------
 // ziggurat tables (Marsaglia & Tsang 2000): kZigLayers layers of equal area V under exp(-x^2/2). Layer 0 is
 // the base strip [0, R] x [0, f(R)] plus the tail beyond R; layer i >= 1 is the rectangle
-// [0, x_i] x [f(x_i), f(x_{i-1})], x_0 = 0 < x_1 < ... < x_{N-1} = R. 2048 layers (R = 4.2164) instead of the
-// usual 256: a candidate misses the accept-at-once region of its layer with probability 0.23 % instead of
-// 1.2 %, so a warp of 32 draws enters the divergent wedge / tail code 7 % of the time instead of 32 %.
+// [0, x_i] x [f(x_i), f(x_{i-1})], x_0 = 0 < x_1 < ... < x_{N-1} = R. 4096 layers (R = 4.3859) instead of the
+// usual 256: a candidate misses the accept-at-once region of its layer with probability 0.12 % instead of
+// 1.2 %, and the candidates that do miss are not resolved where they occur (one lane of 32 running the wedge
+// code) but parked in a per-warp queue and resolved 32 at a time when the warp has finished its share.
 // ---------------------------------------------------------------------------------------------
-constexpr int kZigLayers = 2048;
-constexpr int kZigBits = 11;
+constexpr int kZigLayers = 4096;
+constexpr int kZigThreads = 256;
+constexpr int kZigQueue = 64;  // parked candidates per warp; a warp that collects more resolves the excess in place
 
 struct ZigTables {
   double2 wb[kZigLayers];  // (width of layer i, accept-at-once bound x_{i-1}); layer 0: (V / f(R), R)
@@ -102,77 +104,138 @@ __device__ __forceinline__ void philox_round4(uint32_t (&c)[4], uint32_t k0, uin
   c[3] = lo0;
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+// the ten round keys of a seed: the same for every counter. The generator kernels take them as a launch
+// parameter, so the rounds read them as constant-bank operands: no instructions and no registers
+struct PhiloxKeys {
+  uint32_t a[10], b[10];
+  __host__ __device__ __forceinline__ PhiloxKeys(uint32_t k0, uint32_t k1) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round4(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
+    for (int r = 0; r < 10; ++r) {
+      a[r] = k0 + (uint32_t)r * 0x9E3779B9u;
+      b[r] = k1 + (uint32_t)r * 0xBB67AE85u;
+    }
   }
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], const PhiloxKeys& k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) philox_round4(c, k.a[r], k.b[r]);
 }
 
 __device__ __forceinline__ double open01(uint32_t lo, uint32_t hi) {  // (0, 1) from 64 bits
   return ((double)(long long)((((unsigned long long)hi << 32) | lo) >> 11) + 0.5) * 0x1p-53;
 }
 
-// A candidate's 64 bits: 11 layer index | 1 sign | 52 uniform (the mantissa of a double in [1, 2)).
-__device__ __forceinline__ int zig_layer(unsigned long long r) { return (int)(r & (kZigLayers - 1)); }
-__device__ __forceinline__ double zig_uniform(unsigned long long r) {  // [0, 1)
-  return __longlong_as_double((long long)((r >> 12) | 0x3FF0000000000000ull)) - 1.0;
+// A candidate is two Philox words: hi = 12 bits of layer index | the upper 20 mantissa bits, lo = the lower 32
+// mantissa bits, taken as they come (no shifts); lo's bit 0 is also the sign, so the uniform has 51 free bits.
+__device__ __forceinline__ uint32_t zig_layer(uint32_t hi) { return hi >> 20; }
+__device__ __forceinline__ double zig_mant(uint32_t hi, uint32_t lo) {  // [1, 2)
+  return __hiloint2double((int)((hi & 0x000FFFFFu) | 0x3FF00000u), (int)lo);
 }
-__device__ __forceinline__ double zig_signed(unsigned long long r, double x) { return (r >> kZigBits) & 1u ? -x : x; }
+__device__ __forceinline__ double zig_signed(uint32_t lo, double x) {
+  return __hiloint2double(__double2hiint(x) ^ (int)(lo << 31), __double2loint(x));
+}
 
-// The 0.23 % of candidates that miss the accept-at-once region of their layer: the wedge test, or the tail
-// beyond R for the base layer; a rejected candidate is replaced by fresh ones until one is accepted. Pure
-// function of its arguments -- its random words come from Philox sub-streams of the same counter, keyed by
-// the candidate's slot -- and out of line, so that the common path is straight-line code.
-__device__ __noinline__ double zig_fix(unsigned long long r, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+// A candidate that missed the accept-at-once region of its layer: the wedge test, or the tail beyond R for the
+// base layer; a rejected candidate is replaced by fresh ones until one is accepted. Pure function of its
+// arguments -- its random words come from Philox sub-streams of the same counter, keyed by the candidate's
+// slot -- so the value does not depend on when or by which lane it is resolved.
+__device__ __noinline__ double zig_fix(uint32_t lo, uint32_t hi, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
                                        uint32_t slot) {
+  const PhiloxKeys keys(k0, k1);
   for (uint32_t attempt = 0;; ++attempt) {
     uint32_t c[4] = {c0, c1, slot + 4u * attempt, 0x534C4F57u};  // uniforms of this attempt + the next candidate
-    philox4x32_10(c, k0, k1);
-    const int idx = zig_layer(r);
+    philox4x32_10(c, keys);
+    const uint32_t idx = zig_layer(hi);
     const double2 wb = g_zig.wb[idx];
-    const double x = zig_uniform(r) * wb.x;
-    if (x < wb.y) return zig_signed(r, x);  // (only replacement candidates can land here)
+    const double x = fma(zig_mant(hi, lo), wb.x, -wb.x);
+    if (x < wb.y) return zig_signed(lo, x);  // (only replacement candidates can land here)
     if (idx == 0) {
       const double R = g_zig.r, inv_r = g_zig.inv_r;
       for (uint32_t t = 0;; ++t) {
         uint32_t d[4] = {c0, c1, slot + 4u * attempt, 0x5441494Cu + t};
-        philox4x32_10(d, k0, k1);
+        philox4x32_10(d, keys);
         const double xx = -log(open01(d[0], d[1])) * inv_r;
         const double yy = -log(open01(d[2], d[3]));
-        if (yy + yy > xx * xx) return zig_signed(r, R + xx);
+        if (yy + yy > xx * xx) return zig_signed(lo, R + xx);
       }
     }
     const double fi = g_zig.f[idx], fa = g_zig.f[idx - 1];
-    if (fi + open01(c[0], c[1]) * (fa - fi) < exp(-0.5 * x * x)) return zig_signed(r, x);
-    r = ((unsigned long long)c[3] << 32) | c[2];
+    if (fi + open01(c[0], c[1]) * (fa - fi) < exp(-0.5 * x * x)) return zig_signed(lo, x);
+    lo = c[2];
+    hi = c[3];
   }
 }
 
-// Four unit normals from (seed, counter): two Philox calls give four candidates; all four take the
-// accept-at-once path without a branch, and one test sends the warp to the fix-up code when any missed.
-__device__ __forceinline__ void zig_quad(uint64_t seed, uint64_t ctr, const double2* __restrict__ swb, double (&z)[4]) {
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32);
+struct ZigMiss {  // a parked candidate: tag = (counter - launch offset) * 4 + slot
+  uint32_t lo, hi;
+  uint64_t tag;
+};
+
+// shared memory of a generator CTA: the (width, bound) table, then one queue and one fill count per warp
+constexpr size_t kZigSmem =
+    kZigLayers * sizeof(double2) + (kZigThreads / 32) * (kZigQueue * sizeof(ZigMiss) + sizeof(int));
+
+struct ZigShared {
+  const double2* wb;
+  ZigMiss* queue;  // this warp's
+  int* fill;       // this warp's
+};
+
+__device__ __forceinline__ ZigShared zig_shared_setup(unsigned char* smem) {
+  double2* wb = reinterpret_cast<double2*>(smem);
+  ZigMiss* q = reinterpret_cast<ZigMiss*>(wb + kZigLayers);
+  int* fill = reinterpret_cast<int*>(q + (kZigThreads / 32) * kZigQueue);
+  for (int i = threadIdx.x; i < kZigLayers; i += blockDim.x) wb[i] = g_zig.wb[i];
+  if (threadIdx.x < kZigThreads / 32) fill[threadIdx.x] = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  return {wb, q + warp * kZigQueue, fill + warp};
+}
+
+// Four unit normals from one counter: two Philox calls give four candidates, all four take the accept-at-once
+// path without a branch; the rare candidate that missed leaves a placeholder in z and is parked.
+__device__ __forceinline__ void zig_quad(const PhiloxKeys& keys, uint32_t k0, uint32_t k1, uint64_t ctr, uint64_t offset,
+                                         const ZigShared& sh, double (&z)[4]) {
+  const uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32);
   uint32_t a[4] = {c0, c1, 0u, 0x5A494731u}, b[4] = {c0, c1, 1u, 0x5A494731u};
-  philox4x32_10(a, k0, k1);
-  philox4x32_10(b, k0, k1);
-  const unsigned long long r[4] = {((unsigned long long)a[1] << 32) | a[0], ((unsigned long long)a[3] << 32) | a[2],
-                                   ((unsigned long long)b[1] << 32) | b[0], ((unsigned long long)b[3] << 32) | b[2]};
-  bool miss[4];
+  philox4x32_10(a, keys);
+  philox4x32_10(b, keys);
+  const uint32_t lo[4] = {a[0], a[2], b[0], b[2]}, hi[4] = {a[1], a[3], b[1], b[3]};
+  unsigned miss = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const double2 wb = swb[zig_layer(r[i])];
-    const double x = zig_uniform(r[i]) * wb.x;
-    miss[i] = !(x < wb.y);
-    z[i] = zig_signed(r[i], x);
+    const double2 wb =
+        *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(sh.wb) + ((hi[i] >> 16) & 0xFFF0u));
+    const double x = fma(zig_mant(hi[i], lo[i]), wb.x, -wb.x);  // (m - 1) * width, rounded once
+    if (!(x < wb.y)) miss |= 1u << i;
+    z[i] = zig_signed(lo[i], x);
   }
-  if (miss[0] | miss[1] | miss[2] | miss[3]) {
+  if (miss) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (miss[i]) z[i] = zig_fix(r[i], k0, k1, c0, c1, (uint32_t)i);
+      if (miss >> i & 1u) {
+        const int slot = atomicAdd(sh.fill, 1);
+        if (slot < kZigQueue)
+          sh.queue[slot] = {lo[i], hi[i], (ctr - offset) * 4u + (uint64_t)i};
+        else
+          z[i] = zig_fix(lo[i], hi[i], k0, k1, c0, c1, (uint32_t)i);
+      }
+  }
+}
+
+// Resolves this warp's parked candidates, one per lane, and hands each value to patch(tag / 4, slot, z). Every
+// lane of the warp must call it, after its last zig_quad; the placeholders the lanes stored are ordered before
+// the patches by the warp barrier.
+template <class Patch>
+__device__ __forceinline__ void zig_drain(const ZigShared& sh, uint32_t k0, uint32_t k1, uint64_t offset, Patch patch) {
+  __syncwarp();
+  const int total = min(*sh.fill, kZigQueue);
+  for (int e = threadIdx.x & 31; e < total; e += 32) {
+    const ZigMiss m = sh.queue[e];
+    const uint64_t t = m.tag >> 2, ctr = offset + t;
+    const uint32_t slot = (uint32_t)(m.tag & 3u);
+    patch(t, (int)slot, zig_fix(m.lo, m.hi, k0, k1, (uint32_t)ctr, (uint32_t)(ctr >> 32), slot));
   }
 }
 
@@ -181,20 +244,17 @@ __device__ __forceinline__ void store4_cs(double* p, const double (&v)[4]) {  //
   __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(v[2], v[3]));
 }
 
-__device__ __forceinline__ void zig_stage_tables(double2* swb) {
-  for (int i = threadIdx.x; i < kZigLayers; i += blockDim.x) swb[i] = g_zig.wb[i];
-  __syncthreads();
-}
-
 // out[4q .. 4q+3] come from counter offset + q
-__global__ void __launch_bounds__(256) fill_normal_zig_kernel(double* __restrict__ out, int64_t count, uint64_t seed,
-                                                              uint64_t offset) {
-  __shared__ double2 swb[kZigLayers];
-  zig_stage_tables(swb);
+__global__ void __launch_bounds__(kZigThreads) fill_normal_zig_kernel(double* __restrict__ out, int64_t count,
+                                                                      const __grid_constant__ PhiloxKeys keys,
+                                                                      uint64_t offset) {
+  extern __shared__ __align__(16) unsigned char zig_smem[];
+  const ZigShared sh = zig_shared_setup(zig_smem);
+  const uint32_t k0 = keys.a[0], k1 = keys.b[0];
   const int64_t quads = (count + 3) / 4;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
     double z[4];
-    zig_quad(seed, offset + (uint64_t)q, swb, z);
+    zig_quad(keys, k0, k1, offset + (uint64_t)q, offset, sh, z);
     if (4 * q + 3 < count) {
       store4_cs(out + 4 * q, z);
     } else {
@@ -203,6 +263,10 @@ __global__ void __launch_bounds__(256) fill_normal_zig_kernel(double* __restrict
         if (4 * q + i < count) out[4 * q + i] = z[i];
     }
   }
+  zig_drain(sh, k0, k1, offset, [&](uint64_t t, int slot, double zf) {
+    const int64_t at = (int64_t)(4 * t) + slot;
+    if (at < count) out[at] = zf;
+  });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -210,17 +274,22 @@ __global__ void __launch_bounds__(256) fill_normal_zig_kernel(double* __restrict
 // A thread owns four columns and walks down the rows: sqrt(C) and mean stay in registers.
 // Sample k, quad jq draws from counter offset + k * ceil(n / 4) + jq.
 // ---------------------------------------------------------------------------------------------
-template <bool VEC>
-__global__ void __launch_bounds__(256) sep_ask_rng_kernel(int64_t rows, int64_t n, const int32_t* __restrict__ row_ids,
-                                                          const double* __restrict__ mean, const double* __restrict__ C,
-                                                          const double* __restrict__ sigma_p, uint64_t seed,
-                                                          uint64_t offset, double* __restrict__ X,
-                                                          double* __restrict__ z_out, int mirror) {
-  __shared__ double2 swb[kZigLayers];
-  zig_stage_tables(swb);
+template <bool VEC, bool IDS>  // IDS: rows are redirected through row_ids
+__global__ void __launch_bounds__(kZigThreads) sep_ask_rng_kernel(int64_t rows, int64_t n,
+                                                                  const int32_t* __restrict__ row_ids,
+                                                                  const double* __restrict__ mean,
+                                                                  const double* __restrict__ C,
+                                                                  const double* __restrict__ sigma_p,
+                                                                  const __grid_constant__ PhiloxKeys keys,
+                                                                  uint64_t offset, double* __restrict__ X,
+                                                                  double* __restrict__ z_out, int mirror,
+                                                                  const uint64_t dt /* gridDim.y * ceil(n / 4) */,
+                                                                  const int64_t step /* gridDim.y * n */) {
+  extern __shared__ __align__(16) unsigned char zig_smem[];
+  const ZigShared sh = zig_shared_setup(zig_smem);
+  const uint32_t k0 = keys.a[0], k1 = keys.b[0];
   const int64_t qpr = (n + 3) / 4;
   const int64_t jq = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (jq >= qpr) return;
   const int64_t j0 = jq * 4;
   const double sigma = *sigma_p;
   double sd[4], mu[4];
@@ -230,37 +299,53 @@ __global__ void __launch_bounds__(256) sep_ask_rng_kernel(int64_t rows, int64_t 
     sd[i] = ok ? sqrt(C[j0 + i]) : 0.0;
     mu[i] = ok ? mean[j0 + i] : 0.0;
   }
-  for (int64_t k = blockIdx.y; k < rows; k += gridDim.y) {
-    double z[4], x[4];
-    zig_quad(seed, offset + (uint64_t)(k * qpr + jq), swb, z);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      x[i] = __dadd_rn(__dmul_rn(sd[i], __dmul_rn(sigma, z[i])), mu[i]);  // rng.normal(0, sigma) = 0 + sigma z
-    const int64_t row = row_ids ? row_ids[k] : k;
-    if (VEC) {  // n % 4 == 0: every quad is whole and 32-byte aligned
-      store4_cs(X + row * n + j0, x);
-      if (z_out) store4_cs(z_out + k * n + j0, z);
-    } else {
+  if (jq < qpr) {
+    // sample k of this thread: counter ctr, element `at` of a dense (rows, n) array; both advance by launch constants
+    uint64_t ctr = offset + (uint64_t)blockIdx.y * (uint64_t)qpr + (uint64_t)jq;
+    int64_t at = (int64_t)blockIdx.y * n + j0;
+    const int nrows = (int)rows, stride = (int)gridDim.y;
+    for (int k = blockIdx.y; k < nrows; k += stride, ctr += dt, at += step) {
+      double z[4], x[4];
+      zig_quad(keys, k0, k1, ctr, offset, sh, z);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (j0 + i < n) {
-          X[row * n + j0 + i] = x[i];
-          if (z_out) z_out[k * n + j0 + i] = z[i];
-        }
-    }
-    if (mirror) {  // mirrored sampling (_openai_es.py:163-172): sample k + rows is drawn from -z
-      double y[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] = __dadd_rn(__dmul_rn(sd[i], __dmul_rn(sigma, -z[i])), mu[i]);
-      if (VEC) {
-        store4_cs(X + (k + rows) * n + j0, y);
+        x[i] = __dadd_rn(__dmul_rn(sd[i], __dmul_rn(sigma, z[i])), mu[i]);  // rng.normal(0, sigma) = 0 + sigma z
+      double* xr = X + (IDS ? (int64_t)row_ids[k] * n + j0 : at);
+      if (VEC) {  // n % 4 == 0: every quad is whole and 32-byte aligned
+        store4_cs(xr, x);
+        if (z_out) store4_cs(z_out + at, z);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (j0 + i < n) X[(k + rows) * n + j0 + i] = y[i];
+          if (j0 + i < n) {
+            xr[i] = x[i];
+            if (z_out) z_out[at + i] = z[i];
+          }
+      }
+      if (mirror) {  // mirrored sampling (_openai_es.py:163-172): sample k + rows is drawn from -z
+        double y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = __dadd_rn(__dmul_rn(sd[i], __dmul_rn(sigma, -z[i])), mu[i]);
+        double* xm = X + rows * n + at;
+        if (VEC) {
+          store4_cs(xm, y);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (j0 + i < n) xm[i] = y[i];
+        }
       }
     }
   }
+  zig_drain(sh, k0, k1, offset, [&](uint64_t t, int slot, double zf) {  // (sample, column) of a parked candidate
+    const int64_t k = (int64_t)(t / (uint64_t)qpr), j = 4 * (int64_t)(t % (uint64_t)qpr) + slot;
+    if (j >= n) return;
+    const double s = sqrt(C[j]), m = mean[j];
+    const int64_t row = IDS ? (int64_t)row_ids[k] : k;
+    X[row * n + j] = __dadd_rn(__dmul_rn(s, __dmul_rn(sigma, zf)), m);
+    if (z_out) z_out[k * n + j] = zf;
+    if (mirror) X[(k + rows) * n + j] = __dadd_rn(__dmul_rn(s, __dmul_rn(sigma, -zf)), m);
+  });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -649,6 +734,39 @@ static int opt_in_smem(K kernel, size_t bytes, bool (&done)[64]) {
   return QD_OK;
 }
 
+// A generator kernel runs as one wave of resident CTAs (each stages the 64 KB layer table once and then strides
+// over its share): the CTA count a device holds at once, queried on first use
+template <class K>
+static int zig_resident_ctas(K kernel, int (&ctas)[64], bool (&attr)[64], int* out) {
+  int rc = opt_in_smem(kernel, kZigSmem, attr);
+  if (rc) return rc;
+  int dev = 0;
+  QD_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || ctas[dev] == 0) {
+    int per_sm = 0, sms = 0;
+    QD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kZigThreads, kZigSmem));
+    QD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    QD_REQUIRE(per_sm >= 1 && sms >= 1, "generator kernel does not fit an SM");
+    *out = per_sm * sms;
+    if (dev < 64) ctas[dev] = *out;
+    return QD_OK;
+  }
+  *out = ctas[dev];
+  return QD_OK;
+}
+
+static int launch_fill_zig(double* out, int64_t count, uint64_t seed, uint64_t offset, cudaStream_t s) {
+  static int ctas[64] = {};
+  static bool attr[64] = {};
+  int resident = 0;
+  int rc = zig_resident_ctas(fill_normal_zig_kernel, ctas, attr, &resident);
+  if (rc) return rc;
+  const int64_t want = ((count + 3) / 4 + kZigThreads - 1) / kZigThreads;
+  fill_normal_zig_kernel<<<(unsigned)(want < resident ? want : resident), kZigThreads, kZigSmem, s>>>(
+      out, count, PhiloxKeys((uint32_t)seed, (uint32_t)(seed >> 32)), offset);
+  return check_launch("fill_normal_zig_kernel");
+}
+
 // launch geometry of the two tall-skinny products, shared by the workspace query and the launcher
 struct TdPlan {
   int row_tiles, groups, nsplit;
@@ -771,8 +889,7 @@ extern "C" int qd_fill_normal_zig(double* out, int64_t count, uint64_t seed, uin
   QD_REQUIRE(out && count > 0, "bad arguments");
   int rc = zig_tables_ready();
   if (rc) return rc;
-  fill_normal_zig_kernel<<<grid_for((count + 3) / 4, 256, 6), 256, 0, (cudaStream_t)stream>>>(out, count, seed, offset);
-  return check_launch("fill_normal_zig_kernel");
+  return launch_fill_zig(out, count, seed, offset, (cudaStream_t)stream);
 }
 
 static int sep_ask_rng_impl(int64_t rows, int64_t n, const int32_t* row_ids, const double* mean, const double* C,
@@ -814,18 +931,25 @@ static int sep_ask_rng_impl(int64_t rows, int64_t n, const int32_t* row_ids, con
   int rc = zig_tables_ready();
   if (rc) return rc;
   const int64_t qpr = (n + 3) / 4;
-  const unsigned gx = (unsigned)((qpr + 255) / 256);
-  // ~6 resident CTAs per SM (each stages the 32 KB layer table once); a thread then walks rows / gy samples with
-  // its columns' sqrt(C) and mean in registers
-  int64_t gy = (6 * (int64_t)kNumSMs + gx - 1) / gx;
+  const int64_t gx = (qpr + kZigThreads - 1) / kZigThreads;
+  // one wave of resident CTAs: a thread walks rows / gy samples with its columns' sqrt(C) and mean in registers
+  static int ctas[4][64] = {};
+  static bool attr[4][64] = {};
+  const int variant = (n % 4 == 0 ? 2 : 0) + (row_ids ? 1 : 0);
+  using Kernel = decltype(&sep_ask_rng_kernel<true, true>);
+  const Kernel kernels[4] = {sep_ask_rng_kernel<false, false>, sep_ask_rng_kernel<false, true>,
+                             sep_ask_rng_kernel<true, false>, sep_ask_rng_kernel<true, true>};
+  int resident = 0;
+  if ((rc = zig_resident_ctas(kernels[variant], ctas[variant], attr[variant], &resident))) return rc;
+  QD_REQUIRE(gx <= 0x7fffffff && rows <= 0x7fffffff, "sizes out of range");
+  int64_t gy = resident / gx;
+  if (gy < 1) gy = 1;
   if (gy > rows) gy = rows;
   if (gy > 65535) gy = 65535;
-  const dim3 grid(gx, (unsigned)gy);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (n % 4 == 0)
-    sep_ask_rng_kernel<true><<<grid, 256, 0, s>>>(rows, n, row_ids, mean, C, status, seed, offset, X, z_out, mirror);
-  else
-    sep_ask_rng_kernel<false><<<grid, 256, 0, s>>>(rows, n, row_ids, mean, C, status, seed, offset, X, z_out, mirror);
+  const dim3 grid((unsigned)gx, (unsigned)gy);
+  kernels[variant]<<<grid, kZigThreads, kZigSmem, (cudaStream_t)stream>>>(
+      rows, n, row_ids, mean, C, status, PhiloxKeys((uint32_t)seed, (uint32_t)(seed >> 32)), offset, X, z_out, mirror,
+      (uint64_t)gy * (uint64_t)qpr, gy * n);
   return check_launch("sep_ask_rng_kernel");
 }
 
@@ -915,9 +1039,7 @@ static int lmma_ask_impl(double* z, int generate, uint64_t seed, uint64_t offset
     cudaStream_t bs = side ? side->s[slot] : s;
     double* zb = z + r0 * n;
     if (generate) {  // r0 * n is a multiple of 4 (r0 of 32): the block's quads are the flat fill's quads
-      fill_normal_zig_kernel<<<grid_for((nr * n + 3) / 4, 256, 6), 256, 0, bs>>>(zb, nr * n, seed,
-                                                                               offset + (uint64_t)(r0 * n / 4));
-      if ((rc = check_launch("fill_normal_zig_kernel"))) return rc;
+      if ((rc = launch_fill_zig(zb, nr * n, seed, offset + (uint64_t)(r0 * n / 4), bs))) return rc;
     }
     rc = lmma_block(zb, nr, n, row_ids ? row_ids + r0 : nullptr, mean, status, M, cd, m, row_ids ? X : X + r0 * n,
                     m > 0 ? ws + w.g : nullptr, m > 0 ? ws + w.block0 + slot * w.block_stride : nullptr, w, bs);
