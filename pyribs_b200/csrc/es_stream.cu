@@ -410,6 +410,11 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
   const int bytes = pred ? 8 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {  // !pred: zero fill
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -436,6 +441,7 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
+template <bool WIDE>  // n even and 16-byte aligned operands: the ring is fed 16 bytes per copy instead of 8
 __global__ void __launch_bounds__(256, 2) tall_dots_kernel(const double* __restrict__ A, int64_t rows, int64_t n,
                                                            const double* __restrict__ M, int m, int64_t cols_per_split,
                                                            double* __restrict__ part) {
@@ -448,18 +454,21 @@ __global__ void __launch_bounds__(256, 2) tall_dots_kernel(const double* __restr
   const int64_t cend = cbeg + cols_per_split < n ? cbeg + cols_per_split : n;
   const int nch = (int)((cend - cbeg + kTdCols - 1) / kTdCols);
   // a thread copies the same (row, column) slots of every chunk: 8 of A, 6 of M. Slot i: element i * 256 + t of
-  // the 64-wide tile, i.e. row i * 4 + t / 64, column t % 64; pointers and row predicates are loop invariants
-  const int lc = t & 63, lr = t >> 6;
-  const double* a_src[kTdRows / 4];
-  const double* m_src[kTdVecs / 4];
+  // the 64-wide tile, i.e. row i * 4 + t / 64, column t % 64 (WIDE: 4 of A and 3 of M, two columns each: row
+  // i * 8 + t / 32, columns 2 (t % 32) and the next; split edges and n are even, so a pair is in or out as a whole);
+  // pointers and row predicates are loop invariants
+  constexpr int kW = WIDE ? 2 : 1, kRowStep = 4 * kW;
+  const int lc = WIDE ? 2 * (t & 31) : (t & 63), lr = WIDE ? t >> 5 : t >> 6;
+  const double* a_src[kTdRows / kRowStep];
+  const double* m_src[kTdVecs / kRowStep];
 #pragma unroll
-  for (int i = 0; i < kTdRows / 4; ++i) {
-    const int64_t row = row0 + i * 4 + lr;
+  for (int i = 0; i < kTdRows / kRowStep; ++i) {
+    const int64_t row = row0 + i * kRowStep + lr;
     a_src[i] = row < rows ? A + row * n + cbeg + lc : nullptr;
   }
 #pragma unroll
-  for (int i = 0; i < kTdVecs / 4; ++i) {
-    const int j = j0 + i * 4 + lr;
+  for (int i = 0; i < kTdVecs / kRowStep; ++i) {
+    const int j = j0 + i * kRowStep + lr;
     m_src[i] = j < m ? M + (int64_t)j * n + cbeg + lc : nullptr;
   }
   auto issue = [&](int ch) {
@@ -468,14 +477,20 @@ __global__ void __launch_bounds__(256, 2) tall_dots_kernel(const double* __restr
     const int64_t off = (int64_t)ch * kTdCols;
     const bool okc = cbeg + off + lc < cend;  // false only in the ragged last chunk
 #pragma unroll
-    for (int i = 0; i < kTdRows / 4; ++i) {
+    for (int i = 0; i < kTdRows / kRowStep; ++i) {
       const bool ok = okc && a_src[i] != nullptr;
-      cp_async8(As + i * 4 * kTdLd, ok ? a_src[i] + off : A, ok);
+      if (WIDE)
+        cp_async16(As + i * kRowStep * kTdLd, ok ? a_src[i] + off : A, ok);
+      else
+        cp_async8(As + i * kRowStep * kTdLd, ok ? a_src[i] + off : A, ok);
     }
 #pragma unroll
-    for (int i = 0; i < kTdVecs / 4; ++i) {
+    for (int i = 0; i < kTdVecs / kRowStep; ++i) {
       const bool ok = okc && m_src[i] != nullptr;
-      cp_async8(Ms + i * 4 * kTdLd, ok ? m_src[i] + off : M, ok);
+      if (WIDE)
+        cp_async16(Ms + i * kRowStep * kTdLd, ok ? m_src[i] + off : M, ok);
+      else
+        cp_async8(Ms + i * kRowStep * kTdLd, ok ? m_src[i] + off : M, ok);
     }
   };
   double acc[kTdRows / 8][kTdVecs / 8][2];
@@ -847,7 +862,7 @@ static LmmaWs lmma_ws(int64_t rows, int64_t n, int64_t m) {
 
 struct SideStreams {
   cudaStream_t s[kLmmaSlots];
-  cudaEvent_t fork, join[kLmmaSlots];
+  cudaEvent_t fork, gram, join[kLmmaSlots];
   bool ready = false;
 };
 
@@ -863,6 +878,7 @@ static int side_streams(SideStreams** out) {
       QD_CHECK_CUDA(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming));
     }
     QD_CHECK_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    QD_CHECK_CUDA(cudaEventCreateWithFlags(&p.gram, cudaEventDisableTiming));
     p.ready = true;
   }
   *out = &p;
@@ -873,11 +889,15 @@ static int launch_tall_dots(const double* A, int64_t rows, int64_t n, const doub
                             cudaStream_t s) {
   const TdPlan p = td_plan(rows, n, m);
   QD_REQUIRE(p.groups <= 65535 && p.nsplit <= 65535, "too many direction vectors");
-  static bool attr[64] = {};
-  int rc0 = opt_in_smem(tall_dots_kernel, kTdSmem, attr);
+  static bool attr[64] = {}, attr_wide[64] = {};
+  const bool wide = n % 2 == 0 && (((uintptr_t)A | (uintptr_t)M) & 15u) == 0;
+  int rc0 = wide ? opt_in_smem(tall_dots_kernel<true>, kTdSmem, attr_wide) : opt_in_smem(tall_dots_kernel<false>, kTdSmem, attr);
   if (rc0) return rc0;
-  tall_dots_kernel<<<dim3(p.row_tiles, p.nsplit, p.groups), 256, kTdSmem, s>>>(A, rows, n, M, (int)m,
-                                                                               p.cols_per_split, part);
+  const dim3 grid(p.row_tiles, p.nsplit, p.groups);
+  if (wide)
+    tall_dots_kernel<true><<<grid, 256, kTdSmem, s>>>(A, rows, n, M, (int)m, p.cols_per_split, part);
+  else
+    tall_dots_kernel<false><<<grid, 256, kTdSmem, s>>>(A, rows, n, M, (int)m, p.cols_per_split, part);
   return check_launch("tall_dots_kernel");
 }
 
@@ -1018,20 +1038,21 @@ static int lmma_ask_impl(double* z, int generate, uint64_t seed, uint64_t offset
   const int m = (int)itrs;
   LmmaWs w = {};
   double* ws = workspace;
+  if (m > 0) w = lmma_ws(rows, n, m);
+  const int64_t rb = lmma_block_rows(rows, n);
+  const int64_t nblocks = (rows + rb - 1) / rb;
+  SideStreams* side = nullptr;
+  if (nblocks > 1) {  // the side streams start (with their generators) before G, which only the substitution needs
+    if ((rc = side_streams(&side))) return rc;
+    QD_CHECK_CUDA(cudaEventRecord(side->fork, s));
+    for (int i = 0; i < kLmmaSlots; ++i) QD_CHECK_CUDA(cudaStreamWaitEvent(side->s[i], side->fork, 0));
+  }
   if (m > 0) {
-    w = lmma_ws(rows, n, m);
     if ((rc = launch_tall_dots(M, m, n, M, m, ws + w.gpart, s))) return rc;  // G = M M^T
     sum_splits_kernel<<<grid_for((int64_t)m * m * 32, 256), 256, 0, s>>>(ws + w.gpart, td_plan(m, n, m).nsplit,
                                                                    (int64_t)m * m, ws + w.g);
     if ((rc = check_launch("sum_splits_kernel"))) return rc;
-  }
-  const int64_t rb = lmma_block_rows(rows, n);
-  const int64_t nblocks = (rows + rb - 1) / rb;
-  SideStreams* side = nullptr;
-  if (nblocks > 1) {
-    if ((rc = side_streams(&side))) return rc;
-    QD_CHECK_CUDA(cudaEventRecord(side->fork, s));
-    for (int i = 0; i < kLmmaSlots; ++i) QD_CHECK_CUDA(cudaStreamWaitEvent(side->s[i], side->fork, 0));
+    if (side) QD_CHECK_CUDA(cudaEventRecord(side->gram, s));
   }
   for (int64_t b = 0; b < nblocks; ++b) {
     const int64_t r0 = b * rb, nr = rows - r0 < rb ? rows - r0 : rb;
@@ -1041,6 +1062,7 @@ static int lmma_ask_impl(double* z, int generate, uint64_t seed, uint64_t offset
     if (generate) {  // r0 * n is a multiple of 4 (r0 of 32): the block's quads are the flat fill's quads
       if ((rc = launch_fill_zig(zb, nr * n, seed, offset + (uint64_t)(r0 * n / 4), bs))) return rc;
     }
+    if (side && m > 0 && b < kLmmaSlots) QD_CHECK_CUDA(cudaStreamWaitEvent(bs, side->gram, 0));
     rc = lmma_block(zb, nr, n, row_ids ? row_ids + r0 : nullptr, mean, status, M, cd, m, row_ids ? X : X + r0 * n,
                     m > 0 ? ws + w.g : nullptr, m > 0 ? ws + w.block0 + slot * w.block_stride : nullptr, w, bs);
     if (rc) return rc;
