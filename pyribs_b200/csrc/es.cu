@@ -403,20 +403,50 @@ __global__ void __launch_bounds__(256) lmma_tell_ps_kernel(int64_t n, const doub
   if (threadIdx.x == 0) blocksum[blockIdx.x] = t;
 }
 
-__global__ void __launch_bounds__(256) lmma_tell_m_kernel(int64_t n, int64_t n_vectors, const double* __restrict__ z_mean,
+// m_i <- (1 - cc_i) m_i + sqrt(mueff cc_i (2 - cc_i)) z_mean for every direction vector (_lm_ma_es.py:217-225): a
+// stream over n_vectors x n (654 MB read + written at the default n_vectors = batch size). A CTA owns a column strip
+// of 256 threads (VEC2: two columns each, 16-byte accesses) and a range of vectors whose two coefficients it
+// computes once, into shared memory; z_mean stays in registers.
+constexpr int kLmTellVecs = 128;  // vectors per CTA at most
+
+template <bool VEC2>
+__global__ void __launch_bounds__(256) lmma_tell_m_kernel(int64_t n, int64_t n_vectors, int64_t vecs_per_cta,
+                                                          const double* __restrict__ z_mean,
                                                           const double* __restrict__ new_mean, double* __restrict__ mean,
                                                           double* __restrict__ Mv, const double* __restrict__ cc,
                                                           double csigma, double mueff, double* __restrict__ status,
                                                           const double* __restrict__ blocksum, int nblocks) {
-  const int64_t total = n_vectors * n;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = e / n, j = e - i * n;
-    const double c = cc[i];
-    Mv[e] = __dadd_rn(__dmul_rn(1.0 - c, Mv[e]), __dmul_rn(sqrt(mueff * c * (2.0 - c)), z_mean[j]));
+  __shared__ double keep[kLmTellVecs], gain[kLmTellVecs];
+  const int64_t i0 = (int64_t)blockIdx.y * vecs_per_cta;
+  const int nv = (int)(n_vectors - i0 < vecs_per_cta ? n_vectors - i0 : vecs_per_cta);
+  for (int v = threadIdx.x; v < nv; v += 256) {
+    const double c = cc[i0 + v];
+    keep[v] = 1.0 - c;
+    gain[v] = sqrt(mueff * c * (2.0 - c));
   }
-  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
-    mean[j] = new_mean[j];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  __syncthreads();
+  const int64_t j = (blockIdx.x * (int64_t)256 + threadIdx.x) * (VEC2 ? 2 : 1);
+  if (j < n) {
+    if (VEC2) {  // n even: every pair is whole and 16-byte aligned
+      const double2 zm = *reinterpret_cast<const double2*>(z_mean + j);
+      double2* col = reinterpret_cast<double2*>(Mv + i0 * n + j);
+#pragma unroll 4
+      for (int v = 0; v < nv; ++v) {
+        double2 mv = col[(int64_t)v * (n / 2)];
+        mv.x = __dadd_rn(__dmul_rn(keep[v], mv.x), __dmul_rn(gain[v], zm.x));
+        mv.y = __dadd_rn(__dmul_rn(keep[v], mv.y), __dmul_rn(gain[v], zm.y));
+        col[(int64_t)v * (n / 2)] = mv;
+      }
+      if (blockIdx.y == 0) *reinterpret_cast<double2*>(mean + j) = *reinterpret_cast<const double2*>(new_mean + j);
+    } else {
+      const double zm = z_mean[j];
+      double* col = Mv + i0 * n + j;
+#pragma unroll 4
+      for (int v = 0; v < nv; ++v) col[(int64_t)v * n] = __dadd_rn(__dmul_rn(keep[v], col[(int64_t)v * n]), __dmul_rn(gain[v], zm));
+      if (blockIdx.y == 0) mean[j] = new_mean[j];
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     double ssq = 0.0;
     for (int b = 0; b < nblocks; ++b) ssq += blocksum[b];
     status[kStatusSsq] = ssq;
@@ -958,7 +988,24 @@ extern "C" int qd_lmma_tell(int64_t n, int64_t n_vectors, const double* new_mean
   lmma_tell_ps_kernel<<<nb, 256, 0, s>>>(n, z_mean, ps, csigma, mueff, ws);
   int rc = check_launch("lmma_tell_ps_kernel");
   if (rc) return rc;
-  lmma_tell_m_kernel<<<grid_for(n_vectors * n, 256), 256, 0, s>>>(n, n_vectors, z_mean, new_mean, mean, M, cc, csigma,
-                                                                 mueff, status, ws, nb);
+  // column strips x vector ranges: enough CTAs for eight per SM, at most kLmTellVecs vectors each; with no vectors
+  // one row of CTAs still copies the mean and updates sigma
+  const bool vec2 = n % 2 == 0 && (((uintptr_t)M | (uintptr_t)z_mean | (uintptr_t)mean | (uintptr_t)new_mean) & 15u) == 0;
+  const int64_t gx = vec2 ? (n / 2 + 255) / 256 : (n + 255) / 256;
+  int64_t gy = (8 * (int64_t)kNumSMs + gx - 1) / gx;
+  if (gy > n_vectors) gy = n_vectors;
+  if (gy < 1) gy = 1;
+  int64_t vpc = (n_vectors + gy - 1) / gy;
+  if (vpc > kLmTellVecs) vpc = kLmTellVecs;
+  if (vpc < 1) vpc = 1;
+  gy = n_vectors > 0 ? (n_vectors + vpc - 1) / vpc : 1;
+  QD_REQUIRE(gx <= 0x7fffffff && gy <= 65535, "sizes out of range");
+  const dim3 grid((unsigned)gx, (unsigned)gy);
+  if (vec2)
+    lmma_tell_m_kernel<true><<<grid, 256, 0, s>>>(n, n_vectors, vpc, z_mean, new_mean, mean, M, cc, csigma, mueff, status,
+                                                  ws, nb);
+  else
+    lmma_tell_m_kernel<false><<<grid, 256, 0, s>>>(n, n_vectors, vpc, z_mean, new_mean, mean, M, cc, csigma, mueff, status,
+                                                   ws, nb);
   return check_launch("lmma_tell_m_kernel");
 }

@@ -1,6 +1,6 @@
 """Times the ziggurat generator kernels alone (CUDA events, 20 launches after 5 warm-ups) at configs[3] scale:
 qd_fill_normal_zig (41 M normals), qd_sep_ask_rng (4096 x 10 000, with and without z_out / row_ids), and the
-strategies' own ask / tell. Usage: zig_probe.py"""
+strategies' own ask and tell. Usage: zig_probe.py"""
 import json
 import os
 import sys
@@ -23,6 +23,19 @@ def timed(fn, iters=20, warm=5):
     b.record()
     torch.cuda.synchronize()
     return a.elapsed_time(b) / iters * 1e3  # us
+
+
+def timed_wall(fn, iters=20, warm=5):
+    import time
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / iters * 1e6  # us
 
 
 def main():
@@ -62,7 +75,8 @@ def main():
             es.ask(return_device=True)
             es.tell(rank, None, lam // 2)
         ask = timed(lambda: es.ask(return_device=True), iters=10, warm=2)
-        print(json.dumps({"es": name, **kw, "ask_us": ask}), flush=True)
+        tell = timed_wall(lambda: es.tell(rank, None, lam // 2), iters=10, warm=2)  # (tell runs on the strategy's stream)
+        print(json.dumps({"es": name, **kw, "ask_us": ask, "tell_us": tell}), flush=True)
 
 
 if __name__ == "__main__":
