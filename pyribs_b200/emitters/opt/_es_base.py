@@ -122,6 +122,12 @@ class DeviceES:
         if self._stream is None:
             self._stream = torch.cuda.Stream(device=self._device)
             self._ask_event = torch.cuda.Event()
+        # Entered from the caller's stream, the ES stream first gets behind it: the state tensors were initialised
+        # there, and rankings / injected normals handed in as CUDA tensors are produced there. (Inside a
+        # `with torch.cuda.stream(es_stream)` block the two are the same stream and nothing is recorded.)
+        cur = torch.cuda.current_stream(self._device)
+        if cur != self._stream:
+            self._stream.wait_stream(cur)
         return self._stream
 
     def _enqueue_host_copy(self):

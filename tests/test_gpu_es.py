@@ -70,6 +70,43 @@ def test_es_trace(name):
             assert_close(gpu.invsqrt, g["invsqrt"], RTOL, f"{name} g{gi} invsqrt")
 
 
+@pytest.mark.parametrize("es_name", ["sep_cma_es", "cma_es", "lm_ma_es"])
+def test_es_stream_is_ordered_behind_the_callers_stream(es_name):
+    """A strategy works on its own CUDA stream; its state is initialised, and CUDA-tensor rankings are produced, on
+    the caller's. With the caller's stream kept busy (a 20 ms spin kernel) the strategy must still see both: the
+    first generation equals the oracle's, and a tell fed a ranking computed behind a second spin moves the mean
+    exactly as the same ranking handed over as a NumPy array does."""
+    import torch
+
+    from pyribs_b200.emitters.opt import _get_es
+
+    n, lam = 12, 10
+    x0 = np.linspace(-1, 1, n)
+    rng = np.random.default_rng(5)
+    z = rng.standard_normal((lam, n))
+    ora = O.ORACLE_ES[es_name](0.7, n, lam, seed=1)
+    ora.reset(x0)
+    want = ora.ask(z)
+
+    def build():
+        torch.cuda._sleep(40_000_000)  # ~20 ms of the caller's stream ahead of the constructor's fills
+        es = _get_es(es_name, sigma0=0.7, solution_dim=n, batch_size=lam, seed=1, dtype=np.float64,
+                     lower_bounds=np.full(n, -np.inf), upper_bounds=np.full(n, np.inf))
+        es.reset(x0)
+        return es
+
+    a, b = build(), build()
+    assert_close(a.ask(z=z), want, 1e-9, "first generation behind a busy caller stream")
+    assert_close(b.ask(z=z), want, 1e-9, "first generation behind a busy caller stream")
+    fit = torch.from_numpy(-np.sum((want - 0.3) ** 2, axis=1)).cuda()
+    torch.cuda._sleep(40_000_000)
+    rank_d = torch.argsort(fit, descending=True)  # still queued behind the spin when tell() returns
+    a.tell(rank_d, None, lam // 2)
+    b.tell(rank_d.cpu().numpy(), None, lam // 2)
+    np.testing.assert_array_equal(a.mean, b.mean)
+    assert not np.array_equal(a.mean, x0)
+
+
 def test_cma_own_eigensystem_is_consistent():
     """The cuSOLVER path (no injection): C = B L B^T, C^-1/2 matches NumPy on the same C."""
     from pyribs_b200.emitters.opt import CMAEvolutionStrategy
