@@ -102,6 +102,8 @@ class CMAPool:
         """Samples lambda solutions for every strategy: one refresh sequence for the strategies whose
         eigensystem is stale (_cma_es.py:51-82), one Philox fill, one batched GEMM, one D2H copy."""
         S = self.strategies
+        # X is about to be overwritten: get behind whatever the caller's stream still does with the last round's
+        self._stream.wait_stream(torch.cuda.current_stream(self._device))
         with torch.cuda.device(self._device), torch.cuda.stream(self._stream):
             stale = [e for e, es in enumerate(S) if es.current_eval > es.updated_eval + es.lazy_gap_evals]
             if stale:
