@@ -318,6 +318,24 @@ def es_lines(torch, dev, peak_hbm, cpu=True):
                 t_ask.append(ev[0].elapsed_time(ev[1]))
                 t_tell.append(ev[2].elapsed_time(ev[3]))
         a, t = float(np.median(t_ask)), float(np.median(t_tell))
+        # steady state: generations back to back, no synchronisation in between (the host enqueues generation g + 1
+        # while the GPU runs generation g, as it does in a loop with a GPU evaluator); the ranking is a fixed device
+        # permutation -- the evaluation is not part of this metric -- so the time is ask + tell and nothing else
+        rank_fixed = torch.randperm(lam, device=dev)
+        pe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        # (with the default n_vectors = batch size the LM-MA ask grows by one direction vector per generation until
+        # 4096 are in use: that line is quoted over generations warm + 10 .. warm + 30 and says so)
+        K = 40 if (es_name == "sep_cma_es" or "n_vectors" in kw) else 10
+        for rep in range(2):  # (the first pass warms the loop up)
+            torch.cuda.synchronize()
+            pe[0].record()
+            for g in range(K):
+                X = es.ask(return_device=True)
+                es.tell(rank_fixed, None, mu)
+            cur.wait_stream(es._es_stream())
+            pe[1].record()
+            torch.cuda.synchronize()
+        steady_ms = pe[0].elapsed_time(pe[1]) / K
         # end to end: NumPy out of ask (D2H of the lam x n samples), NumPy ranking into tell
         e2e = []
         for g in range(4):
@@ -341,9 +359,14 @@ def es_lines(torch, dev, peak_hbm, cpu=True):
                         "lm_ma_es": "fill_normal_zig + tall_dots (fp64 mma) + lmma_coef + lmma_out (fp64 mma) / "
                                     "wsum_partial_kernel x2 + lmma_tell_*"}[es_name] + ", csrc/es_stream.cu, es.cu",
              "workload": f"{es_name} n={n} lambda={lam} mu={mu}" + (f" n_vectors={m}" if m else ""),
-             "metric": "emitter ask+tell solutions/sec", "solutions_per_s": lam / ((a + t) * 1e-3),
-             "bound": "hbm", "achieved": (ask_b + tell_b) / ((a + t) * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
-             "frac": (ask_b + tell_b) / ((a + t) * 1e-3) / 1e9 / peak_hbm,
+             "metric": "emitter ask+tell solutions/sec", "solutions_per_s": lam / (steady_ms * 1e-3),
+             "ms_per_generation": steady_ms,
+             "timing": f"solutions_per_s / ms_per_generation / achieved / frac: {K} generations back to back (ask + tell, "
+                       "fixed device ranking, no synchronisation between generations); ask_ms / tell_ms: one call from "
+                       "an idle GPU, host launch latency included (solutions_per_s_single_calls is their sum's rate)",
+             "solutions_per_s_single_calls": lam / ((a + t) * 1e-3),
+             "bound": "hbm", "achieved": (ask_b + tell_b) / (steady_ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+             "frac": (ask_b + tell_b) / (steady_ms * 1e-3) / 1e9 / peak_hbm,
              "ask_ms": a, "tell_ms": t, "ask_GBps": ask_b / a / 1e6, "tell_GBps": tell_b / t / 1e6,
              "algorithmic_bytes": ask_b + tell_b,
              "e2e": {"value": lam / e2e_s, "unit": "solutions/s", "d2h_bytes_per_step": lam * n * 8,
