@@ -71,7 +71,7 @@ def main():
                      lower_bounds=np.full(n, -np.inf), upper_bounds=np.full(n, np.inf), **kw)
         es.reset(np.zeros(n))
         rank = torch.randperm(lam, device="cuda")
-        for _ in range(3):
+        for _ in range(24):  # LM-MA uses min(generations, n_vectors) direction vectors: let all 20 come into play
             es.ask(return_device=True)
             es.tell(rank, None, lam // 2)
         ask = timed(lambda: es.ask(return_device=True), iters=10, warm=2)
