@@ -1,11 +1,12 @@
 // A13 / A14 at configs[3] scale (solution_dim = 10 000, batch 4096): the streaming side of the evolution
 // strategies (reference ribs/emitters/opt/_sep_cma_es.py:140-191, _lm_ma_es.py:126-194).
 //
-//   * unit normals: Philox4x32-10 bits through a ziggurat (the method NumPy's Generator.standard_normal
-//     uses, numpy/random/src/distributions: one table look-up, one multiply and one compare for almost all
-//     samples; wedges and the tail by rejection in fp64). 52-bit uniforms, exact N(0,1) law, at a fraction
-//     of the instruction count of a double-precision Box-Muller, which made the fill kernel compute-bound
-//     (213 us for 41 M normals against 50 us of HBM time).
+//   * unit normals: Philox4x32-10 bits through a 4096-layer ziggurat (the method NumPy's
+//     Generator.standard_normal uses, numpy/random/src/distributions: one table look-up, one fused multiply-add
+//     and one compare for 99.88 % of the samples; wedges and the tail by rejection in fp64, parked per warp and
+//     resolved 32 at a time). 51-bit uniforms, N(0,1) law, at a fraction of the instruction count of a
+//     double-precision Box-Muller, which made the fill kernel compute-bound (213 us for 41 M normals against
+//     50 us of HBM time; this generator: 82 us, bound by the IMAD.WIDE rate of Philox's multiplies).
 //   * sep-CMA ask: generator fused with the transform -- X is the only HBM traffic (lambda * n * 8 bytes).
 //   * LM-MA ask: the reference applies `itrs` rank-one transforms d <- (1-c_j) d + c_j m_j (m_j . d) one
 //     after the other to every sample row (:136-144). With d_j = Q_j (z + sum_{i<j} t_i m_i),
